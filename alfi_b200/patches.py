@@ -1,0 +1,130 @@
+"""PCPATCH dof-set construction and patch colouring (host side, vectorised numpy).
+
+Restates what PETSc's PCPATCH derives from the point sets handed to it by the constructors of
+:mod:`alfi_b200.relaxation` / :mod:`alfi_b200.transfer` (selected in alfi/solver.py:318-344 and
+alfi/transfer.py:100-113); PETSc's source is not in the reference tree, the semantics are
+those written down in SURVEY.md Appendix A.1:
+
+* ``ht``  = the user's point set; ``cht`` = closure of every cell in the star of a point of ht;
+* patch cells = cells of ``cht`` (ascending);
+* patch dofs = dofs attached to points of ``ht`` minus the global Dirichlet dofs; dofs seen on
+  ``cht`` but not attached to ``ht`` are artificial boundary conditions and are dropped;
+* local numbering = first encounter walking patch cells in order, nodes in ``cell_node_list``
+  order, components innermost;
+* patches with no dofs are kept (empty) so patch indices stay aligned with the iteration set.
+
+The literal, loop-based restatement used as the checker is ``oracle/pcpatch.py``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import scipy.sparse as sp
+
+__all__ = ["PatchSet", "patch_dofs_from_points", "points_to_csr", "greedy_colouring"]
+
+
+@dataclass
+class PatchSet:
+    offsets: np.ndarray        # int64 (npatch+1)
+    dofs: np.ndarray           # int32 scalar dof indices, patch-local order
+    order: np.ndarray          # int32 iteration set (indices into patches)
+    bs: int
+    colours: np.ndarray | None = None     # int32 (npatch,), greedy colouring in iteration order
+
+    @property
+    def npatch(self):
+        return self.offsets.size - 1
+
+    @property
+    def sizes(self):
+        return np.diff(self.offsets)
+
+    def patch(self, i):
+        return self.dofs[self.offsets[i]:self.offsets[i + 1]]
+
+
+def points_to_csr(point_lists, npoints):
+    """list of int arrays (possibly with duplicates, as the reference produces) → CSR boolean."""
+    lens = np.fromiter((len(p) for p in point_lists), dtype=np.int64, count=len(point_lists))
+    rows = np.repeat(np.arange(len(point_lists)), lens)
+    cols = np.concatenate([np.asarray(p, dtype=np.int64) for p in point_lists]) if len(point_lists) else np.empty(0, np.int64)
+    H = sp.csr_matrix((np.ones(rows.size, dtype=np.int32), (rows, cols)), shape=(len(point_lists), npoints))
+    H.sum_duplicates()
+    H.data[:] = 1
+    H.sort_indices()
+    return H
+
+
+def patch_dofs_from_points(plex, V, H, bc_nodes=None, order=None) -> PatchSet:
+    """Patch dof lists for point sets H (CSR npatch x npoints) on space V (see module doc)."""
+    npatch = H.shape[0]
+    bs = V.bs
+    nn = np.int64(V.nnodes)
+    H = H.tocsr().astype(np.int32)
+    # patch cells: cells in the star of any point of ht
+    Hc = (H @ plex.star.astype(np.int32)).tocsr()[:, plex.cStart:plex.cEnd].tocsr()
+    Hc.sort_indices()
+    # owned nodes: nodes attached to points of ht
+    npt = plex.node_points(V)
+    NP = sp.csr_matrix((np.ones(V.nnodes, dtype=np.int32), (npt, np.arange(V.nnodes))),
+                       shape=(plex.npoints, V.nnodes))
+    O = (H @ NP).tocsr()
+    O.sort_indices()
+    okeys = np.repeat(np.arange(npatch, dtype=np.int64), np.diff(O.indptr)) * nn + O.indices
+    # walk (patch, cell, local node)
+    nl = V.cell_nodes.shape[1]
+    pc_patch = np.repeat(np.arange(npatch, dtype=np.int64), np.diff(Hc.indptr))
+    nodes = V.cell_nodes[Hc.indices]                            # (npairs, nl)
+    keys = (pc_patch[:, None] * nn + nodes).ravel()
+    pos = np.searchsorted(okeys, keys)
+    pos[pos == okeys.size] = 0
+    keep = okeys[pos] == keys if okeys.size else np.zeros(keys.size, dtype=bool)
+    if bc_nodes is not None and len(bc_nodes):
+        isbc = np.zeros(V.nnodes, dtype=bool)
+        isbc[np.asarray(bc_nodes)] = True
+        keep &= ~isbc[nodes.ravel()]
+    kept = keys[keep]
+    _, first = np.unique(kept, return_index=True)
+    first.sort()
+    sel = kept[first]                                           # first-encounter order, grouped by patch
+    p_of = sel // nn
+    node = sel % nn
+    counts = np.bincount(p_of, minlength=npatch).astype(np.int64)
+    offsets = np.zeros(npatch + 1, dtype=np.int64)
+    np.cumsum(counts * bs, out=offsets[1:])
+    dofs = (node[:, None] * bs + np.arange(bs)[None, :]).ravel().astype(np.int32)
+    if order is None:
+        order = np.arange(npatch, dtype=np.int32)
+    return PatchSet(offsets, dofs, np.asarray(order, dtype=np.int32), bs)
+
+
+def greedy_colouring(ps: PatchSet, ndofs: int) -> np.ndarray:
+    """Greedy colouring: patches in iteration-set order, lowest free colour, conflict = shared dof.
+
+    The reference has no colouring (PETSc applies patches sequentially); this definition is
+    ours and is what makes the device scatter-add race-free and deterministic.
+    Patches that appear several times in the iteration set (multi-sweep sort orders) keep the
+    colour of their first visit.
+    """
+    used = np.zeros(ndofs, dtype=np.uint64)
+    colours = np.full(ps.npatch, -1, dtype=np.int32)
+    one = np.uint64(1)
+    for p in ps.order:
+        if colours[p] >= 0:
+            continue
+        d = ps.dofs[ps.offsets[p]:ps.offsets[p + 1]]
+        if d.size == 0:
+            colours[p] = 0
+            continue
+        m = int(np.bitwise_or.reduce(used[d]))
+        c = 0
+        while (m >> c) & 1:
+            c += 1
+        if c >= 64:
+            raise RuntimeError("more than 64 colours needed")
+        colours[p] = c
+        used[d] |= one << np.uint64(c)
+    ps.colours = colours
+    return colours

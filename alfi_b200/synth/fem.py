@@ -1,0 +1,389 @@
+"""Vector Lagrange finite elements on the synthetic meshes + assembly of the velocity block.
+
+Stands in for UFL/TSFC/PyOP2 assembly (host side; in a deployment Firedrake does this and hands
+the BAIJ values over once per Newton step).  The operator is the (1,1) block of the Newton
+linearisation of the reference's residuals:
+
+* Scott–Vogelius (alfi/solver.py:613-623):
+  ``nu*(2 sym grad u, grad v) + gamma*(div u, div v) + advect*((w.grad)u + (u.grad)w, v)``
+* [Pk]^d–P0 (alfi/solver.py:562-572): same with ``gamma*(cell_avg(div u), div v)``.
+
+and the transfer forms of alfi/transfer.py:295-309 (SV) / 319-332 (PkP0).
+
+Everything is reduced to reference tensors contracted with the affine cell geometry, so the
+assembly is a handful of dense matmuls per chunk of cells.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field
+from functools import lru_cache
+
+import numpy as np
+import scipy.sparse as sp
+from scipy.special import roots_jacobi
+
+from .mesh import LOCAL_EDGES, LOCAL_FACES, SimplexMesh
+
+__all__ = ["LagrangeElement", "VectorSpace", "assemble_velocity_block", "BSR", "reference_tensors"]
+
+
+# --------------------------------------------------------------------------- reference element
+def _lattice(dim: int, k: int):
+    """Barycentric coordinates of the Pk nodes, entity by entity.
+
+    Returns (bary (n, dim+1), entity list [(edim, local entity index, #nodes)]) in the order
+    vertices, edges (low→high vertex), faces, cell interior.  Supports k <= 3.
+    """
+    if not 1 <= k <= 3:
+        raise NotImplementedError("Lagrange degree 1..3 only")
+    nvl = dim + 1
+    pts, ents = [], []
+    for v in range(nvl):
+        lam = np.zeros(nvl)
+        lam[v] = 1.0
+        pts.append(lam)
+        ents.append((0, v, 1))
+    for e, (a, b) in enumerate(LOCAL_EDGES[dim]):
+        for j in range(1, k):
+            lam = np.zeros(nvl)
+            lam[a] = (k - j) / k
+            lam[b] = j / k
+            pts.append(lam)
+        ents.append((1, e, k - 1))
+    if k == 3:
+        if dim == 2:
+            pts.append(np.full(3, 1.0 / 3.0))
+            ents.append((2, 0, 1))
+        else:
+            for f, (a, b, c) in enumerate(LOCAL_FACES[3]):
+                lam = np.zeros(4)
+                lam[[a, b, c]] = 1.0 / 3.0
+                pts.append(lam)
+                ents.append((2, f, 1))
+    return np.array(pts), ents
+
+
+def _monomials(dim: int, k: int):
+    return [e for e in itertools.product(range(k + 1), repeat=dim) if sum(e) <= k]
+
+
+def _eval_monomials(expo, x, deriv=None):
+    """x: (..., dim).  deriv=None → values (..., nmono); deriv=a → d/dx_a."""
+    out = np.ones(x.shape[:-1] + (len(expo),))
+    for m, e in enumerate(expo):
+        v = np.ones(x.shape[:-1])
+        for a, p in enumerate(e):
+            if deriv == a:
+                v = v * (p * x[..., a] ** (p - 1) if p > 0 else 0.0)
+            else:
+                v = v * x[..., a] ** p
+        out[..., m] = v
+    return out
+
+
+def simplex_quadrature(dim: int, degree: int):
+    """Collapsed Gauss–Jacobi rule on the reference simplex, exact to ``degree``."""
+    n = degree // 2 + 1
+    x0, w0 = roots_jacobi(n, 0, 0)
+    x0, w0 = (x0 + 1) / 2, w0 / 2
+    x1, w1 = roots_jacobi(n, 1, 0)
+    x1, w1 = (x1 + 1) / 2, w1 / 4
+    if dim == 2:
+        X1, X0 = np.meshgrid(x1, x0, indexing="ij")
+        W = np.outer(w1, w0)
+        pts = np.stack([X1.ravel(), (X0 * (1 - X1)).ravel()], axis=1)
+        return pts, W.ravel()
+    x2, w2 = roots_jacobi(n, 2, 0)
+    x2, w2 = (x2 + 1) / 2, w2 / 8
+    X2, X1, X0 = np.meshgrid(x2, x1, x0, indexing="ij")
+    W = w2[:, None, None] * w1[None, :, None] * w0[None, None, :]
+    a = X2
+    b = X1 * (1 - X2)
+    c = X0 * (1 - X1) * (1 - X2)
+    return np.stack([a.ravel(), b.ravel(), c.ravel()], axis=1), W.ravel()
+
+
+@dataclass(frozen=True)
+class LagrangeElement:
+    dim: int
+    degree: int
+
+    @property
+    def nodes_bary(self):
+        return _lattice(self.dim, self.degree)[0]
+
+    @property
+    def entities(self):
+        return _lattice(self.dim, self.degree)[1]
+
+    @property
+    def nnodes(self):
+        return self.nodes_bary.shape[0]
+
+    @property
+    def nodes_ref(self):
+        return self.nodes_bary[:, 1:]      # reference coords: vertex 0 at origin, vertex i at e_i
+
+    def _coeffs(self):
+        return _coeffs(self.dim, self.degree)
+
+    def tabulate(self, x):
+        """Basis values at reference points x (npts, dim) → (npts, nnodes)."""
+        expo = _monomials(self.dim, self.degree)
+        return _eval_monomials(expo, x) @ self._coeffs()
+
+    def tabulate_grad(self, x):
+        """Reference gradients → (npts, nnodes, dim)."""
+        expo = _monomials(self.dim, self.degree)
+        C = self._coeffs()
+        return np.stack([_eval_monomials(expo, x, deriv=a) @ C for a in range(self.dim)], axis=-1)
+
+
+@lru_cache(maxsize=None)
+def _coeffs(dim, k):
+    nodes = _lattice(dim, k)[0][:, 1:]
+    V = _eval_monomials(_monomials(dim, k), nodes)
+    return np.linalg.inv(V)             # column i = monomial coefficients of basis function i
+
+
+@lru_cache(maxsize=None)
+def reference_tensors(dim: int, k: int):
+    """Exact reference integrals used by the assembly (see module docstring).
+
+    K[a,b,i,j] = ∫ d_a phi_i d_b phi_j          T1[k,a,i,j] = ∫ phi_k phi_i d_a phi_j
+    T2[k,a,i,j] = ∫ d_a phi_k phi_i phi_j       Dv[a,i] = ∫ d_a phi_i       M[i,j] = ∫ phi_i phi_j
+    """
+    el = LagrangeElement(dim, k)
+    x, w = simplex_quadrature(dim, 3 * k)
+    phi = el.tabulate(x)                # (q, n)
+    dphi = el.tabulate_grad(x)          # (q, n, dim)
+    K = np.einsum("q,qia,qjb->abij", w, dphi, dphi)
+    T1 = np.einsum("q,qk,qi,qja->kaij", w, phi, phi, dphi)
+    T2 = np.einsum("q,qka,qi,qj->kaij", w, dphi, phi, phi)
+    Dv = np.einsum("q,qia->ai", w, dphi)
+    Mm = np.einsum("q,qi,qj->ij", w, phi, phi)
+    return dict(K=K, T1=T1, T2=T2, Dv=Dv, M=Mm)
+
+
+# --------------------------------------------------------------------------- function space
+@dataclass
+class VectorSpace:
+    """[Pk]^d on a SimplexMesh; node numbering = first encounter walking cells in order."""
+    mesh: SimplexMesh
+    degree: int
+    element: LagrangeElement = field(init=False)
+    cell_nodes: np.ndarray = field(init=False, repr=False)      # (nc, nnodes_local)
+    nnodes: int = field(init=False)
+    node_coords: np.ndarray = field(init=False, repr=False)
+    # node ids attached to each mesh entity, -1 padded: vertex (nv,1), edge (ne,k-1), face/cell
+    vertex_nodes: np.ndarray = field(init=False, repr=False)
+    edge_nodes: np.ndarray = field(init=False, repr=False)
+    face_nodes: np.ndarray = field(init=False, repr=False)      # 3-D faces (k==3) else empty
+    cell_int_nodes: np.ndarray = field(init=False, repr=False)  # 2-D k==3 else empty
+
+    def __post_init__(self):
+        m, k = self.mesh, self.degree
+        d = m.dim
+        self.element = el = LagrangeElement(d, k)
+        nv, ne, nf, nc = m.nv, m.ne, m.nf, m.nc
+        cols = [m.cells]                                    # provisional ids, entity blocks
+        off = nv
+        per_edge = k - 1
+        if per_edge:
+            ce = m.cell_edges
+            cols.append((off + ce[:, :, None] * per_edge + np.arange(per_edge)[None, None, :]).reshape(nc, -1))
+            off += ne * per_edge
+        if k == 3:
+            if d == 3:
+                cols.append(off + m.cell_faces)
+                off += nf
+            else:
+                cols.append((off + np.arange(nc))[:, None])
+                off += nc
+        prov = np.concatenate(cols, axis=1).astype(np.int64)
+        uniq, first = np.unique(prov.ravel(), return_index=True)
+        order = np.argsort(first, kind="stable")
+        new = np.empty(off, dtype=np.int64)
+        new[uniq[order]] = np.arange(uniq.size)
+        assert uniq.size == off
+        self.cell_nodes = new[prov]
+        self.nnodes = int(off)
+        self.vertex_nodes = new[:nv].reshape(nv, 1)
+        o = nv
+        self.edge_nodes = new[o:o + ne * per_edge].reshape(ne, per_edge)
+        o += ne * per_edge
+        if k == 3 and d == 3:
+            self.face_nodes = new[o:o + nf].reshape(nf, 1)
+            self.cell_int_nodes = np.empty((nc, 0), dtype=np.int64)
+        elif k == 3 and d == 2:
+            self.face_nodes = np.empty((0, 0), dtype=np.int64)
+            self.cell_int_nodes = new[o:o + nc].reshape(nc, 1)
+        else:
+            self.face_nodes = np.empty((nf, 0), dtype=np.int64)
+            self.cell_int_nodes = np.empty((nc, 0), dtype=np.int64)
+        # node coordinates
+        xc = np.einsum("nl,cld->cnd", el.nodes_bary, m.coords[m.cells])
+        self.node_coords = np.empty((self.nnodes, d))
+        self.node_coords[self.cell_nodes.ravel()] = xc.reshape(-1, d)
+
+    @property
+    def bs(self):
+        return self.mesh.dim
+
+    @property
+    def ndofs(self):
+        return self.nnodes * self.bs
+
+    def boundary_nodes(self, tol=1e-12):
+        x, L = self.node_coords, self.mesh.length
+        return np.flatnonzero(np.any((np.abs(x) < tol) | (np.abs(x - L) < tol), axis=1))
+
+    def interpolate(self, fn):
+        """Nodal interpolant of fn(x)->(n, d); returns (nnodes, d)."""
+        return np.asarray(fn(self.node_coords), dtype=np.float64)
+
+
+# --------------------------------------------------------------------------- BSR container
+@dataclass
+class BSR:
+    """Block CSR, square blocks stored row-major: vals[(k, r, c)]."""
+    nbrows: int
+    bs: int
+    rowptr: np.ndarray      # int32 (nbrows+1)
+    colidx: np.ndarray      # int32 (nnzb), ascending within a row
+    vals: np.ndarray        # float64 (nnzb, bs, bs)
+
+    @property
+    def nnzb(self):
+        return self.colidx.size
+
+    def to_scipy(self):
+        return sp.bsr_matrix((self.vals, self.colidx, self.rowptr),
+                             shape=(self.nbrows * self.bs, self.nbrows * self.bs))
+
+    def to_csr(self):
+        A = self.to_scipy().tocsr()
+        A.sort_indices()
+        return A
+
+    def copy(self):
+        return BSR(self.nbrows, self.bs, self.rowptr, self.colidx, self.vals.copy())
+
+
+class BlockPattern:
+    """Node–node sparsity of a space + the scatter map from (cell, i, j) to a block slot."""
+
+    def __init__(self, V: VectorSpace, chunk: int = 1 << 15):
+        cn = V.cell_nodes
+        nn = np.int64(V.nnodes)
+        nl = cn.shape[1]
+        keys = (cn[:, :, None] * nn + cn[:, None, :]).reshape(-1)
+        self.perm = np.argsort(keys, kind="stable")
+        ks = keys[self.perm]
+        start = np.flatnonzero(np.concatenate(([True], ks[1:] != ks[:-1])))
+        self.start = start
+        uk = ks[start]
+        rows = (uk // nn).astype(np.int64)
+        self.colidx = (uk % nn).astype(np.int32)
+        self.rowptr = np.zeros(V.nnodes + 1, dtype=np.int32)
+        np.add.at(self.rowptr, rows + 1, 1)
+        self.rowptr = np.cumsum(self.rowptr).astype(np.int32)
+        self.rows = rows
+        self.nl = nl
+        self.nnzb = uk.size
+
+    def scatter(self, elem: np.ndarray) -> np.ndarray:
+        """elem: (nc, nl, nl) scalar contributions → (nnzb,) summed per block slot."""
+        v = elem.reshape(-1)[self.perm]
+        return np.add.reduceat(v, self.start)
+
+
+def cell_geometry(mesh: SimplexMesh):
+    """G[c,a,b] = (J^-1)[a,b] (so d/dx_b = sum_a G[a,b] d/dxi_a) and |det J|."""
+    X = mesh.coords[mesh.cells]                 # (nc, d+1, d)
+    J = np.transpose(X[:, 1:, :] - X[:, :1, :], (0, 2, 1))   # J[:, :, a] = v_a - v_0
+    det = np.linalg.det(J)
+    G = np.linalg.inv(J)
+    return G, np.abs(det)
+
+
+def element_matrices(V: VectorSpace, nu: float, gamma: float, wind=None, advect: float = 1.0,
+                     divform: str = "sv", cells=slice(None), parts=("visc", "div", "adv")):
+    """Dense element tensors E[c, i, r, j, s] (test node i comp r, trial node j comp s)."""
+    mesh, d, k = V.mesh, V.mesh.dim, V.degree
+    rt = reference_tensors(d, k)
+    G, det = cell_geometry(mesh)
+    G, det = G[cells], det[cells]
+    nc = G.shape[0]
+    nl = V.element.nnodes
+    E = np.zeros((nc, nl, d, nl, d))
+    need_K = ("visc" in parts and nu != 0.0) or ("div" in parts and divform == "sv" and gamma != 0.0)
+    if need_K:
+        # Kp[c,x,y,i,j] = det * sum_ab G[a,x] G[b,y] K[a,b,i,j]
+        Kp = np.einsum("c,cax,cby,abij->cxyij", det, G, G, rt["K"], optimize=True)
+        if "visc" in parts and nu != 0.0:
+            lap = np.einsum("cxxij->cij", Kp)
+            for r in range(d):
+                E[:, :, r, :, r] += nu * lap
+            # nu * d_r phi_j d_s phi_i = nu * Kp[s, r, i, j]
+            E += nu * np.einsum("csrij->cirjs", Kp)
+        if "div" in parts and divform == "sv" and gamma != 0.0:
+            E += gamma * np.einsum("crsij->cirjs", Kp)
+    if "div" in parts and divform == "pkp0" and gamma != 0.0:
+        dv = np.einsum("c,car,ai->cir", det, G, rt["Dv"])          # ∫ d_r phi_i
+        vol = det / (2.0 if d == 2 else 6.0)
+        E += gamma * np.einsum("c,cir,cjs->cirjs", 1.0 / vol, dv, dv)
+    if "adv" in parts and wind is not None and advect != 0.0:
+        W = wind[V.cell_nodes[cells]]                               # (nc, nl, d)  W[c,k,b]
+        # (w.grad u_j, v_i): delta_rs det sum_{k,a} (sum_b W[k,b] G[a,b]) T1[k,a,i,j]
+        cw = np.einsum("ckb,cab->cka", W, G)
+        A1 = np.einsum("c,cka,kaij->cij", det, cw, rt["T1"], optimize=True)
+        for r in range(d):
+            E[:, :, r, :, r] += advect * A1
+        # (u_j.grad w, v_i)_{r,s} = det sum_{k,a} W[k,r] G[a,s] T2[k,a,i,j]
+        A2 = np.einsum("c,ckr,cas,kaij->cirjs", det, W, G, rt["T2"], optimize=True)
+        E += advect * A2
+    return E
+
+
+def assemble_velocity_block(V: VectorSpace, nu: float, gamma: float, wind=None, advect: float = 1.0,
+                            divform: str = "sv", bc_nodes=None, pattern: BlockPattern | None = None,
+                            parts=("visc", "div", "adv"), chunk: int = 8192) -> BSR:
+    """Assemble the velocity block as BSR(bs=d); Dirichlet rows/cols zeroed, unit diagonal.
+
+    Mirrors what Firedrake hands PETSc for `fieldsplit_0` with
+    ``default_sub_matrix_type = "baij"`` (alfi/solver.py:512).
+    """
+    d = V.bs
+    pat = pattern or BlockPattern(V)
+    nc, nl = V.mesh.nc, V.element.nnodes
+    vals = np.zeros((pat.nnzb, d, d))
+    # element tensors in chunks, then one scatter per (r, s) component
+    Efull = np.empty((nc, nl, d, nl, d)) if nc * (nl * d) ** 2 * 8 < 6e9 else None
+    if Efull is not None:
+        for c0 in range(0, nc, chunk):
+            sl = slice(c0, min(nc, c0 + chunk))
+            Efull[sl] = element_matrices(V, nu, gamma, wind, advect, divform, sl, parts)
+        for r in range(d):
+            for s in range(d):
+                vals[:, r, s] = pat.scatter(np.ascontiguousarray(Efull[:, :, r, :, s]))
+    else:                                   # pragma: no cover - very large meshes
+        raise MemoryError("mesh too large for in-core assembly")
+    A = BSR(V.nnodes, d, pat.rowptr, pat.colidx, vals)
+    if bc_nodes is not None:
+        apply_dirichlet(A, bc_nodes, pat.rows)
+    return A
+
+
+def apply_dirichlet(A: BSR, bc_nodes, rows=None):
+    """Zero block rows and columns of the Dirichlet nodes, identity on their diagonal blocks."""
+    if rows is None:
+        rows = np.repeat(np.arange(A.nbrows), np.diff(A.rowptr))
+    isbc = np.zeros(A.nbrows, dtype=bool)
+    isbc[np.asarray(bc_nodes)] = True
+    kill = isbc[rows] | isbc[A.colidx]
+    A.vals[kill] = 0.0
+    diag = kill & (rows == A.colidx)
+    A.vals[diag] = np.eye(A.bs)
+    return A

@@ -1,0 +1,183 @@
+"""Synthetic simplicial meshes standing in for Firedrake/DMPlex (host side, numpy).
+
+The reference builds its meshes with Firedrake (`RectangleMesh(..., diagonal="left")`,
+examples/ldc2d/ldc2d.py:17-21; `BoxMesh`, examples/ldc3d/ldc3d.py:13-16), refines them
+uniformly and Alfeld-splits every level (alfi/bary.py:16-27, 29-194).  None of that stack is
+available here, so this module generates the same family of meshes directly:
+
+* Kuhn (Freudenthal) triangulations of ``[0, L]^d`` with ``M`` cells per side.  The Kuhn mesh
+  with ``2M`` cells per side is the red refinement of the one with ``M`` (Bey), so the uniform
+  hierarchy is ``M_l = N * 2**l`` and is nested.
+* Alfeld (barycentric) split: macro cell ``c`` becomes cells ``c*(d+1) .. c*(d+1)+d`` — the
+  numbering alfi/bary.py:148-157 relies on — macro vertices keep their ids (label
+  ``MacroVertices`` = 1, alfi/bary.py:18-19) and the barycentre of macro cell ``c`` is vertex
+  ``nv_macro + c``.
+
+Cells always list their vertices in ascending global id, so local edge/face orientations agree
+between neighbouring cells and no orientation fix-up is needed for P3 edge nodes.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field
+
+import numpy as np
+
+__all__ = ["SimplexMesh", "kuhn_mesh", "alfeld_split", "LOCAL_EDGES", "LOCAL_FACES"]
+
+# local sub-entity -> local vertices, lexicographic
+LOCAL_EDGES = {2: [(0, 1), (0, 2), (1, 2)],
+               3: [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]}
+LOCAL_FACES = {2: [], 3: [(0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3)]}
+
+
+def _unique_rows(keys: np.ndarray):
+    """Unique of 1-D int64 keys → (unique keys, inverse)."""
+    uniq, inv = np.unique(keys, return_inverse=True)
+    return uniq, inv.astype(np.int64)
+
+
+@dataclass
+class SimplexMesh:
+    dim: int
+    coords: np.ndarray            # (nv, dim) float64
+    cells: np.ndarray             # (nc, dim+1) int64, each row ascending
+    macro_vertex: np.ndarray | None = None   # (nv,) bool, Alfeld meshes only
+    macro: "SimplexMesh | None" = None       # the mesh this one is the Alfeld split of
+    length: float = 2.0
+    M: int = 0                               # cells per side of the underlying Kuhn grid
+    # derived topology
+    edges: np.ndarray = field(default=None, repr=False)       # (ne, 2)
+    faces: np.ndarray = field(default=None, repr=False)       # (nf, 3) (3-D only)
+    cell_edges: np.ndarray = field(default=None, repr=False)  # (nc, n_local_edges)
+    cell_faces: np.ndarray = field(default=None, repr=False)  # (nc, 4) (3-D only)
+
+    @property
+    def nv(self):
+        return self.coords.shape[0]
+
+    @property
+    def nc(self):
+        return self.cells.shape[0]
+
+    @property
+    def ne(self):
+        return self.edges.shape[0]
+
+    @property
+    def nf(self):
+        return 0 if self.faces is None else self.faces.shape[0]
+
+    def build_topology(self):
+        d, nv = self.dim, np.int64(self.nv)
+        c = self.cells
+        le = LOCAL_EDGES[d]
+        ek = np.stack([c[:, a] * nv + c[:, b] for a, b in le], axis=1)
+        uniq, inv = _unique_rows(ek.ravel())
+        self.edges = np.stack([uniq // nv, uniq % nv], axis=1)
+        self.cell_edges = inv.reshape(c.shape[0], len(le))
+        if d == 3:
+            lf = LOCAL_FACES[3]
+            fk = np.stack([(c[:, a] * nv + c[:, b]) * nv + c[:, e] for a, b, e in lf], axis=1)
+            uniq, inv = _unique_rows(fk.ravel())
+            self.faces = np.stack([uniq // (nv * nv), (uniq // nv) % nv, uniq % nv], axis=1)
+            self.cell_faces = inv.reshape(c.shape[0], 4)
+        return self
+
+    # ---- facets (codim 1): edges in 2-D, faces in 3-D ----
+    @property
+    def facets(self):
+        return self.edges if self.dim == 2 else self.faces
+
+    @property
+    def cell_facets(self):
+        return self.cell_edges if self.dim == 2 else self.cell_faces
+
+    def boundary_vertex_mask(self, tol=1e-12):
+        x = self.coords
+        return np.any((np.abs(x) < tol) | (np.abs(x - self.length) < tol), axis=1)
+
+
+def kuhn_mesh(dim: int, M: int, length: float = 2.0) -> SimplexMesh:
+    """Kuhn triangulation of [0, length]^dim with M cells per side.
+
+    2-D: each square (ll, lr, ur, ul) is cut along lr–ul (Firedrake ``diagonal="left"``,
+    examples/ldc2d/ldc2d.py:11-12).  3-D: six tetrahedra per cube sharing the main diagonal
+    (Firedrake ``BoxMesh``, examples/ldc3d/ldc3d.py:13-15).
+    """
+    n1 = M + 1
+    ax = np.arange(n1)
+    if dim == 2:
+        # vertex id = i + n1*j  (x fastest)
+        J, I = np.meshgrid(ax, ax, indexing="ij")
+        coords = np.stack([I.ravel(), J.ravel()], axis=1) * (length / M)
+        j, i = np.meshgrid(np.arange(M), np.arange(M), indexing="ij")
+        i, j = i.ravel(), j.ravel()
+        ll = i + n1 * j
+        lr = ll + 1
+        ul = ll + n1
+        ur = ul + 1
+        cells = np.stack([np.stack([ll, lr, ul], 1), np.stack([lr, ur, ul], 1)], axis=1).reshape(-1, 3)
+    elif dim == 3:
+        K, J, I = np.meshgrid(ax, ax, ax, indexing="ij")
+        coords = np.stack([I.ravel(), J.ravel(), K.ravel()], axis=1) * (length / M)
+        k, j, i = np.meshgrid(np.arange(M), np.arange(M), np.arange(M), indexing="ij")
+        base = (i + n1 * (j + n1 * k)).ravel()
+        step = np.array([1, n1, n1 * n1])
+        tets = []
+        for perm in itertools.permutations(range(3)):
+            v0 = base
+            v1 = v0 + step[perm[0]]
+            v2 = v1 + step[perm[1]]
+            v3 = v2 + step[perm[2]]
+            tets.append(np.stack([v0, v1, v2, v3], 1))
+        cells = np.stack(tets, axis=1).reshape(-1, 4)
+    else:
+        raise ValueError("dim must be 2 or 3")
+    cells = np.sort(cells.astype(np.int64), axis=1)
+    m = SimplexMesh(dim=dim, coords=coords.astype(np.float64), cells=cells, length=length, M=M)
+    return m.build_topology()
+
+
+def alfeld_split(macro: SimplexMesh) -> SimplexMesh:
+    """Barycentric refinement with the numbering conventions of alfi/bary.py:16-27,148-157."""
+    d = macro.dim
+    nvm, ncm = macro.nv, macro.nc
+    bary = macro.coords[macro.cells].mean(axis=1)
+    coords = np.concatenate([macro.coords, bary], axis=0)
+    bid = nvm + np.arange(ncm, dtype=np.int64)
+    sub = []
+    for r in range(d + 1):
+        cc = macro.cells.copy()
+        cc[:, r] = bid             # replace local vertex r by the barycentre
+        sub.append(cc)
+    cells = np.sort(np.stack(sub, axis=1).reshape(-1, d + 1), axis=1)
+    mv = np.zeros(nvm + ncm, dtype=bool)
+    mv[:nvm] = True
+    m = SimplexMesh(dim=d, coords=coords, cells=cells, macro_vertex=mv, macro=macro,
+                    length=macro.length, M=macro.M)
+    return m.build_topology()
+
+
+def locate_in_kuhn(mesh: SimplexMesh, pts: np.ndarray) -> np.ndarray:
+    """Index of the Kuhn cell of ``mesh`` (a plain Kuhn mesh) containing each point.
+
+    Used to build ``coarse_to_fine_cells`` of the uniform hierarchy by locating fine-cell
+    centroids (strictly interior, so there are no ties).
+    """
+    d, M, h = mesh.dim, mesh.M, mesh.length / mesh.M
+    g = pts / h
+    ijk = np.clip(np.floor(g).astype(np.int64), 0, M - 1)
+    frac = g - ijk
+    if d == 2:
+        cube = ijk[:, 0] + M * ijk[:, 1]
+        # cell 0 = (ll, lr, ul): x + y <= 1 ; cell 1 = (lr, ur, ul)
+        which = (frac.sum(axis=1) > 1.0).astype(np.int64)
+        return cube * 2 + which
+    cube = ijk[:, 0] + M * (ijk[:, 1] + M * ijk[:, 2])
+    # tet for permutation perm: frac[perm0] >= frac[perm1] >= frac[perm2]
+    order = np.argsort(-frac, axis=1, kind="stable")
+    perms = list(itertools.permutations(range(3)))
+    lut = {p: n for n, p in enumerate(perms)}
+    which = np.array([lut[tuple(o)] for o in order.tolist()], dtype=np.int64)
+    return cube * 6 + which
