@@ -1,0 +1,192 @@
+// Internal declarations of libalfib (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "alfib.h"
+
+#define ALFIB_MAX_LEVELS 16
+#define ALFIB_TILE_ROWS 64          // rows per apply tile (one warp, double2 per lane)
+#define ALFIB_MAX_KRYLOV 32         // upper bound on FGMRES(m) per level
+
+struct DeviceError {
+  int code;
+  std::string msg;
+};
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      throw DeviceError{ALFIB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)};      \
+  } while (0)
+
+#define ALFIB_REQUIRE(cond, what)                                                              \
+  do {                                                                                         \
+    if (!(cond)) throw DeviceError{ALFIB_EINVAL, std::string(what)};                           \
+  } while (0)
+
+template <class T>
+struct DBuf {                       // device buffer owned by the library
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    if (count == n && p) return;
+    release();
+    if (count) {
+      cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+      if (e != cudaSuccess)
+        throw DeviceError{ALFIB_ENOMEM, "cudaMalloc of " + std::to_string(count * sizeof(T)) + " bytes: " +
+                                            cudaGetErrorString(e)};
+    }
+    n = count;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void upload(const T* host, size_t count, cudaStream_t s) {
+    alloc(count);
+    if (count) CUDA_TRY(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+};
+
+// One set of patches (the smoother's vertex/macro stars or the transfer's cell patches):
+// index sets, colouring, inverse factors in the tiled apply layout, and the warp work list.
+struct PatchSet {
+  int npatch = 0;
+  int maxn = 0;
+  int ncolour = 0;
+  bool repeated = false;            // a patch occurs twice in the iteration set
+  bool factored = false;
+  std::vector<int64_t> h_off;       // npatch+1
+  std::vector<int32_t> h_dofs, h_order, h_colour;
+  std::vector<int64_t> h_soff;      // element offset of each patch's factor storage (npatch+1)
+  std::vector<int> colour_work_start;   // ncolour+1, ranges of the work list
+  DBuf<int64_t> off, soff;
+  DBuf<int32_t> dofs, sorted, sperm, forder;
+  DBuf<int2> work;                  // (patch, tile) per warp, colour-major
+  int nwork = 0;
+  double* store = nullptr;          // inverse factors, tiled layout
+  int64_t store_elems = 0;
+  bool store_owned = false;
+  DBuf<double> store_buf;
+};
+
+struct Level {
+  int n_nodes = 0, bs = 0, n = 0;
+  int64_t nnzb = 0;
+  DBuf<int32_t> rowptr, colidx, bc, cb;
+  DBuf<double> vals, dvals, a0vals;
+  int nbc = 0, ncb = 0;
+  bool has_values = false, has_transfer = false, has_d = false;
+  PatchSet ps[2];
+  // standard prolongation (scalar CSR, fine nodes x coarse nodes) and its transpose
+  int p_rows = 0, p_cols = 0;
+  DBuf<int32_t> p_rowptr, p_colidx, pt_rowptr, pt_colidx;
+  DBuf<double> p_vals, pt_vals;
+  // cycle work vectors (allocated by alfib_cycle_setup / alfib_smooth)
+  DBuf<double> b, x, r, w, t1, t2, t3, t4, V, Z;
+  int krylov_m = 0;
+};
+
+struct EventRec;
+struct alfib_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int deterministic = 0, sync_always = 0, robust_restrict = 1, transfer_refine = 1;
+  Level* levels[ALFIB_MAX_LEVELS] = {nullptr};
+  int nlevels = 0, smoothing = 0;
+  int num_sms = 148;
+  int64_t launches = 0;
+  // patch factor workspace (one slot per resident CTA) + status word + work counter
+  DBuf<double> fwork;
+  DBuf<int> finfo;
+  // reductions / Krylov scalars
+  DBuf<double> partial, scal;
+  // staging for host-pointer calls
+  DBuf<double> stage_in, stage_in2, stage_out;
+  // coarse solve
+  cusolverDnHandle_t cusolver = nullptr;
+  DBuf<double> coarse_lu, coarse_work;
+  DBuf<int> coarse_piv, coarse_info;
+  int coarse_n = 0;
+  bool coarse_factored = false;
+  // profiling
+  int profile = 0;
+  double ev_ms[ALFIB_MAX_LEVELS][ALFIB_EV_COUNT] = {{0}};
+  int64_t ev_calls[ALFIB_MAX_LEVELS][ALFIB_EV_COUNT] = {{0}};
+  std::vector<struct EventRec> ev_pool;
+  int ev_used = 0;
+};
+
+// CUDA-event timing of one kernel family on one level (opt-in).  Events are recorded on the
+// ctx stream without synchronising and resolved lazily (profile_flush), so profiling does not
+// perturb the timed region beyond the event records themselves.
+struct EventRec {
+  cudaEvent_t a, b;
+  int id, level;
+};
+void profile_flush(alfib_ctx* c);
+
+struct ScopedEvent {
+  alfib_ctx* c;
+  int slot = -1;
+  ScopedEvent(alfib_ctx* ctx, int ev, int level = 0) : c(ctx) {
+    if (!c->profile) return;
+    if (c->ev_used == (int)c->ev_pool.size()) {
+      if (c->ev_pool.size() >= 8192) {
+        profile_flush(c);
+      } else {
+        EventRec r;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        c->ev_pool.push_back(r);
+      }
+    }
+    slot = c->ev_used++;
+    c->ev_pool[slot].id = ev;
+    c->ev_pool[slot].level = level;
+    cudaEventRecord(c->ev_pool[slot].a, c->stream);
+  }
+  ~ScopedEvent() {
+    if (slot >= 0) cudaEventRecord(c->ev_pool[slot].b, c->stream);
+  }
+};
+
+inline int roundup2(int n) { return (n + 1) & ~1; }
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- kernels (implemented in the .cu files; all enqueue on ctx->stream) ----------------------
+// spmv.cu
+void launch_bsr_spmv(alfib_ctx* c, const Level& L, const double* vals, const double* x, double* y,
+                     const double* b /* nullptr: y = A x ; else y = b - A x */);
+void launch_csr_apply(alfib_ctx* c, int nrows, int bs, const int32_t* rowptr, const int32_t* colidx,
+                      const double* vals, const double* x, double* y);
+void launch_transpose_blocks(alfib_ctx* c, double* vals, int64_t nnzb, int bs);
+// patch_apply.cu
+void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, double* y);
+// patch_factor.cu
+void launch_patch_factor(alfib_ctx* c, const Level& L, PatchSet& ps, const double* vals);
+void patch_extract_inverse(alfib_ctx* c, const PatchSet& ps, int patch, double* host_out);
+// vector.cu
+void launch_set_rows(alfib_ctx* c, double* y, const double* x /* nullptr: zero */, const int32_t* idx, int nidx);
+void launch_axpby(alfib_ctx* c, int n, double a, const double* x, double b, double* y);   // y = a x + b y
+void launch_sub(alfib_ctx* c, int n, const double* a, const double* b, double* out);       // out = a - b
+void launch_bsr_to_dense(alfib_ctx* c, const Level& L, double* dense /* col-major n x n */);
+// krylov.cu
+void fgmres_device(alfib_ctx* c, Level& L, int level, int m, const double* b, double* x);
+// cycle.cu
+void smoother_apply_device(alfib_ctx* c, Level& L, int level, const double* x, double* y);
+void prolong_device(alfib_ctx* c, Level& Lf, int level, const double* coarse, double* fine);
+void restrict_device(alfib_ctx* c, Level& Lf, Level& Lc, int level, const double* fine, double* coarse);
+void coarse_factor_device(alfib_ctx* c);
+void coarse_solve_device(alfib_ctx* c, const double* b, double* x);
+void cycle_apply_device(alfib_ctx* c, const double* b, double* x);

@@ -1,0 +1,633 @@
+// C-ABI entry points of libalfib (see include/alfib.h for the contract of each function and the
+// reference interface it replaces).  Host-side bookkeeping only; kernels live in the other files.
+#include <algorithm>
+#include <cstring>
+#include <exception>
+#include <numeric>
+
+#include "alfib_internal.h"
+
+namespace {
+
+template <class F>
+int guarded(alfib_ctx* c, F&& f) {
+  if (!c) return ALFIB_EINVAL;
+  try {
+    CUDA_TRY(cudaSetDevice(c->device));
+    f();
+    if (c->sync_always) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ALFIB_OK;
+  } catch (const DeviceError& e) {
+    c->err = e.msg;
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    c->err = "host allocation failed";
+    return ALFIB_ENOMEM;
+  } catch (const std::exception& e) {
+    c->err = e.what();
+    return ALFIB_EINVAL;
+  }
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+void release_patchset(PatchSet& ps) {
+  ps.off.release();
+  ps.soff.release();
+  ps.dofs.release();
+  ps.sorted.release();
+  ps.sperm.release();
+  ps.forder.release();
+  ps.work.release();
+  ps.store_buf.release();
+}
+
+Level& get_level(alfib_ctx* c, int level) {
+  ALFIB_REQUIRE(level >= 0 && level < ALFIB_MAX_LEVELS && c->levels[level], "no such level");
+  return *c->levels[level];
+}
+
+// Input vector: device pointers pass through, host pointers are staged.
+const double* in_vec(alfib_ctx* c, const double* p, size_t n, DBuf<double>& stage) {
+  ALFIB_REQUIRE(p != nullptr, "null vector");
+  if (is_device_ptr(p)) return p;
+  if (stage.n < n) stage.alloc(n);
+  CUDA_TRY(cudaMemcpyAsync(stage.p, p, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return stage.p;
+}
+
+struct OutVec {                      // output vector: compute into dev, copy back if host
+  alfib_ctx* c;
+  double* user;
+  double* dev;
+  size_t n;
+  bool host;
+  OutVec(alfib_ctx* ctx, double* p, size_t count) : c(ctx), user(p), n(count) {
+    ALFIB_REQUIRE(p != nullptr, "null vector");
+    host = !is_device_ptr(p);
+    if (host) {
+      if (c->stage_out.n < n) c->stage_out.alloc(n);
+      dev = c->stage_out.p;
+    } else {
+      dev = p;
+    }
+  }
+  void load() {                      // for in/out vectors
+    if (host) CUDA_TRY(cudaMemcpyAsync(dev, user, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  void finish() {
+    if (host) {
+      CUDA_TRY(cudaMemcpyAsync(user, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+  }
+};
+
+void upload_values(alfib_ctx* c, Level& L, DBuf<double>& dst, const double* vals, int block_col_major) {
+  ALFIB_REQUIRE(L.nnzb > 0, "set the BSR pattern first");
+  const size_t count = (size_t)L.nnzb * L.bs * L.bs;
+  dst.alloc(count);
+  const cudaMemcpyKind kind = is_device_ptr(vals) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CUDA_TRY(cudaMemcpyAsync(dst.p, vals, count * sizeof(double), kind, c->stream));
+  if (block_col_major) launch_transpose_blocks(c, dst.p, L.nnzb, L.bs);
+}
+
+// Greedy colouring in iteration order — same definition as
+// alfi_b200.patches.greedy_colouring, so host and library agree bit for bit.
+void greedy_colour(PatchSet& ps, int ndofs) {
+  std::vector<uint64_t> used(ndofs, 0);
+  ps.h_colour.assign(ps.npatch, -1);
+  for (int32_t p : ps.h_order) {
+    if (ps.h_colour[p] >= 0) continue;
+    uint64_t m = 0;
+    for (int64_t k = ps.h_off[p]; k < ps.h_off[p + 1]; ++k) m |= used[ps.h_dofs[k]];
+    int col = 0;
+    while (col < 64 && ((m >> col) & 1)) ++col;
+    if (col >= 64) throw DeviceError{ALFIB_EINVAL, "more than 64 colours needed"};
+    if (ps.h_off[p + 1] == ps.h_off[p]) col = 0;
+    ps.h_colour[p] = col;
+    for (int64_t k = ps.h_off[p]; k < ps.h_off[p + 1]; ++k) used[ps.h_dofs[k]] |= (uint64_t(1) << col);
+  }
+  for (auto& col : ps.h_colour)
+    if (col < 0) col = 0;               // patches not in the iteration set are never applied
+}
+
+}  // namespace
+
+void profile_flush(alfib_ctx* c) {
+  if (c->ev_used == 0) return;
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < c->ev_used; ++i) {
+    float ms = 0;
+    const EventRec& r = c->ev_pool[i];
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      c->ev_ms[r.level][r.id] += ms;
+      c->ev_calls[r.level][r.id] += 1;
+    }
+  }
+  c->ev_used = 0;
+}
+
+extern "C" {
+
+int alfib_create(int device, alfib_ctx** out) {
+  if (!out) return ALFIB_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return ALFIB_ECUDA;
+  alfib_ctx* c = new (std::nothrow) alfib_ctx();
+  if (!c) return ALFIB_ENOMEM;
+  c->device = device;
+  int rc = guarded(c, [&] {
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+  });
+  if (rc != ALFIB_OK) {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return ALFIB_OK;
+}
+
+int alfib_destroy(alfib_ctx* c) {
+  if (!c) return ALFIB_EINVAL;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto& L : c->levels) {
+    if (!L) continue;
+    for (auto& ps : L->ps) release_patchset(ps);
+    for (auto* b : {&L->rowptr, &L->colidx, &L->bc, &L->cb, &L->p_rowptr, &L->p_colidx, &L->pt_rowptr, &L->pt_colidx})
+      b->release();
+    for (auto* b : {&L->vals, &L->dvals, &L->a0vals, &L->p_vals, &L->pt_vals, &L->b, &L->x, &L->r, &L->w, &L->t1,
+                    &L->t2, &L->t3, &L->t4, &L->V, &L->Z})
+      b->release();
+    delete L;
+    L = nullptr;
+  }
+  for (auto* b : {&c->fwork, &c->partial, &c->scal, &c->stage_in, &c->stage_in2, &c->stage_out, &c->coarse_lu,
+                  &c->coarse_work})
+    b->release();
+  c->finfo.release();
+  c->coarse_piv.release();
+  c->coarse_info.release();
+  if (c->cusolver) cusolverDnDestroy(c->cusolver);
+  for (auto& r : c->ev_pool) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return ALFIB_OK;
+}
+
+const char* alfib_last_error(const alfib_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int alfib_set_option(alfib_ctx* c, int key, int value) {
+  return guarded(c, [&] {
+    switch (key) {
+      case ALFIB_OPT_DETERMINISTIC: c->deterministic = value != 0; break;
+      case ALFIB_OPT_SYNC_ALWAYS: c->sync_always = value != 0; break;
+      case ALFIB_OPT_ROBUST_RESTRICT: c->robust_restrict = value != 0; break;
+      case ALFIB_OPT_TRANSFER_REFINE: c->transfer_refine = value != 0; break;
+      default: throw DeviceError{ALFIB_EINVAL, "unknown option"};
+    }
+  });
+}
+
+int alfib_set_deterministic(alfib_ctx* c, int flag) { return alfib_set_option(c, ALFIB_OPT_DETERMINISTIC, flag); }
+
+int alfib_synchronize(alfib_ctx* c) {
+  return guarded(c, [&] { CUDA_TRY(cudaStreamSynchronize(c->stream)); });
+}
+
+int64_t alfib_launch_count(const alfib_ctx* c) { return c ? c->launches : -1; }
+
+void* alfib_stream(alfib_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int alfib_comm_init(alfib_ctx* c, const void*, int rank, int nranks) {
+  return guarded(c, [&] {
+    ALFIB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank");
+    // Patches are rank-local units: with replicated level vectors every rank solves its own
+    // patches and the host-side shim sums contributions (see alfi_b200/dist.py).  No data-path
+    // communicator is needed inside the library for that mode.
+  });
+}
+
+// ---- level operator ---------------------------------------------------------------------------
+int alfib_level_create(alfib_ctx* c, int level, int n_nodes, int bs) {
+  return guarded(c, [&] {
+    ALFIB_REQUIRE(level >= 0 && level < ALFIB_MAX_LEVELS, "level out of range");
+    ALFIB_REQUIRE(n_nodes > 0 && (bs == 2 || bs == 3), "n_nodes > 0 and bs in {2,3} required");
+    ALFIB_REQUIRE(!c->levels[level], "level already exists");
+    Level* L = new Level();
+    L->n_nodes = n_nodes;
+    L->bs = bs;
+    L->n = n_nodes * bs;
+    c->levels[level] = L;
+  });
+}
+
+int alfib_level_set_bsr_pattern(alfib_ctx* c, int level, int64_t nnzb, const int32_t* rowptr, const int32_t* colidx) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(rowptr && colidx && nnzb > 0, "bad pattern");
+    ALFIB_REQUIRE(rowptr[0] == 0 && rowptr[L.n_nodes] == nnzb, "rowptr does not match nnzb");
+    for (int64_t k = 0; k < nnzb; ++k) ALFIB_REQUIRE(colidx[k] >= 0 && colidx[k] < L.n_nodes, "column index out of range");
+    L.nnzb = nnzb;
+    L.rowptr.upload(rowptr, L.n_nodes + 1, c->stream);
+    L.colidx.upload(colidx, nnzb, c->stream);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int alfib_level_set_bsr_values(alfib_ctx* c, int level, const double* vals, int block_col_major) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(vals, "null values");
+    upload_values(c, L, L.vals, vals, block_col_major);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    L.has_values = true;
+    L.ps[ALFIB_PATCHES_SMOOTHER].factored = false;
+    if (level == 0) c->coarse_factored = false;
+  });
+}
+
+int alfib_level_set_bc(alfib_ctx* c, int level, int32_t nbc, const int32_t* bc_dofs) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(nbc >= 0 && (nbc == 0 || bc_dofs), "bad bc list");
+    for (int i = 0; i < nbc; ++i) ALFIB_REQUIRE(bc_dofs[i] >= 0 && bc_dofs[i] < L.n, "bc dof out of range");
+    L.nbc = nbc;
+    L.bc.upload(bc_dofs, nbc, c->stream);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int alfib_spmv(alfib_ctx* c, int level, const double* x, double* y) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(L.has_values, "level has no values");
+    const double* dx = in_vec(c, x, L.n, c->stage_in);
+    OutVec out(c, y, L.n);
+    ScopedEvent ev(c, ALFIB_EV_MATMULT, level);
+    launch_bsr_spmv(c, L, L.vals.p, dx, out.dev, nullptr);
+    out.finish();
+  });
+}
+
+int alfib_residual(alfib_ctx* c, int level, const double* b, const double* x, double* r) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(L.has_values, "level has no values");
+    const double* db = in_vec(c, b, L.n, c->stage_in);
+    const double* dx = in_vec(c, x, L.n, c->stage_in2);
+    OutVec out(c, r, L.n);
+    ScopedEvent ev(c, ALFIB_EV_MATMULT, level);
+    launch_bsr_spmv(c, L, L.vals.p, dx, out.dev, db);
+    out.finish();
+  });
+}
+
+// ---- patches ----------------------------------------------------------------------------------
+int alfib_level_set_patches(alfib_ctx* c, int level, int which, int32_t npatch, const int64_t* offsets,
+                            const int32_t* dofs, int32_t norder, const int32_t* order, const int32_t* colours) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(which == 0 || which == 1, "which must be 0 or 1");
+    ALFIB_REQUIRE(npatch >= 0 && offsets && offsets[0] == 0, "bad offsets");
+    PatchSet& ps = L.ps[which];
+    release_patchset(ps);
+    ps = PatchSet();
+    ps.npatch = npatch;
+    ps.h_off.assign(offsets, offsets + npatch + 1);
+    const int64_t total = offsets[npatch];
+    ALFIB_REQUIRE(total == 0 || dofs, "null dof list");
+    ps.h_dofs.assign(dofs, dofs + total);
+    for (int p = 0; p < npatch; ++p) {
+      ALFIB_REQUIRE(offsets[p + 1] >= offsets[p], "offsets must be non-decreasing");
+      ps.maxn = std::max<int>(ps.maxn, (int)(offsets[p + 1] - offsets[p]));
+    }
+    for (int64_t k = 0; k < total; ++k) ALFIB_REQUIRE(dofs[k] >= 0 && dofs[k] < L.n, "patch dof out of range");
+    if (order) {
+      ps.h_order.assign(order, order + norder);
+      for (int32_t p : ps.h_order) ALFIB_REQUIRE(p >= 0 && p < npatch, "iteration set entry out of range");
+    } else {
+      ps.h_order.resize(npatch);
+      std::iota(ps.h_order.begin(), ps.h_order.end(), 0);
+    }
+    {
+      std::vector<char> seen(npatch, 0);
+      for (int32_t p : ps.h_order) {
+        if (seen[p]) ps.repeated = true;
+        seen[p] = 1;
+      }
+    }
+    if (colours) {
+      ps.h_colour.assign(colours, colours + npatch);
+      for (int32_t col : ps.h_colour) ALFIB_REQUIRE(col >= 0 && col < 64, "colour out of range");
+    } else {
+      greedy_colour(ps, L.n);
+    }
+    ps.ncolour = npatch ? 1 + *std::max_element(ps.h_colour.begin(), ps.h_colour.end()) : 0;
+
+    // sorted dof lists for the gather, factor storage offsets
+    std::vector<int32_t> sorted(total), sperm(total);
+    ps.h_soff.assign(npatch + 1, 0);
+    for (int p = 0; p < npatch; ++p) {
+      const int64_t o = offsets[p];
+      const int n = (int)(offsets[p + 1] - o);
+      std::vector<int32_t> idx(n);
+      std::iota(idx.begin(), idx.end(), 0);
+      std::sort(idx.begin(), idx.end(), [&](int a, int b) { return dofs[o + a] < dofs[o + b]; });
+      for (int i = 0; i < n; ++i) {
+        sorted[o + i] = dofs[o + idx[i]];
+        sperm[o + i] = idx[i];
+        if (i) ALFIB_REQUIRE(sorted[o + i] != sorted[o + i - 1], "duplicate dof inside a patch");
+      }
+      ps.h_soff[p + 1] = ps.h_soff[p] + (int64_t)n * roundup2(n);
+    }
+    ps.store_elems = ps.h_soff[npatch];
+    // factor order: largest patches first
+    std::vector<int32_t> forder(npatch);
+    std::iota(forder.begin(), forder.end(), 0);
+    std::stable_sort(forder.begin(), forder.end(), [&](int a, int b) {
+      return offsets[a + 1] - offsets[a] > offsets[b + 1] - offsets[b];
+    });
+    // apply work list: colour-major, iteration order inside a colour, tiles ascending
+    std::vector<int2> work;
+    ps.colour_work_start.assign(ps.ncolour + 1, 0);
+    for (int col = 0; col < ps.ncolour; ++col) {
+      ps.colour_work_start[col] = (int)work.size();
+      for (int32_t p : ps.h_order) {
+        if (ps.h_colour[p] != col) continue;
+        const int n = (int)(offsets[p + 1] - offsets[p]);
+        for (int t = 0; t * ALFIB_TILE_ROWS < n; ++t) work.push_back(make_int2(p, t));
+      }
+    }
+    if (ps.ncolour) ps.colour_work_start[ps.ncolour] = (int)work.size();
+    ps.nwork = (int)work.size();
+
+    ps.off.upload(ps.h_off.data(), npatch + 1, c->stream);
+    ps.soff.upload(ps.h_soff.data(), npatch + 1, c->stream);
+    ps.dofs.upload(ps.h_dofs.data(), total, c->stream);
+    ps.sorted.upload(sorted.data(), total, c->stream);
+    ps.sperm.upload(sperm.data(), total, c->stream);
+    ps.forder.upload(forder.data(), npatch, c->stream);
+    ps.work.upload(work.data(), work.size(), c->stream);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int64_t alfib_patch_storage_bytes(alfib_ctx* c, int level, int which) {
+  if (!c || level < 0 || level >= ALFIB_MAX_LEVELS || !c->levels[level] || which < 0 || which > 1) return -1;
+  return c->levels[level]->ps[which].store_elems * (int64_t)sizeof(double);
+}
+
+int alfib_patch_bind_storage(alfib_ctx* c, int level, int which, void* dev_ptr, int64_t bytes) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(which == 0 || which == 1, "which must be 0 or 1");
+    PatchSet& ps = L.ps[which];
+    ALFIB_REQUIRE(dev_ptr && is_device_ptr(dev_ptr), "storage must be a device pointer");
+    ALFIB_REQUIRE(bytes >= ps.store_elems * (int64_t)sizeof(double), "storage too small");
+    ALFIB_REQUIRE(((uintptr_t)dev_ptr & 15) == 0, "storage must be 16-byte aligned");
+    ps.store_buf.release();
+    ps.store = static_cast<double*>(dev_ptr);
+    ps.store_owned = false;
+    ps.factored = false;
+  });
+}
+
+static void ensure_storage(PatchSet& ps) {
+  if (!ps.store) {
+    ps.store_buf.alloc((size_t)std::max<int64_t>(ps.store_elems, 2));
+    ps.store = ps.store_buf.p;
+    ps.store_owned = true;
+  }
+}
+
+int alfib_level_factor(alfib_ctx* c, int level) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(L.has_values, "level has no values");
+    PatchSet& ps = L.ps[ALFIB_PATCHES_SMOOTHER];
+    ALFIB_REQUIRE(ps.npatch > 0, "no smoother patches on this level");
+    ensure_storage(ps);
+    ScopedEvent ev(c, ALFIB_EV_PCSETUP_PATCH, level);
+    launch_patch_factor(c, L, ps, L.vals.p);
+  });
+}
+
+int alfib_smoother_apply(alfib_ctx* c, int level, const double* x, double* y) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    const double* dx = in_vec(c, x, L.n, c->stage_in);
+    OutVec out(c, y, L.n);
+    ALFIB_REQUIRE(dx != out.dev, "x and y must not alias");
+    smoother_apply_device(c, L, level, dx, out.dev);
+    out.finish();
+  });
+}
+
+int alfib_get_colours(alfib_ctx* c, int level, int which, int32_t* colours) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE((which == 0 || which == 1) && colours, "bad arguments");
+    const PatchSet& ps = L.ps[which];
+    std::copy(ps.h_colour.begin(), ps.h_colour.end(), colours);
+  });
+}
+
+int alfib_get_patch_inverse(alfib_ctx* c, int level, int which, int32_t patch, double* out) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE((which == 0 || which == 1) && out, "bad arguments");
+    patch_extract_inverse(c, L.ps[which], patch, out);
+  });
+}
+
+// ---- transfer ---------------------------------------------------------------------------------
+int alfib_transfer_set(alfib_ctx* c, int level, int32_t n_fine_nodes, int32_t n_coarse_nodes,
+                       const int32_t* P_rowptr, const int32_t* P_colidx, const double* P_vals, int32_t ncb,
+                       const int32_t* cb_dofs) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(level >= 1, "transfers live on levels >= 1");
+    Level& Lc = get_level(c, level - 1);
+    ALFIB_REQUIRE(n_fine_nodes == L.n_nodes && n_coarse_nodes == Lc.n_nodes, "P shape does not match the levels");
+    ALFIB_REQUIRE(P_rowptr && P_colidx && P_vals && P_rowptr[0] == 0, "bad prolongation matrix");
+    const int64_t nnz = P_rowptr[n_fine_nodes];
+    for (int64_t k = 0; k < nnz; ++k) ALFIB_REQUIRE(P_colidx[k] >= 0 && P_colidx[k] < n_coarse_nodes, "P column out of range");
+    L.p_rows = n_fine_nodes;
+    L.p_cols = n_coarse_nodes;
+    L.p_rowptr.upload(P_rowptr, n_fine_nodes + 1, c->stream);
+    L.p_colidx.upload(P_colidx, nnz, c->stream);
+    L.p_vals.upload(P_vals, nnz, c->stream);
+    // explicit transpose (CSR of P^T), rows in ascending fine-node order => fixed summation order
+    std::vector<int32_t> trow(n_coarse_nodes + 1, 0), tcol(nnz);
+    std::vector<double> tval(nnz);
+    for (int64_t k = 0; k < nnz; ++k) trow[P_colidx[k] + 1]++;
+    for (int i = 0; i < n_coarse_nodes; ++i) trow[i + 1] += trow[i];
+    std::vector<int32_t> cursor(trow.begin(), trow.end() - 1);
+    for (int i = 0; i < n_fine_nodes; ++i)
+      for (int k = P_rowptr[i]; k < P_rowptr[i + 1]; ++k) {
+        const int dst = cursor[P_colidx[k]]++;
+        tcol[dst] = i;
+        tval[dst] = P_vals[k];
+      }
+    L.pt_rowptr.upload(trow.data(), n_coarse_nodes + 1, c->stream);
+    L.pt_colidx.upload(tcol.data(), nnz, c->stream);
+    L.pt_vals.upload(tval.data(), nnz, c->stream);
+    ALFIB_REQUIRE(ncb >= 0 && (ncb == 0 || cb_dofs), "bad coarse-boundary list");
+    for (int i = 0; i < ncb; ++i) ALFIB_REQUIRE(cb_dofs[i] >= 0 && cb_dofs[i] < L.n, "coarse-boundary dof out of range");
+    L.ncb = ncb;
+    L.cb.upload(cb_dofs, ncb, c->stream);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    L.has_transfer = true;
+  });
+}
+
+int alfib_transfer_update(alfib_ctx* c, int level, const double* A0_vals, const double* D_vals, int block_col_major) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(L.has_transfer, "alfib_transfer_set first");
+    ALFIB_REQUIRE(A0_vals || D_vals, "nothing to update");
+    if (D_vals) {
+      upload_values(c, L, L.dvals, D_vals, block_col_major);
+      L.has_d = true;
+    }
+    if (A0_vals) {
+      PatchSet& ps = L.ps[ALFIB_PATCHES_TRANSFER];
+      ALFIB_REQUIRE(ps.npatch > 0, "no transfer cell patches on this level");
+      upload_values(c, L, L.a0vals, A0_vals, block_col_major);
+      ensure_storage(ps);
+      {
+        ScopedEvent ev(c, ALFIB_EV_PCSETUP_PATCH, level);
+        launch_patch_factor(c, L, ps, L.a0vals.p);
+      }
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int alfib_prolong(alfib_ctx* c, int level, const double* coarse, double* fine) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    Level& Lc = get_level(c, level - 1);
+    const double* dc = in_vec(c, coarse, Lc.n, c->stage_in);
+    OutVec out(c, fine, L.n);
+    prolong_device(c, L, level, dc, out.dev);
+    out.finish();
+  });
+}
+
+int alfib_restrict(alfib_ctx* c, int level, const double* fine, double* coarse) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    Level& Lc = get_level(c, level - 1);
+    const double* df = in_vec(c, fine, L.n, c->stage_in);
+    OutVec out(c, coarse, Lc.n);
+    restrict_device(c, L, Lc, level, df, out.dev);
+    out.finish();
+  });
+}
+
+// ---- smoother / cycle -------------------------------------------------------------------------
+int alfib_smooth(alfib_ctx* c, int level, int m, const double* b, double* x) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(L.has_values, "level has no values");
+    const double* db = in_vec(c, b, L.n, c->stage_in);
+    OutVec out(c, x, L.n);
+    out.load();
+    fgmres_device(c, L, level, m, db, out.dev);
+    out.finish();
+  });
+}
+
+int alfib_coarse_factor(alfib_ctx* c) {
+  return guarded(c, [&] { coarse_factor_device(c); });
+}
+
+int alfib_coarse_solve(alfib_ctx* c, const double* b, double* x) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, 0);
+    const double* db = in_vec(c, b, L.n, c->stage_in);
+    OutVec out(c, x, L.n);
+    coarse_solve_device(c, db, out.dev);
+    out.finish();
+  });
+}
+
+int alfib_cycle_setup(alfib_ctx* c, int nlevels, int smoothing) {
+  return guarded(c, [&] {
+    ALFIB_REQUIRE(nlevels >= 1 && nlevels <= ALFIB_MAX_LEVELS, "bad level count");
+    ALFIB_REQUIRE(smoothing >= 1 && smoothing <= ALFIB_MAX_KRYLOV, "bad smoothing count");
+    for (int l = 0; l < nlevels; ++l) {
+      Level& L = get_level(c, l);
+      for (auto* v : {&L.b, &L.x, &L.w, &L.r, &L.t1, &L.t2}) v->alloc(L.n);
+      if (l > 0) ALFIB_REQUIRE(L.has_transfer, "level without transfer");
+    }
+    c->nlevels = nlevels;
+    c->smoothing = smoothing;
+  });
+}
+
+int alfib_cycle_apply(alfib_ctx* c, const double* b, double* x) {
+  return guarded(c, [&] {
+    ALFIB_REQUIRE(c->nlevels >= 1, "alfib_cycle_setup first");
+    Level& L = get_level(c, c->nlevels - 1);
+    const double* db = in_vec(c, b, L.n, c->stage_in);
+    OutVec out(c, x, L.n);
+    cycle_apply_device(c, db, out.dev);
+    out.finish();
+  });
+}
+
+// ---- instrumentation --------------------------------------------------------------------------
+int alfib_profile(alfib_ctx* c, int enable) {
+  return guarded(c, [&] {
+    if (!enable) profile_flush(c);
+    c->profile = enable != 0;
+  });
+}
+
+int alfib_profile_get(alfib_ctx* c, int level, double* ms, int64_t* calls) {
+  return guarded(c, [&] {
+    ALFIB_REQUIRE(level >= -1 && level < ALFIB_MAX_LEVELS, "level out of range");
+    profile_flush(c);
+    for (int i = 0; i < ALFIB_EV_COUNT; ++i) {
+      double t = 0;
+      int64_t n = 0;
+      for (int l = 0; l < ALFIB_MAX_LEVELS; ++l)
+        if (level < 0 || l == level) {
+          t += c->ev_ms[l][i];
+          n += c->ev_calls[l][i];
+        }
+      if (ms) ms[i] = t;
+      if (calls) calls[i] = n;
+    }
+  });
+}
+
+int alfib_profile_reset(alfib_ctx* c) {
+  return guarded(c, [&] {
+    profile_flush(c);
+    for (int l = 0; l < ALFIB_MAX_LEVELS; ++l)
+      for (int i = 0; i < ALFIB_EV_COUNT; ++i) {
+        c->ev_ms[l][i] = 0;
+        c->ev_calls[l][i] = 0;
+      }
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// fieldsplit_0 = richardson(1) + PCMG "full" with V inner cycles, FGMRES(m)/PatchPC smoothing on
+// every level > 0, Schoeberl transfers, direct coarse solve (alfi/solver.py:359-379;
+// alfi/transfer.py:186-275; PCMG semantics restated in SURVEY Appendix A.5/A.6).
+#include "alfib_internal.h"
+
+#define CUSOLVER_TRY(expr)                                                                      \
+  do {                                                                                          \
+    cusolverStatus_t _s = (expr);                                                               \
+    if (_s != CUSOLVER_STATUS_SUCCESS)                                                          \
+      throw DeviceError{ALFIB_ECUDA, std::string(#expr) + ": cusolver status " + std::to_string((int)_s)}; \
+  } while (0)
+
+// PCApply_PATCH (additive): y = sum_i R_i^T A_i^-1 R_i x ; y[bc] = x[bc]
+void smoother_apply_device(alfib_ctx* c, Level& L, int level, const double* x, double* y) {
+  PatchSet& ps = L.ps[ALFIB_PATCHES_SMOOTHER];
+  ALFIB_REQUIRE(ps.factored, "alfib_level_factor has not been called for this level");
+  ScopedEvent ev(c, ALFIB_EV_PCPATCH_APPLY, level);
+  CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * L.n, c->stream));
+  launch_patch_apply(c, ps, x, y);
+  launch_set_rows(c, y, x, L.bc.p, L.nbc);
+}
+
+// transfer.py:254-257 — PatchPC apply of the transfer solver: y = blockdiag(A0)^-1 b on the
+// (disjoint) cell patches, y[cb] = b[cb]
+static void cell_block_solve(alfib_ctx* c, Level& L, const double* b, double* y) {
+  PatchSet& ps = L.ps[ALFIB_PATCHES_TRANSFER];
+  ALFIB_REQUIRE(ps.factored, "alfib_transfer_update has not been called for this level");
+  CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * L.n, c->stream));
+  launch_patch_apply(c, ps, b, y);
+  launch_set_rows(c, y, b, L.cb.p, L.ncb);
+}
+
+// The same solve followed by one step of iterative refinement, t += S (b - A0 t).  The explicit
+// inverse applied as a GEMV loses ~eps*|A0^-1|*|b| — and here |b| = |gamma D rhs| is ~1e4..1e6
+// times |t| — while the reference's LU solve (transfer.py:112-113) does not; one refinement
+// step restores LU-level accuracy for one extra SpMV + block apply (measured: 1.7e-6 -> 6e-11
+// on the 3-D SV k=3 cell patches at gamma = 1e4, nu = 0.02).
+static void cell_block_solve_refined(alfib_ctx* c, Level& L, const double* b, double* y) {
+  cell_block_solve(c, L, b, y);
+  if (!c->transfer_refine || !L.a0vals.p) return;
+  L.t3.alloc(L.n);
+  L.t4.alloc(L.n);
+  launch_bsr_spmv(c, L, L.a0vals.p, y, L.t3.p, b);                     // r = b - A0 y
+  CUDA_TRY(cudaMemsetAsync(L.t4.p, 0, sizeof(double) * L.n, c->stream));
+  launch_patch_apply(c, L.ps[ALFIB_PATCHES_TRANSFER], L.t3.p, L.t4.p); // dy = S r (patch rows only)
+  launch_axpby(c, L.n, 1.0, L.t4.p, 1.0, y);
+}
+
+// fine = (I - A0^-1 gamma D) P_H coarse, fine[bc] = 0   (transfer.py:246-259; Appendix A.6)
+void prolong_device(alfib_ctx* c, Level& L, int level, const double* coarse, double* fine) {
+  ALFIB_REQUIRE(L.has_transfer, "alfib_transfer_set has not been called for this level");
+  ScopedEvent ev(c, ALFIB_EV_PROLONG, level);
+  L.t1.alloc(L.n);
+  L.t2.alloc(L.n);
+  L.r.alloc(L.n);
+  double* rhs = L.r.p;
+  launch_csr_apply(c, L.p_rows, L.bs, L.p_rowptr.p, L.p_colidx.p, L.p_vals.p, coarse, rhs);
+  if (L.has_d) {
+    launch_bsr_spmv(c, L, L.dvals.p, rhs, L.t1.p, nullptr);          // b = gamma D rhs
+    launch_set_rows(c, L.t1.p, nullptr, L.cb.p, L.ncb);              // coarse-boundary rows zeroed
+    cell_block_solve_refined(c, L, L.t1.p, L.t2.p);                  // t = A0^-1 b
+    launch_sub(c, L.n, rhs, L.t2.p, fine);                           // fine = rhs - t
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(fine, rhs, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  launch_set_rows(c, fine, nullptr, L.bc.p, L.nbc);
+}
+
+// coarse = P_H^T (I - gamma D A0^-1) fine, coarse[bc_c] = 0   (transfer.py:261-275; A.6)
+void restrict_device(alfib_ctx* c, Level& L, Level& Lc, int level, const double* fine, double* coarse) {
+  ALFIB_REQUIRE(L.has_transfer, "alfib_transfer_set has not been called for this level");
+  ScopedEvent ev(c, ALFIB_EV_RESTRICT, level);
+  const double* src = fine;
+  if (L.has_d && c->robust_restrict) {
+    L.t1.alloc(L.n);
+    L.t2.alloc(L.n);
+    CUDA_TRY(cudaMemcpyAsync(L.t1.p, fine, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, c->stream));
+    launch_set_rows(c, L.t1.p, nullptr, L.cb.p, L.ncb);              // bcs.apply(tildeu)
+    cell_block_solve_refined(c, L, L.t1.p, L.t2.p);                  // r = A0^-1 t
+    launch_bsr_spmv(c, L, L.dvals.p, L.t2.p, L.t1.p, nullptr);       // b = gamma D r (no bcs)
+    launch_sub(c, L.n, fine, L.t1.p, L.t2.p);                        // r2 = fine - b
+    src = L.t2.p;
+  }
+  launch_csr_apply(c, L.p_cols, L.bs, L.pt_rowptr.p, L.pt_colidx.p, L.pt_vals.p, src, coarse);
+  launch_set_rows(c, coarse, nullptr, Lc.bc.p, Lc.nbc);
+}
+
+// Dense LU of the level-0 operator with cuSOLVER (the north star allows a gathered dense LU;
+// replaces AssembledPC + telescope + superlu_dist, solver.py:369-378).
+void coarse_factor_device(alfib_ctx* c) {
+  Level* L0 = c->levels[0];
+  ALFIB_REQUIRE(L0 && L0->has_values, "level 0 has no operator values");
+  ScopedEvent ev(c, ALFIB_EV_COARSE);
+  if (!c->cusolver) {
+    CUSOLVER_TRY(cusolverDnCreate(&c->cusolver));
+    CUSOLVER_TRY(cusolverDnSetStream(c->cusolver, c->stream));
+  }
+  const int n = L0->n;
+  c->coarse_n = n;
+  c->coarse_lu.alloc((size_t)n * n);
+  c->coarse_piv.alloc(n);
+  c->coarse_info.alloc(1);
+  launch_bsr_to_dense(c, *L0, c->coarse_lu.p);
+  int lwork = 0;
+  CUSOLVER_TRY(cusolverDnDgetrf_bufferSize(c->cusolver, n, n, c->coarse_lu.p, n, &lwork));
+  c->coarse_work.alloc(lwork);
+  CUSOLVER_TRY(cusolverDnDgetrf(c->cusolver, n, n, c->coarse_lu.p, n, c->coarse_work.p, c->coarse_piv.p,
+                                c->coarse_info.p));
+  int info = 0;
+  CUDA_TRY(cudaMemcpyAsync(&info, c->coarse_info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (info != 0) throw DeviceError{ALFIB_ESINGULAR, "coarse LU failed, info = " + std::to_string(info)};
+  c->coarse_work.release();
+  c->coarse_factored = true;
+}
+
+void coarse_solve_device(alfib_ctx* c, const double* b, double* x) {
+  ALFIB_REQUIRE(c->coarse_factored, "alfib_coarse_factor has not been called");
+  ScopedEvent ev(c, ALFIB_EV_COARSE);
+  const int n = c->coarse_n;
+  if (x != b) CUDA_TRY(cudaMemcpyAsync(x, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+  CUSOLVER_TRY(cusolverDnDgetrs(c->cusolver, CUBLAS_OP_N, n, 1, c->coarse_lu.p, n, c->coarse_piv.p, x, n,
+                                c->coarse_info.p));
+}
+
+// One V visit on level l: b, x are the level's own vectors (Appendix A.5)
+static void vcycle(alfib_ctx* c, int l) {
+  Level& L = *c->levels[l];
+  if (l == 0) {
+    coarse_solve_device(c, L.b.p, L.x.p);
+    return;
+  }
+  Level& Lc = *c->levels[l - 1];
+  fgmres_device(c, L, l, c->smoothing, L.b.p, L.x.p);                         // pre-smooth
+  {
+    ScopedEvent ev(c, ALFIB_EV_MATMULT, l);
+    launch_bsr_spmv(c, L, L.vals.p, L.x.p, L.w.p, L.b.p);                     // r = b - A x
+  }
+  restrict_device(c, L, Lc, l, L.w.p, Lc.b.p);
+  CUDA_TRY(cudaMemsetAsync(Lc.x.p, 0, sizeof(double) * Lc.n, c->stream));
+  vcycle(c, l - 1);
+  prolong_device(c, L, l, Lc.x.p, L.w.p);
+  launch_axpby(c, L.n, 1.0, L.w.p, 1.0, L.x.p);                               // x += P x_c
+  fgmres_device(c, L, l, c->smoothing, L.b.p, L.x.p);                         // post-smooth
+}
+
+// PCMG full: restrict b to every level, then for l = 0..L-2: V(l), x_{l+1} = P x_l ; V(L-1)
+void cycle_apply_device(alfib_ctx* c, const double* b, double* x) {
+  const int nl = c->nlevels;
+  ALFIB_REQUIRE(nl >= 1, "alfib_cycle_setup has not been called");
+  Level& Lt = *c->levels[nl - 1];
+  CUDA_TRY(cudaMemcpyAsync(Lt.b.p, b, sizeof(double) * Lt.n, cudaMemcpyDeviceToDevice, c->stream));
+  for (int l = nl - 1; l > 0; --l) restrict_device(c, *c->levels[l], *c->levels[l - 1], l, c->levels[l]->b.p,
+                                                   c->levels[l - 1]->b.p);
+  CUDA_TRY(cudaMemsetAsync(c->levels[0]->x.p, 0, sizeof(double) * c->levels[0]->n, c->stream));
+  for (int l = 0; l < nl - 1; ++l) {
+    vcycle(c, l);
+    prolong_device(c, *c->levels[l + 1], l + 1, c->levels[l]->x.p, c->levels[l + 1]->x.p);
+  }
+  vcycle(c, nl - 1);
+  CUDA_TRY(cudaMemcpyAsync(x, Lt.x.p, sizeof(double) * Lt.n, cudaMemcpyDeviceToDevice, c->stream));
+}

@@ -1,0 +1,192 @@
+// Level smoother: FGMRES(m) exactly as alfi configures the mg_levels KSP (alfi/solver.py:313-317):
+// right-preconditioned, classical Gram-Schmidt without refinement, `convergence_test skip`
+// => exactly m iterations, nonzero initial guess.  Everything stays on the
+// device — dots are two-pass (fixed-order, bitwise reproducible) reductions, the (m+1) x m
+// Hessenberg least-squares problem is solved by one thread with Givens rotations — so a whole
+// smoother call is a fixed sequence of launches with no host synchronisation.
+//
+// HBM-bound BLAS-1; algorithmic bytes per call ~ 8 N (m^2 + 8 m)  (SURVEY §8d).
+#include "alfib_internal.h"
+
+namespace {
+
+constexpr int RT = 256;            // threads per reduction block
+constexpr int RGRID = 592;         // fixed reduction grid (4 x 148 SMs) => fixed summation order
+constexpr int MAXV = ALFIB_MAX_KRYLOV + 1;
+
+// partial[j * RGRID + block] = sum over the block's slice of V_j[i] * w[i],  j < nv
+__global__ void __launch_bounds__(RT) multi_dot_kernel(int n, int nv, const double* __restrict__ V, int64_t ldv,
+                                                       const double* __restrict__ w, double* __restrict__ partial) {
+  __shared__ double red[RT / 32];
+  const int tid = threadIdx.x;
+  for (int j0 = 0; j0 < nv; j0 += 4) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * RT + tid; i < n; i += (int64_t)RGRID * RT) {
+      const double wi = w[i];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        if (j0 + jj < nv) acc[jj] = fma(V[(int64_t)(j0 + jj) * ldv + i], wi, acc[jj]);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      if (j0 + jj >= nv) break;
+      double v = acc[jj];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if ((tid & 31) == 0) red[tid >> 5] = v;
+      __syncthreads();
+      if (tid < 32) {
+        v = tid < RT / 32 ? red[tid] : 0.0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (tid == 0) partial[(int64_t)(j0 + jj) * RGRID + blockIdx.x] = v;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// out[j] = op(sum_b partial[j*RGRID + b]);  one warp per j, fixed order.  mode 0: plain sum,
+// mode 1: sqrt (norm).  Optionally also writes 1/out (0 if out == 0) to inv.
+__global__ void finalize_kernel(int nv, const double* __restrict__ partial, double* __restrict__ out, int mode,
+                                double* __restrict__ inv) {
+  const int j = blockIdx.x, lane = threadIdx.x;
+  if (j >= nv) return;
+  double v = 0.0;
+  for (int b = lane; b < RGRID; b += 32) v += partial[(int64_t)j * RGRID + b];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) {
+    if (mode == 1) v = sqrt(v);
+    out[j] = v;
+    if (inv) inv[j] = v > 0.0 ? 1.0 / v : 0.0;
+  }
+}
+
+// w[i] += sign * sum_j coef[j] V_j[i];  if partial != nullptr also accumulates |w|^2 partials
+__global__ void __launch_bounds__(RT) maxpy_kernel(int n, int nv, const double* __restrict__ coef, double sign,
+                                                   const double* __restrict__ V, int64_t ldv, double* __restrict__ w,
+                                                   double* __restrict__ partial) {
+  __shared__ double red[RT / 32];
+  __shared__ double cf[MAXV];
+  const int tid = threadIdx.x;
+  if (tid < nv) cf[tid] = sign * coef[tid];
+  __syncthreads();
+  double nrm = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * RT + tid; i < n; i += (int64_t)RGRID * RT) {
+    double v = w[i];
+    for (int j = 0; j < nv; ++j) v = fma(cf[j], V[(int64_t)j * ldv + i], v);
+    w[i] = v;
+    nrm = fma(v, v, nrm);
+  }
+  if (partial) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nrm += __shfl_down_sync(0xffffffffu, nrm, o);
+    if ((tid & 31) == 0) red[tid >> 5] = nrm;
+    __syncthreads();
+    if (tid < 32) {
+      nrm = tid < RT / 32 ? red[tid] : 0.0;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) nrm += __shfl_down_sync(0xffffffffu, nrm, o);
+      if (tid == 0) partial[blockIdx.x] = nrm;
+    }
+  }
+}
+
+// out[i] = scale[0] * in[i]
+__global__ void scale_kernel(int n, const double* __restrict__ scale, const double* __restrict__ in,
+                             double* __restrict__ out) {
+  const double s = scale[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = s * in[i];
+}
+
+// Solve min || beta e1 - H y || for the (m+1) x m Hessenberg matrix (column-major, ld = MAXV)
+// by Givens rotations — the update PETSc's FGMRES performs.  A zero pivot (happy breakdown)
+// gives y_j = 0.
+__global__ void hessenberg_solve_kernel(int m, double* __restrict__ H, const double* __restrict__ beta,
+                                        double* __restrict__ y) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double g[MAXV];
+  for (int i = 0; i <= m; ++i) g[i] = 0.0;
+  g[0] = beta[0];
+  for (int j = 0; j < m; ++j) {
+    const double a = H[j + j * MAXV], b = H[j + 1 + j * MAXV];
+    const double r = hypot(a, b);
+    const double c = r == 0.0 ? 1.0 : a / r, s = r == 0.0 ? 0.0 : b / r;
+    for (int col = j; col < m; ++col) {
+      const double t0 = H[j + col * MAXV], t1 = H[j + 1 + col * MAXV];
+      H[j + col * MAXV] = c * t0 + s * t1;
+      H[j + 1 + col * MAXV] = -s * t0 + c * t1;
+    }
+    const double g0 = g[j], g1 = g[j + 1];
+    g[j] = c * g0 + s * g1;
+    g[j + 1] = -s * g0 + c * g1;
+  }
+  for (int j = m - 1; j >= 0; --j) {
+    double v = g[j];
+    for (int k = j + 1; k < m; ++k) v -= H[j + k * MAXV] * y[k];
+    const double d = H[j + j * MAXV];
+    y[j] = d == 0.0 ? 0.0 : v / d;
+  }
+}
+
+}  // namespace
+
+// scal layout: [0, MAXV*MAXV) H ; then beta, inv, y[MAXV], h[MAXV]
+void fgmres_device(alfib_ctx* c, Level& L, int level, int m, const double* b, double* x) {
+  ALFIB_REQUIRE(m >= 1 && m <= ALFIB_MAX_KRYLOV, "smoothing iterations out of range");
+  const int n = L.n;
+  if (L.krylov_m < m) {
+    L.V.alloc((size_t)(m + 1) * n);
+    L.Z.alloc((size_t)m * n);
+    L.krylov_m = m;
+  }
+  L.w.alloc(n);
+  c->partial.alloc((size_t)MAXV * RGRID);
+  c->scal.alloc(MAXV * MAXV + 2 + 2 * MAXV);
+  double* H = c->scal.p;
+  double* beta = H + MAXV * MAXV;
+  double* inv = beta + 1;
+  double* y = inv + 1;
+  double* V = L.V.p;
+  double* Z = L.Z.p;
+  double* w = L.w.p;
+  cudaStream_t s = c->stream;
+  CUDA_TRY(cudaMemsetAsync(H, 0, sizeof(double) * MAXV * MAXV, s));
+
+  // r0 = b - A x ; beta = |r0| ; v0 = r0 / beta
+  {
+    ScopedEvent ev(c, ALFIB_EV_MATMULT, level);
+    launch_bsr_spmv(c, L, L.vals.p, x, w, b);
+  }
+  {
+    ScopedEvent ev(c, ALFIB_EV_KSP_GMRES_ORTHOG, level);
+    multi_dot_kernel<<<RGRID, RT, 0, s>>>(n, 1, w, n, w, c->partial.p);
+    finalize_kernel<<<1, 32, 0, s>>>(1, c->partial.p, beta, 1, inv);
+    scale_kernel<<<RGRID, RT, 0, s>>>(n, inv, w, V);
+    c->launches += 3;
+  }
+  for (int k = 0; k < m; ++k) {
+    double* vk = V + (size_t)k * n;
+    double* zk = Z + (size_t)k * n;
+    smoother_apply_device(c, L, level, vk, zk);                      // z_k = M^-1 v_k
+    {
+      ScopedEvent ev(c, ALFIB_EV_MATMULT, level);
+      launch_bsr_spmv(c, L, L.vals.p, zk, w, nullptr);        // w = A z_k
+    }
+    ScopedEvent ev(c, ALFIB_EV_KSP_GMRES_ORTHOG, level);
+    double* hcol = H + (size_t)k * MAXV;
+    multi_dot_kernel<<<RGRID, RT, 0, s>>>(n, k + 1, V, n, w, c->partial.p);    // h = V^T w  (CGS)
+    finalize_kernel<<<k + 1, 32, 0, s>>>(k + 1, c->partial.p, hcol, 0, nullptr);
+    maxpy_kernel<<<RGRID, RT, 0, s>>>(n, k + 1, hcol, -1.0, V, n, w, c->partial.p);   // w -= V h, |w|^2
+    finalize_kernel<<<1, 32, 0, s>>>(1, c->partial.p, hcol + k + 1, 1, inv);
+    scale_kernel<<<RGRID, RT, 0, s>>>(n, inv, w, V + (size_t)(k + 1) * n);
+    c->launches += 5;
+  }
+  ScopedEvent ev(c, ALFIB_EV_KSP_GMRES_ORTHOG, level);
+  hessenberg_solve_kernel<<<1, 32, 0, s>>>(m, H, beta, y);
+  maxpy_kernel<<<RGRID, RT, 0, s>>>(n, m, y, 1.0, Z, n, x, nullptr);          // x += Z y
+  c->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+}

@@ -1,0 +1,109 @@
+// Additive-Schwarz patch apply:  y += sum_i R_i^T A_i^{-1} R_i x   (PCApply_PATCH, additive, no
+// partition of unity — alfi/solver.py:318-324).
+//
+// The explicit inverses (patch_pc_patch_dense_inverse, alfi/solver.py:602) are stored in a
+// layout made for streaming: patch i with n rows is cut into tiles of 64 rows; a tile is
+// column-major with `rows_t` (even) rows per column, so the double2 of lane l in column c holds
+// rows (2l, 2l+1) and a warp reads one contiguous 16*rows_t/2-byte run per column and one
+// contiguous 64*n*8-byte region overall.  One warp = one (patch, tile) work item; the gathered
+// right-hand side x[I_i] is fetched 32 entries at a time by the lanes and broadcast with
+// shuffles, so no shared memory or block barrier is needed and warps of one CTA may work on
+// different patches.  Roofline: HBM; algorithmic bytes sum_i (8 n_i^2 + 4 n_i) + 16 N.
+//
+// Scatter-add is race-free by colouring in deterministic mode (one launch per colour, plain
+// stores: patches of one colour share no dof, tiles of one patch own disjoint rows) or uses
+// fp64 atomicAdd in a single launch otherwise.
+#include "alfib_internal.h"
+
+namespace {
+
+template <bool ATOMIC>
+__global__ void __launch_bounds__(128) patch_apply_kernel(const int2* __restrict__ work, int nwork,
+                                                          const int64_t* __restrict__ poff,
+                                                          const int32_t* __restrict__ pdofs,
+                                                          const int64_t* __restrict__ soff,
+                                                          const double* __restrict__ store,
+                                                          const double* __restrict__ x, double* __restrict__ y) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nwork) return;
+  const int2 wk = work[w];
+  const int64_t o = poff[wk.x];
+  const int n = (int)(poff[wk.x + 1] - o);
+  const int32_t* __restrict__ I = pdofs + o;
+  const int row0 = wk.y * ALFIB_TILE_ROWS;
+  int rows = n - row0;
+  rows = rows > ALFIB_TILE_ROWS ? ALFIB_TILE_ROWS : ((rows + 1) & ~1);
+  const int half = rows >> 1;                       // double2 per column of this tile
+  const bool active = lane < half;
+  const double2* __restrict__ T =
+      reinterpret_cast<const double2*>(store + soff[wk.x] + (int64_t)row0 * n) + (active ? lane : 0);
+
+  double acc0 = 0.0, acc1 = 0.0;
+  // software-pipelined gather of x[I[c]] for the next 32 columns
+  double xv = (lane < n) ? __ldg(x + I[lane]) : 0.0;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int cn = c0 + 32 + lane;
+    const double xnext = (cn < n) ? __ldg(x + I[cn]) : 0.0;
+    const int cnt = (n - c0) < 32 ? (n - c0) : 32;
+    const double2* __restrict__ Tc = T + (int64_t)c0 * half;
+    if (cnt == 32) {
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const double xc = __shfl_sync(0xffffffffu, xv, j);
+        if (active) {
+          const double2 a = __ldcs(Tc + (int64_t)j * half);
+          acc0 = fma(a.x, xc, acc0);
+          acc1 = fma(a.y, xc, acc1);
+        }
+      }
+    } else {
+      for (int j = 0; j < cnt; ++j) {
+        const double xc = __shfl_sync(0xffffffffu, xv, j);
+        if (active) {
+          const double2 a = __ldcs(Tc + (int64_t)j * half);
+          acc0 = fma(a.x, xc, acc0);
+          acc1 = fma(a.y, xc, acc1);
+        }
+      }
+    }
+    xv = xnext;
+  }
+  if (active) {
+    const int r = row0 + 2 * lane;
+    if (ATOMIC) {
+      atomicAdd(y + I[r], acc0);
+      if (r + 1 < n) atomicAdd(y + I[r + 1], acc1);
+    } else {
+      y[I[r]] += acc0;
+      if (r + 1 < n) y[I[r + 1]] += acc1;
+    }
+  }
+}
+
+}  // namespace
+
+void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, double* y) {
+  if (ps.nwork == 0) return;
+  const int threads = 128, wpb = threads / 32;
+  const bool coloured = c->deterministic && !ps.repeated;
+  if (!coloured && ps.ncolour > 1) {
+    patch_apply_kernel<true><<<cdiv(ps.nwork, wpb), threads, 0, c->stream>>>(
+        ps.work.p, ps.nwork, ps.off.p, ps.dofs.p, ps.soff.p, ps.store, x, y);
+    c->launches++;
+  } else {
+    // one launch per colour; a single colour (disjoint cell patches) never needs atomics
+    for (int col = 0; col < ps.ncolour; ++col) {
+      const int s = ps.colour_work_start[col], e = ps.colour_work_start[col + 1];
+      if (e == s) continue;
+      if (ps.repeated)
+        patch_apply_kernel<true><<<cdiv(e - s, wpb), threads, 0, c->stream>>>(
+            ps.work.p + s, e - s, ps.off.p, ps.dofs.p, ps.soff.p, ps.store, x, y);
+      else
+        patch_apply_kernel<false><<<cdiv(e - s, wpb), threads, 0, c->stream>>>(
+            ps.work.p + s, e - s, ps.off.p, ps.dofs.p, ps.soff.p, ps.store, x, y);
+      c->launches++;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+}

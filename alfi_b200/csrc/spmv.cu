@@ -1,0 +1,136 @@
+// Sparse kernels: BSR residual/SpMV of the level operator, scalar-CSR (x) I_bs prolongation.
+//
+// Reference: PETSc MatMult_SeqBAIJ on the `baij` velocity block (alfi/solver.py:512) and the
+// firedrake.mg prolong/restrict kernels behind `standard_transfer` (alfi/transfer.py:284-290).
+//
+// BSR SpMV: one warp per block row.  The row's values are a contiguous run of nnzb*bs*bs
+// doubles; lanes walk it with 128-bit loads (the run is re-based to an even element so every
+// double2 is 16-byte aligned, out-of-run halves are masked).  HBM-bound: algorithmic bytes
+// nnzb*(8 bs^2 + 4) + 4(nbrows+1) + 16 N  (SURVEY §8d).
+#include "alfib_internal.h"
+
+namespace {
+
+template <int BS>
+__global__ void __launch_bounds__(256) bsr_spmv_kernel(int nbrows, const int32_t* __restrict__ rowptr,
+                                                       const int32_t* __restrict__ colidx,
+                                                       const double* __restrict__ vals,
+                                                       const double* __restrict__ x, double* __restrict__ y,
+                                                       const double* __restrict__ b) {
+  constexpr int B2 = BS * BS;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= nbrows) return;
+  const int64_t start = (int64_t)rowptr[warp] * B2;
+  const int64_t end = (int64_t)rowptr[warp + 1] * B2;
+  double acc[BS];
+#pragma unroll
+  for (int r = 0; r < BS; ++r) acc[r] = 0.0;
+  const double2* v2 = reinterpret_cast<const double2*>(vals);
+  for (int64_t e = (start & ~int64_t(1)) + 2 * lane; e < end; e += 64) {
+    const double2 a = __ldcs(v2 + (e >> 1));
+    const double av[2] = {a.x, a.y};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t q = e + h;
+      if (q >= start && q < end) {
+        const int64_t blk = q / B2;
+        const int rem = (int)(q - blk * B2);
+        const int r = rem / BS, cc = rem - r * BS;
+        const double xv = __ldg(x + (int64_t)__ldg(colidx + blk) * BS + cc);
+#pragma unroll
+        for (int rr = 0; rr < BS; ++rr)
+          if (rr == r) acc[rr] = fma(av[h], xv, acc[rr]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < BS; ++r)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc[r] += __shfl_down_sync(0xffffffffu, acc[r], o);
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < BS; ++r) {
+      const int64_t i = (int64_t)warp * BS + r;
+      y[i] = b ? b[i] - acc[r] : acc[r];
+    }
+  }
+}
+
+// y[node, :] = sum_k vals[k] * x[col[k], :]   (scalar CSR acting on bs-interleaved vectors)
+template <int BS>
+__global__ void csr_apply_kernel(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                 const double* __restrict__ vals, const double* __restrict__ x,
+                                 double* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  double acc[BS];
+#pragma unroll
+  for (int r = 0; r < BS; ++r) acc[r] = 0.0;
+  for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+    const double v = vals[k];
+    const double* xc = x + (int64_t)colidx[k] * BS;
+#pragma unroll
+    for (int r = 0; r < BS; ++r) acc[r] = fma(v, xc[r], acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < BS; ++r) y[(int64_t)i * BS + r] = acc[r];
+}
+
+template <int BS>
+__global__ void transpose_blocks_kernel(double* vals, int64_t nnzb) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnzb) return;
+  double* v = vals + k * BS * BS;
+#pragma unroll
+  for (int r = 0; r < BS; ++r)
+#pragma unroll
+    for (int c = r + 1; c < BS; ++c) {
+      const double t = v[r * BS + c];
+      v[r * BS + c] = v[c * BS + r];
+      v[c * BS + r] = t;
+    }
+}
+
+}  // namespace
+
+void launch_bsr_spmv(alfib_ctx* c, const Level& L, const double* vals, const double* x, double* y,
+                     const double* b) {
+  const int threads = 256;
+  const int blocks = cdiv((int64_t)L.n_nodes * 32, threads);
+  if (L.bs == 2)
+    bsr_spmv_kernel<2><<<blocks, threads, 0, c->stream>>>(L.n_nodes, L.rowptr.p, L.colidx.p, vals, x, y, b);
+  else if (L.bs == 3)
+    bsr_spmv_kernel<3><<<blocks, threads, 0, c->stream>>>(L.n_nodes, L.rowptr.p, L.colidx.p, vals, x, y, b);
+  else
+    throw DeviceError{ALFIB_EINVAL, "block size must be 2 or 3"};
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_csr_apply(alfib_ctx* c, int nrows, int bs, const int32_t* rowptr, const int32_t* colidx,
+                      const double* vals, const double* x, double* y) {
+  const int threads = 256;
+  const int blocks = cdiv(nrows, threads);
+  if (blocks == 0) return;
+  if (bs == 2)
+    csr_apply_kernel<2><<<blocks, threads, 0, c->stream>>>(nrows, rowptr, colidx, vals, x, y);
+  else if (bs == 3)
+    csr_apply_kernel<3><<<blocks, threads, 0, c->stream>>>(nrows, rowptr, colidx, vals, x, y);
+  else
+    throw DeviceError{ALFIB_EINVAL, "block size must be 2 or 3"};
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_transpose_blocks(alfib_ctx* c, double* vals, int64_t nnzb, int bs) {
+  const int threads = 256;
+  const int blocks = cdiv(nnzb, threads);
+  if (blocks == 0) return;
+  if (bs == 2)
+    transpose_blocks_kernel<2><<<blocks, threads, 0, c->stream>>>(vals, nnzb);
+  else
+    transpose_blocks_kernel<3><<<blocks, threads, 0, c->stream>>>(vals, nnzb);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+}

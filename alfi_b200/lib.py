@@ -1,0 +1,315 @@
+"""ctypes binding of libalfib.so — the thin C-ABI hand-over the north star asks for.
+
+`Context` owns one `alfib_ctx` (one process <-> one GPU).  Vector arguments may be numpy arrays
+(host; copied by the library inside the call) or torch CUDA tensors (device; passed as raw
+``data_ptr()`` — PyTorch is used for buffer ownership only).  There is **no CPU fallback**: if
+the shared library is missing or no GPU is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["load_library", "Context", "AlfibError", "EVENT_NAMES", "LIB_PATH"]
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libalfib.so")
+_lib = None
+
+# PETSc event names alfi reports (alfi/driver.py:80) in ALFIB_EV_* order
+EVENT_NAMES = ["PCPATCHApply", "MatMult", "SchoeberlProlong", "SchoeberlRestrict",
+               "KSPGMRESOrthog", "MGCoarseSolve", "PCSetUp_PATCH"]
+
+PATCHES_SMOOTHER, PATCHES_TRANSFER = 0, 1
+OPT_DETERMINISTIC, OPT_SYNC_ALWAYS, OPT_ROBUST_RESTRICT = 1, 2, 3
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.c_void_p          # host or device pointer to double
+
+# every symbol include/alfib.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "alfib_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "alfib_destroy": (C.c_int, [C.c_void_p]),
+    "alfib_last_error": (C.c_char_p, [C.c_void_p]),
+    "alfib_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "alfib_set_deterministic": (C.c_int, [C.c_void_p, C.c_int]),
+    "alfib_synchronize": (C.c_int, [C.c_void_p]),
+    "alfib_launch_count": (C.c_int64, [C.c_void_p]),
+    "alfib_stream": (C.c_void_p, [C.c_void_p]),
+    "alfib_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "alfib_level_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "alfib_level_set_bsr_pattern": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _i32p]),
+    "alfib_level_set_bsr_values": (C.c_int, [C.c_void_p, C.c_int, _f64p, C.c_int]),
+    "alfib_level_set_bc": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, _i32p]),
+    "alfib_spmv": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
+    "alfib_residual": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p, _f64p]),
+    "alfib_level_set_patches": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int32, _i64p, _i32p, C.c_int32,
+                                          _i32p, _i32p]),
+    "alfib_patch_storage_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int]),
+    "alfib_patch_bind_storage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
+    "alfib_level_factor": (C.c_int, [C.c_void_p, C.c_int]),
+    "alfib_smoother_apply": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
+    "alfib_get_colours": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i32p]),
+    "alfib_get_patch_inverse": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int32, _f64p]),
+    "alfib_transfer_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, C.c_int32, _i32p, _i32p, _f64p, C.c_int32,
+                                     _i32p]),
+    "alfib_transfer_update": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p, C.c_int]),
+    "alfib_prolong": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
+    "alfib_restrict": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
+    "alfib_smooth": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f64p, _f64p]),
+    "alfib_coarse_factor": (C.c_int, [C.c_void_p]),
+    "alfib_coarse_solve": (C.c_int, [C.c_void_p, _f64p, _f64p]),
+    "alfib_cycle_setup": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "alfib_cycle_apply": (C.c_int, [C.c_void_p, _f64p, _f64p]),
+    "alfib_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "alfib_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), _i64p]),
+    "alfib_profile_reset": (C.c_int, [C.c_void_p]),
+}
+
+
+class AlfibError(RuntimeError):
+    pass
+
+
+def load_library(path: str | None = None):
+    """dlopen libalfib.so and bind every declared symbol.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise AlfibError("libalfib.so not found at %s — run `python -m alfi_b200.build` "
+                         "(there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ptr(arr, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+class _Vec:
+    """Resolve a numpy array / torch tensor to a raw pointer, keeping the owner alive."""
+
+    def __init__(self, obj, n=None, writable=False):
+        self.owner = obj
+        if isinstance(obj, np.ndarray):
+            if obj.dtype != np.float64 or not obj.flags.c_contiguous:
+                if writable:
+                    raise AlfibError("output arrays must be C-contiguous float64")
+                obj = np.ascontiguousarray(obj, dtype=np.float64)
+                self.owner = obj
+            self.ptr = obj.ctypes.data
+            size = obj.size
+        elif hasattr(obj, "data_ptr"):         # torch tensor (device or pinned host)
+            import torch
+            if obj.dtype != torch.float64 or not obj.is_contiguous():
+                raise AlfibError("tensors must be contiguous float64")
+            self.ptr = obj.data_ptr()
+            size = obj.numel()
+        else:
+            raise AlfibError("expected a numpy array or a torch tensor")
+        if n is not None and size != n:
+            raise AlfibError("vector has %d entries, expected %d" % (size, n))
+
+
+class Context:
+    """One GPU, one alfib_ctx.  Mirrors include/alfib.h one to one."""
+
+    def __init__(self, device: int = 0, deterministic: bool = False):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.alfib_create(device, C.byref(h))
+        if rc != 0 or not h:
+            raise AlfibError("alfib_create(device=%d) failed with code %d — a CUDA device is required "
+                             "(no CPU fallback)" % (device, rc))
+        self.h = h
+        self.device = device
+        self._sizes = {}
+        self._keep = []
+        if deterministic:
+            self.set_deterministic(True)
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise AlfibError("alfib error %d: %s" % (rc, self.lib.alfib_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.alfib_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # noqa: BLE001
+            pass
+
+    def set_deterministic(self, flag=True):
+        self._check(self.lib.alfib_set_deterministic(self.h, int(flag)))
+
+    def set_option(self, key, value):
+        self._check(self.lib.alfib_set_option(self.h, key, int(value)))
+
+    def synchronize(self):
+        self._check(self.lib.alfib_synchronize(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.alfib_launch_count(self.h))
+
+    @property
+    def stream(self):
+        return int(self.lib.alfib_stream(self.h) or 0)
+
+    def level_sizes(self):
+        return dict(self._sizes)
+
+    # -- level operator
+    def level_create(self, level, n_nodes, bs):
+        self._check(self.lib.alfib_level_create(self.h, level, n_nodes, bs))
+        self._sizes[level] = n_nodes * bs
+
+    def set_bsr_pattern(self, level, rowptr, colidx):
+        rowptr, colidx = _i32(rowptr), _i32(colidx)
+        self._check(self.lib.alfib_level_set_bsr_pattern(self.h, level, colidx.size, _ptr(rowptr, C.c_int32),
+                                                         _ptr(colidx, C.c_int32)))
+
+    def set_bsr_values(self, level, vals, block_col_major=False):
+        v = _Vec(vals)
+        self._check(self.lib.alfib_level_set_bsr_values(self.h, level, v.ptr, int(block_col_major)))
+
+    def set_bc(self, level, bc_dofs):
+        bc = _i32(bc_dofs)
+        self._check(self.lib.alfib_level_set_bc(self.h, level, bc.size, _ptr(bc, C.c_int32)))
+
+    def spmv(self, level, x, y):
+        n = self._sizes[level]
+        vx, vy = _Vec(x, n), _Vec(y, n, True)
+        self._check(self.lib.alfib_spmv(self.h, level, vx.ptr, vy.ptr))
+        return y
+
+    def residual(self, level, b, x, r):
+        n = self._sizes[level]
+        vb, vx, vr = _Vec(b, n), _Vec(x, n), _Vec(r, n, True)
+        self._check(self.lib.alfib_residual(self.h, level, vb.ptr, vx.ptr, vr.ptr))
+        return r
+
+    # -- patches
+    def set_patches(self, level, offsets, dofs, order=None, colours=None, which=PATCHES_SMOOTHER):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        dofs = _i32(dofs)
+        npatch = offsets.size - 1
+        order_a = _i32(order) if order is not None else None
+        col_a = _i32(colours) if colours is not None else None
+        self._check(self.lib.alfib_level_set_patches(
+            self.h, level, which, npatch, _ptr(offsets, C.c_int64), _ptr(dofs, C.c_int32),
+            0 if order_a is None else order_a.size,
+            None if order_a is None else _ptr(order_a, C.c_int32),
+            None if col_a is None else _ptr(col_a, C.c_int32)))
+
+    def patch_storage_bytes(self, level, which=PATCHES_SMOOTHER):
+        return int(self.lib.alfib_patch_storage_bytes(self.h, level, which))
+
+    def bind_patch_storage(self, level, tensor, which=PATCHES_SMOOTHER):
+        """Hand a torch CUDA uint8/float64 tensor to the library as factor storage."""
+        nbytes = tensor.numel() * tensor.element_size()
+        self._keep.append(tensor)
+        self._check(self.lib.alfib_patch_bind_storage(self.h, level, which, tensor.data_ptr(), nbytes))
+
+    def factor(self, level):
+        self._check(self.lib.alfib_level_factor(self.h, level))
+
+    def smoother_apply(self, level, x, y):
+        n = self._sizes[level]
+        vx, vy = _Vec(x, n), _Vec(y, n, True)
+        self._check(self.lib.alfib_smoother_apply(self.h, level, vx.ptr, vy.ptr))
+        return y
+
+    def colours(self, level, npatch, which=PATCHES_SMOOTHER):
+        out = np.empty(npatch, dtype=np.int32)
+        self._check(self.lib.alfib_get_colours(self.h, level, which, _ptr(out, C.c_int32)))
+        return out
+
+    def patch_inverse(self, level, patch, n, which=PATCHES_SMOOTHER):
+        out = np.empty((n, n), dtype=np.float64)
+        self._check(self.lib.alfib_get_patch_inverse(self.h, level, which, patch, out.ctypes.data))
+        return out
+
+    # -- transfer
+    def set_transfer(self, level, P, cb_dofs):
+        """P: scipy CSR (fine nodes x coarse nodes), scalar."""
+        P = P.tocsr()
+        P.sort_indices()
+        rp, ci = _i32(P.indptr), _i32(P.indices)
+        pv = np.ascontiguousarray(P.data, dtype=np.float64)
+        cb = _i32(cb_dofs)
+        self._check(self.lib.alfib_transfer_set(self.h, level, P.shape[0], P.shape[1], _ptr(rp, C.c_int32),
+                                                _ptr(ci, C.c_int32), pv.ctypes.data, cb.size, _ptr(cb, C.c_int32)))
+
+    def transfer_update(self, level, a0_vals, d_vals, block_col_major=False):
+        a0 = _Vec(a0_vals) if a0_vals is not None else None
+        dv = _Vec(d_vals) if d_vals is not None else None
+        self._check(self.lib.alfib_transfer_update(self.h, level, None if a0 is None else a0.ptr,
+                                                   None if dv is None else dv.ptr, int(block_col_major)))
+
+    def prolong(self, level, coarse, fine):
+        vc, vf = _Vec(coarse, self._sizes[level - 1]), _Vec(fine, self._sizes[level], True)
+        self._check(self.lib.alfib_prolong(self.h, level, vc.ptr, vf.ptr))
+        return fine
+
+    def restrict(self, level, fine, coarse):
+        vf, vc = _Vec(fine, self._sizes[level]), _Vec(coarse, self._sizes[level - 1], True)
+        self._check(self.lib.alfib_restrict(self.h, level, vf.ptr, vc.ptr))
+        return coarse
+
+    # -- smoother / cycle
+    def smooth(self, level, m, b, x):
+        n = self._sizes[level]
+        vb, vx = _Vec(b, n), _Vec(x, n, True)
+        self._check(self.lib.alfib_smooth(self.h, level, m, vb.ptr, vx.ptr))
+        return x
+
+    def coarse_factor(self):
+        self._check(self.lib.alfib_coarse_factor(self.h))
+
+    def coarse_solve(self, b, x):
+        vb, vx = _Vec(b, self._sizes[0]), _Vec(x, self._sizes[0], True)
+        self._check(self.lib.alfib_coarse_solve(self.h, vb.ptr, vx.ptr))
+        return x
+
+    def cycle_setup(self, nlevels, smoothing):
+        self._check(self.lib.alfib_cycle_setup(self.h, nlevels, smoothing))
+        self._nlevels = nlevels
+
+    def cycle_apply(self, b, x):
+        n = self._sizes[self._nlevels - 1]
+        vb, vx = _Vec(b, n), _Vec(x, n, True)
+        self._check(self.lib.alfib_cycle_apply(self.h, vb.ptr, vx.ptr))
+        return x
+
+    # -- instrumentation
+    def profile(self, enable=True):
+        self._check(self.lib.alfib_profile(self.h, int(enable)))
+
+    def profile_reset(self):
+        self._check(self.lib.alfib_profile_reset(self.h))
+
+    def profile_get(self, level=-1):
+        """{PETSc event name: (milliseconds, calls)} accumulated since the last reset."""
+        ms = (C.c_double * len(EVENT_NAMES))()
+        calls = (C.c_int64 * len(EVENT_NAMES))()
+        self._check(self.lib.alfib_profile_get(self.h, level, ms, calls))
+        return {name: (ms[i], int(calls[i])) for i, name in enumerate(EVENT_NAMES)}

@@ -1,0 +1,111 @@
+"""Host-side driver: loads per-level hand-over data into the CUDA library and runs the cycle.
+
+This is what the petsc4py plugins of :mod:`alfi_b200.pc` wrap.  The input is whatever produces
+the per-level data — Firedrake/alfi in a deployment, :mod:`alfi_b200.synth` here.  Data handed
+over per level (`LevelInput`): BSR pattern + values of the velocity operator, Dirichlet dofs,
+smoother patch dof sets, and (levels >= 1) the standard prolongation, the cell patches, the
+coarse-boundary dofs and the A0 / gamma*D values of the Schöberl transfer.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .lib import PATCHES_SMOOTHER, PATCHES_TRANSFER, Context
+
+__all__ = ["LevelInput", "DeviceMultigrid", "level_input_from_synth"]
+
+
+@dataclass
+class LevelInput:
+    n_nodes: int
+    bs: int
+    rowptr: np.ndarray
+    colidx: np.ndarray
+    vals: np.ndarray                      # (nnzb, bs, bs) row-major blocks
+    bc_dofs: np.ndarray
+    patch_offsets: np.ndarray | None = None
+    patch_dofs: np.ndarray | None = None
+    patch_order: np.ndarray | None = None
+    patch_colours: np.ndarray | None = None
+    P: object | None = None               # scipy CSR, scalar
+    cell_offsets: np.ndarray | None = None
+    cell_dofs: np.ndarray | None = None
+    cb_dofs: np.ndarray | None = None
+    a0_vals: np.ndarray | None = None
+    d_vals: np.ndarray | None = None
+
+
+def level_input_from_synth(ld) -> LevelInput:
+    """alfi_b200.synth.problem.LevelData → LevelInput."""
+    li = LevelInput(ld.V.nnodes, ld.V.bs, ld.A.rowptr, ld.A.colidx, ld.A.vals, ld.bc_dofs)
+    if ld.patches is not None:
+        ps = ld.patches
+        li.patch_offsets, li.patch_dofs, li.patch_order, li.patch_colours = ps.offsets, ps.dofs, ps.order, ps.colours
+    if ld.P is not None:
+        li.P = ld.P
+        if ld.cell_patches is not None:
+            li.cell_offsets, li.cell_dofs = ld.cell_patches.offsets, ld.cell_patches.dofs
+            li.cb_dofs = ld.cb_dofs
+            li.a0_vals, li.d_vals = ld.A0.vals, ld.D.vals
+    return li
+
+
+class DeviceMultigrid:
+    """The velocity-block multigrid of alfi/solver.py:359-379 resident on one GPU."""
+
+    def __init__(self, levels: list[LevelInput], smoothing: int, device: int = 0, deterministic: bool = False,
+                 robust_restrict: bool = True, ctx: Context | None = None, torch_storage: bool = False):
+        self.ctx = ctx or Context(device, deterministic)
+        self.nlevels = len(levels)
+        self.smoothing = smoothing
+        self.sizes = [li.n_nodes * li.bs for li in levels]
+        self._storage = []
+        c = self.ctx
+        c.set_option(3, robust_restrict)
+        for l, li in enumerate(levels):
+            c.level_create(l, li.n_nodes, li.bs)
+            c.set_bsr_pattern(l, li.rowptr, li.colidx)
+            c.set_bc(l, li.bc_dofs)
+            if l > 0:
+                c.set_patches(l, li.patch_offsets, li.patch_dofs, li.patch_order, li.patch_colours, PATCHES_SMOOTHER)
+                if torch_storage:
+                    self._bind(l, PATCHES_SMOOTHER)
+                cb = li.cb_dofs if li.cb_dofs is not None else np.empty(0, np.int32)
+                c.set_transfer(l, li.P, cb)
+                if li.cell_offsets is not None:
+                    c.set_patches(l, li.cell_offsets, li.cell_dofs, None, np.zeros(li.cell_offsets.size - 1, np.int32),
+                                  PATCHES_TRANSFER)
+                    if torch_storage:
+                        self._bind(l, PATCHES_TRANSFER)
+        self.update_operators(levels)
+        self.update_transfers(levels)
+        c.cycle_setup(self.nlevels, smoothing)
+
+    def _bind(self, level, which):
+        """PyTorch owns the big factor buffers (north star: torch for buffer ownership only)."""
+        import torch
+        nbytes = self.ctx.patch_storage_bytes(level, which)
+        buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device="cuda:%d" % self.ctx.device)
+        self._storage.append(buf)
+        self.ctx.bind_patch_storage(level, buf, which)
+
+    def update_operators(self, levels):
+        """Once per Newton step: new BSR values on every level, patch factors, coarse LU."""
+        c = self.ctx
+        for l, li in enumerate(levels):
+            c.set_bsr_values(l, li.vals)
+            if l > 0:
+                c.factor(l)
+        c.coarse_factor()
+
+    def update_transfers(self, levels):
+        """Once per (nu, gamma): transfer.py:238-244."""
+        for l, li in enumerate(levels):
+            if l > 0 and li.a0_vals is not None:
+                self.ctx.transfer_update(l, li.a0_vals, li.d_vals)
+
+    def apply(self, b, x):
+        """x = one fieldsplit_0 application (F-cycle) of b."""
+        return self.ctx.cycle_apply(b, x)

@@ -1,0 +1,176 @@
+"""Synthetic lid-driven-cavity inputs for the velocity-block multigrid (host side).
+
+Produces, for one of the BASELINE.json configurations, exactly what a Firedrake/alfi run would
+hand to the hot path on every level: the BAIJ velocity operator (alfi/solver.py:512,562-572,
+613-623), the Dirichlet node list (examples/ldc2d/ldc2d.py:23-26, ldc3d/ldc3d.py:17-20), the
+smoother's patch dof sets (alfi/solver.py:331-344), the standard prolongation ``P_H`` and the
+Schöberl-transfer operators (alfi/transfer.py:293-332).  Wind = nodal interpolant of the lid
+profile extension, evaluated on every level (the reference injects it).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from ..patches import PatchSet, greedy_colouring, patch_dofs_from_points
+from ..relaxation import macro_star_points, star_points, iteration_order
+from ..transfer import cell_patch_set
+from .fem import BSR, BlockPattern, VectorSpace, assemble_velocity_block
+from .hierarchy import Level, build_hierarchy, prolongation_matrix
+
+__all__ = ["Config", "CONFIGS", "LevelData", "Problem", "build_problem", "lid_wind"]
+
+
+@dataclass(frozen=True)
+class Config:
+    name: str
+    dim: int
+    N: int
+    nref: int
+    discretisation: str          # "sv" | "pkp0"
+    k: int
+    patch: str                   # "star" | "macro"
+    bary: bool
+    re: float = 100.0
+    gamma: float = 1.0e4
+    smoothing: int | None = None
+    macro_expand: str = "vertices"
+    sort_order: str | None = None
+    length: float = 2.0
+
+    @property
+    def m(self):
+        return self.smoothing if self.smoothing is not None else (10 if self.dim > 2 else 6)
+
+    @property
+    def nu(self):
+        return self.length * 1.0 / self.re          # char_L * char_U / Re (alfi/solver.py:267)
+
+
+CONFIGS = {
+    # BASELINE.json configs[0..4]; sizes per SURVEY §8d
+    "ldc2d-sv-k2": Config("ldc2d-sv-k2", 2, 10, 1, "sv", 2, "macro", True, re=1000.0),
+    "ldc2d-pkp0": Config("ldc2d-pkp0", 2, 16, 3, "pkp0", 2, "star", False, re=10000.0),
+    "ldc3d-sv-k3": Config("ldc3d-sv-k3", 3, 4, 2, "sv", 3, "macro", True, re=5000.0),
+    # scaled-down members of the same families (tests, smoke, CPU-baseline sample)
+    "ldc2d-sv-k2-tiny": Config("ldc2d-sv-k2-tiny", 2, 2, 1, "sv", 2, "macro", True, re=100.0),
+    "ldc2d-pkp0-tiny": Config("ldc2d-pkp0-tiny", 2, 2, 2, "pkp0", 2, "star", False, re=100.0),
+    "ldc3d-sv-k3-tiny": Config("ldc3d-sv-k3-tiny", 3, 1, 1, "sv", 3, "macro", True, re=100.0),
+    "ldc3d-sv-k3-small": Config("ldc3d-sv-k3-small", 3, 2, 1, "sv", 3, "macro", True, re=5000.0),
+    "ldc3d-sv-k3-half": Config("ldc3d-sv-k3-half", 3, 2, 2, "sv", 3, "macro", True, re=5000.0),
+}
+
+
+def lid_wind(x):
+    """Lid profile of examples/ldc2d/ldc2d.py:32 / ldc3d/ldc3d.py:26 extended to the interior."""
+    d = x.shape[1]
+    w = np.zeros_like(x)
+    prof = x[:, 0] ** 2 * (2 - x[:, 0]) ** 2 * (0.25 * x[:, 1] ** 2)
+    if d == 3:
+        prof = prof * x[:, 2] ** 2 * (2 - x[:, 2]) ** 2
+    w[:, 0] = prof
+    return w
+
+
+@dataclass
+class LevelData:
+    index: int
+    level: Level
+    V: VectorSpace
+    pattern: BlockPattern
+    bc_nodes: np.ndarray                 # int32 node indices of the global Dirichlet condition
+    A: BSR | None = None                 # level operator
+    patches: PatchSet | None = None      # smoother patches (None on level 0)
+    P: object | None = None              # scalar CSR prolongation from level index-1
+    cell_patches: PatchSet | None = None
+    cb_nodes: np.ndarray | None = None   # coarse-boundary nodes of the transfer (T2)
+    A0: BSR | None = None                # nu*visc + gamma*div  (transfer patch operator)
+    D: BSR | None = None                 # gamma * div-div form  (transfer rhs operator)
+
+    @property
+    def ndofs(self):
+        return self.V.ndofs
+
+    @property
+    def bc_dofs(self):
+        bs = self.V.bs
+        return (self.bc_nodes[:, None] * bs + np.arange(bs)[None, :]).ravel().astype(np.int32)
+
+    @property
+    def cb_dofs(self):
+        bs = self.V.bs
+        return (self.cb_nodes[:, None] * bs + np.arange(bs)[None, :]).ravel().astype(np.int32)
+
+
+@dataclass
+class Problem:
+    config: Config
+    levels: list[LevelData]
+    nu: float
+    gamma: float
+
+    @property
+    def finest(self):
+        return self.levels[-1]
+
+
+def smoother_patches(cfg: Config, ld: LevelData) -> PatchSet:
+    plex = ld.level.plex
+    if cfg.patch == "macro":
+        H, ents = macro_star_points(plex, cfg.macro_expand)
+    else:
+        H, ents = star_points(plex)
+    order = None
+    if cfg.sort_order:
+        coords = np.array([plex.point_coords(p) for p in ents])
+        order = iteration_order(coords, cfg.sort_order)
+    ps = patch_dofs_from_points(plex, ld.V, H, bc_nodes=ld.bc_nodes, order=order)
+    greedy_colouring(ps, ld.V.ndofs)
+    return ps
+
+
+def assemble_level(cfg: Config, ld: LevelData, nu: float, gamma: float, advect: float = 1.0):
+    """(Re)assemble the level operator — the once-per-Newton-step hand-over."""
+    wind = ld.V.interpolate(lid_wind)
+    ld.A = assemble_velocity_block(ld.V, nu, gamma, wind=wind, advect=advect,
+                                   divform=cfg.discretisation, bc_nodes=ld.bc_nodes, pattern=ld.pattern)
+    return ld.A
+
+
+def assemble_transfer(cfg: Config, ld: LevelData, nu: float, gamma: float):
+    """(Re)assemble the Schöberl transfer operators — once per (nu, gamma), transfer.py:238-244."""
+    ld.A0 = assemble_velocity_block(ld.V, nu, gamma, wind=None, divform=cfg.discretisation,
+                                    pattern=ld.pattern, parts=("visc", "div"))
+    ld.D = assemble_velocity_block(ld.V, 0.0, gamma, wind=None, divform=cfg.discretisation,
+                                   pattern=ld.pattern, parts=("div",))
+    return ld.A0, ld.D
+
+
+def build_problem(cfg: Config | str, nu: float | None = None, with_transfer: bool = True,
+                  verbose: bool = False, gamma: float | None = None) -> Problem:
+    import dataclasses
+    import time
+    if isinstance(cfg, str):
+        cfg = CONFIGS[cfg]
+    if gamma is not None:
+        cfg = dataclasses.replace(cfg, gamma=gamma)
+    nu = cfg.nu if nu is None else nu
+    t0 = time.time()
+    hier = build_hierarchy(cfg.dim, cfg.N, cfg.nref, cfg.bary, cfg.length)
+    levels = []
+    for lev in hier:
+        V = VectorSpace(lev.mesh, cfg.k)
+        ld = LevelData(lev.index, lev, V, BlockPattern(V), V.boundary_nodes().astype(np.int32))
+        assemble_level(cfg, ld, nu, cfg.gamma)
+        if lev.index > 0:
+            ld.patches = smoother_patches(cfg, ld)
+            ld.P = prolongation_matrix(levels[-1].V, V, hier[lev.index - 1].c2f)
+            if with_transfer:
+                ld.cell_patches, ld.cb_nodes = cell_patch_set(hier, lev.index, V, cfg.bary)
+                assemble_transfer(cfg, ld, nu, cfg.gamma)
+        levels.append(ld)
+        if verbose:
+            print("[synth] level %d: %d dofs, %d patches, %.1fs" % (
+                lev.index, V.ndofs, 0 if ld.patches is None else ld.patches.npatch, time.time() - t0), flush=True)
+    return Problem(cfg, levels, nu, cfg.gamma)

@@ -1,0 +1,209 @@
+"""Robust (Schöberl) transfer — host side; drop-in surface of ``alfi.transfer``.
+
+Mirrors alfi/transfer.py:
+
+* ``CoarseCellPatches`` / ``CoarseCellMacroPatches`` (transfer.py:13-88): patch constructors
+  ``obj(pc) -> (patches, iterationSet)``, one patch per coarse (macro) cell, made of the closure
+  points of its fine cells minus points whose ``prolongation`` label is in ``[0, level]``;
+* ``fix_coarse_boundaries`` (transfer.py:121-158): all dofs in the closure of every fine facet
+  inherited from a coarser level;
+* ``AutoSchoeberlTransfer.prolong/restrict`` (transfer.py:186-275) with the rebuild-on-
+  parameter-change logic of transfer.py:173-184, 238-244;
+* ``SVSchoeberlTransfer`` / ``PkP0SchoeberlTransfer`` forms (transfer.py:293-332) and
+  ``NullTransfer`` (transfer.py:359-366).
+
+The arithmetic (``P_H`` SpMV, ``gamma*D`` SpMV, block-diagonal cell-patch solve, axpy) runs in
+the CUDA library through :class:`alfi_b200.lib.Context`; this module only prepares index sets
+and forwards buffers.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+from .patches import PatchSet, patch_dofs_from_points, points_to_csr
+from .relaxation import _make_is
+
+__all__ = ["CoarseCellPatches", "CoarseCellMacroPatches", "coarse_cell_points",
+           "fix_coarse_boundaries", "fix_coarse_boundaries_loop", "AutoSchoeberlTransfer",
+           "SVSchoeberlTransfer", "PkP0SchoeberlTransfer", "NullTransfer"]
+
+
+def _hierarchy_of(pc):
+    """(list of levels, fine level index) for the PC's DM.
+
+    With Firedrake this is ``get_level(ctx._x.ufl_domain())`` (transfer.py:19-22); the synthetic
+    stand-in stores the same information on the ``ctx`` attribute.
+    """
+    ctx = pc.getAttr("ctx")
+    return ctx.hierarchy, ctx.level
+
+
+class CoarseCellPatches:
+    """One patch per coarse cell (transfer.py:13-46)."""
+    macro = False
+
+    def __call__(self, pc):
+        dmf = pc.getDM()
+        levels, level = _hierarchy_of(pc)
+        c2f = levels[level - 1].c2f
+        tdim = dmf.getDimension()
+        patches = []
+        for i, fine_cells in enumerate(c2f):
+            # d+1 coarse bary cells map to the same fine cells: build that patch once
+            # (transfer.py:69-73; synthetic numbering has firedrake == plex cell ids)
+            if self.macro and i % (tdim + 1) != 0:
+                continue
+            entities = []
+            for fp in fine_cells:
+                pts, _ = dmf.getTransitiveClosure(int(fp), True)
+                for pt in pts:
+                    value = dmf.getLabelValue("prolongation", pt)
+                    if not (value > -1 and value <= level):
+                        entities.append(pt)
+            patches.append(_make_is(np.unique(entities)))
+        return patches, _make_is(np.arange(len(patches)))
+
+
+class CoarseCellMacroPatches(CoarseCellPatches):
+    """One patch per coarse *macro* cell (transfer.py:49-88)."""
+    macro = True
+
+
+def coarse_cell_points(levels, level, macro):
+    """Vectorised CoarseCell[Macro]Patches: CSR boolean (npatch x npoints of the fine plex)."""
+    fine, coarse = levels[level], levels[level - 1]
+    plex = fine.plex
+    d = plex.dim
+    c2f = coarse.c2f[::d + 1] if macro else coarse.c2f
+    npatch, nf = c2f.shape
+    G = sp.csr_matrix((np.ones(c2f.size, dtype=np.int32),
+                       (np.repeat(np.arange(npatch), nf), c2f.ravel())), shape=(npatch, plex.npoints))
+    H = (G @ plex.closure.astype(np.int32)).tocsr()
+    lab = plex.labels["prolongation"]
+    keep = ~((lab > -1) & (lab <= level))
+    H = (H @ sp.diags(keep.astype(np.int32), format="csr", dtype=np.int32)).tocsr()
+    H.eliminate_zeros()
+    H.data[:] = 1
+    H.sort_indices()
+    return H
+
+
+def fix_coarse_boundaries(plex, V, level):
+    """Node list of the homogeneous Dirichlet condition on coarse-level facets, vectorised.
+
+    transfer.py:121-158 walks every facet; if its ``prolongation`` label is in ``[0, level]``
+    all dofs of all points in its closure are constrained.  Returns sorted unique *node*
+    indices (every component of a node is constrained).
+    """
+    f0, f1 = plex.getHeightStratum(1)
+    lab = plex.labels["prolongation"][f0:f1]
+    fac = np.flatnonzero((lab > -1) & (lab <= level)) + f0
+    pts = np.unique(plex.closure[fac].indices)
+    onpt = np.zeros(plex.npoints, dtype=bool)
+    onpt[pts] = True
+    return np.flatnonzero(onpt[plex.node_points(V)]).astype(np.int32)
+
+
+def fix_coarse_boundaries_loop(plex, V, level):
+    """Literal loop form of transfer.py:128-144 (used by the tests as the checker)."""
+    npt = plex.node_points(V)
+    by_point = {}
+    for n, p in enumerate(npt):
+        by_point.setdefault(int(p), []).append(n)
+    nodes = []
+    for p in range(*plex.getHeightStratum(1)):
+        value = plex.getLabelValue("prolongation", p)
+        if value > -1 and value <= level:
+            closure, _ = plex.getTransitiveClosure(p)
+            for c in closure:
+                nodes.extend(by_point.get(int(c), []))
+    return np.unique(nodes).astype(np.int32)
+
+
+def cell_patch_set(levels, level, V, macro) -> tuple[PatchSet, np.ndarray]:
+    """(cell-patch dof sets, coarse-boundary node list) for the transfer onto ``level``."""
+    plex = levels[level].plex
+    H = coarse_cell_points(levels, level, macro)
+    cb = fix_coarse_boundaries(plex, V, level)
+    return patch_dofs_from_points(plex, V, H, bc_nodes=cb), cb
+
+
+class AutoSchoeberlTransfer:
+    """``prolong(coarse, fine)`` / ``restrict(fine, coarse)`` on device (transfer.py:91-290).
+
+    ``parameters = (nu, gamma)`` are objects convertible with ``float()`` (Firedrake Constants
+    in a deployment).  ``backend`` is an :class:`alfi_b200.lib.Context` whose levels already hold
+    the transfer operators (`Context.set_transfer`); ``values_for(level, nu, gamma)`` must return
+    the re-assembled ``(A0 values, D values)`` when the parameters changed.
+    """
+
+    def __init__(self, parameters, tdim, hierarchy, backend=None, values_for=None):
+        self.parameters = parameters
+        self.tdim = tdim
+        self.hierarchy = hierarchy
+        self.prev_parameters = {}
+        self.force_rebuild_d = {}
+        self.backend = backend
+        self.values_for = values_for
+        self.patch_constructor = (CoarseCellMacroPatches if hierarchy == "bary" else CoarseCellPatches)
+
+    def force_rebuild(self):
+        self.force_rebuild_d = {k: True for k in self.prev_parameters}
+
+    def rebuild(self, key):
+        if self.force_rebuild_d.get(key, False):
+            self.force_rebuild_d[key] = False
+            return True
+        prev = self.prev_parameters.get(key, [])
+        return any(float(p) != q for q, p in zip(prev, self.parameters))
+
+    def _ensure(self, level):
+        first = level not in self.prev_parameters
+        if first or self.rebuild(level):
+            nu, gamma = (float(p) for p in self.parameters)
+            if self.values_for is not None:
+                a0, dvals = self.values_for(level, nu, gamma)
+                self.backend.transfer_update(level, a0, dvals)
+            self.prev_parameters[level] = [float(p) for p in self.parameters]
+
+    def prolong(self, coarse, fine, level=None):
+        """fine <- (I - A0^-1 gamma D) P_H coarse   (transfer.py:246-259)."""
+        level = self._level_of(fine) if level is None else level
+        self._ensure(level)
+        self.backend.prolong(level, coarse, fine)
+
+    def restrict(self, fine, coarse, level=None):
+        """coarse <- P_H^T (I - gamma D A0^-1) fine   (transfer.py:261-275)."""
+        level = self._level_of(fine) if level is None else level
+        self._ensure(level)
+        self.backend.restrict(level, fine, coarse)
+
+    def _level_of(self, fine):
+        n = fine.size
+        for lev, ndofs in self.backend.level_sizes().items():
+            if ndofs == n:
+                return lev
+        raise KeyError("no level with %d dofs" % n)
+
+
+class SVSchoeberlTransfer(AutoSchoeberlTransfer):
+    """A0 = nu(2 sym grad u, grad v) + gamma(div u, div v);  D = (div u, div v)
+    (transfer.py:293-309)."""
+    divform = "sv"
+
+
+class PkP0SchoeberlTransfer(AutoSchoeberlTransfer):
+    """Same with cell-averaged divergence (transfer.py:312-332)."""
+    divform = "pkp0"
+
+
+class NullTransfer:
+    """Fills the destination with NaN (transfer.py:359-366); used for the pressure space."""
+
+    def transfer(self, src, dest):
+        dest[...] = np.nan
+
+    inject = transfer
+    prolong = transfer
+    restrict = transfer

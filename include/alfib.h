@@ -1,0 +1,162 @@
+/* alfib — B200-native velocity-block multigrid for alfi's augmented-Lagrangian preconditioner.
+ *
+ * C ABI of libalfib.so.  This is the drop-in boundary: everything above it (alfi's solver
+ * dictionaries, Firedrake forms, mesh hierarchies, continuation drivers) stays Python and is
+ * unchanged; everything below is hand-written CUDA for sm_100a.  Each entry point names the
+ * reference interface it replaces (paths relative to the alfi repository).  The arithmetic
+ * the reference delegates to PETSc/Firedrake (PCPATCH, MatMult_SeqBAIJ, KSPFGMRES, PCMG,
+ * firedrake.mg prolong/restrict) is restated in SURVEY.md Appendix A.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ALFIB_E* code on failure; the message is
+ *     available from alfib_last_error(ctx).  Nothing throws across the ABI.
+ *   - vector / value pointers may be HOST or DEVICE pointers; the library detects which
+ *     (cudaPointerGetAttributes).  Host buffers are borrowed for the duration of the call and
+ *     copied; the library never keeps or frees caller memory.  Index arrays are host pointers.
+ *   - one ctx per process <-> one GPU; calls are serialised by the caller (PETSc's single
+ *     Python thread); work runs on the ctx's own non-default stream and calls return after
+ *     host-visible results are complete (device-pointer calls return after enqueue unless
+ *     ALFIB_SYNC_ALWAYS is set with alfib_set_option).
+ *   - FP64 everywhere, int32 indices (PETSc int32 build), int64 patch offsets.
+ *   - levels are numbered 0 (coarsest) .. L-1 (finest) like PCMG.
+ */
+#ifndef ALFIB_H
+#define ALFIB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct alfib_ctx alfib_ctx;
+
+enum {
+  ALFIB_OK = 0,
+  ALFIB_EINVAL = -1,   /* bad argument / call order */
+  ALFIB_ECUDA = -2,    /* CUDA runtime, cuSOLVER or NCCL failure */
+  ALFIB_ESINGULAR = -3,/* a patch (or the coarse) matrix is numerically singular */
+  ALFIB_ENOMEM = -4
+};
+
+/* which set of patches of a level an operation addresses */
+enum { ALFIB_PATCHES_SMOOTHER = 0, ALFIB_PATCHES_TRANSFER = 1 };
+
+/* alfib_set_option keys */
+enum {
+  ALFIB_OPT_DETERMINISTIC = 1, /* 1: colour-ordered scatter-add + two-pass reductions (bitwise
+                                  reproducible); 0: atomicAdd scatter in one launch            */
+  ALFIB_OPT_SYNC_ALWAYS = 2,   /* 1: synchronise the stream before every return                */
+  ALFIB_OPT_ROBUST_RESTRICT = 3,/* 1: Schoeberl restriction (alfi --restriction, solver.py:595,
+                                  646); 0: plain P_H^T (firedrake restrict)                    */
+  ALFIB_OPT_TRANSFER_REFINE = 4 /* 1 (default): one step of iterative refinement after the
+                                  explicit-inverse cell-patch solve of the transfer, which
+                                  restores the accuracy of the reference's LU solve            */
+};
+
+/* ---- context ------------------------------------------------------------------------------ */
+int alfib_create(int device, alfib_ctx** out);
+int alfib_destroy(alfib_ctx* ctx);
+const char* alfib_last_error(const alfib_ctx* ctx);
+int alfib_set_option(alfib_ctx* ctx, int key, int value);
+/* convenience wrapper named in SURVEY §8b */
+int alfib_set_deterministic(alfib_ctx* ctx, int flag);
+int alfib_synchronize(alfib_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches claim) */
+int64_t alfib_launch_count(const alfib_ctx* ctx);
+/* CUDA stream handle (cudaStream_t) the ctx enqueues on, for event timing by the caller */
+void* alfib_stream(alfib_ctx* ctx);
+
+/* Multi-GPU: one rank per GPU, partition = the DMPlex vertex-overlap partition the reference
+ * already uses (solver.py:604-605, 661-662).  `nccl_unique_id` is the 128-byte ncclUniqueId
+ * broadcast by the host (mpi4py in a deployment).  Without this call the ctx is serial.       */
+int alfib_comm_init(alfib_ctx* ctx, const void* nccl_unique_id, int rank, int nranks);
+
+/* ---- level operator: replaces the BAIJ Mat PETSc holds for fieldsplit_0 on each level
+ *      (parameters["default_sub_matrix_type"] = "baij", solver.py:512)                        */
+int alfib_level_create(alfib_ctx* ctx, int level, int n_nodes, int bs);
+int alfib_level_set_bsr_pattern(alfib_ctx* ctx, int level, int64_t nnzb,
+                                const int32_t* rowptr, const int32_t* colidx);
+/* once per Newton step: the single hand-over of UFL/TSFC assembly output.
+ * block_col_major = 1 for PETSc's BAIJ in-block layout, 0 for row-major blocks (scipy).        */
+int alfib_level_set_bsr_values(alfib_ctx* ctx, int level, const double* vals, int block_col_major);
+/* global Dirichlet dofs of the level (DirichletBC.nodes x components; ldc*.py bcs)             */
+int alfib_level_set_bc(alfib_ctx* ctx, int level, int32_t nbc, const int32_t* bc_dofs);
+
+/* MatMult / residual on the level operator (PETSc MatMult_SeqBAIJ)          */
+int alfib_spmv(alfib_ctx* ctx, int level, const double* x, double* y);
+int alfib_residual(alfib_ctx* ctx, int level, const double* b, const double* x, double* r);
+
+/* ---- patches: replaces PCPATCH's per-patch index sets, operators and factorisations
+ *      (pc_python_type firedrake.PatchPC, solver.py:318-344; transfer.py:100-113).
+ *      `which` selects the smoother's patches or the transfer's cell patches.
+ *      offsets[npatch+1] index into dofs (scalar dof numbers in patch-local order);
+ *      order[norder] is the iteration set (relaxation.py:141-149); colours[npatch] may be NULL,
+ *      then a greedy colouring in iteration order is computed.                    */
+int alfib_level_set_patches(alfib_ctx* ctx, int level, int which, int32_t npatch,
+                            const int64_t* offsets, const int32_t* dofs, int32_t norder,
+                            const int32_t* order, const int32_t* colours);
+/* bytes of device storage the inverse factors of that patch set need                          */
+int64_t alfib_patch_storage_bytes(alfib_ctx* ctx, int level, int which);
+/* optional: caller-owned device buffer (a torch tensor's data_ptr()) for the factors; if never
+ * called the library allocates.                                                               */
+int alfib_patch_bind_storage(alfib_ctx* ctx, int level, int which, void* dev_ptr, int64_t bytes);
+/* per Newton step (PCSetUp_PATCH; patch_pc_patch_save_operators + sub_pc_type lu +
+ * dense_inverse, solver.py:320,327,602): A_i = A[I_i,I_i] gathered from the level's BSR values,
+ * inverted in place by blocked Gauss-Jordan with partial (row) pivoting.                       */
+int alfib_level_factor(alfib_ctx* ctx, int level);
+/* PCApply_PATCH additive, no partition of unity (solver.py:321-322): y = sum_i R_i^T A_i^-1 R_i x,
+ * then y[bc] = x[bc].                                                                          */
+int alfib_smoother_apply(alfib_ctx* ctx, int level, const double* x, double* y);
+/* copy the colours in use back (npatch int32) — for the bit-exactness test                     */
+int alfib_get_colours(alfib_ctx* ctx, int level, int which, int32_t* colours);
+/* debugging / tests: dense inverse of patch p in row-major n x n (host pointer)                */
+int alfib_get_patch_inverse(alfib_ctx* ctx, int level, int which, int32_t patch, double* out);
+
+/* ---- robust transfer: replaces AutoSchoeberlTransfer.prolong/restrict (transfer.py:186-275)
+ *      between `level-1` and `level`.  P is the scalar CSR of the standard prolongation
+ *      (firedrake prolong, transfer.py:284-290) acting per component; cell patches come through
+ *      alfib_level_set_patches(which = TRANSFER); cb_dofs are the coarse-boundary dofs of
+ *      fix_coarse_boundaries (transfer.py:121-158).                                            */
+int alfib_transfer_set(alfib_ctx* ctx, int level, int32_t n_fine_nodes, int32_t n_coarse_nodes,
+                       const int32_t* P_rowptr, const int32_t* P_colidx, const double* P_vals,
+                       int32_t ncb, const int32_t* cb_dofs);
+/* once per (nu, gamma) (transfer.py:173-184, 238-244): BSR values, on the level's pattern, of
+ * A0 = nu(2 sym grad u, grad v) + gamma(div u, div v) and of gamma*D = gamma(div u, div v)
+ * (transfer.py:295-309 / 319-332); gathers + inverts the cell patches.  A0_vals may be NULL to
+ * keep the previous factors (only D changes), both NULL is an error.                           */
+int alfib_transfer_update(alfib_ctx* ctx, int level, const double* A0_vals, const double* D_vals,
+                          int block_col_major);
+int alfib_prolong(alfib_ctx* ctx, int level, const double* coarse, double* fine);
+int alfib_restrict(alfib_ctx* ctx, int level, const double* fine, double* coarse);
+
+/* ---- level smoother and cycle: replaces the mg_levels KSP (fgmres, max_it = smoothing,
+ *      convergence_test skip; solver.py:313-317) and fieldsplit_0 = richardson(1) + PCMG full
+ *      with a direct coarse solve (solver.py:359-379).                                         */
+int alfib_smooth(alfib_ctx* ctx, int level, int m, const double* b, double* x);
+/* dense LU of the level-0 operator (replaces AssembledPC + telescope + superlu_dist)           */
+int alfib_coarse_factor(alfib_ctx* ctx);
+int alfib_coarse_solve(alfib_ctx* ctx, const double* b, double* x);
+int alfib_cycle_setup(alfib_ctx* ctx, int nlevels, int smoothing);
+/* one application of fieldsplit_0: x = Fcycle(b) on the finest level                           */
+int alfib_cycle_apply(alfib_ctx* ctx, const double* b, double* x);
+
+/* ---- instrumentation: names follow the PETSc events alfi reports (driver.py:80)              */
+enum {
+  ALFIB_EV_PCPATCH_APPLY = 0, ALFIB_EV_MATMULT = 1, ALFIB_EV_PROLONG = 2, ALFIB_EV_RESTRICT = 3,
+  ALFIB_EV_KSP_GMRES_ORTHOG = 4, ALFIB_EV_COARSE = 5, ALFIB_EV_PCSETUP_PATCH = 6, ALFIB_EV_COUNT = 7
+};
+/* enable/disable CUDA-event timing per kernel family and level.  Events are recorded on the ctx
+ * stream without synchronising and resolved when read, so the timed region is not perturbed.  */
+int alfib_profile(alfib_ctx* ctx, int enable);
+/* accumulated milliseconds and call counts per event since the last reset; level = -1 sums
+ * over all levels                                                                             */
+int alfib_profile_get(alfib_ctx* ctx, int level, double* ms /*[ALFIB_EV_COUNT]*/,
+                      int64_t* calls /*[ALFIB_EV_COUNT]*/);
+int alfib_profile_reset(alfib_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALFIB_H */
