@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Benchmark of the velocity-block multigrid hot path (BASELINE.json metric).
+
+A "step" is one application of `fieldsplit_0` (richardson(1) + PCMG-full F-cycle with
+FGMRES(m)/patch smoothing, Schoeberl transfers, direct coarse solve — alfi/solver.py:359-379)
+on the ldc3d Scott-Vogelius k=3 barycentric workload (BASELINE.json configs[4] at the size that
+fits one GPU: baseN 4, nref 2 — 1 458 867 velocity dofs, 4 913 macro-star patches, 48 GB of
+patch inverses).  `value` = finest-level velocity dofs / time of one step, inputs resident in
+HBM; `e2e` = the same through the C-ABI with pinned host vectors (H2D + D2H inside the timed
+region).  The JSON line also carries the roofline of the dominant kernel (finest-level patch
+apply), the CPU baseline (oracle restatement timed on a bounded sample) and the clocks seen.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_CONFIG = "ldc3d-sv-k3"
+CPU_SAMPLE_CONFIG = {"ldc3d-sv-k3": "ldc3d-sv-k3-half", "ldc2d-sv-k2": "ldc2d-sv-k2", "ldc2d-pkp0": "ldc2d-pkp0"}
+METRIC = "V-cycle DoF/s (finest-level velocity dofs per second of one fieldsplit_0 PCMG-full application)"
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------- algorithmic bytes
+def smoother_bytes(ld):
+    """B_s = sum_i (8 n_i^2 + 4 n_i) + 8 N (x read) + 8 N (y written)   (SURVEY §8d)."""
+    n = ld.patches.sizes.astype(np.float64)
+    return float((8 * n * n + 4 * n).sum() + 16 * ld.ndofs)
+
+
+def spmv_bytes(ld):
+    bs = ld.V.bs
+    return float(ld.A.nnzb * (8 * bs * bs + 4) + 4 * (ld.V.nnodes + 1) + 16 * ld.ndofs)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU oracle arm
+def run_oracle(sample_name, steps, warmup):
+    """Time the CPU restatement (oracle/) on a bounded sample of the workload."""
+    from alfi_b200.synth.problem import build_problem
+    from oracle import cport
+    from oracle import hotpath as hp
+    t0 = time.time()
+    prob = build_problem(sample_name)
+    levels = [hp.level_from_host(l, "inverse") for l in prob.levels]
+    cport.accelerate(levels, [None if l.patches is None else l.patches.colours for l in prob.levels])
+    log("oracle sample %s: %d dofs, setup %.1fs" % (sample_name, prob.finest.ndofs, time.time() - t0))
+    rng = np.random.default_rng(20261017)
+    b = rng.standard_normal(prob.finest.ndofs)
+    b[prob.finest.bc_dofs] = 0.0
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(limits=1, user_api="blas"):      # BLAS-1 only; keeps the cores for OpenMP
+        for _ in range(warmup):
+            hp.fcycle(levels, b, prob.config.m)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            hp.fcycle(levels, b, prob.config.m)
+        dt = (time.perf_counter() - t0) / steps
+    cores = cport.num_threads()
+    return {"value": prob.finest.ndofs / dt, "unit": "DoF/s", "cores": cores, "kind": "port",
+            "sample": "%s: same mesh family/element/patches, %d velocity dofs, %d levels, %.2f s per F-cycle "
+                      "(C/OpenMP patch apply + SpMV, numpy BLAS-1; CPU restatement, not PETSc)" % (sample_name, prob.finest.ndofs, len(levels), dt)}, dt
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU path cannot be built here (PETSc/Firedrake absent),
+    so the oracle port of the same algorithm is timed on the host cores (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = CPU_SAMPLE_CONFIG.get(args.config, args.config)
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    base, dt = run_oracle(sample, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "DoF/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.config, "sample": sample}, "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "DoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from alfi_b200.build import build
+    from alfi_b200.multigrid import DeviceMultigrid, level_input_from_synth
+    from alfi_b200.synth.problem import build_problem
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    build()
+
+    t0 = time.time()
+    prob = build_problem(args.config, verbose=(rank == 0))
+    cfg = prob.config
+    log("rank %d: problem built in %.1fs" % (rank, time.time() - t0))
+    t0 = time.time()
+    mg = DeviceMultigrid([level_input_from_synth(l) for l in prob.levels], cfg.m, device=local,
+                         deterministic=bool(args.deterministic), torch_storage=True)
+    mg.ctx.synchronize()
+    setup_s = time.time() - t0
+    log("rank %d: device setup (upload + factor) %.1fs" % (rank, setup_s))
+
+    n = prob.finest.ndofs
+    rng = np.random.default_rng(20261017 + rank)
+    bh = torch.empty(n, dtype=torch.float64).pin_memory()
+    xh = torch.empty(n, dtype=torch.float64).pin_memory()
+    bnp = rng.standard_normal(n)
+    bnp[prob.finest.bc_dofs] = 0.0
+    bh.copy_(torch.from_numpy(bnp))
+    bd = bh.cuda()
+    xd = torch.empty_like(bd)
+    stream = torch.cuda.ExternalStream(mg.ctx.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps (value) ------------------------------------------------------
+    for _ in range(args.warmup):
+        mg.apply(bd, xd)
+    mg.ctx.synchronize()
+    mg.ctx.profile(True)
+    mg.ctx.profile_reset()
+    launches0 = mg.ctx.launches
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        mg.apply(bd, xd)
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (mg.ctx.launches - launches0) // args.steps
+    prof_fine = mg.ctx.profile_get(len(prob.levels) - 1)
+    prof_all = mg.ctx.profile_get(-1)
+    mg.ctx.profile(False)
+
+    # ---- end to end through the C-ABI with host buffers --------------------------------------
+    bhn, xhn = bh.numpy(), xh.numpy()
+    for _ in range(max(1, args.warmup // 2)):
+        mg.apply(bhn, xhn)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mg.apply(bhn, xhn)          # H2D of b, cycle, D2H of x, stream sync — all inside the call
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+
+    # sanity: the cycle must reduce the residual (a fast wrong answer is not a result)
+    xres = torch.from_numpy(xhn.copy()).cuda()
+    rres = torch.empty_like(xres)
+    mg.ctx.residual(len(prob.levels) - 1, bd, xres, rres)
+    mg.ctx.synchronize()
+    red = float(torch.linalg.norm(rres) / torch.linalg.norm(bd))
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, sustained copy)"
+    except Exception:       # noqa: BLE001
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    fine = prob.finest
+    bs_bytes = smoother_bytes(fine)
+    app_ms, app_calls = prof_fine["PCPATCHApply"]
+    achieved = bs_bytes / (app_ms / max(app_calls, 1) * 1e-3) / 1e9 if app_calls else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "patch_apply_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.config)
+        except Exception:   # noqa: BLE001
+            traffic = None
+    roofline = {"kernel": "patch_apply_kernel (finest-level PCApply_PATCH: memset + colour launches + bc fix-up)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bs_bytes, "launches_timed": app_calls,
+                "avg_ms": app_ms / max(app_calls, 1),
+                "share_of_step": app_ms / args.steps / ms if app_calls else None}
+    breakdown = {k: {"ms_per_step": v[0] / args.steps, "calls_per_step": v[1] / args.steps} for k, v in prof_all.items()}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu, _ = run_oracle(CPU_SAMPLE_CONFIG.get(args.config, args.config), 1, 1)
+        except Exception as e:      # noqa: BLE001
+            cpu = {"value": None, "unit": "DoF/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+
+    total = n * world
+    line = {
+        "metric": METRIC, "value": total / (ms * 1e-3), "unit": "DoF/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.config, "mesh": "Kuhn %d^%d x 2^%d, Alfeld split" % (cfg.N, cfg.dim, cfg.nref),
+                   "velocity_dofs": n, "levels": len(prob.levels), "smoothing": cfg.m, "re": cfg.re, "gamma": cfg.gamma,
+                   "patches_finest": int(fine.patches.npatch), "max_patch_dofs": int(fine.patches.sizes.max()),
+                   "factor_bytes_finest": float((fine.patches.sizes.astype(float) ** 2).sum() * 8),
+                   "l2_policy": "inputs larger than L2 (48 GB of patch inverses streamed per smoother application)",
+                   "deterministic": bool(args.deterministic), "parallelism": "replicas x%d" % world},
+        "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "DoF/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "breakdown_ms": breakdown, "setup_s": {"device_upload_factor": setup_s},
+        "residual_reduction": red,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=DEFAULT_CONFIG)
+    ap.add_argument("--deterministic", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

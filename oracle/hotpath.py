@@ -117,6 +117,7 @@ class OracleLevel:
     c_factors: list | None = None
     # coarse solve
     coarse_lu: object | None = None
+    ckernels: object | None = None          # oracle/cport.py C kernels, if attached
 
     @property
     def n(self):
@@ -240,10 +241,16 @@ def _hessenberg_lsq(H, g):
 
 
 # --------------------------------------------------------------------------- C1: PCMG full
+def _A(lv):
+    ck = getattr(lv, "ckernels", None)          # optional C/OpenMP kernels (oracle/cport.py)
+    return ck.spmv if ck is not None else (lambda v: lv.A @ v)
+
+
 def smooth(lv: OracleLevel, b, x, m):
-    Aop = lambda v: lv.A @ v
-    Mop = lambda v: smoother_apply(v, lv.offsets, lv.dofs, lv.order, lv.factors, lv.bc_dofs)
-    return fgmres(Aop, Mop, b, x, m)
+    ck = getattr(lv, "ckernels", None)
+    Mop = ck.smoother_apply if ck is not None else (
+        lambda v: smoother_apply(v, lv.offsets, lv.dofs, lv.order, lv.factors, lv.bc_dofs))
+    return fgmres(_A(lv), Mop, b, x, m)
 
 
 def coarse_solve(lv: OracleLevel, b):
@@ -256,7 +263,7 @@ def vcycle(levels, l, b, x, m, robust_restrict=True):
     if l == 0:
         return coarse_solve(lv, b)
     x = smooth(lv, b, x, m)
-    r = b - lv.A @ x
+    r = b - _A(lv)(x)
     bc = restrict(lv, r, levels[l - 1].bc_dofs, robust=robust_restrict)
     xc = vcycle(levels, l - 1, bc, np.zeros_like(bc), m, robust_restrict)
     x = x + prolong(lv, xc)

@@ -133,7 +133,7 @@ def test_transfers(loaded, name):
     for l in range(1, len(olv)):
         lv, lc = olv[l], olv[l - 1]
         c, f = _vec(lc, 30 + l), _vec(lv, 40 + l)
-        kappa = _kappa([f[1] for f in lv.c_factors])
+        kappa = _kappa(hp.patch_matrices(prob.levels[l].A0.to_csr(), lv.c_offsets, lv.c_dofs))
         got = mg.ctx.prolong(l, c, np.empty(lv.n))
         assert rel(got, hp.prolong(lv, c)) <= _tol(kappa), (rel(got, hp.prolong(lv, c)), kappa)
         got = mg.ctx.restrict(l, f, np.empty(lc.n))
@@ -151,7 +151,8 @@ def test_fgmres_smoother(loaded, name):
         b, x0 = _vec(lv, 50 + l), _vec(lv, 60 + l)
         x = mg.ctx.smooth(l, m, b, x0.copy())
         xo = hp.smooth(lv, b, x0, m)
-        assert rel(x, xo) <= 1e-9, (l, rel(x, xo))
+        kappa = _kappa(hp.patch_matrices(lv.A, lv.offsets, lv.dofs))
+        assert rel(x, xo) <= _tol(kappa), (l, rel(x, xo), kappa)
 
 
 @pytest.mark.parametrize("name", SMALL)
@@ -160,11 +161,13 @@ def test_coarse_and_cycle(loaded, name):
     prob, mg, olv = loaded(name)
     b0 = _vec(olv[0], 70)
     x0 = mg.ctx.coarse_solve(b0, np.empty_like(b0))
-    assert rel(x0, hp.coarse_solve(olv[0], b0)) <= 1e-10
+    kc = np.linalg.cond(olv[0].A.toarray())
+    assert rel(x0, hp.coarse_solve(olv[0], b0)) <= _tol(kc), (rel(x0, hp.coarse_solve(olv[0], b0)), kc)
     b = _vec(olv[-1], 71)
     x = mg.apply(b, np.empty_like(b))
     xo = hp.fcycle(olv, b, prob.config.m)
-    assert rel(x, xo) <= 1e-8, rel(x, xo)
+    kappa = max(_kappa(hp.patch_matrices(lv.A, lv.offsets, lv.dofs)) for lv in olv[1:])
+    assert rel(x, xo) <= _tol(max(kappa, kc)), (rel(x, xo), kappa, kc)
 
 
 def test_device_pointers_and_torch_storage(problems):
@@ -172,7 +175,8 @@ def test_device_pointers_and_torch_storage(problems):
     import torch
     from alfi_b200.multigrid import DeviceMultigrid, level_input_from_synth
     prob = problems("ldc2d-sv-k2-tiny")
-    mg = DeviceMultigrid([level_input_from_synth(l) for l in prob.levels], prob.config.m, torch_storage=True)
+    mg = DeviceMultigrid([level_input_from_synth(l) for l in prob.levels], prob.config.m, torch_storage=True,
+                         deterministic=True)
     n = prob.finest.ndofs
     b = np.random.default_rng(1).standard_normal(n)
     b[prob.finest.bc_dofs] = 0
@@ -181,7 +185,7 @@ def test_device_pointers_and_torch_storage(problems):
     xd = torch.empty(n, dtype=torch.float64, device="cuda")
     mg.apply(bd, xd)
     mg.ctx.synchronize()
-    assert rel(xd.cpu().numpy(), xh) <= 1e-12
+    assert np.array_equal(xd.cpu().numpy(), xh)      # deterministic mode: bitwise identical
 
 
 def test_errors_are_reported(problems):
