@@ -5,6 +5,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -91,6 +92,9 @@ struct Level {
   int p_rows = 0, p_cols = 0;
   DBuf<int32_t> p_rowptr, p_colidx, pt_rowptr, pt_colidx;
   DBuf<double> p_vals, pt_vals;
+  // block rows [row_start[r], row_start[r+1]) of every BSR operator on this level belong to rank r
+  std::vector<int64_t> row_start;       // in block rows, nranks+1 entries
+  std::vector<int64_t> dof_start;       // the same in scalar dofs
   // cycle work vectors (allocated by alfib_cycle_setup / alfib_smooth)
   DBuf<double> b, x, r, w, t1, t2, t3, t4, V, Z;
   int krylov_m = 0;
@@ -106,6 +110,9 @@ struct alfib_ctx {
   int nlevels = 0, smoothing = 0;
   int num_sms = 148;
   int64_t launches = 0;
+  // multi-GPU (comm.cu): NCCL communicator, rank layout
+  void* comm = nullptr;
+  int rank = 0, nranks = 1;
   // patch factor workspace (one slot per resident CTA) + status word + work counter
   DBuf<double> fwork;
   DBuf<int> finfo;
@@ -171,6 +178,12 @@ void launch_bsr_spmv(alfib_ctx* c, const Level& L, const double* vals, const dou
 void launch_csr_apply(alfib_ctx* c, int nrows, int bs, const int32_t* rowptr, const int32_t* colidx,
                       const double* vals, const double* x, double* y);
 void launch_transpose_blocks(alfib_ctx* c, double* vals, int64_t nnzb, int bs);
+// comm.cu
+void comm_unique_id(void* out128);
+void comm_init(alfib_ctx* c, const void* id128, int rank, int nranks);
+void comm_destroy(alfib_ctx* c);
+void comm_allreduce_sum(alfib_ctx* c, double* y, size_t n);
+void comm_allgather_rows(alfib_ctx* c, double* y, const std::vector<int64_t>& dof_start);
 // patch_apply.cu
 void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, double* y);
 // patch_factor.cu

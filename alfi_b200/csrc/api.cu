@@ -50,6 +50,16 @@ void release_patchset(PatchSet& ps) {
   ps.store_buf.release();
 }
 
+// equal split of the block rows across ranks (contiguous ranges)
+void set_row_partition(alfib_ctx* c, Level& L) {
+  L.row_start.assign(c->nranks + 1, 0);
+  L.dof_start.assign(c->nranks + 1, 0);
+  for (int r = 0; r <= c->nranks; ++r) {
+    L.row_start[r] = (int64_t)L.n_nodes * r / c->nranks;
+    L.dof_start[r] = L.row_start[r] * L.bs;
+  }
+}
+
 Level& get_level(alfib_ctx* c, int level) {
   ALFIB_REQUIRE(level >= 0 && level < ALFIB_MAX_LEVELS && c->levels[level], "no such level");
   return *c->levels[level];
@@ -179,6 +189,7 @@ int alfib_destroy(alfib_ctx* c) {
   c->finfo.release();
   c->coarse_piv.release();
   c->coarse_info.release();
+  comm_destroy(c);
   if (c->cusolver) cusolverDnDestroy(c->cusolver);
   for (auto& r : c->ev_pool) {
     cudaEventDestroy(r.a);
@@ -213,12 +224,21 @@ int64_t alfib_launch_count(const alfib_ctx* c) { return c ? c->launches : -1; }
 
 void* alfib_stream(alfib_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
-int alfib_comm_init(alfib_ctx* c, const void*, int rank, int nranks) {
+int alfib_comm_unique_id(void* out128) {
+  if (!out128) return ALFIB_EINVAL;
+  try {
+    comm_unique_id(out128);
+    return ALFIB_OK;
+  } catch (const DeviceError& e) {
+    return e.code;
+  }
+}
+
+int alfib_comm_init(alfib_ctx* c, const void* nccl_unique_id, int rank, int nranks) {
   return guarded(c, [&] {
-    ALFIB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank");
-    // Patches are rank-local units: with replicated level vectors every rank solves its own
-    // patches and the host-side shim sums contributions (see alfi_b200/dist.py).  No data-path
-    // communicator is needed inside the library for that mode.
+    comm_init(c, nccl_unique_id, rank, nranks);
+    for (auto* L : c->levels)
+      if (L) set_row_partition(c, *L);
   });
 }
 
@@ -232,6 +252,7 @@ int alfib_level_create(alfib_ctx* c, int level, int n_nodes, int bs) {
     L->n_nodes = n_nodes;
     L->bs = bs;
     L->n = n_nodes * bs;
+    set_row_partition(c, *L);
     c->levels[level] = L;
   });
 }
@@ -420,7 +441,10 @@ int alfib_level_factor(alfib_ctx* c, int level) {
     Level& L = get_level(c, level);
     ALFIB_REQUIRE(L.has_values, "level has no values");
     PatchSet& ps = L.ps[ALFIB_PATCHES_SMOOTHER];
-    ALFIB_REQUIRE(ps.npatch > 0, "no smoother patches on this level");
+    if (ps.npatch == 0) {                 // a rank may own no patch of a small level
+      ps.factored = true;
+      return;
+    }
     ensure_storage(ps);
     ScopedEvent ev(c, ALFIB_EV_PCSETUP_PATCH, level);
     launch_patch_factor(c, L, ps, L.vals.p);
@@ -507,12 +531,13 @@ int alfib_transfer_update(alfib_ctx* c, int level, const double* A0_vals, const 
     }
     if (A0_vals) {
       PatchSet& ps = L.ps[ALFIB_PATCHES_TRANSFER];
-      ALFIB_REQUIRE(ps.npatch > 0, "no transfer cell patches on this level");
       upload_values(c, L, L.a0vals, A0_vals, block_col_major);
-      ensure_storage(ps);
-      {
+      if (ps.npatch > 0) {
+        ensure_storage(ps);
         ScopedEvent ev(c, ALFIB_EV_PCSETUP_PATCH, level);
         launch_patch_factor(c, L, ps, L.a0vals.p);
+      } else {
+        ps.factored = true;
       }
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));

@@ -17,6 +17,7 @@ void smoother_apply_device(alfib_ctx* c, Level& L, int level, const double* x, d
   ScopedEvent ev(c, ALFIB_EV_PCPATCH_APPLY, level);
   CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * L.n, c->stream));
   launch_patch_apply(c, ps, x, y);
+  comm_allreduce_sum(c, y, L.n);                    // ghost->owner sum + owner->ghost broadcast
   launch_set_rows(c, y, x, L.bc.p, L.nbc);
 }
 
@@ -27,6 +28,7 @@ static void cell_block_solve(alfib_ctx* c, Level& L, const double* b, double* y)
   ALFIB_REQUIRE(ps.factored, "alfib_transfer_update has not been called for this level");
   CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * L.n, c->stream));
   launch_patch_apply(c, ps, b, y);
+  comm_allreduce_sum(c, y, L.n);
   launch_set_rows(c, y, b, L.cb.p, L.ncb);
 }
 
@@ -43,6 +45,7 @@ static void cell_block_solve_refined(alfib_ctx* c, Level& L, const double* b, do
   launch_bsr_spmv(c, L, L.a0vals.p, y, L.t3.p, b);                     // r = b - A0 y
   CUDA_TRY(cudaMemsetAsync(L.t4.p, 0, sizeof(double) * L.n, c->stream));
   launch_patch_apply(c, L.ps[ALFIB_PATCHES_TRANSFER], L.t3.p, L.t4.p); // dy = S r (patch rows only)
+  comm_allreduce_sum(c, L.t4.p, L.n);
   launch_axpby(c, L.n, 1.0, L.t4.p, 1.0, y);
 }
 

@@ -12,13 +12,13 @@
 namespace {
 
 template <int BS>
-__global__ void __launch_bounds__(256) bsr_spmv_kernel(int nbrows, const int32_t* __restrict__ rowptr,
+__global__ void __launch_bounds__(256) bsr_spmv_kernel(int row0, int nbrows, const int32_t* __restrict__ rowptr,
                                                        const int32_t* __restrict__ colidx,
                                                        const double* __restrict__ vals,
                                                        const double* __restrict__ x, double* __restrict__ y,
                                                        const double* __restrict__ b) {
   constexpr int B2 = BS * BS;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int warp = row0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (warp >= nbrows) return;
   const int64_t start = (int64_t)rowptr[warp] * B2;
@@ -97,15 +97,22 @@ __global__ void transpose_blocks_kernel(double* vals, int64_t nnzb) {
 void launch_bsr_spmv(alfib_ctx* c, const Level& L, const double* vals, const double* x, double* y,
                      const double* b) {
   const int threads = 256;
-  const int blocks = cdiv((int64_t)L.n_nodes * 32, threads);
-  if (L.bs == 2)
-    bsr_spmv_kernel<2><<<blocks, threads, 0, c->stream>>>(L.n_nodes, L.rowptr.p, L.colidx.p, vals, x, y, b);
-  else if (L.bs == 3)
-    bsr_spmv_kernel<3><<<blocks, threads, 0, c->stream>>>(L.n_nodes, L.rowptr.p, L.colidx.p, vals, x, y, b);
-  else
-    throw DeviceError{ALFIB_EINVAL, "block size must be 2 or 3"};
-  c->launches++;
-  CUDA_TRY(cudaGetLastError());
+  // multi-GPU: this rank computes its own block rows, then the owned rows are broadcast
+  const bool sharded = c->nranks > 1 && !L.row_start.empty();
+  const int row0 = sharded ? (int)L.row_start[c->rank] : 0;
+  const int row1 = sharded ? (int)L.row_start[c->rank + 1] : L.n_nodes;
+  const int blocks = cdiv((int64_t)(row1 - row0) * 32, threads);
+  if (blocks > 0) {
+    if (L.bs == 2)
+      bsr_spmv_kernel<2><<<blocks, threads, 0, c->stream>>>(row0, row1, L.rowptr.p, L.colidx.p, vals, x, y, b);
+    else if (L.bs == 3)
+      bsr_spmv_kernel<3><<<blocks, threads, 0, c->stream>>>(row0, row1, L.rowptr.p, L.colidx.p, vals, x, y, b);
+    else
+      throw DeviceError{ALFIB_EINVAL, "block size must be 2 or 3"};
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (sharded) comm_allgather_rows(c, y, L.dof_start);
 }
 
 void launch_csr_apply(alfib_ctx* c, int nrows, int bs, const int32_t* rowptr, const int32_t* colidx,

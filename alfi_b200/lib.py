@@ -38,6 +38,7 @@ SIGNATURES = {
     "alfib_synchronize": (C.c_int, [C.c_void_p]),
     "alfib_launch_count": (C.c_int64, [C.c_void_p]),
     "alfib_stream": (C.c_void_p, [C.c_void_p]),
+    "alfib_comm_unique_id": (C.c_int, [C.c_void_p]),
     "alfib_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "alfib_level_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "alfib_level_set_bsr_pattern": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _i32p]),
@@ -173,6 +174,20 @@ class Context:
     @property
     def stream(self):
         return int(self.lib.alfib_stream(self.h) or 0)
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte ncclUniqueId (call on rank 0, broadcast to the others)."""
+        buf = C.create_string_buffer(128)
+        rc = load_library().alfib_comm_unique_id(buf)
+        if rc != 0:
+            raise AlfibError("alfib_comm_unique_id failed (%d)" % rc)
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes | None, rank: int, nranks: int):
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        self._check(self.lib.alfib_comm_init(self.h, buf, rank, nranks))
+        self.rank, self.nranks = rank, nranks
 
     def level_sizes(self):
         return dict(self._sizes)

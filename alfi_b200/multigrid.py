@@ -56,27 +56,47 @@ class DeviceMultigrid:
     """The velocity-block multigrid of alfi/solver.py:359-379 resident on one GPU."""
 
     def __init__(self, levels: list[LevelInput], smoothing: int, device: int = 0, deterministic: bool = False,
-                 robust_restrict: bool = True, ctx: Context | None = None, torch_storage: bool = False):
+                 robust_restrict: bool = True, ctx: Context | None = None, torch_storage: bool = False,
+                 rank: int = 0, nranks: int = 1, unique_id: bytes | None = None):
+        """With nranks > 1 every rank passes the same global `levels`; this rank keeps the patches
+        `alfi_b200.dist.partition_patches` assigns to it (in a deployment each rank would only
+        ever see its own) and the library adds the NCCL exchange steps."""
+        from .dist import partition_patches, shard_patch_arrays
         self.ctx = ctx or Context(device, deterministic)
         self.nlevels = len(levels)
         self.smoothing = smoothing
         self.sizes = [li.n_nodes * li.bs for li in levels]
+        self.rank, self.nranks = rank, nranks
         self._storage = []
+        self.local_patches = {}
         c = self.ctx
         c.set_option(3, robust_restrict)
+        if nranks > 1:
+            c.comm_init(unique_id, rank, nranks)
         for l, li in enumerate(levels):
             c.level_create(l, li.n_nodes, li.bs)
             c.set_bsr_pattern(l, li.rowptr, li.colidx)
             c.set_bc(l, li.bc_dofs)
             if l > 0:
-                c.set_patches(l, li.patch_offsets, li.patch_dofs, li.patch_order, li.patch_colours, PATCHES_SMOOTHER)
+                off, dofs, order, cols = li.patch_offsets, li.patch_dofs, li.patch_order, li.patch_colours
+                if nranks > 1:
+                    owner = partition_patches(off, dofs, nranks)
+                    off, dofs, order, cols, mine = shard_patch_arrays(off, dofs, order, cols, owner, rank)
+                    self.local_patches[(l, PATCHES_SMOOTHER)] = mine
+                c.set_patches(l, off, dofs, order, cols, PATCHES_SMOOTHER)
                 if torch_storage:
                     self._bind(l, PATCHES_SMOOTHER)
                 cb = li.cb_dofs if li.cb_dofs is not None else np.empty(0, np.int32)
                 c.set_transfer(l, li.P, cb)
                 if li.cell_offsets is not None:
-                    c.set_patches(l, li.cell_offsets, li.cell_dofs, None, np.zeros(li.cell_offsets.size - 1, np.int32),
-                                  PATCHES_TRANSFER)
+                    off, dofs = li.cell_offsets, li.cell_dofs
+                    cols = np.zeros(off.size - 1, np.int32)
+                    order = None
+                    if nranks > 1:
+                        owner = partition_patches(off, dofs, nranks)
+                        off, dofs, order, cols, mine = shard_patch_arrays(off, dofs, None, cols, owner, rank)
+                        self.local_patches[(l, PATCHES_TRANSFER)] = mine
+                    c.set_patches(l, off, dofs, order, cols, PATCHES_TRANSFER)
                     if torch_storage:
                         self._bind(l, PATCHES_TRANSFER)
         self.update_operators(levels)

@@ -68,9 +68,17 @@ int64_t alfib_launch_count(const alfib_ctx* ctx);
 /* CUDA stream handle (cudaStream_t) the ctx enqueues on, for event timing by the caller */
 void* alfib_stream(alfib_ctx* ctx);
 
-/* Multi-GPU: one rank per GPU, partition = the DMPlex vertex-overlap partition the reference
- * already uses (solver.py:604-605, 661-662).  `nccl_unique_id` is the 128-byte ncclUniqueId
- * broadcast by the host (mpi4py in a deployment).  Without this call the ctx is serial.       */
+/* Multi-GPU: one rank per GPU on one NVSwitch box.  Each rank passes only ITS patches to
+ * alfib_level_set_patches (the owned vertices of the DMPlex vertex-overlap partition the
+ * reference uses, solver.py:604-605, 661-662, relaxation.py:120-121); level vectors are
+ * replicated, block rows of the operators are split evenly.  The library then inserts the two
+ * exchange steps of the path on its stream: ncclAllReduce(sum) after every patch apply (the
+ * PetscSF reduce + bcast around PCApply_PATCH) and a grouped ncclBroadcast of the owned rows
+ * after every SpMV (the VecScatter of MatMult_MPIBAIJ).  `nccl_unique_id` is the 128-byte
+ * ncclUniqueId made by alfib_comm_unique_id on rank 0 and broadcast by the host (mpi4py in a
+ * deployment, torch.distributed here).  Call before alfib_cycle_setup; without it the ctx is
+ * serial.                                                                                     */
+int alfib_comm_unique_id(void* out128 /* 128 bytes, filled on rank 0 */);
 int alfib_comm_init(alfib_ctx* ctx, const void* nccl_unique_id, int rank, int nranks);
 
 /* ---- level operator: replaces the BAIJ Mat PETSc holds for fieldsplit_0 on each level
