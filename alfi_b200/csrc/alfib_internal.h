@@ -122,7 +122,8 @@ struct alfib_ctx {
   DBuf<double> stage_in, stage_in2, stage_out;
   // coarse solve
   cusolverDnHandle_t cusolver = nullptr;
-  DBuf<double> coarse_lu, coarse_work;
+  DBuf<double> coarse_lu, coarse_work, coarse_inv, coarse_partial, coarse_r, coarse_dx;
+  int64_t coarse_ld = 0;
   DBuf<int> coarse_piv, coarse_info;
   int coarse_n = 0;
   bool coarse_factored = false;

@@ -184,7 +184,7 @@ int alfib_destroy(alfib_ctx* c) {
     L = nullptr;
   }
   for (auto* b : {&c->fwork, &c->partial, &c->scal, &c->stage_in, &c->stage_in2, &c->stage_out, &c->coarse_lu,
-                  &c->coarse_work})
+                  &c->coarse_work, &c->coarse_inv, &c->coarse_partial, &c->coarse_r, &c->coarse_dx})
     b->release();
   c->finfo.release();
   c->coarse_piv.release();

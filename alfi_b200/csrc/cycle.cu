@@ -1,6 +1,8 @@
 // fieldsplit_0 = richardson(1) + PCMG "full" with V inner cycles, FGMRES(m)/PatchPC smoothing on
 // every level > 0, Schoeberl transfers, direct coarse solve (alfi/solver.py:359-379;
 // alfi/transfer.py:186-275; PCMG semantics restated in SURVEY Appendix A.5/A.6).
+#include <algorithm>
+
 #include "alfib_internal.h"
 
 #define CUSOLVER_TRY(expr)                                                                      \
@@ -88,21 +90,109 @@ void restrict_device(alfib_ctx* c, Level& L, Level& Lc, int level, const double*
   launch_set_rows(c, coarse, nullptr, Lc.bc.p, Lc.nbc);
 }
 
-// Dense LU of the level-0 operator with cuSOLVER (the north star allows a gathered dense LU;
-// replaces AssembledPC + telescope + superlu_dist, solver.py:369-378).
+// Coarse level: explicit dense inverse, applied as a row-sharded streaming GEMV.
+// Setup (per Newton step): BSR -> dense, cuSOLVER getrf + getrs against the identity (the north
+// star allows a gathered dense LU for the coarsest level; replaces AssembledPC + telescope +
+// superlu_dist, solver.py:369-378).  Apply: x = Ainv b, then one step of iterative refinement
+// x += Ainv (b - A x) so the result is as accurate as an LU solve.  The GEMV reads the
+// column-major inverse with 128-bit loads, 64 rows per warp, the column range split over the
+// warps of a CTA and over KSPLIT CTAs; partial sums go through a fixed-order two-pass reduction
+// (deterministic).  HBM-bound: 8 n^2 bytes per application, and it shards by rows over ranks.
+namespace {
+
+constexpr int KSPLIT = 8;          // column chunks per row tile (grid.y)
+constexpr int GW = 8;              // warps per CTA, each takes an interleaved part of the chunk
+
+__global__ void set_identity_kernel(double* B, int64_t n, int64_t ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) B[i + i * ld] = 1.0;
+}
+
+__global__ void __launch_bounds__(GW * 32) dense_gemv_kernel(const double* __restrict__ A, int64_t ld, int n,
+                                                             int tile0, const double* __restrict__ x,
+                                                             double* __restrict__ partial) {
+  __shared__ double red[GW][ALFIB_TILE_ROWS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row0 = (tile0 + blockIdx.x) * ALFIB_TILE_ROWS;
+  const int r = row0 + 2 * lane;
+  const bool active = r < n;                      // ld is even and >= n+1 when n is odd: r+1 < ld
+  const int per = (n + KSPLIT - 1) / KSPLIT;
+  const int c0 = blockIdx.y * per, c1 = min(n, c0 + per);
+  double acc0 = 0.0, acc1 = 0.0;
+  const double2* __restrict__ Ap = reinterpret_cast<const double2*>(A + r);
+  if (active) {
+#pragma unroll 4
+    for (int c = c0 + warp; c < c1; c += GW) {
+      const double2 a = __ldcs(Ap + (int64_t)c * (ld >> 1));
+      const double xc = __ldg(x + c);
+      acc0 = fma(a.x, xc, acc0);
+      acc1 = fma(a.y, xc, acc1);
+    }
+  }
+  red[warp][2 * lane] = acc0;
+  red[warp][2 * lane + 1] = acc1;
+  __syncthreads();
+  if (threadIdx.x < ALFIB_TILE_ROWS) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < GW; ++w) v += red[w][threadIdx.x];
+    const int rr = row0 + threadIdx.x;
+    if (rr < n) partial[(int64_t)blockIdx.y * n + rr] = v;
+  }
+}
+
+// y[i] (+)= sum_k partial[k*n + i] for rows [r0, r1)
+__global__ void gemv_reduce_kernel(int n, int r0, int r1, const double* __restrict__ partial, double* __restrict__ y,
+                                   int accumulate) {
+  const int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= r1) return;
+  double v = 0.0;
+#pragma unroll
+  for (int k = 0; k < KSPLIT; ++k) v += partial[(int64_t)k * n + i];
+  y[i] = accumulate ? y[i] + v : v;
+}
+
+void coarse_gemv(alfib_ctx* c, const double* b, double* y, int accumulate) {
+  const int n = c->coarse_n;
+  const int ntile = (n + ALFIB_TILE_ROWS - 1) / ALFIB_TILE_ROWS;
+  const int t0 = (int)((int64_t)ntile * c->rank / c->nranks), t1 = (int)((int64_t)ntile * (c->rank + 1) / c->nranks);
+  const int r0 = std::min(n, t0 * ALFIB_TILE_ROWS), r1 = std::min(n, t1 * ALFIB_TILE_ROWS);
+  if (t1 > t0) {
+    dense_gemv_kernel<<<dim3(t1 - t0, KSPLIT), GW * 32, 0, c->stream>>>(c->coarse_inv.p, c->coarse_ld, n, t0, b,
+                                                                        c->coarse_partial.p);
+    gemv_reduce_kernel<<<cdiv(r1 - r0, 256), 256, 0, c->stream>>>(n, r0, r1, c->coarse_partial.p, y, accumulate);
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (c->nranks > 1) {
+    std::vector<int64_t> start(c->nranks + 1);
+    for (int r = 0; r <= c->nranks; ++r)
+      start[r] = std::min<int64_t>(n, (int64_t)ntile * r / c->nranks * ALFIB_TILE_ROWS);
+    comm_allgather_rows(c, y, start);
+  }
+}
+
+}  // namespace
+
 void coarse_factor_device(alfib_ctx* c) {
   Level* L0 = c->levels[0];
   ALFIB_REQUIRE(L0 && L0->has_values, "level 0 has no operator values");
-  ScopedEvent ev(c, ALFIB_EV_COARSE);
+  ScopedEvent ev(c, ALFIB_EV_COARSE, 0);
   if (!c->cusolver) {
     CUSOLVER_TRY(cusolverDnCreate(&c->cusolver));
     CUSOLVER_TRY(cusolverDnSetStream(c->cusolver, c->stream));
   }
   const int n = L0->n;
+  const int64_t ld = roundup2(n);
   c->coarse_n = n;
+  c->coarse_ld = ld;
   c->coarse_lu.alloc((size_t)n * n);
+  c->coarse_inv.alloc((size_t)ld * n);
   c->coarse_piv.alloc(n);
   c->coarse_info.alloc(1);
+  c->coarse_partial.alloc((size_t)KSPLIT * n);
+  c->coarse_r.alloc(n);
+  c->coarse_dx.alloc(n);
   launch_bsr_to_dense(c, *L0, c->coarse_lu.p);
   int lwork = 0;
   CUSOLVER_TRY(cusolverDnDgetrf_bufferSize(c->cusolver, n, n, c->coarse_lu.p, n, &lwork));
@@ -113,17 +203,25 @@ void coarse_factor_device(alfib_ctx* c) {
   CUDA_TRY(cudaMemcpyAsync(&info, c->coarse_info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   if (info != 0) throw DeviceError{ALFIB_ESINGULAR, "coarse LU failed, info = " + std::to_string(info)};
+  CUDA_TRY(cudaMemsetAsync(c->coarse_inv.p, 0, sizeof(double) * ld * n, c->stream));
+  set_identity_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(c->coarse_inv.p, n, ld);
+  c->launches++;
+  CUSOLVER_TRY(cusolverDnDgetrs(c->cusolver, CUBLAS_OP_N, n, n, c->coarse_lu.p, n, c->coarse_piv.p, c->coarse_inv.p,
+                                (int)ld, c->coarse_info.p));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->coarse_work.release();
+  c->coarse_lu.release();
   c->coarse_factored = true;
 }
 
 void coarse_solve_device(alfib_ctx* c, const double* b, double* x) {
   ALFIB_REQUIRE(c->coarse_factored, "alfib_coarse_factor has not been called");
-  ScopedEvent ev(c, ALFIB_EV_COARSE);
-  const int n = c->coarse_n;
-  if (x != b) CUDA_TRY(cudaMemcpyAsync(x, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-  CUSOLVER_TRY(cusolverDnDgetrs(c->cusolver, CUBLAS_OP_N, n, 1, c->coarse_lu.p, n, c->coarse_piv.p, x, n,
-                                c->coarse_info.p));
+  ALFIB_REQUIRE(x != b, "coarse solve: x and b must not alias");
+  Level& L0 = *c->levels[0];
+  ScopedEvent ev(c, ALFIB_EV_COARSE, 0);
+  coarse_gemv(c, b, x, 0);                                              // x = Ainv b
+  launch_bsr_spmv(c, L0, L0.vals.p, x, c->coarse_r.p, b);               // r = b - A x
+  coarse_gemv(c, c->coarse_r.p, x, 1);                                  // x += Ainv r
 }
 
 // One V visit on level l: b, x are the level's own vectors (Appendix A.5)

@@ -3,55 +3,56 @@
 // Reference: PETSc MatMult_SeqBAIJ on the `baij` velocity block (alfi/solver.py:512) and the
 // firedrake.mg prolong/restrict kernels behind `standard_transfer` (alfi/transfer.py:284-290).
 //
-// BSR SpMV: one warp per block row.  The row's values are a contiguous run of nnzb*bs*bs
-// doubles; lanes walk it with 128-bit loads (the run is re-based to an even element so every
-// double2 is 16-byte aligned, out-of-run halves are masked).  HBM-bound: algorithmic bytes
-// nnzb*(8 bs^2 + 4) + 4(nbrows+1) + 16 N  (SURVEY §8d).
+// BSR SpMV: half a warp per block row (kernel below).  HBM-bound: algorithmic bytes
+// nnzb*(8 bs^2 + 4) + 4(nbrows+1) + 16 N  (SURVEY §8d).  Measured (ncu, profiles/): 2.1x faster
+// than a warp-per-row kernel walking the row's flat value run with 128-bit loads, because the
+// 13 independent loads per lane hide the colidx -> x dependency; a 72-byte 3x3 block cannot be
+// 16-byte aligned for every block, so the values are read as 8-byte loads that coalesce in L1.
 #include "alfib_internal.h"
 
 namespace {
 
+// 16 lanes per block row, one whole bs x bs block per lane and iteration.  All loads of
+// an iteration (1 column index, bs x-entries, bs*bs values) are independent except colidx -> x,
+// so every lane keeps 1 + bs + bs*bs requests in flight; the strided 8-byte value loads of a
+// half-warp cover one contiguous 16*bs*bs*8-byte run and coalesce in L1.
 template <int BS>
-__global__ void __launch_bounds__(256) bsr_spmv_kernel(int row0, int nbrows, const int32_t* __restrict__ rowptr,
-                                                       const int32_t* __restrict__ colidx,
-                                                       const double* __restrict__ vals,
-                                                       const double* __restrict__ x, double* __restrict__ y,
-                                                       const double* __restrict__ b) {
+__global__ void __launch_bounds__(256) bsr_spmv_block_kernel(int row0, int nbrows, const int32_t* __restrict__ rowptr,
+                                                             const int32_t* __restrict__ colidx,
+                                                             const double* __restrict__ vals,
+                                                             const double* __restrict__ x, double* __restrict__ y,
+                                                             const double* __restrict__ b) {
   constexpr int B2 = BS * BS;
-  const int warp = row0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (warp >= nbrows) return;
-  const int64_t start = (int64_t)rowptr[warp] * B2;
-  const int64_t end = (int64_t)rowptr[warp + 1] * B2;
+  const int row = row0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+  const int l16 = threadIdx.x & 15;
   double acc[BS];
 #pragma unroll
   for (int r = 0; r < BS; ++r) acc[r] = 0.0;
-  const double2* v2 = reinterpret_cast<const double2*>(vals);
-  for (int64_t e = (start & ~int64_t(1)) + 2 * lane; e < end; e += 64) {
-    const double2 a = __ldcs(v2 + (e >> 1));
-    const double av[2] = {a.x, a.y};
+  if (row < nbrows) {
+    const int k1 = __ldg(rowptr + row + 1);
+#pragma unroll 2
+    for (int k = __ldg(rowptr + row) + l16; k < k1; k += 16) {
+      const double* __restrict__ v = vals + (int64_t)k * B2;
+      const double* __restrict__ xc = x + (int64_t)__ldg(colidx + k) * BS;
+      double vv[B2], xx[BS];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int64_t q = e + h;
-      if (q >= start && q < end) {
-        const int64_t blk = q / B2;
-        const int rem = (int)(q - blk * B2);
-        const int r = rem / BS, cc = rem - r * BS;
-        const double xv = __ldg(x + (int64_t)__ldg(colidx + blk) * BS + cc);
+      for (int i = 0; i < B2; ++i) vv[i] = __ldg(v + i);
 #pragma unroll
-        for (int rr = 0; rr < BS; ++rr)
-          if (rr == r) acc[rr] = fma(av[h], xv, acc[rr]);
-      }
+      for (int i = 0; i < BS; ++i) xx[i] = __ldg(xc + i);
+#pragma unroll
+      for (int r = 0; r < BS; ++r)
+#pragma unroll
+        for (int cc = 0; cc < BS; ++cc) acc[r] = fma(vv[r * BS + cc], xx[cc], acc[r]);
     }
   }
 #pragma unroll
   for (int r = 0; r < BS; ++r)
 #pragma unroll
-    for (int o = 16; o; o >>= 1) acc[r] += __shfl_down_sync(0xffffffffu, acc[r], o);
-  if (lane == 0) {
+    for (int o = 8; o; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o, 16);
+  if (row < nbrows && l16 == 0) {
 #pragma unroll
     for (int r = 0; r < BS; ++r) {
-      const int64_t i = (int64_t)warp * BS + r;
+      const int64_t i = (int64_t)row * BS + r;
       y[i] = b ? b[i] - acc[r] : acc[r];
     }
   }
@@ -101,12 +102,12 @@ void launch_bsr_spmv(alfib_ctx* c, const Level& L, const double* vals, const dou
   const bool sharded = c->nranks > 1 && !L.row_start.empty();
   const int row0 = sharded ? (int)L.row_start[c->rank] : 0;
   const int row1 = sharded ? (int)L.row_start[c->rank + 1] : L.n_nodes;
-  const int blocks = cdiv((int64_t)(row1 - row0) * 32, threads);
+  const int blocks = cdiv((int64_t)(row1 - row0) * 16, threads);
   if (blocks > 0) {
     if (L.bs == 2)
-      bsr_spmv_kernel<2><<<blocks, threads, 0, c->stream>>>(row0, row1, L.rowptr.p, L.colidx.p, vals, x, y, b);
+      bsr_spmv_block_kernel<2><<<blocks, threads, 0, c->stream>>>(row0, row1, L.rowptr.p, L.colidx.p, vals, x, y, b);
     else if (L.bs == 3)
-      bsr_spmv_kernel<3><<<blocks, threads, 0, c->stream>>>(row0, row1, L.rowptr.p, L.colidx.p, vals, x, y, b);
+      bsr_spmv_block_kernel<3><<<blocks, threads, 0, c->stream>>>(row0, row1, L.rowptr.p, L.colidx.p, vals, x, y, b);
     else
       throw DeviceError{ALFIB_EINVAL, "block size must be 2 or 3"};
     c->launches++;

@@ -235,7 +235,7 @@ def ours(args):
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel ------------------------------------------------------
+    # ---- roofline (rank 0's own kernel; with N > 1 the bytes are those of rank 0's patches) of the dominant kernel ------------------------------------------------------
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, sustained copy)"
@@ -243,6 +243,11 @@ def ours(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     fine = prob.finest
     bs_bytes = smoother_bytes(fine)
+    if world > 1:       # this rank streams only its own patches
+        from alfi_b200.lib import PATCHES_SMOOTHER
+        mine = mg.local_patches[(len(prob.levels) - 1, PATCHES_SMOOTHER)]
+        nloc = fine.patches.sizes[mine].astype(np.float64)
+        bs_bytes = float((8 * nloc * nloc + 4 * nloc).sum() + 16 * fine.ndofs)
     app_ms, app_calls = prof_fine["PCPATCHApply"]
     achieved = bs_bytes / (app_ms / max(app_calls, 1) * 1e-3) / 1e9 if app_calls else None
     traffic = None
@@ -290,6 +295,16 @@ def ours(args):
     print(json.dumps(line), flush=True)
 
 
+def _finish():
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+    except Exception:       # noqa: BLE001
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -305,6 +320,7 @@ def main():
         reference_arm(args)
     else:
         ours(args)
+        _finish()
 
 
 if __name__ == "__main__":
