@@ -129,3 +129,26 @@ class DeviceMultigrid:
     def apply(self, b, x):
         """x = one fieldsplit_0 application (F-cycle) of b."""
         return self.ctx.cycle_apply(b, x)
+
+
+class DeviceBackend:
+    """`fieldsplit_0` backend for alfi_b200.synth.outer.ContinuationSolver on the GPU."""
+
+    def __init__(self, smoothing, device=0, deterministic=False, **kw):
+        self.smoothing, self.device, self.deterministic, self.kw = smoothing, device, deterministic, kw
+        self.mg = None
+
+    def setup(self, levels):
+        self.mg = DeviceMultigrid(levels, self.smoothing, device=self.device, deterministic=self.deterministic, **self.kw)
+        self._out = np.empty(levels[-1].n_nodes * levels[-1].bs)
+
+    def update_operators(self, levels):
+        self.mg.update_operators(levels)
+
+    def update_transfers(self, levels):
+        self.mg.update_transfers(levels)
+
+    def apply(self, b):
+        out = np.empty_like(self._out)
+        self.mg.apply(np.ascontiguousarray(b), out)
+        return out

@@ -334,16 +334,20 @@ def element_matrices(V: VectorSpace, nu: float, gamma: float, wind=None, advect:
         dv = np.einsum("c,car,ai->cir", det, G, rt["Dv"])          # ∫ d_r phi_i
         vol = det / (2.0 if d == 2 else 6.0)
         E += gamma * np.einsum("c,cir,cjs->cirjs", 1.0 / vol, dv, dv)
-    if "adv" in parts and wind is not None and advect != 0.0:
+    adv1 = "adv" in parts or "adv1" in parts          # (w.grad u, v)   — the convective part
+    adv2 = "adv" in parts or "adv2" in parts          # (u.grad w, v)   — the Newton part
+    if (adv1 or adv2) and wind is not None and advect != 0.0:
         W = wind[V.cell_nodes[cells]]                               # (nc, nl, d)  W[c,k,b]
-        # (w.grad u_j, v_i): delta_rs det sum_{k,a} (sum_b W[k,b] G[a,b]) T1[k,a,i,j]
-        cw = np.einsum("ckb,cab->cka", W, G)
-        A1 = np.einsum("c,cka,kaij->cij", det, cw, rt["T1"], optimize=True)
-        for r in range(d):
-            E[:, :, r, :, r] += advect * A1
-        # (u_j.grad w, v_i)_{r,s} = det sum_{k,a} W[k,r] G[a,s] T2[k,a,i,j]
-        A2 = np.einsum("c,ckr,cas,kaij->cirjs", det, W, G, rt["T2"], optimize=True)
-        E += advect * A2
+        if adv1:
+            # (w.grad u_j, v_i): delta_rs det sum_{k,a} (sum_b W[k,b] G[a,b]) T1[k,a,i,j]
+            cw = np.einsum("ckb,cab->cka", W, G)
+            A1 = np.einsum("c,cka,kaij->cij", det, cw, rt["T1"], optimize=True)
+            for r in range(d):
+                E[:, :, r, :, r] += advect * A1
+        if adv2:
+            # (u_j.grad w, v_i)_{r,s} = det sum_{k,a} W[k,r] G[a,s] T2[k,a,i,j]
+            A2 = np.einsum("c,ckr,cas,kaij->cirjs", det, W, G, rt["T2"], optimize=True)
+            E += advect * A2
     return E
 
 
@@ -374,6 +378,39 @@ def assemble_velocity_block(V: VectorSpace, nu: float, gamma: float, wind=None, 
     if bc_nodes is not None:
         apply_dirichlet(A, bc_nodes, pat.rows)
     return A
+
+
+# --------------------------------------------------------------------------- pressure space
+def assemble_divergence(V: VectorSpace, kq: int):
+    """B (pressure dofs x velocity dofs) of  -(div u, q)  with q in discontinuous P_kq
+    (alfi/solver.py:564-571, 615-622: ``- p*div(v) - div(u)*q``), and the block-diagonal inverse
+    of the pressure mass matrix used by DGMassInv (alfi/solver.py:15-38).  Pressure dofs are
+    numbered cell by cell."""
+    mesh, d, k = V.mesh, V.mesh.dim, V.degree
+    G, det = cell_geometry(mesh)
+    el = V.element
+    nc, nl = mesh.nc, el.nnodes
+    x, w = simplex_quadrature(d, k + kq)
+    dphi = el.tabulate_grad(x)                                   # (q, nl, d)
+    if kq == 0:
+        psi = np.ones((x.shape[0], 1))
+    else:
+        psi = LagrangeElement(d, kq).tabulate(x)                 # (q, nq)
+    nq = psi.shape[1]
+    Bref = np.einsum("q,qi,qja->aij", w, psi, dphi)              # ∫ psi_i d_a phi_j
+    Mref = np.einsum("q,qi,qj->ij", w, psi, psi)
+    # Bc[c, i, j, s] = -det sum_a G[a,s] Bref[a,i,j]
+    Bc = -np.einsum("c,cas,aij->cijs", det, G, Bref)
+    rows = np.repeat(np.arange(nc * nq).reshape(nc, nq, 1, 1), nl, axis=2)
+    rows = np.repeat(rows, d, axis=3)
+    cols = (V.cell_nodes[:, None, :, None] * d + np.arange(d)[None, None, None, :])
+    cols = np.broadcast_to(cols, (nc, nq, nl, d))
+    B = sp.csr_matrix((Bc.ravel(), (rows.ravel(), cols.ravel())), shape=(nc * nq, V.ndofs))
+    B.sum_duplicates()
+    Minv_blocks = np.linalg.inv(Mref)[None, :, :] / det[:, None, None]
+    Minv = sp.block_diag(list(Minv_blocks), format="csr") if nc * nq < 200000 else \
+        sp.bsr_matrix((Minv_blocks, np.arange(nc), np.arange(nc + 1)), shape=(nc * nq, nc * nq)).tocsr()
+    return B, Minv
 
 
 def apply_dirichlet(A: BSR, bc_nodes, rows=None):

@@ -1,0 +1,72 @@
+"""Newton continuation around the velocity-block PC (north-star condition 3).
+
+CPU: the stand-in outer solver (alfi_b200/synth/outer.py) with the oracle backend converges like
+the reference is documented to (few Krylov iterations per Newton step, exactly divergence-free
+Scott-Vogelius velocity).  GPU: with the CUDA library as `fieldsplit_0` the Krylov iteration
+counts per Newton step match the oracle's within +-1 and the final velocity / pressure agree to
+1e-8 relative."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from alfi_b200.synth.outer import ContinuationSolver, fgmres_outer
+from alfi_b200.synth.problem import CONFIGS
+from oracle.backend import OracleBackend
+
+SMALL2D = dataclasses.replace(CONFIGS["ldc2d-sv-k2"], N=4)
+RES = (1, 10, 100)
+
+
+def test_outer_fgmres_solves_a_dense_system():
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((60, 60)) + 8 * np.eye(60)
+    b = rng.standard_normal(60)
+    x, its, hist = fgmres_outer(lambda v: A @ v, lambda v: v / 8.0, b, 1e-12, 0.0, maxit=200, restart=20)
+    assert np.linalg.norm(A @ x - b) <= 1e-10 * np.linalg.norm(b)
+    assert its > 20                      # went through a restart
+    assert all(h1 <= h0 * (1 + 1e-12) for h0, h1 in zip(hist, hist[1:]))
+
+
+@pytest.fixture(scope="module")
+def oracle_run():
+    s = ContinuationSolver(SMALL2D, OracleBackend(SMALL2D.m))
+    infos = [s.solve(re) for re in RES]
+    return s, infos
+
+
+def test_continuation_with_oracle_backend(oracle_run):
+    s, infos = oracle_run
+    for info in infos:
+        assert info["nonlinear_iter"] <= 5
+        assert info["linear_iter"] / max(info["nonlinear_iter"], 1) <= 10      # Reynolds-robust
+        assert info["residual"] <= max(1e-8, 1e-9 * info["residual0"])         # snes_atol / snes_rtol
+    # Scott-Vogelius on the barycentric mesh: the discrete velocity is exactly divergence free
+    assert np.linalg.norm(s.B @ s.u.ravel()) <= 1e-12
+    assert abs(s.p.mean()) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_iteration_counts_match_on_gpu(oracle_run):
+    from alfi_b200.multigrid import DeviceBackend
+    so, io = oracle_run
+    sd = ContinuationSolver(SMALL2D, DeviceBackend(SMALL2D.m, deterministic=True))
+    idev = [sd.solve(re) for re in RES]
+    for a, b in zip(io, idev):
+        assert a["nonlinear_iter"] == b["nonlinear_iter"], (a, b)
+        assert abs(a["linear_iter"] - b["linear_iter"]) <= a["nonlinear_iter"], (a, b)    # +-1 per Newton step
+    assert np.linalg.norm(sd.u - so.u) <= 1e-8 * np.linalg.norm(so.u)
+    assert np.linalg.norm(sd.p - so.p) <= 1e-8 * max(np.linalg.norm(so.p), 1e-300)
+
+
+@pytest.mark.gpu
+def test_iteration_counts_match_on_gpu_3d():
+    from alfi_b200.multigrid import DeviceBackend
+    cfg = CONFIGS["ldc3d-sv-k3-tiny"]
+    so = ContinuationSolver(cfg, OracleBackend(cfg.m))
+    sd = ContinuationSolver(cfg, DeviceBackend(cfg.m, deterministic=True))
+    for re in (1, 10):
+        a, b = so.solve(re), sd.solve(re)
+        assert a["nonlinear_iter"] == b["nonlinear_iter"], (a, b)
+        assert abs(a["linear_iter"] - b["linear_iter"]) <= a["nonlinear_iter"], (a, b)
+    assert np.linalg.norm(sd.u - so.u) <= 1e-8 * np.linalg.norm(so.u)
