@@ -4,20 +4,33 @@
 // with LAPACK getrf+getri through PETSc).
 //
 // One persistent CTA per SM takes patches from an atomic counter (largest first).  The patch
-// matrix lives column-major in a per-CTA global workspace slot (13 MB for n = 1275, so L2/HBM
-// resident) and is inverted in place by *blocked Gauss-Jordan with partial row pivoting*:
-//   for each panel K of NB columns
-//     1. panel -> shared memory; NB unblocked Gauss-Jordan steps on all n rows of the panel,
-//        pivot = first max |.| among the not-yet-pivoted rows (LAPACK idamax rule);
-//     2. the NB row swaps are applied to every other column, R = W[K, :] is set aside and
-//        W[K, :] zeroed;
-//     3. rank-NB update W[:, J] += N * R with N = the transformed panel (one row per thread,
-//        N[r, 0:NB] in registers, R staged through shared memory 64 columns at a time).
+// matrix lives column-major in a per-CTA global workspace slot (13 MB for n = 1275) and is
+// inverted in place by *two-level blocked Gauss-Jordan with partial row pivoting*:
+//
+//   for each outer block KO of NBO = 64 columns
+//     for each inner panel K of NB (16) columns of KO                      [O(n NBO^2) work]
+//       1. panel -> shared memory; NB unblocked Gauss-Jordan steps on all n rows of the panel,
+//          pivot = first max |.| among the not-yet-pivoted rows (LAPACK idamax rule);
+//       2. the panel's row swaps, R = W[K, .] and the rank-NB update are applied to the other
+//          columns *of the outer block only* (one row per thread, N[r, 0:NB] in registers);
+//     far update, all columns outside KO                                   [the O(n^3) part]
+//       3. all NBO row swaps in order, R = W[KO, far] set aside (k-major), W[KO, far] zeroed;
+//       4. W[:, far] += N * R with N = W[:, KO]: a rank-64 FP64 GEMM, 256 x 64 tiles of W per
+//          CTA iteration, 8 x 4 accumulators per thread, N and R tiles staged in shared memory
+//          (128 + 32 KB), W read and written once per outer block with 128-bit accesses.
 //   A^{-1} = W with the column swaps undone in reverse order; that permutation is folded into
 //   the final pass that writes the 64-row-tiled apply layout (patch_apply.cu).
-// Flops 2 n^3 per patch; the update is the only O(n^3) part and streams W once per panel.
+//
+// The far columns see the composition of the NBO/NB inner transformations as one rank-NBO
+// update  C <- Z_KO C + N_all C[KO, :]  because in-place Gauss-Jordan keeps, in the columns it has
+// eliminated, the image of the corresponding unit vectors (validated in numpy first, see
+// DESIGN.md §3.2).  Flops 2 n^3 per patch; arithmetic intensity of the far update 8 flop/byte, so
+// it is bound by the FP64 pipe, not by HBM (the one-level version streamed W once per 16 columns
+// and sat at ~1.5 TB/s aggregate).
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
+#include <cuda_pipeline.h>
 #include <numeric>
 
 #include "alfib_internal.h"
@@ -25,8 +38,10 @@
 namespace {
 
 constexpr int FT = 512;        // threads per CTA
-constexpr int CC = 64;         // columns per staged R chunk
-constexpr int UC = 8;          // columns whose loads are issued together in the update
+constexpr int NBO = 64;        // outer block (rank of the far update)
+constexpr int TR = 256;        // rows of W per far tile
+constexpr int TC = 64;         // columns of W per far tile
+constexpr int UC = 8;          // columns whose loads are issued together in the in-block update
 
 struct FactorArgs {
   int npatch;
@@ -44,10 +59,37 @@ struct FactorArgs {
   const double* vals;
   // workspace
   double* work;
-  int64_t slot_elems;          // per CTA: W (maxn*ld) + R (maxn*NB)
+  int64_t slot_elems;          // per CTA: W (maxn*ld) + R (NBO*maxn)
   int maxn;
   int* counter;
   int* info;                   // 0 or (1 + index of a singular patch)
+  long long* timing;           // optional per-phase clock64 totals (ALFIB_FACTOR_TIMING=1), else null
+};
+
+enum { PH_GATHER, PH_PANEL_LOAD, PH_INNER_GJ, PH_INBLOCK, PH_FAR_SWAP, PH_FAR_NS, PH_FAR_RS, PH_FAR_MMA, PH_PACK, PH_COUNT };
+
+// thread 0 of a CTA accumulates the cycles between phase boundaries (all boundaries follow a barrier)
+struct PhaseClock {
+  long long t0, acc[PH_COUNT];
+  bool on;
+  __device__ void start(bool enable) {
+    on = enable;
+    if (on) {
+      for (int i = 0; i < PH_COUNT; ++i) acc[i] = 0;
+      t0 = clock64();
+    }
+  }
+  __device__ void mark(int phase) {
+    if (on) {
+      const long long t = clock64();
+      acc[phase] += t - t0;
+      t0 = t;
+    }
+  }
+  __device__ void flush(long long* out) {
+    if (on)
+      for (int i = 0; i < PH_COUNT; ++i) atomicAdd((unsigned long long*)out + i, (unsigned long long)acc[i]);
+  }
 };
 
 __device__ __forceinline__ int lookup(const int32_t* sd, int n, int key) {
@@ -61,30 +103,44 @@ __device__ __forceinline__ int lookup(const int32_t* sd, int n, int key) {
   return -1;
 }
 
+__host__ __device__ inline size_t front_doubles(int maxn, int NB) {
+  // the front region holds either the inner panel (+ its R staging) or the far tiles
+  const size_t ldp = (size_t)((maxn + 1) & ~1);
+  const size_t inner = ldp * NB + (size_t)NBO * NB;
+  const size_t far = (size_t)NBO * TR + 2 * (size_t)NBO * TC;      // N tile + double-buffered R tiles
+  return inner > far ? inner : far;
+}
+
 template <int NB>
 __global__ void __launch_bounds__(FT, 1) patch_factor_kernel(FactorArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int ldp_max = (a.maxn + 1) & ~1;
   // shared memory carve-up
-  double* panel = reinterpret_cast<double*>(smem_raw);                 // ldp_max * NB
-  double* Rs = panel + (size_t)ldp_max * NB;                           // CC * NB
-  double* pr = Rs + CC * NB;                                           // NB
-  double* red_v = pr + NB;                                             // 33
+  double* front = reinterpret_cast<double*>(smem_raw);
+  double* panel = front;                                               // ldp_max * NB
+  double* Rs = panel + (size_t)ldp_max * NB;                           // NBO * NB (in-block R)
+  double* Ns = front;                                                  // NBO * TR   (far phase)
+  double* Rsm = Ns + (size_t)NBO * TR;                                 // 2 x NBO * TC (far phase)
+  double* pr = front + front_doubles(a.maxn, NB);                      // NB
+  double* red_v = pr + NB;                                             // 34
   int* red_i = reinterpret_cast<int*>(red_v + 34);                     // 34
-  int* ipiv = red_i + 34;                                              // maxn
-  int* s_next = ipiv + a.maxn;                                         // 1
-  // the gather's lookup tables alias the panel (used before the factorisation starts)
-  int* sd = reinterpret_cast<int*>(panel);
+  int* swapA = red_i + 34;                                             // NBO
+  int* swapB = swapA + NBO;                                            // NBO
+  int* s_misc = swapB + NBO;                                           // [0] next patch, [1] nswap
+  int* ipiv = s_misc + 2;                                              // maxn
+  // the gather's lookup tables alias the front region (used before the factorisation starts)
+  int* sd = reinterpret_cast<int*>(front);
   int* sp = sd + a.maxn;
 
   double* W = a.work + (size_t)blockIdx.x * a.slot_elems;
-  double* Rg = W + (size_t)a.maxn * ldp_max;
+  double* Rg = W + (size_t)a.maxn * ldp_max;                           // NBO x ldr, k-major
+  const int ldr = (a.maxn + TC - 1) & ~(TC - 1);
 
   for (;;) {
-    if (tid == 0) *s_next = atomicAdd(a.counter, 1);
+    if (tid == 0) s_misc[0] = atomicAdd(a.counter, 1);
     __syncthreads();
-    const int q = *s_next;
+    const int q = s_misc[0];
     __syncthreads();
     if (q >= a.npatch) break;
     const int p = a.forder[q];
@@ -94,6 +150,8 @@ __global__ void __launch_bounds__(FT, 1) patch_factor_kernel(FactorArgs a) {
     const int ld = (n + 1) & ~1;
     const int ldp = ld;
     const int32_t* I = a.pdofs + o;
+    PhaseClock pc;
+    pc.start(a.timing != nullptr && tid == 0);
 
     // ---- gather A[I, I] into W (column-major) ----------------------------------------------
     for (int64_t i = tid; i < (int64_t)n * ld; i += FT) W[i] = 0.0;
@@ -118,112 +176,120 @@ __global__ void __launch_bounds__(FT, 1) patch_factor_kernel(FactorArgs a) {
       }
     }
     __syncthreads();
+    pc.mark(PH_GATHER);
 
-    // ---- blocked Gauss-Jordan ---------------------------------------------------------------
-    for (int k0 = 0; k0 < n; k0 += NB) {
-      const int nb = (n - k0) < NB ? (n - k0) : NB;
-      // 1. panel to shared memory
-      for (int c = 0; c < nb; ++c)
-        for (int r = tid; r < n; r += FT) panel[r + c * ldp] = W[r + (size_t)(k0 + c) * ld];
-      __syncthreads();
-      for (int j = 0; j < nb; ++j) {
-        const int kj = k0 + j;
-        double best = -1.0;
-        int bi = INT_MAX;
-        for (int r = kj + tid; r < n; r += FT) {
-          const double v = fabs(panel[r + j * ldp]);
-          if (v > best) { best = v; bi = r; }
-        }
-#pragma unroll
-        for (int off = 16; off; off >>= 1) {
-          const double ov = __shfl_down_sync(0xffffffffu, best, off);
-          const int oi = __shfl_down_sync(0xffffffffu, bi, off);
-          if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if ((tid & 31) == 0) { red_v[tid >> 5] = best; red_i[tid >> 5] = bi; }
+    // ---- two-level blocked Gauss-Jordan -----------------------------------------------------
+    for (int k0 = 0; k0 < n; k0 += NBO) {
+      const int nbo = (n - k0) < NBO ? (n - k0) : NBO;
+      if (tid == 0) s_misc[1] = 0;
+      for (int q0 = k0; q0 < k0 + nbo; q0 += NB) {
+        const int nb = (k0 + nbo - q0) < NB ? (k0 + nbo - q0) : NB;
+        // 1. inner panel to shared memory, NB Gauss-Jordan steps
+        for (int c = 0; c < nb; ++c)
+          for (int r = tid; r < n; r += FT) panel[r + c * ldp] = W[r + (size_t)(q0 + c) * ld];
         __syncthreads();
-        if (tid < 32) {
-          best = tid < FT / 32 ? red_v[tid] : -1.0;
-          bi = tid < FT / 32 ? red_i[tid] : INT_MAX;
+        pc.mark(PH_PANEL_LOAD);
+        for (int j = 0; j < nb; ++j) {
+          const int kj = q0 + j;
+          double best = -1.0;
+          int bi = INT_MAX;
+          for (int r = kj + tid; r < n; r += FT) {
+            const double v = fabs(panel[r + j * ldp]);
+            if (v > best) { best = v; bi = r; }
+          }
 #pragma unroll
           for (int off = 16; off; off >>= 1) {
             const double ov = __shfl_down_sync(0xffffffffu, best, off);
             const int oi = __shfl_down_sync(0xffffffffu, bi, off);
             if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
           }
-          if (tid == 0) {
-            if (!(best > 0.0)) { bi = kj; atomicCAS(a.info, 0, p + 1); }
-            red_i[32] = bi;
-            red_v[32] = best;
-            ipiv[kj] = bi;
+          if ((tid & 31) == 0) { red_v[tid >> 5] = best; red_i[tid >> 5] = bi; }
+          __syncthreads();
+          if (tid < 32) {
+            best = tid < FT / 32 ? red_v[tid] : -1.0;
+            bi = tid < FT / 32 ? red_i[tid] : INT_MAX;
+#pragma unroll
+            for (int off = 16; off; off >>= 1) {
+              const double ov = __shfl_down_sync(0xffffffffu, best, off);
+              const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+              if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (tid == 0) {
+              if (!(best > 0.0)) { bi = kj; atomicCAS(a.info, 0, p + 1); }
+              red_i[32] = bi;
+              red_v[32] = best;
+              ipiv[kj] = bi;
+              if (bi != kj) {                       // remember the swap for the far columns
+                const int s = s_misc[1]++;
+                swapA[s] = kj;
+                swapB[s] = bi;
+              }
+            }
+          }
+          __syncthreads();
+          const int pv = red_i[32];
+          const bool singular = !(red_v[32] > 0.0);
+          if (tid < nb && pv != kj) {
+            const double t0 = panel[kj + tid * ldp];
+            panel[kj + tid * ldp] = panel[pv + tid * ldp];
+            panel[pv + tid * ldp] = t0;
+          }
+          __syncthreads();
+          const double d = singular ? 0.0 : 1.0 / panel[kj + j * ldp];
+          if (tid < NB) pr[tid] = (tid == j || tid >= nb) ? 0.0 : panel[kj + tid * ldp] * d;
+          __syncthreads();
+          for (int r = tid; r < n; r += FT) {
+            if (r == kj) {
+#pragma unroll
+              for (int jj = 0; jj < NB; ++jj)
+                if (jj < nb) panel[kj + jj * ldp] = (jj == j) ? d : pr[jj];
+            } else {
+              const double f = panel[r + j * ldp];
+#pragma unroll
+              for (int jj = 0; jj < NB; ++jj)
+                if (jj < nb) panel[r + jj * ldp] = fma(-f, pr[jj], panel[r + jj * ldp]);
+              panel[r + j * ldp] = -f * d;
+            }
+          }
+          __syncthreads();
+        }
+        pc.mark(PH_INNER_GJ);
+        // 2. the other columns of the outer block: this panel's swaps, R aside, zero pivot rows
+        if (tid < nbo) {
+          const int c = k0 + tid;
+          const bool inpanel = c >= q0 && c < q0 + nb;
+          double* col = W + (size_t)c * ld;
+          if (!inpanel) {
+            for (int j = 0; j < nb; ++j) {
+              const int kj = q0 + j, pv = ipiv[kj];
+              if (pv != kj) {
+                const double t0 = col[kj];
+                col[kj] = col[pv];
+                col[pv] = t0;
+              }
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < NB; ++t) {
+            double v = 0.0;
+            if (!inpanel && t < nb) { v = col[q0 + t]; col[q0 + t] = 0.0; }
+            Rs[tid * NB + t] = v;
           }
         }
         __syncthreads();
-        const int pv = red_i[32];
-        const bool singular = !(red_v[32] > 0.0);
-        if (tid < nb && pv != kj) {
-          const double t0 = panel[kj + tid * ldp];
-          panel[kj + tid * ldp] = panel[pv + tid * ldp];
-          panel[pv + tid * ldp] = t0;
-        }
-        __syncthreads();
-        const double d = singular ? 0.0 : 1.0 / panel[kj + j * ldp];
-        if (tid < NB) pr[tid] = (tid == j || tid >= nb) ? 0.0 : panel[kj + tid * ldp] * d;
-        __syncthreads();
-        for (int r = tid; r < n; r += FT) {
-          if (r == kj) {
-#pragma unroll
-            for (int jj = 0; jj < NB; ++jj)
-              if (jj < nb) panel[kj + jj * ldp] = (jj == j) ? d : pr[jj];
-          } else {
-            const double f = panel[r + j * ldp];
-#pragma unroll
-            for (int jj = 0; jj < NB; ++jj)
-              if (jj < nb) panel[r + jj * ldp] = fma(-f, pr[jj], panel[r + jj * ldp]);
-            panel[r + j * ldp] = -f * d;
-          }
-        }
-        __syncthreads();
-      }
-      // 2. row swaps on the other columns, set R aside, zero the pivot rows
-      for (int c = tid; c < n; c += FT) {
-        if (c >= k0 && c < k0 + nb) continue;
-        double* col = W + (size_t)c * ld;
-        for (int j = 0; j < nb; ++j) {
-          const int kj = k0 + j, pv = ipiv[kj];
-          if (pv != kj) {
-            const double t0 = col[kj];
-            col[kj] = col[pv];
-            col[pv] = t0;
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < NB; ++t) {
-          double v = 0.0;
-          if (t < nb) { v = col[k0 + t]; col[k0 + t] = 0.0; }
-          Rg[(size_t)c * NB + t] = v;
-        }
-      }
-      __syncthreads();
-      // 3. rank-NB update of all other columns, R staged CC columns at a time
-      for (int cc0 = 0; cc0 < n; cc0 += CC) {
-        const int ccn = (n - cc0) < CC ? (n - cc0) : CC;
-        for (int i = tid; i < ccn * NB; i += FT) Rs[i] = Rg[(size_t)cc0 * NB + i];
-        __syncthreads();
+        //    rank-NB update of those columns, one row per thread
         for (int r = tid; r < n; r += FT) {
           double N[NB];
 #pragma unroll
           for (int t = 0; t < NB; ++t) N[t] = (t < nb) ? panel[r + t * ldp] : 0.0;
-          double* Wr = W + r;
-          // UC columns at a time: all loads first (memory-level parallelism — with one load in
-          // flight per thread the update ran at ~7 GB/s per SM), then the FMAs, then the stores
-          for (int ci0 = 0; ci0 < ccn; ci0 += UC) {
+          double* Wr = W + r + (size_t)k0 * ld;
+          for (int ci0 = 0; ci0 < nbo; ci0 += UC) {
             double w[UC];
 #pragma unroll
             for (int u = 0; u < UC; ++u) {
-              const int cg = cc0 + ci0 + u;
-              const bool ok = (ci0 + u < ccn) && !(cg >= k0 && cg < k0 + nb);
-              w[u] = ok ? Wr[(size_t)cg * ld] : 0.0;
+              const int cg = k0 + ci0 + u;
+              const bool ok = (ci0 + u < nbo) && !(cg >= q0 && cg < q0 + nb);
+              w[u] = ok ? Wr[(size_t)(ci0 + u) * ld] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < UC; ++u) {
@@ -233,21 +299,168 @@ __global__ void __launch_bounds__(FT, 1) patch_factor_kernel(FactorArgs a) {
             }
 #pragma unroll
             for (int u = 0; u < UC; ++u) {
-              const int cg = cc0 + ci0 + u;
-              if ((ci0 + u < ccn) && !(cg >= k0 && cg < k0 + nb)) Wr[(size_t)cg * ld] = w[u];
+              const int cg = k0 + ci0 + u;
+              if ((ci0 + u < nbo) && !(cg >= q0 && cg < q0 + nb)) Wr[(size_t)(ci0 + u) * ld] = w[u];
             }
           }
         }
+        // panel back
+        for (int c = 0; c < nb; ++c)
+          for (int r = tid; r < n; r += FT) W[r + (size_t)(q0 + c) * ld] = panel[r + c * ldp];
         __syncthreads();
+        pc.mark(PH_INBLOCK);
       }
-      // panel back
-      for (int c = 0; c < nb; ++c)
-        for (int r = tid; r < n; r += FT) W[r + (size_t)(k0 + c) * ld] = panel[r + c * ldp];
-      __syncthreads();
+
+      // ---- far update: every column outside the outer block ---------------------------------
+      const int nfar = n - nbo;
+      if (nfar > 0) {
+        const int nswap = s_misc[1];
+        // 3. swaps in order (rare for these matrices), then R = W[KO, far] set aside k-major and
+        //    the pivot rows zeroed.  The 64 x 64 blocks of R are transposed through shared memory
+        //    so that both the column-major reads of W and the k-major writes of Rg are coalesced
+        //    (a thread-per-column walk cost as much as the whole rank-64 update).
+        if (nswap > 0) {
+          // the swaps of one column are dependent; a thread interleaves those of 4 columns
+          for (int f0 = tid; f0 < nfar; f0 += 4 * FT) {
+            double* col[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int f = f0 + u * FT;
+              col[u] = f < nfar ? W + (size_t)(f < k0 ? f : f + nbo) * ld : nullptr;
+            }
+            for (int s = 0; s < nswap; ++s) {
+              const int ra = swapA[s], rb = swapB[s];
+              double va[4], vb[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (col[u]) { va[u] = col[u][ra]; vb[u] = col[u][rb]; }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (col[u]) { col[u][ra] = vb[u]; col[u][rb] = va[u]; }
+            }
+          }
+          __syncthreads();
+        }
+        {
+          double* Tt = front;                        // 64 x 65 transposition tile
+          for (int fc0 = 0; fc0 < nfar; fc0 += TC) {
+#pragma unroll
+            for (int it = 0; it < NBO * TC / FT; ++it) {
+              const int idx = tid + it * FT;
+              const int k = idx & (NBO - 1), cc = idx / NBO;
+              const int f = fc0 + cc;
+              double v = 0.0;
+              if (k < nbo && f < nfar) {
+                double* ptr = W + (size_t)(f < k0 ? f : f + nbo) * ld + k0 + k;
+                v = *ptr;
+                *ptr = 0.0;
+              }
+              Tt[cc * (NBO + 1) + k] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < NBO * TC / FT; ++it) {
+              const int idx = tid + it * FT;
+              const int cc = idx & (TC - 1), k = idx / TC;
+              Rg[(size_t)k * ldr + fc0 + cc] = Tt[cc * (NBO + 1) + k];
+            }
+            __syncthreads();
+          }
+        }
+        pc.mark(PH_FAR_SWAP);
+        // 4. W[:, far] += W[:, KO] * R : 256 x 64 tiles, 8 x 4 accumulators per thread
+        const int tx = tid & 31, ty = tid >> 5;
+        for (int rt0 = 0; rt0 < n; rt0 += TR) {
+          __syncthreads();                           // previous tile's readers are done with Ns
+          for (int idx = tid; idx < NBO * TR; idx += FT) {
+            const int k = idx / TR, r = idx - k * TR;
+            Ns[idx] = (k < nbo && rt0 + r < n) ? W[rt0 + r + (size_t)(k0 + k) * ld] : 0.0;
+          }
+          // thread (tx, ty) owns rows rt0 + 64*i2 + 2*tx + {0,1} (i2 < 4) and columns fc0 + 4*ty + j:
+          // a warp reads 512 contiguous bytes of Ns per 128-bit shared load (no bank conflicts) and
+          // of W per 128-bit global access; the R values of a warp are broadcasts
+          const int row = rt0 + 2 * tx;
+          pc.mark(PH_FAR_NS);
+          // R tiles are double-buffered: chunk c+1 is fetched with cp.async while chunk c is used
+          auto fetch_r = [&](double* dst, int fc) {
+#pragma unroll
+            for (int it = 0; it < NBO * TC / 2 / FT; ++it) {
+              const int idx = tid + it * FT;
+              const int k = idx / (TC / 2), c2 = idx - k * (TC / 2);
+              __pipeline_memcpy_async(dst + k * TC + 2 * c2, Rg + (size_t)k * ldr + fc + 2 * c2, 16);
+            }
+            __pipeline_commit();
+          };
+          fetch_r(Rsm, 0);
+          int buf = 0;
+          for (int fc0 = 0; fc0 < nfar; fc0 += TC, buf ^= 1) {
+            __pipeline_wait_prior(0);                // this thread's part of the current chunk landed
+            __syncthreads();                         // everyone's did; Ns written; old readers done
+            pc.mark(PH_FAR_RS);
+            if (fc0 + TC < nfar) fetch_r(Rsm + (buf ^ 1) * NBO * TC, fc0 + TC);
+            double acc[8][4];
+            double* cptr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int f = fc0 + ty * 4 + j;
+              cptr[j] = (f < nfar) ? W + (size_t)(f < k0 ? f : f + nbo) * ld + row : nullptr;
+#pragma unroll
+              for (int i2 = 0; i2 < 4; ++i2) {
+                const int r = row + 64 * i2;
+                if (cptr[j] && r + 1 < n) {
+                  const double2 v = *reinterpret_cast<const double2*>(cptr[j] + 64 * i2);
+                  acc[2 * i2][j] = v.x;
+                  acc[2 * i2 + 1][j] = v.y;
+                } else {
+                  acc[2 * i2][j] = (cptr[j] && r < n) ? cptr[j][64 * i2] : 0.0;
+                  acc[2 * i2 + 1][j] = 0.0;
+                }
+              }
+            }
+            const double2* __restrict__ ap = reinterpret_cast<const double2*>(Ns) + tx;
+            const double2* __restrict__ bp = reinterpret_cast<const double2*>(Rsm + buf * NBO * TC + ty * 4);
+#pragma unroll 4
+            for (int k = 0; k < NBO; ++k) {
+              double av[8], bv[4];
+#pragma unroll
+              for (int i2 = 0; i2 < 4; ++i2) {
+                const double2 t = ap[k * (TR / 2) + 32 * i2];
+                av[2 * i2] = t.x;
+                av[2 * i2 + 1] = t.y;
+              }
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const double2 t = bp[k * (TC / 2) + j];
+                bv[2 * j] = t.x;
+                bv[2 * j + 1] = t.y;
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (!cptr[j]) continue;
+#pragma unroll
+              for (int i2 = 0; i2 < 4; ++i2) {
+                const int r = row + 64 * i2;
+                if (r + 1 < n)
+                  *reinterpret_cast<double2*>(cptr[j] + 64 * i2) = make_double2(acc[2 * i2][j], acc[2 * i2 + 1][j]);
+                else if (r < n)
+                  cptr[j][64 * i2] = acc[2 * i2][j];
+              }
+            }
+            pc.mark(PH_FAR_MMA);
+          }
+        }
+        __syncthreads();
+        pc.mark(PH_FAR_MMA);
+      }
     }
 
     // ---- undo the pivoting (column swaps in reverse) and write the tiled apply layout --------
-    int* src = sd;               // the panel region is free again
+    int* src = sd;               // the front region is free again
     if (tid == 0) {
       for (int c = 0; c < n; ++c) src[c] = c;
       for (int k = n - 1; k >= 0; --k) {
@@ -272,22 +485,24 @@ __global__ void __launch_bounds__(FT, 1) patch_factor_kernel(FactorArgs a) {
       }
     }
     __syncthreads();
+    pc.mark(PH_PACK);
+    pc.flush(a.timing);
   }
 }
 
 size_t factor_smem_bytes(int maxn, int NB) {
-  const size_t ldp = (maxn + 1) & ~1;
-  size_t doubles = ldp * NB + CC * NB + NB + 34;
-  size_t ints = 34 + maxn + 2;
-  size_t panel_bytes = ldp * NB * sizeof(double);
+  size_t doubles = front_doubles(maxn, NB) + NB + 34;
+  size_t ints = 34 + 2 * NBO + 2 + maxn + 2;
   size_t bytes = doubles * sizeof(double) + ints * sizeof(int);
-  // lookup tables alias the panel: need 2*maxn ints inside it
-  if (panel_bytes < 2 * (size_t)maxn * sizeof(int)) bytes += 2 * (size_t)maxn * sizeof(int) - panel_bytes;
+  // lookup tables alias the front region: 2*maxn ints must fit in it
+  const size_t front_bytes = front_doubles(maxn, NB) * sizeof(double);
+  if (front_bytes < 2 * (size_t)maxn * sizeof(int)) bytes += 2 * (size_t)maxn * sizeof(int) - front_bytes;
   return bytes + 16;
 }
 
 template <int NB>
 void run_factor(alfib_ctx* c, FactorArgs a, size_t smem, int grid) {
+  static_assert(NBO % NB == 0, "inner panel must divide the outer block");
   CUDA_TRY(cudaFuncSetAttribute(patch_factor_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   patch_factor_kernel<NB><<<grid, FT, smem, c->stream>>>(a);
   c->launches++;
@@ -299,17 +514,15 @@ void run_factor(alfib_ctx* c, FactorArgs a, size_t smem, int grid) {
 void launch_patch_factor(alfib_ctx* c, const Level& L, PatchSet& ps, const double* vals) {
   if (ps.npatch == 0 || ps.maxn == 0) { ps.factored = true; return; }
   const int maxn = ps.maxn;
-  const size_t budget = 200 * 1024;
-  int NB = 32;
+  const size_t budget = 220 * 1024;
+  int NB = 16;
   while (NB > 4 && factor_smem_bytes(maxn, NB) > budget) NB >>= 1;
   if (factor_smem_bytes(maxn, NB) > budget)
     throw DeviceError{ALFIB_EINVAL, "patch too large for the shared-memory panel (n = " + std::to_string(maxn) + ")"};
   const size_t smem = factor_smem_bytes(maxn, NB);
   const int ldmax = roundup2(maxn);
-  const int64_t slot = (int64_t)maxn * ldmax + (int64_t)maxn * NB;
-  // resident CTAs: one per SM for large panels, more when shared memory allows
-  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / smem));
-  int grid = std::min(ps.npatch, c->num_sms * per_sm);
+  const int64_t slot = (int64_t)maxn * ldmax + (int64_t)NBO * ((maxn + TC - 1) & ~(TC - 1));
+  const int grid = std::min(ps.npatch, c->num_sms);          // >= 160 KB of shared memory: one CTA per SM
   c->fwork.alloc((size_t)grid * slot);
   c->finfo.alloc(2);
   CUDA_TRY(cudaMemsetAsync(c->finfo.p, 0, 2 * sizeof(int), c->stream));
@@ -332,8 +545,15 @@ void launch_patch_factor(alfib_ctx* c, const Level& L, PatchSet& ps, const doubl
   a.maxn = maxn;
   a.counter = c->finfo.p + 1;
   a.info = c->finfo.p;
+  a.timing = nullptr;
+  static const bool want_timing = getenv("ALFIB_FACTOR_TIMING") != nullptr;
+  DBuf<long long> tbuf;
+  if (want_timing) {
+    tbuf.alloc(PH_COUNT);
+    CUDA_TRY(cudaMemsetAsync(tbuf.p, 0, PH_COUNT * sizeof(long long), c->stream));
+    a.timing = tbuf.p;
+  }
   switch (NB) {
-    case 32: run_factor<32>(c, a, smem, grid); break;
     case 16: run_factor<16>(c, a, smem, grid); break;
     case 8: run_factor<8>(c, a, smem, grid); break;
     default: run_factor<4>(c, a, smem, grid); break;
@@ -341,6 +561,18 @@ void launch_patch_factor(alfib_ctx* c, const Level& L, PatchSet& ps, const doubl
   int info[2] = {0, 0};
   CUDA_TRY(cudaMemcpyAsync(info, c->finfo.p, sizeof(info), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (want_timing) {
+    long long t[PH_COUNT];
+    CUDA_TRY(cudaMemcpy(t, tbuf.p, sizeof(t), cudaMemcpyDeviceToHost));
+    static const char* names[PH_COUNT] = {"gather", "panel_load", "inner_gj", "inblock", "far_swap", "far_Ns",
+                                          "far_Rs", "far_mma", "pack"};
+    double tot = 0;
+    for (int i = 0; i < PH_COUNT; ++i) tot += (double)t[i];
+    fprintf(stderr, "[alfib factor timing] npatch=%d maxn=%d NB=%d grid=%d:", ps.npatch, maxn, NB, grid);
+    for (int i = 0; i < PH_COUNT; ++i) fprintf(stderr, " %s %.1f%%", names[i], 100.0 * t[i] / tot);
+    fprintf(stderr, "  (sum %.1f Mcycles per CTA)\n", tot / grid / 1e6);
+    tbuf.release();
+  }
   if (info[0] != 0)
     throw DeviceError{ALFIB_ESINGULAR, "patch " + std::to_string(info[0] - 1) + " is singular"};
   ps.factored = true;
