@@ -105,7 +105,10 @@ struct alfib_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  int deterministic = 0, sync_always = 0, robust_restrict = 1, transfer_refine = 1;
+  int deterministic = 0, sync_always = 0, robust_restrict = 1, transfer_refine = 1, use_graph = 1;
+  void* graph_exec = nullptr;        // captured F-cycle (cudaGraphExec_t)
+  int cycles_run = 0;
+  int64_t graph_launches = 0;
   Level* levels[ALFIB_MAX_LEVELS] = {nullptr};
   int nlevels = 0, smoothing = 0;
   int num_sms = 148;
@@ -204,3 +207,4 @@ void restrict_device(alfib_ctx* c, Level& Lf, Level& Lc, int level, const double
 void coarse_factor_device(alfib_ctx* c);
 void coarse_solve_device(alfib_ctx* c, const double* b, double* x);
 void cycle_apply_device(alfib_ctx* c, const double* b, double* x);
+void cycle_graph_invalidate(alfib_ctx* c);

@@ -189,6 +189,7 @@ int alfib_destroy(alfib_ctx* c) {
   c->finfo.release();
   c->coarse_piv.release();
   c->coarse_info.release();
+  cycle_graph_invalidate(c);
   comm_destroy(c);
   if (c->cusolver) cusolverDnDestroy(c->cusolver);
   for (auto& r : c->ev_pool) {
@@ -204,11 +205,13 @@ const char* alfib_last_error(const alfib_ctx* c) { return c ? c->err.c_str() : "
 
 int alfib_set_option(alfib_ctx* c, int key, int value) {
   return guarded(c, [&] {
+    cycle_graph_invalidate(c);
     switch (key) {
       case ALFIB_OPT_DETERMINISTIC: c->deterministic = value != 0; break;
       case ALFIB_OPT_SYNC_ALWAYS: c->sync_always = value != 0; break;
       case ALFIB_OPT_ROBUST_RESTRICT: c->robust_restrict = value != 0; break;
       case ALFIB_OPT_TRANSFER_REFINE: c->transfer_refine = value != 0; break;
+      case ALFIB_OPT_CUDA_GRAPH: c->use_graph = value != 0; break;
       default: throw DeviceError{ALFIB_EINVAL, "unknown option"};
     }
   });
@@ -236,6 +239,7 @@ int alfib_comm_unique_id(void* out128) {
 
 int alfib_comm_init(alfib_ctx* c, const void* nccl_unique_id, int rank, int nranks) {
   return guarded(c, [&] {
+    cycle_graph_invalidate(c);
     comm_init(c, nccl_unique_id, rank, nranks);
     for (auto* L : c->levels)
       if (L) set_row_partition(c, *L);
@@ -245,6 +249,7 @@ int alfib_comm_init(alfib_ctx* c, const void* nccl_unique_id, int rank, int nran
 // ---- level operator ---------------------------------------------------------------------------
 int alfib_level_create(alfib_ctx* c, int level, int n_nodes, int bs) {
   return guarded(c, [&] {
+    cycle_graph_invalidate(c);
     ALFIB_REQUIRE(level >= 0 && level < ALFIB_MAX_LEVELS, "level out of range");
     ALFIB_REQUIRE(n_nodes > 0 && (bs == 2 || bs == 3), "n_nodes > 0 and bs in {2,3} required");
     ALFIB_REQUIRE(!c->levels[level], "level already exists");
@@ -259,6 +264,7 @@ int alfib_level_create(alfib_ctx* c, int level, int n_nodes, int bs) {
 
 int alfib_level_set_bsr_pattern(alfib_ctx* c, int level, int64_t nnzb, const int32_t* rowptr, const int32_t* colidx) {
   return guarded(c, [&] {
+    cycle_graph_invalidate(c);
     Level& L = get_level(c, level);
     ALFIB_REQUIRE(rowptr && colidx && nnzb > 0, "bad pattern");
     ALFIB_REQUIRE(rowptr[0] == 0 && rowptr[L.n_nodes] == nnzb, "rowptr does not match nnzb");
@@ -284,6 +290,7 @@ int alfib_level_set_bsr_values(alfib_ctx* c, int level, const double* vals, int 
 
 int alfib_level_set_bc(alfib_ctx* c, int level, int32_t nbc, const int32_t* bc_dofs) {
   return guarded(c, [&] {
+    cycle_graph_invalidate(c);
     Level& L = get_level(c, level);
     ALFIB_REQUIRE(nbc >= 0 && (nbc == 0 || bc_dofs), "bad bc list");
     for (int i = 0; i < nbc; ++i) ALFIB_REQUIRE(bc_dofs[i] >= 0 && bc_dofs[i] < L.n, "bc dof out of range");
@@ -322,6 +329,7 @@ int alfib_residual(alfib_ctx* c, int level, const double* b, const double* x, do
 int alfib_level_set_patches(alfib_ctx* c, int level, int which, int32_t npatch, const int64_t* offsets,
                             const int32_t* dofs, int32_t norder, const int32_t* order, const int32_t* colours) {
   return guarded(c, [&] {
+    cycle_graph_invalidate(c);
     Level& L = get_level(c, level);
     ALFIB_REQUIRE(which == 0 || which == 1, "which must be 0 or 1");
     ALFIB_REQUIRE(npatch >= 0 && offsets && offsets[0] == 0, "bad offsets");
@@ -415,6 +423,7 @@ int64_t alfib_patch_storage_bytes(alfib_ctx* c, int level, int which) {
 
 int alfib_patch_bind_storage(alfib_ctx* c, int level, int which, void* dev_ptr, int64_t bytes) {
   return guarded(c, [&] {
+    cycle_graph_invalidate(c);
     Level& L = get_level(c, level);
     ALFIB_REQUIRE(which == 0 || which == 1, "which must be 0 or 1");
     PatchSet& ps = L.ps[which];
@@ -484,6 +493,7 @@ int alfib_transfer_set(alfib_ctx* c, int level, int32_t n_fine_nodes, int32_t n_
                        const int32_t* P_rowptr, const int32_t* P_colidx, const double* P_vals, int32_t ncb,
                        const int32_t* cb_dofs) {
   return guarded(c, [&] {
+    cycle_graph_invalidate(c);
     Level& L = get_level(c, level);
     ALFIB_REQUIRE(level >= 1, "transfers live on levels >= 1");
     Level& Lc = get_level(c, level - 1);
@@ -569,6 +579,7 @@ int alfib_restrict(alfib_ctx* c, int level, const double* fine, double* coarse) 
 // ---- smoother / cycle -------------------------------------------------------------------------
 int alfib_smooth(alfib_ctx* c, int level, int m, const double* b, double* x) {
   return guarded(c, [&] {
+    cycle_graph_invalidate(c);             // may reallocate the Krylov bases
     Level& L = get_level(c, level);
     ALFIB_REQUIRE(L.has_values, "level has no values");
     const double* db = in_vec(c, b, L.n, c->stage_in);
@@ -595,6 +606,7 @@ int alfib_coarse_solve(alfib_ctx* c, const double* b, double* x) {
 
 int alfib_cycle_setup(alfib_ctx* c, int nlevels, int smoothing) {
   return guarded(c, [&] {
+    cycle_graph_invalidate(c);
     ALFIB_REQUIRE(nlevels >= 1 && nlevels <= ALFIB_MAX_LEVELS, "bad level count");
     ALFIB_REQUIRE(smoothing >= 1 && smoothing <= ALFIB_MAX_KRYLOV, "bad smoothing count");
     for (int l = 0; l < nlevels; ++l) {

@@ -246,11 +246,8 @@ static void vcycle(alfib_ctx* c, int l) {
 }
 
 // PCMG full: restrict b to every level, then for l = 0..L-2: V(l), x_{l+1} = P x_l ; V(L-1)
-void cycle_apply_device(alfib_ctx* c, const double* b, double* x) {
+static void cycle_body(alfib_ctx* c) {
   const int nl = c->nlevels;
-  ALFIB_REQUIRE(nl >= 1, "alfib_cycle_setup has not been called");
-  Level& Lt = *c->levels[nl - 1];
-  CUDA_TRY(cudaMemcpyAsync(Lt.b.p, b, sizeof(double) * Lt.n, cudaMemcpyDeviceToDevice, c->stream));
   for (int l = nl - 1; l > 0; --l) restrict_device(c, *c->levels[l], *c->levels[l - 1], l, c->levels[l]->b.p,
                                                    c->levels[l - 1]->b.p);
   CUDA_TRY(cudaMemsetAsync(c->levels[0]->x.p, 0, sizeof(double) * c->levels[0]->n, c->stream));
@@ -259,5 +256,56 @@ void cycle_apply_device(alfib_ctx* c, const double* b, double* x) {
     prolong_device(c, *c->levels[l + 1], l + 1, c->levels[l]->x.p, c->levels[l + 1]->x.p);
   }
   vcycle(c, nl - 1);
+}
+
+void cycle_graph_invalidate(alfib_ctx* c) {
+  if (c->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)c->graph_exec);
+  c->graph_exec = nullptr;
+  c->cycles_run = 0;
+}
+
+// The F-cycle is a fixed sequence of a few hundred launches without host synchronisation: after
+// one eager application (which performs all lazy allocations) it is captured into a CUDA graph
+// and replayed, which removes the launch overhead that dominates the small 2-D configurations.
+// Profiling (per-kernel events) and ALFIB_OPT_CUDA_GRAPH = 0 keep the eager path.
+void cycle_apply_device(alfib_ctx* c, const double* b, double* x) {
+  const int nl = c->nlevels;
+  ALFIB_REQUIRE(nl >= 1, "alfib_cycle_setup has not been called");
+  Level& Lt = *c->levels[nl - 1];
+  CUDA_TRY(cudaMemcpyAsync(Lt.b.p, b, sizeof(double) * Lt.n, cudaMemcpyDeviceToDevice, c->stream));
+  const bool want_graph = c->use_graph && !c->profile;
+  if (!want_graph) {
+    cycle_body(c);
+  } else if (c->graph_exec) {
+    CUDA_TRY(cudaGraphLaunch((cudaGraphExec_t)c->graph_exec, c->stream));
+    c->launches += c->graph_launches;
+  } else if (c->cycles_run == 0) {
+    cycle_body(c);                                   // eager warm-up: allocations happen here
+    c->cycles_run = 1;
+  } else {
+    const int64_t before = c->launches;
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    try {
+      cycle_body(c);
+    } catch (...) {
+      cudaStreamEndCapture(c->stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    CUDA_TRY(cudaStreamEndCapture(c->stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {                          // fall back to eager launches for good
+      cudaGetLastError();
+      c->use_graph = 0;
+      cycle_body(c);
+    } else {
+      c->graph_exec = exec;
+      c->graph_launches = c->launches - before;
+      CUDA_TRY(cudaGraphLaunch(exec, c->stream));
+    }
+  }
   CUDA_TRY(cudaMemcpyAsync(x, Lt.x.p, sizeof(double) * Lt.n, cudaMemcpyDeviceToDevice, c->stream));
 }

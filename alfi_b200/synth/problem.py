@@ -9,6 +9,7 @@ profile extension, evaluated on every level (the reference injects
 """
 from __future__ import annotations
 
+import sys
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -172,5 +173,6 @@ def build_problem(cfg: Config | str, nu: float | None = None, with_transfer: boo
         levels.append(ld)
         if verbose:
             print("[synth] level %d: %d dofs, %d patches, %.1fs" % (
-                lev.index, V.ndofs, 0 if ld.patches is None else ld.patches.npatch, time.time() - t0), flush=True)
+                lev.index, V.ndofs, 0 if ld.patches is None else ld.patches.npatch, time.time() - t0),
+                file=sys.stderr, flush=True)
     return Problem(cfg, levels, nu, cfg.gamma)

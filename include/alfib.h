@@ -50,9 +50,11 @@ enum {
   ALFIB_OPT_SYNC_ALWAYS = 2,   /* 1: synchronise the stream before every return                */
   ALFIB_OPT_ROBUST_RESTRICT = 3,/* 1: Schoeberl restriction (alfi --restriction, solver.py:595,
                                   646); 0: plain P_H^T (firedrake restrict)                    */
-  ALFIB_OPT_TRANSFER_REFINE = 4 /* 1 (default): one step of iterative refinement after the
+  ALFIB_OPT_TRANSFER_REFINE = 4,/* 1 (default): one step of iterative refinement after the
                                   explicit-inverse cell-patch solve of the transfer, which
                                   restores the accuracy of the reference's LU solve            */
+  ALFIB_OPT_CUDA_GRAPH = 5      /* 1 (default): alfib_cycle_apply replays a captured CUDA graph
+                                  from its third call on (profiling keeps the eager path)      */
 };
 
 /* ---- context ------------------------------------------------------------------------------ */
