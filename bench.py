@@ -119,6 +119,26 @@ def run_oracle(sample_name, steps, warmup):
                       "(C/OpenMP patch apply + SpMV, numpy BLAS-1; CPU restatement, not PETSc)" % (sample_name, prob.finest.ndofs, len(levels), dt)}, dt
 
 
+CONT_CONFIG = "ldc2d-sv-k2"                      # BASELINE.json configs[0]: Re 10 -> 1000 continuation
+CONT_RES = [10, 100] + list(range(200, 1001, 100))
+
+
+def run_continuation(backend, label):
+    """Full Newton continuation (alfi/driver.py:95-129) of BASELINE configs[0] around `backend` as the
+    fieldsplit_0 preconditioner; assembly and the outer FGMRES/Schur loop run on the host."""
+    from alfi_b200.synth.outer import ContinuationSolver
+    from alfi_b200.synth.problem import CONFIGS
+    cfg = CONFIGS[CONT_CONFIG]
+    solver = ContinuationSolver(cfg, backend)
+    t0 = time.perf_counter()
+    infos = [solver.solve(re) for re in CONT_RES]
+    dt = time.perf_counter() - t0
+    return {"config": CONT_CONFIG, "velocity_dofs": solver.nu_dofs, "pressure_dofs": solver.np_dofs, "re": CONT_RES,
+            "time_s": dt, "nonlinear_iter": [i["nonlinear_iter"] for i in infos],
+            "linear_iter": [i["linear_iter"] for i in infos], "final_residual": float(infos[-1]["residual"]),
+            "fieldsplit_0": label}, solver
+
+
 def reference_arm(args):
     """`--impl reference`: the reference's CPU path cannot be built here (PETSc/Firedrake absent),
     so the oracle port of the same algorithm is timed on the host cores (kind = "port")."""
@@ -266,11 +286,32 @@ def ours(args):
     breakdown = {k: {"ms_per_step": v[0] / args.steps, "calls_per_step": v[1] / args.steps} for k, v in prof_all.items()}
 
     cpu = None
+    continuation = None
     if not args.no_cpu_baseline:
         try:
             cpu, _ = run_oracle(CPU_SAMPLE_CONFIG.get(args.config, args.config), 1, 1)
         except Exception as e:      # noqa: BLE001
             cpu = {"value": None, "unit": "DoF/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+    if not args.no_continuation and world == 1:
+        try:
+            from alfi_b200.multigrid import DeviceBackend
+            from alfi_b200.synth.problem import CONFIGS as _C
+            mg.ctx.close()
+            del mg
+            torch.cuda.empty_cache()
+            continuation, sdev = run_continuation(DeviceBackend(_C[CONT_CONFIG].m, device=local), "CUDA library (alfib_cycle_apply)")
+            if cpu is not None:
+                from oracle.backend import OracleBackend
+                cref, sref = run_continuation(OracleBackend(_C[CONT_CONFIG].m), "CPU oracle (numpy)")
+                cpu["continuation"] = cref
+                per_newton_ok = all(abs(a - b) <= max(n, 1) for a, b, n in
+                                    zip(cref["linear_iter"], continuation["linear_iter"], cref["nonlinear_iter"]))
+                continuation["iteration_parity"] = bool(per_newton_ok and
+                                                        cref["nonlinear_iter"] == continuation["nonlinear_iter"])
+                continuation["velocity_rel_diff_vs_cpu"] = float(np.linalg.norm(sdev.u - sref.u) / np.linalg.norm(sref.u))
+                continuation["pressure_rel_diff_vs_cpu"] = float(np.linalg.norm(sdev.p - sref.p) / np.linalg.norm(sref.p))
+        except Exception as e:      # noqa: BLE001
+            continuation = {"error": repr(e)}
 
     total = n            # N > 1: the same problem sharded over the ranks (strong scaling)
     line = {
@@ -289,7 +330,7 @@ def ours(args):
         "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "DoF/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "breakdown_ms": breakdown, "setup_s": {"device_upload_factor": setup_s},
+        "breakdown_ms": breakdown, "setup_s": {"device_upload_factor": setup_s}, "continuation": continuation,
         "residual_reduction": red,
     }
     print(json.dumps(line), flush=True)
@@ -314,6 +355,7 @@ def main():
     ap.add_argument("--config", default=DEFAULT_CONFIG)
     ap.add_argument("--deterministic", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-continuation", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
