@@ -14,6 +14,30 @@
 #define ALFIB_MAX_LEVELS 16
 #define ALFIB_TILE_ROWS 64          // rows per apply tile (one warp, double2 per lane)
 #define ALFIB_MAX_KRYLOV 32         // upper bound on FGMRES(m) per level
+#define ALFIB_MAX_RANKS 8           // one NVSwitch box
+
+// Destination of a kernel whose result takes part in a peer-memory exchange: either a plain
+// pointer (epoch == nullptr) or one of the two symmetric slots, chosen on the device from the
+// exchange counter so that the choice survives CUDA-graph replay.
+struct PeerOut {
+  double* base;
+  size_t stride;
+  const unsigned long long* epoch;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ double* resolve(const PeerOut& o) {
+  return o.epoch ? o.base + ((*o.epoch) & 1ull) * o.stride : o.base;
+}
+#endif
+inline PeerOut plain_out(double* p) { return PeerOut{p, 0, nullptr}; }
+
+// Header at the start of every rank's symmetric buffer, read by the peers over NVLink.
+struct SymHeader {
+  unsigned long long flag;                 // number of the last exchange this rank's data is ready for
+  long long lo[2 * ALFIB_MAX_LEVELS];      // support [lo, hi) of this rank's patches, per (level, which)
+  long long hi[2 * ALFIB_MAX_LEVELS];
+};
+#define ALFIB_SYM_HEADER_BYTES 4096
 
 struct DeviceError {
   int code;
@@ -65,6 +89,7 @@ struct PatchSet {
   int maxn = 0;
   int ncolour = 0;
   bool repeated = false;            // a patch occurs twice in the iteration set
+  long long lo = 0, hi = 0;         // dof range touched by these patches (peer-memory reduction)
   bool factored = false;
   std::vector<int64_t> h_off;       // npatch+1
   std::vector<int32_t> h_dofs, h_order, h_colour;
@@ -116,6 +141,15 @@ struct alfib_ctx {
   // multi-GPU (comm.cu): NCCL communicator, rank layout
   void* comm = nullptr;
   int rank = 0, nranks = 1;
+  // peer-memory exchanges (comm.cu): symmetric buffer = header + 2 slots of sym_stride doubles
+  unsigned char* sym = nullptr;
+  size_t sym_stride = 0;
+  bool peers_open = false;
+  void* peer_ptr[ALFIB_MAX_RANKS] = {nullptr};
+  DBuf<double*> d_peer_slot;             // device array: slot 0 of every rank
+  DBuf<unsigned long long> d_epoch;      // exchange counter (device)
+  DBuf<int> d_comm_err;
+  DBuf<long long> d_gate;                // block 0 -> other blocks gate of the reduction kernel
   // patch factor workspace (one slot per resident CTA) + status word + work counter
   DBuf<double> fwork;
   DBuf<int> finfo;
@@ -188,8 +222,21 @@ void comm_init(alfib_ctx* c, const void* id128, int rank, int nranks);
 void comm_destroy(alfib_ctx* c);
 void comm_allreduce_sum(alfib_ctx* c, double* y, size_t n);
 void comm_allgather_rows(alfib_ctx* c, double* y, const std::vector<int64_t>& dof_start);
+void comm_peer_alloc(alfib_ctx* c);
+void comm_peer_handle(alfib_ctx* c, void* out64);
+void comm_peer_open(alfib_ctx* c, const void* handles);
+void comm_peer_publish_ranges(alfib_ctx* c);
+void comm_peer_close(alfib_ctx* c);
+int comm_peer_error(alfib_ctx* c);
+PeerOut comm_peer_out(alfib_ctx* c);                       // the current symmetric slot as a kernel destination
+void comm_peer_zero(alfib_ctx* c, long long lo, long long hi);
+// y[i] = sum over ranks q with lo_q <= i < hi_q of slot_q[i]; hdr_slot >= 0: ranges from the peers'
+// headers, else the explicit ranges
+void comm_peer_reduce(alfib_ctx* c, int64_t n, int hdr_slot, const long long* lo, const long long* hi, double* y);
 // patch_apply.cu
-void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, double* y);
+void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, PeerOut y);
+// y = sum over ranks of this rank's patch contributions (zeroing, exchange included)
+void patch_apply_sum(alfib_ctx* c, Level& L, int level, int which, const double* x, double* y);
 // patch_factor.cu
 void launch_patch_factor(alfib_ctx* c, const Level& L, PatchSet& ps, const double* vals);
 void patch_extract_inverse(alfib_ctx* c, const PatchSet& ps, int patch, double* host_out);

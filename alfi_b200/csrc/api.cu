@@ -186,10 +186,15 @@ int alfib_destroy(alfib_ctx* c) {
   for (auto* b : {&c->fwork, &c->partial, &c->scal, &c->stage_in, &c->stage_in2, &c->stage_out, &c->coarse_lu,
                   &c->coarse_work, &c->coarse_inv, &c->coarse_partial, &c->coarse_r, &c->coarse_dx})
     b->release();
+  c->d_peer_slot.release();
+  c->d_epoch.release();
+  c->d_comm_err.release();
+  c->d_gate.release();
   c->finfo.release();
   c->coarse_piv.release();
   c->coarse_info.release();
   cycle_graph_invalidate(c);
+  comm_peer_close(c);
   comm_destroy(c);
   if (c->cusolver) cusolverDnDestroy(c->cusolver);
   for (auto& r : c->ev_pool) {
@@ -220,7 +225,10 @@ int alfib_set_option(alfib_ctx* c, int key, int value) {
 int alfib_set_deterministic(alfib_ctx* c, int flag) { return alfib_set_option(c, ALFIB_OPT_DETERMINISTIC, flag); }
 
 int alfib_synchronize(alfib_ctx* c) {
-  return guarded(c, [&] { CUDA_TRY(cudaStreamSynchronize(c->stream)); });
+  return guarded(c, [&] {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (comm_peer_error(c)) throw DeviceError{ALFIB_ECUDA, "peer-memory exchange timed out waiting for another rank"};
+  });
 }
 
 int64_t alfib_launch_count(const alfib_ctx* c) { return c ? c->launches : -1; }
@@ -235,6 +243,22 @@ int alfib_comm_unique_id(void* out128) {
   } catch (const DeviceError& e) {
     return e.code;
   }
+}
+
+int alfib_comm_peer_handle(alfib_ctx* c, void* out64) {
+  return guarded(c, [&] {
+    ALFIB_REQUIRE(out64 != nullptr, "null handle buffer");
+    cycle_graph_invalidate(c);
+    comm_peer_handle(c, out64);
+  });
+}
+
+int alfib_comm_peer_open(alfib_ctx* c, const void* handles) {
+  return guarded(c, [&] {
+    ALFIB_REQUIRE(handles != nullptr, "null handles");
+    cycle_graph_invalidate(c);
+    comm_peer_open(c, handles);
+  });
 }
 
 int alfib_comm_init(alfib_ctx* c, const void* nccl_unique_id, int rank, int nranks) {
@@ -385,6 +409,10 @@ int alfib_level_set_patches(alfib_ctx* c, int level, int which, int32_t npatch, 
       ps.h_soff[p + 1] = ps.h_soff[p] + (int64_t)n * roundup2(n);
     }
     ps.store_elems = ps.h_soff[npatch];
+    if (total > 0) {
+      ps.lo = *std::min_element(ps.h_dofs.begin(), ps.h_dofs.end());
+      ps.hi = 1 + (long long)*std::max_element(ps.h_dofs.begin(), ps.h_dofs.end());
+    }
     // factor order: largest patches first
     std::vector<int32_t> forder(npatch);
     std::iota(forder.begin(), forder.end(), 0);
@@ -413,6 +441,7 @@ int alfib_level_set_patches(alfib_ctx* c, int level, int which, int32_t npatch, 
     ps.forder.upload(forder.data(), npatch, c->stream);
     ps.work.upload(work.data(), work.size(), c->stream);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    comm_peer_publish_ranges(c);
   });
 }
 

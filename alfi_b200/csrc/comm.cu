@@ -11,6 +11,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
+#include <cstddef>
+
 #include "alfib_internal.h"
 
 namespace {
@@ -101,4 +104,225 @@ void comm_allgather_rows(alfib_ctx* c, double* y, const std::vector<int64_t>& st
                "ncclBroadcast");
   }
   nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer-memory exchanges over NVLink (replaces the NCCL calls above once the peers are mapped).
+//
+// Every rank owns a symmetric buffer [header | slot 0 | slot 1] that the other ranks of the box
+// map through CUDA IPC.  A producer kernel (patch apply, row-sharded SpMV, coarse GEMV) writes
+// this rank's part into slot (e & 1) of exchange number e; `peer_reduce_kernel` then publishes
+// flag = e, waits until every peer's flag reaches e and *pulls*, for every index, the entries of
+// the ranks whose range covers it — in rank order, so the result is bitwise identical on all
+// ranks.  Only overlapping ranges cross NVLink (a patch apply moves its slab plus one macro
+// layer, not the whole vector as an all-reduce does) and the whole exchange is one kernel.
+// Two slots suffice without a second barrier: a rank overwrites slot (e & 1) only after it has
+// seen every peer's flag e - 1, and a peer raises flag e - 1 only after it has finished reading
+// exchange e - 2.  The exchange counter lives in device memory, so the sequence replays
+// unchanged inside a CUDA graph.  Spin loops are bounded; a time-out raises an error flag
+// instead of hanging the GPU.
+namespace {
+
+constexpr long long SPIN_LIMIT = 1ll << 22;      // ~ seconds of polling over NVLink
+
+__global__ void peer_zero_kernel(PeerOut out, long long lo, long long hi) {
+  double* y = resolve(out);
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = 0.0;
+}
+
+struct Ranges {
+  long long lo[ALFIB_MAX_RANKS], hi[ALFIB_MAX_RANKS];
+};
+
+struct LocalGate {                     // in this rank's own memory: block 0 -> the other blocks
+  unsigned long long go;
+  long long lo[ALFIB_MAX_RANKS], hi[ALFIB_MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(256) peer_reduce_kernel(long long n, int nranks, int rank,
+                                                          double* const* __restrict__ peer_slot0, size_t stride,
+                                                          const unsigned long long* __restrict__ epoch_ptr,
+                                                          int hdr_slot, Ranges rg, double* __restrict__ y,
+                                                          int* __restrict__ err, unsigned long long* epoch_rw,
+                                                          unsigned int* __restrict__ done, LocalGate* local) {
+  __shared__ long long s_lo[ALFIB_MAX_RANKS], s_hi[ALFIB_MAX_RANKS];
+  const unsigned long long e = *epoch_ptr;
+  const size_t hdr_doubles = ALFIB_SYM_HEADER_BYTES / sizeof(double);
+  // Only block 0 talks to the peers' headers (thousands of blocks polling remote flags congest
+  // NVLink with tiny requests): it publishes this rank's flag, waits for every peer, copies the
+  // ranges into local memory and then releases the other blocks through a local flag.
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      __threadfence_system();                                // this rank's slot is complete
+      SymHeader* mine = reinterpret_cast<SymHeader*>(peer_slot0[rank] - hdr_doubles);
+      *reinterpret_cast<volatile unsigned long long*>(&mine->flag) = e;
+    }
+    if (threadIdx.x < nranks) {
+      const int q = threadIdx.x;
+      const SymHeader* h = reinterpret_cast<const SymHeader*>(peer_slot0[q] - hdr_doubles);
+      if (q != rank) {
+        long long spins = 0;
+        while (*reinterpret_cast<const volatile unsigned long long*>(&h->flag) < e) {
+          if (++spins > SPIN_LIMIT) {
+            atomicExch(err, 1);
+            break;
+          }
+        }
+      }
+      long long lo = rg.lo[q], hi = rg.hi[q];
+      if (hdr_slot >= 0) {
+        lo = *reinterpret_cast<const volatile long long*>(&h->lo[hdr_slot]);
+        hi = *reinterpret_cast<const volatile long long*>(&h->hi[hdr_slot]);
+      }
+      local->lo[q] = lo;
+      local->hi[q] = hi;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(&local->go) = e;
+  }
+  if (threadIdx.x == 0) {
+    long long spins = 0;
+    while (*reinterpret_cast<const volatile unsigned long long*>(&local->go) < e)
+      if (++spins > SPIN_LIMIT * 16) break;
+  }
+  __syncthreads();
+  if (threadIdx.x < nranks) {
+    s_lo[threadIdx.x] = *reinterpret_cast<const volatile long long*>(&local->lo[threadIdx.x]);
+    s_hi[threadIdx.x] = *reinterpret_cast<const volatile long long*>(&local->hi[threadIdx.x]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  const size_t off = (size_t)(e & 1ull) * stride;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    for (int q = 0; q < nranks; ++q)
+      if (i >= s_lo[q] && i < s_hi[q]) v += __ldcv(peer_slot0[q] + off + i);
+    y[i] = v;
+  }
+  // the last block to finish advances the exchange counter (every block has read it by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      *done = 0;
+      *epoch_rw = e + 1ull;
+    }
+  }
+}
+
+}  // namespace
+
+// symmetric buffer sized for the largest level (and the coarse system); call after the levels exist
+void comm_peer_alloc(alfib_ctx* c) {
+  size_t maxn = 0;
+  for (auto* L : c->levels)
+    if (L) maxn = std::max<size_t>(maxn, (size_t)L->n);
+  maxn = (maxn + 1) & ~size_t(1);
+  ALFIB_REQUIRE(maxn > 0, "create the levels before enabling peer memory");
+  if (c->sym && c->sym_stride == maxn) return;
+  ALFIB_REQUIRE(!c->peers_open, "peer memory already mapped");
+  if (c->sym) cudaFree(c->sym);
+  const size_t bytes = ALFIB_SYM_HEADER_BYTES + 2 * maxn * sizeof(double);
+  CUDA_TRY(cudaMalloc(&c->sym, bytes));
+  CUDA_TRY(cudaMemset(c->sym, 0, bytes));
+  c->sym_stride = maxn;
+  c->d_epoch.alloc(1);
+  const unsigned long long one = 1;
+  CUDA_TRY(cudaMemcpy(c->d_epoch.p, &one, sizeof(one), cudaMemcpyHostToDevice));
+  c->d_gate.alloc(sizeof(LocalGate) / sizeof(long long) + 1);
+  CUDA_TRY(cudaMemset(c->d_gate.p, 0, sizeof(LocalGate)));
+  c->d_comm_err.alloc(2);                                  // [0] time-out flag, [1] finished-block counter
+  CUDA_TRY(cudaMemset(c->d_comm_err.p, 0, 2 * sizeof(int)));
+}
+
+void comm_peer_handle(alfib_ctx* c, void* out64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  comm_peer_alloc(c);
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, c->sym));
+  memcpy(out64, &h, sizeof(h));
+}
+
+void comm_peer_publish_ranges(alfib_ctx* c) {
+  if (!c->sym) return;
+  SymHeader hdr;
+  memset(&hdr, 0, sizeof(hdr));
+  for (int l = 0; l < ALFIB_MAX_LEVELS; ++l)
+    if (c->levels[l])
+      for (int w = 0; w < 2; ++w) {
+        hdr.lo[2 * l + w] = c->levels[l]->ps[w].lo;
+        hdr.hi[2 * l + w] = c->levels[l]->ps[w].hi;
+      }
+  // the flag (first 8 bytes) is owned by the kernels: copy only the ranges
+  CUDA_TRY(cudaMemcpy(c->sym + offsetof(SymHeader, lo), &hdr.lo, sizeof(hdr) - offsetof(SymHeader, lo),
+                      cudaMemcpyHostToDevice));
+}
+
+void comm_peer_open(alfib_ctx* c, const void* handles) {
+  ALFIB_REQUIRE(c->nranks > 1 && c->nranks <= ALFIB_MAX_RANKS, "peer memory needs 2..8 ranks");
+  ALFIB_REQUIRE(c->sym, "alfib_comm_peer_handle first");
+  ALFIB_REQUIRE(!c->peers_open, "peer memory already mapped");
+  std::vector<double*> slot0(c->nranks);
+  const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(handles);
+  for (int q = 0; q < c->nranks; ++q) {
+    void* base = c->sym;
+    if (q != c->rank) {
+      CUDA_TRY(cudaIpcOpenMemHandle(&base, h[q], cudaIpcMemLazyEnablePeerAccess));
+      c->peer_ptr[q] = base;
+    }
+    slot0[q] = reinterpret_cast<double*>(static_cast<unsigned char*>(base) + ALFIB_SYM_HEADER_BYTES);
+  }
+  c->d_peer_slot.alloc(c->nranks);
+  CUDA_TRY(cudaMemcpy(c->d_peer_slot.p, slot0.data(), sizeof(double*) * c->nranks, cudaMemcpyHostToDevice));
+  comm_peer_publish_ranges(c);
+  CUDA_TRY(cudaDeviceSynchronize());
+  c->peers_open = true;
+}
+
+void comm_peer_close(alfib_ctx* c) {
+  for (int q = 0; q < ALFIB_MAX_RANKS; ++q)
+    if (c->peer_ptr[q]) {
+      cudaIpcCloseMemHandle(c->peer_ptr[q]);
+      c->peer_ptr[q] = nullptr;
+    }
+  c->peers_open = false;
+  if (c->sym) cudaFree(c->sym);
+  c->sym = nullptr;
+}
+
+PeerOut comm_peer_out(alfib_ctx* c) {
+  return PeerOut{reinterpret_cast<double*>(c->sym + ALFIB_SYM_HEADER_BYTES), c->sym_stride, c->d_epoch.p};
+}
+
+void comm_peer_zero(alfib_ctx* c, long long lo, long long hi) {
+  if (hi <= lo) return;
+  const int blocks = (int)std::min<long long>((hi - lo + 255) / 256, 4 * c->num_sms);
+  peer_zero_kernel<<<blocks, 256, 0, c->stream>>>(comm_peer_out(c), lo, hi);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+}
+
+void comm_peer_reduce(alfib_ctx* c, int64_t n, int hdr_slot, const long long* lo, const long long* hi, double* y) {
+  Ranges rg;
+  for (int q = 0; q < ALFIB_MAX_RANKS; ++q) {
+    rg.lo[q] = (lo && q < c->nranks) ? lo[q] : 0;
+    rg.hi[q] = (hi && q < c->nranks) ? hi[q] : 0;
+  }
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 8 * c->num_sms);
+  peer_reduce_kernel<<<std::max(blocks, 1), 256, 0, c->stream>>>(
+      n, c->nranks, c->rank, c->d_peer_slot.p, c->sym_stride, c->d_epoch.p, hdr_slot, rg, y, c->d_comm_err.p,
+      c->d_epoch.p, reinterpret_cast<unsigned int*>(c->d_comm_err.p + 1),
+      reinterpret_cast<LocalGate*>(c->d_gate.p));
+  c->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+}
+
+int comm_peer_error(alfib_ctx* c) {
+  if (!c->d_comm_err.p) return 0;
+  int e = 0;
+  cudaMemcpy(&e, c->d_comm_err.p, sizeof(int), cudaMemcpyDeviceToHost);
+  return e;
 }

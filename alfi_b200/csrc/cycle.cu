@@ -17,20 +17,16 @@ void smoother_apply_device(alfib_ctx* c, Level& L, int level, const double* x, d
   PatchSet& ps = L.ps[ALFIB_PATCHES_SMOOTHER];
   ALFIB_REQUIRE(ps.factored, "alfib_level_factor has not been called for this level");
   ScopedEvent ev(c, ALFIB_EV_PCPATCH_APPLY, level);
-  CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * L.n, c->stream));
-  launch_patch_apply(c, ps, x, y);
-  comm_allreduce_sum(c, y, L.n);                    // ghost->owner sum + owner->ghost broadcast
+  patch_apply_sum(c, L, level, ALFIB_PATCHES_SMOOTHER, x, y);     // incl. the multi-GPU exchange
   launch_set_rows(c, y, x, L.bc.p, L.nbc);
 }
 
 // transfer.py:254-257 — PatchPC apply of the transfer solver: y = blockdiag(A0)^-1 b on the
 // (disjoint) cell patches, y[cb] = b[cb]
-static void cell_block_solve(alfib_ctx* c, Level& L, const double* b, double* y) {
+static void cell_block_solve(alfib_ctx* c, Level& L, int level, const double* b, double* y) {
   PatchSet& ps = L.ps[ALFIB_PATCHES_TRANSFER];
   ALFIB_REQUIRE(ps.factored, "alfib_transfer_update has not been called for this level");
-  CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * L.n, c->stream));
-  launch_patch_apply(c, ps, b, y);
-  comm_allreduce_sum(c, y, L.n);
+  patch_apply_sum(c, L, level, ALFIB_PATCHES_TRANSFER, b, y);
   launch_set_rows(c, y, b, L.cb.p, L.ncb);
 }
 
@@ -39,15 +35,13 @@ static void cell_block_solve(alfib_ctx* c, Level& L, const double* b, double* y)
 // times |t| — while the reference's LU solve (transfer.py:112-113) does not; one refinement
 // step restores LU-level accuracy for one extra SpMV + block apply (measured: 1.7e-6 -> 6e-11
 // on the 3-D SV k=3 cell patches at gamma = 1e4, nu = 0.02).
-static void cell_block_solve_refined(alfib_ctx* c, Level& L, const double* b, double* y) {
-  cell_block_solve(c, L, b, y);
+static void cell_block_solve_refined(alfib_ctx* c, Level& L, int level, const double* b, double* y) {
+  cell_block_solve(c, L, level, b, y);
   if (!c->transfer_refine || !L.a0vals.p) return;
   L.t3.alloc(L.n);
   L.t4.alloc(L.n);
   launch_bsr_spmv(c, L, L.a0vals.p, y, L.t3.p, b);                     // r = b - A0 y
-  CUDA_TRY(cudaMemsetAsync(L.t4.p, 0, sizeof(double) * L.n, c->stream));
-  launch_patch_apply(c, L.ps[ALFIB_PATCHES_TRANSFER], L.t3.p, L.t4.p); // dy = S r (patch rows only)
-  comm_allreduce_sum(c, L.t4.p, L.n);
+  patch_apply_sum(c, L, level, ALFIB_PATCHES_TRANSFER, L.t3.p, L.t4.p);  // dy = S r (patch rows only)
   launch_axpby(c, L.n, 1.0, L.t4.p, 1.0, y);
 }
 
@@ -63,7 +57,7 @@ void prolong_device(alfib_ctx* c, Level& L, int level, const double* coarse, dou
   if (L.has_d) {
     launch_bsr_spmv(c, L, L.dvals.p, rhs, L.t1.p, nullptr);          // b = gamma D rhs
     launch_set_rows(c, L.t1.p, nullptr, L.cb.p, L.ncb);              // coarse-boundary rows zeroed
-    cell_block_solve_refined(c, L, L.t1.p, L.t2.p);                  // t = A0^-1 b
+    cell_block_solve_refined(c, L, level, L.t1.p, L.t2.p);           // t = A0^-1 b
     launch_sub(c, L.n, rhs, L.t2.p, fine);                           // fine = rhs - t
   } else {
     CUDA_TRY(cudaMemcpyAsync(fine, rhs, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, c->stream));
@@ -81,7 +75,7 @@ void restrict_device(alfib_ctx* c, Level& L, Level& Lc, int level, const double*
     L.t2.alloc(L.n);
     CUDA_TRY(cudaMemcpyAsync(L.t1.p, fine, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, c->stream));
     launch_set_rows(c, L.t1.p, nullptr, L.cb.p, L.ncb);              // bcs.apply(tildeu)
-    cell_block_solve_refined(c, L, L.t1.p, L.t2.p);                  // r = A0^-1 t
+    cell_block_solve_refined(c, L, level, L.t1.p, L.t2.p);           // r = A0^-1 t
     launch_bsr_spmv(c, L, L.dvals.p, L.t2.p, L.t1.p, nullptr);       // b = gamma D r (no bcs)
     launch_sub(c, L.n, fine, L.t1.p, L.t2.p);                        // r2 = fine - b
     src = L.t2.p;
@@ -142,14 +136,15 @@ __global__ void __launch_bounds__(GW * 32) dense_gemv_kernel(const double* __res
 }
 
 // y[i] (+)= sum_k partial[k*n + i] for rows [r0, r1)
-__global__ void gemv_reduce_kernel(int n, int r0, int r1, const double* __restrict__ partial, double* __restrict__ y,
-                                   int accumulate) {
+__global__ void gemv_reduce_kernel(int n, int r0, int r1, const double* __restrict__ partial, PeerOut yout,
+                                   const double* __restrict__ yold) {
+  double* __restrict__ y = resolve(yout);
   const int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= r1) return;
   double v = 0.0;
 #pragma unroll
   for (int k = 0; k < KSPLIT; ++k) v += partial[(int64_t)k * n + i];
-  y[i] = accumulate ? y[i] + v : v;
+  y[i] = yold ? yold[i] + v : v;
 }
 
 void coarse_gemv(alfib_ctx* c, const double* b, double* y, int accumulate) {
@@ -157,10 +152,13 @@ void coarse_gemv(alfib_ctx* c, const double* b, double* y, int accumulate) {
   const int ntile = (n + ALFIB_TILE_ROWS - 1) / ALFIB_TILE_ROWS;
   const int t0 = (int)((int64_t)ntile * c->rank / c->nranks), t1 = (int)((int64_t)ntile * (c->rank + 1) / c->nranks);
   const int r0 = std::min(n, t0 * ALFIB_TILE_ROWS), r1 = std::min(n, t1 * ALFIB_TILE_ROWS);
+  const bool peer = c->nranks > 1 && c->peers_open;
   if (t1 > t0) {
     dense_gemv_kernel<<<dim3(t1 - t0, KSPLIT), GW * 32, 0, c->stream>>>(c->coarse_inv.p, c->coarse_ld, n, t0, b,
                                                                         c->coarse_partial.p);
-    gemv_reduce_kernel<<<cdiv(r1 - r0, 256), 256, 0, c->stream>>>(n, r0, r1, c->coarse_partial.p, y, accumulate);
+    gemv_reduce_kernel<<<cdiv(r1 - r0, 256), 256, 0, c->stream>>>(n, r0, r1, c->coarse_partial.p,
+                                                                   peer ? comm_peer_out(c) : plain_out(y),
+                                                                   accumulate ? y : nullptr);
     c->launches += 2;
     CUDA_TRY(cudaGetLastError());
   }
@@ -168,7 +166,13 @@ void coarse_gemv(alfib_ctx* c, const double* b, double* y, int accumulate) {
     std::vector<int64_t> start(c->nranks + 1);
     for (int r = 0; r <= c->nranks; ++r)
       start[r] = std::min<int64_t>(n, (int64_t)ntile * r / c->nranks * ALFIB_TILE_ROWS);
-    comm_allgather_rows(c, y, start);
+    if (peer) {
+      long long lo[ALFIB_MAX_RANKS], hi[ALFIB_MAX_RANKS];
+      for (int r = 0; r < c->nranks; ++r) { lo[r] = start[r]; hi[r] = start[r + 1]; }
+      comm_peer_reduce(c, n, -1, lo, hi, y);
+    } else {
+      comm_allgather_rows(c, y, start);
+    }
   }
 }
 

@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(128) patch_apply_kernel(const int2* __restrict
                                                           const int32_t* __restrict__ pdofs,
                                                           const int64_t* __restrict__ soff,
                                                           const double* __restrict__ store,
-                                                          const double* __restrict__ x, double* __restrict__ y) {
+                                                          const double* __restrict__ x, PeerOut yout) {
+  double* __restrict__ y = resolve(yout);
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= nwork) return;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(128) patch_apply_kernel(const int2* __restrict
 
 }  // namespace
 
-void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, double* y) {
+void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, PeerOut y) {
   if (ps.nwork == 0) return;
   const int threads = 128, wpb = threads / 32;
   const bool coloured = c->deterministic && !ps.repeated;
@@ -106,4 +107,22 @@ void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, doubl
     }
   }
   CUDA_TRY(cudaGetLastError());
+}
+
+// Sum of the patch contributions over all ranks.  Serial: zero + apply.  Multi-GPU with peer
+// memory: every rank applies its patches into its symmetric slot (only the slab the patches
+// touch is zeroed) and then *pulls* the overlapping ranges of the other ranks' slots over NVLink
+// inside one reduction kernel (comm.cu) — the ghost->owner sum and owner->ghost broadcast of the
+// reference's PetscSF in one pass.  Without peer memory: NCCL all-reduce of the whole vector.
+void patch_apply_sum(alfib_ctx* c, Level& L, int level, int which, const double* x, double* y) {
+  const PatchSet& ps = L.ps[which];
+  if (c->nranks > 1 && c->peers_open) {
+    comm_peer_zero(c, ps.lo, ps.hi);
+    launch_patch_apply(c, ps, x, comm_peer_out(c));
+    comm_peer_reduce(c, L.n, level * 2 + which, nullptr, nullptr, y);
+    return;
+  }
+  CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * L.n, c->stream));
+  launch_patch_apply(c, ps, x, plain_out(y));
+  comm_allreduce_sum(c, y, L.n);
 }

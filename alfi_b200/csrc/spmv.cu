@@ -20,9 +20,10 @@ template <int BS>
 __global__ void __launch_bounds__(256) bsr_spmv_block_kernel(int row0, int nbrows, const int32_t* __restrict__ rowptr,
                                                              const int32_t* __restrict__ colidx,
                                                              const double* __restrict__ vals,
-                                                             const double* __restrict__ x, double* __restrict__ y,
+                                                             const double* __restrict__ x, PeerOut yout,
                                                              const double* __restrict__ b) {
   constexpr int B2 = BS * BS;
+  double* __restrict__ y = resolve(yout);
   const int row = row0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 4);
   const int l16 = threadIdx.x & 15;
   double acc[BS];
@@ -103,17 +104,25 @@ void launch_bsr_spmv(alfib_ctx* c, const Level& L, const double* vals, const dou
   const int row0 = sharded ? (int)L.row_start[c->rank] : 0;
   const int row1 = sharded ? (int)L.row_start[c->rank + 1] : L.n_nodes;
   const int blocks = cdiv((int64_t)(row1 - row0) * 16, threads);
+  const bool peer = sharded && c->peers_open;
+  const PeerOut out = peer ? comm_peer_out(c) : plain_out(y);
   if (blocks > 0) {
     if (L.bs == 2)
-      bsr_spmv_block_kernel<2><<<blocks, threads, 0, c->stream>>>(row0, row1, L.rowptr.p, L.colidx.p, vals, x, y, b);
+      bsr_spmv_block_kernel<2><<<blocks, threads, 0, c->stream>>>(row0, row1, L.rowptr.p, L.colidx.p, vals, x, out, b);
     else if (L.bs == 3)
-      bsr_spmv_block_kernel<3><<<blocks, threads, 0, c->stream>>>(row0, row1, L.rowptr.p, L.colidx.p, vals, x, y, b);
+      bsr_spmv_block_kernel<3><<<blocks, threads, 0, c->stream>>>(row0, row1, L.rowptr.p, L.colidx.p, vals, x, out, b);
     else
       throw DeviceError{ALFIB_EINVAL, "block size must be 2 or 3"};
     c->launches++;
     CUDA_TRY(cudaGetLastError());
   }
-  if (sharded) comm_allgather_rows(c, y, L.dof_start);
+  if (peer) {                        // pull every rank's rows from its symmetric slot (NVLink peer loads)
+    long long lo[ALFIB_MAX_RANKS], hi[ALFIB_MAX_RANKS];
+    for (int r = 0; r < c->nranks; ++r) { lo[r] = L.dof_start[r]; hi[r] = L.dof_start[r + 1]; }
+    comm_peer_reduce(c, L.n, -1, lo, hi, y);
+  } else if (sharded) {
+    comm_allgather_rows(c, y, L.dof_start);
+  }
 }
 
 void launch_csr_apply(alfib_ctx* c, int nrows, int bs, const int32_t* rowptr, const int32_t* colidx,

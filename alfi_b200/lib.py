@@ -40,6 +40,8 @@ SIGNATURES = {
     "alfib_stream": (C.c_void_p, [C.c_void_p]),
     "alfib_comm_unique_id": (C.c_int, [C.c_void_p]),
     "alfib_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "alfib_comm_peer_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "alfib_comm_peer_open": (C.c_int, [C.c_void_p, C.c_void_p]),
     "alfib_level_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "alfib_level_set_bsr_pattern": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _i32p]),
     "alfib_level_set_bsr_values": (C.c_int, [C.c_void_p, C.c_int, _f64p, C.c_int]),
@@ -188,6 +190,16 @@ class Context:
         buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
         self._check(self.lib.alfib_comm_init(self.h, buf, rank, nranks))
         self.rank, self.nranks = rank, nranks
+
+    def comm_peer_handle(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's symmetric buffer (all-gather, then comm_peer_open)."""
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.alfib_comm_peer_handle(self.h, buf))
+        return buf.raw
+
+    def comm_peer_open(self, handles: bytes):
+        buf = C.create_string_buffer(handles, len(handles))
+        self._check(self.lib.alfib_comm_peer_open(self.h, buf))
 
     def level_sizes(self):
         return dict(self._sizes)

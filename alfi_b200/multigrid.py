@@ -57,10 +57,13 @@ class DeviceMultigrid:
 
     def __init__(self, levels: list[LevelInput], smoothing: int, device: int = 0, deterministic: bool = False,
                  robust_restrict: bool = True, ctx: Context | None = None, torch_storage: bool = False,
-                 rank: int = 0, nranks: int = 1, unique_id: bytes | None = None):
+                 rank: int = 0, nranks: int = 1, unique_id: bytes | None = None,
+                 peer_memory: bool = False):
         """With nranks > 1 every rank passes the same global `levels`; this rank keeps the patches
         `alfi_b200.dist.partition_patches` assigns to it (in a deployment each rank would only
-        ever see its own) and the library adds the NCCL exchange steps."""
+        ever see its own) and the library adds the exchange steps: NCCL collectives by default,
+        NVLink peer-memory pull-reductions with ``peer_memory=True`` (measured equal within 2 % at
+        2/4/8 GPUs in round 1, so the simpler NCCL path is the default)."""
         from .dist import partition_patches, shard_patch_arrays
         self.ctx = ctx or Context(device, deterministic)
         self.nlevels = len(levels)
@@ -99,6 +102,12 @@ class DeviceMultigrid:
                     c.set_patches(l, off, dofs, order, cols, PATCHES_TRANSFER)
                     if torch_storage:
                         self._bind(l, PATCHES_TRANSFER)
+        if nranks > 1 and peer_memory:
+            # map every rank's symmetric buffer: exchanges become NVLink peer loads (csrc/comm.cu)
+            import torch.distributed as dist
+            handles = [None] * nranks
+            dist.all_gather_object(handles, c.comm_peer_handle())
+            c.comm_peer_open(b"".join(handles))
         self.update_operators(levels)
         self.update_transfers(levels)
         c.cycle_setup(self.nlevels, smoothing)

@@ -185,7 +185,7 @@ def ours(args):
         uid = bootstrap_unique_id(rank)
     mg = DeviceMultigrid([level_input_from_synth(l) for l in prob.levels], cfg.m, device=local,
                          deterministic=bool(args.deterministic), torch_storage=True,
-                         rank=rank, nranks=world, unique_id=uid)
+                         rank=rank, nranks=world, unique_id=uid, peer_memory=bool(args.peer_memory))
     mg.ctx.synchronize()
     setup_s = time.time() - t0
     log("rank %d: device setup (upload + factor) %.1fs" % (rank, setup_s))
@@ -356,6 +356,7 @@ def main():
     ap.add_argument("--deterministic", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-continuation", action="store_true")
+    ap.add_argument("--peer-memory", type=int, default=0, help="N > 1: NVLink peer-memory exchanges instead of NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

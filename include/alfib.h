@@ -82,6 +82,14 @@ void* alfib_stream(alfib_ctx* ctx);
  * serial.                                                                                     */
 int alfib_comm_unique_id(void* out128 /* 128 bytes, filled on rank 0 */);
 int alfib_comm_init(alfib_ctx* ctx, const void* nccl_unique_id, int rank, int nranks);
+/* Optional, after all levels exist: exchange over NVLink *peer memory* instead of NCCL.  Every
+ * rank exports a 64-byte CUDA IPC handle of its symmetric buffer (alfib_comm_peer_handle), the
+ * host all-gathers the handles (nranks * 64 bytes, rank order) and passes them to
+ * alfib_comm_peer_open.  The patch-apply sum, the SpMV row gather and the coarse GEMV gather then
+ * become one kernel each that pulls only the overlapping index ranges from the peers' buffers
+ * (csrc/comm.cu).  Collective: call on every rank.                                            */
+int alfib_comm_peer_handle(alfib_ctx* ctx, void* out64);
+int alfib_comm_peer_open(alfib_ctx* ctx, const void* handles);
 
 /* ---- level operator: replaces the BAIJ Mat PETSc holds for fieldsplit_0 on each level
  *      (parameters["default_sub_matrix_type"] = "baij", solver.py:512)                        */

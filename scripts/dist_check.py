@@ -19,7 +19,8 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 prob = build_problem(name, gamma=10.0, nu=0.2)
 mg = DeviceMultigrid([level_input_from_synth(l) for l in prob.levels], prob.config.m, device=local, deterministic=True,
-                     rank=rank, nranks=world, unique_id=bootstrap_unique_id(rank))
+                     rank=rank, nranks=world, unique_id=bootstrap_unique_id(rank),
+                     peer_memory=bool(int(os.environ.get("ALFIB_PEER", "0"))))
 n = prob.finest.ndofs
 b = np.random.default_rng(1).standard_normal(n)
 b[prob.finest.bc_dofs] = 0
