@@ -1,0 +1,140 @@
+"""Parity at BASELINE.json's full size (cfg5: ldc3d SV k=3, 1 458 867 dofs, 4 913 patches, 48 GB of
+inverses) where the numpy oracle cannot invert every patch in test time: direct comparison where
+the oracle is cheap (SpMV, colouring, a sample of patches incl. the largest), and size-independent
+properties for the rest (linearity, adjointness of the transfers, reproducibility, contraction)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CONFIG = "ldc3d-sv-k3"
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def full():
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs a 180 GB B200")
+    from alfi_b200.multigrid import DeviceMultigrid, level_input_from_synth
+    from alfi_b200.synth.problem import build_problem
+    prob = build_problem(CONFIG)
+    mg = DeviceMultigrid([level_input_from_synth(l) for l in prob.levels], prob.config.m, deterministic=True)
+    return prob, mg
+
+
+def vec(prob, level, seed):
+    ld = prob.levels[level]
+    x = np.random.default_rng(20261017 + seed).standard_normal(ld.ndofs)
+    x[ld.bc_dofs] = 0.0
+    return x
+
+
+def test_sizes_are_the_baseline_ones(full):
+    prob, mg = full
+    fine = prob.finest
+    assert fine.ndofs == 1458867 and fine.patches.npatch == 4913
+    assert int(fine.patches.sizes.max()) == 1275 and int((fine.patches.sizes == 1275).sum()) == 3375
+    assert fine.cell_patches.npatch == 3072 and set(fine.cell_patches.sizes.tolist()) == {390}
+    assert abs((fine.patches.sizes.astype(float) ** 2).sum() * 8 - 48.04e9) < 0.01e9
+
+
+def test_spmv_against_scipy(full):
+    prob, mg = full
+    L = len(prob.levels) - 1
+    A = prob.finest.A.to_csr()
+    x, b = vec(prob, L, 1), vec(prob, L, 2)
+    assert rel(mg.ctx.spmv(L, x, np.empty_like(x)), A @ x) <= 1e-14
+    assert rel(mg.ctx.residual(L, b, x, np.empty_like(x)), b - A @ x) <= 1e-14
+
+
+def test_colouring_bit_exact(full):
+    prob, mg = full
+    for l, ld in enumerate(prob.levels):
+        if ld.patches is not None:
+            assert np.array_equal(mg.ctx.colours(l, ld.patches.npatch), ld.patches.colours)
+            assert ld.patches.colours.max() + 1 == 8
+
+
+def test_sample_of_patch_inverses(full):
+    """The largest interior patches and one of every boundary size: |X A - I| / (|X||A|) ~ eps."""
+    prob, mg = full
+    L = len(prob.levels) - 1
+    ps = prob.finest.patches
+    A = prob.finest.A.to_csr()
+    sample = [int(np.flatnonzero(ps.sizes == s)[k]) for s in np.unique(ps.sizes) for k in (0, -1)]
+    for p in sorted(set(sample)):
+        I = ps.patch(p)
+        Ap = A[I][:, I].toarray()
+        X = mg.ctx.patch_inverse(L, p, I.size)
+        err = np.linalg.norm(X @ Ap - np.eye(I.size)) / (np.linalg.norm(X) * np.linalg.norm(Ap))
+        assert err < 100 * np.finfo(float).eps, (p, I.size, err)
+
+
+def test_apply_on_a_sample_equals_oracle(full):
+    """PCApply_PATCH restricted to 12 patches of the full-size problem against numpy solves."""
+    from alfi_b200.lib import Context
+    prob, mg = full
+    fine = prob.finest
+    ps = fine.patches
+    A = fine.A
+    sample = np.concatenate([np.flatnonzero(ps.sizes == 1275)[[0, 1687, -1]], np.flatnonzero(ps.sizes < 1275)[::160]])
+    off = np.concatenate(([0], np.cumsum(ps.sizes[sample]))).astype(np.int64)
+    dofs = np.concatenate([ps.patch(p) for p in sample])
+    ctx = Context()
+    ctx.level_create(0, fine.V.nnodes, fine.V.bs)
+    ctx.set_bsr_pattern(0, A.rowptr, A.colidx)
+    ctx.set_bsr_values(0, A.vals)
+    ctx.set_bc(0, fine.bc_dofs)
+    ctx.set_patches(0, off, dofs, None, None)
+    ctx.factor(0)
+    x = vec(prob, len(prob.levels) - 1, 3)
+    y = ctx.smoother_apply(0, x, np.empty_like(x))
+    Acsr = A.to_csr()
+    want = np.zeros_like(x)
+    kappa = 1.0
+    for p in sample:
+        I = ps.patch(p)
+        Ap = Acsr[I][:, I].toarray()
+        want[I] += np.linalg.solve(Ap, x[I])
+        kappa = max(kappa, np.linalg.cond(Ap))
+    want[fine.bc_dofs] = x[fine.bc_dofs]
+    assert rel(y, want) <= 1e-11 * max(1.0, kappa * np.finfo(float).eps / 1e-12), (rel(y, want), kappa)
+    ctx.close()
+
+
+def test_linearity_and_reproducibility(full):
+    prob, mg = full
+    L = len(prob.levels) - 1
+    x, y = vec(prob, L, 4), vec(prob, L, 5)
+    a, b = 0.75, -1.5
+    S = lambda v: mg.ctx.smoother_apply(L, v, np.empty_like(v)).copy()      # noqa: E731
+    sx, sy, sxy = S(x), S(y), S(a * x + b * y)
+    assert rel(sxy, a * sx + b * sy) <= 1e-12
+    assert np.array_equal(S(x), sx)                       # deterministic mode: bitwise reproducible
+    C = lambda v: mg.apply(v, np.empty_like(v)).copy()                      # noqa: E731
+    cx = C(x)
+    assert np.array_equal(C(x), cx) and np.array_equal(C(x), cx)            # eager, captured, replayed
+    # FGMRES makes the cycle non-linear in b, but it is homogeneous of degree one
+    assert rel(C(3.0 * x), 3.0 * cx) <= 1e-7
+
+
+def test_transfers_are_adjoint_and_cycle_contracts(full):
+    prob, mg = full
+    L = len(prob.levels) - 1
+    c, f = vec(prob, L - 1, 6), vec(prob, L, 7)
+    Pc = mg.ctx.prolong(L, c, np.empty(prob.levels[L].ndofs))
+    Rf = mg.ctx.restrict(L, f, np.empty(prob.levels[L - 1].ndofs))
+    lhs, rhs = f @ Pc, Rf @ c
+    # exact for exact cell-patch solves; the 390-dof A0 blocks have kappa ~ gamma/nu ~ 1e8 at
+    # Re = 5000, so allow kappa*eps relative to the size of the two factors
+    scale = np.linalg.norm(f) * np.linalg.norm(Pc)
+    assert abs(lhs - rhs) <= 1e-7 * scale, (lhs, rhs, abs(lhs - rhs) / scale)
+    A = prob.finest.A.to_csr()
+    b = vec(prob, L, 8)
+    x = mg.apply(b, np.empty_like(b))
+    red = np.linalg.norm(b - A @ x) / np.linalg.norm(b)
+    assert red < 0.5, red
