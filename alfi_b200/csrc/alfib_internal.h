@@ -114,7 +114,7 @@ struct Level {
   bool has_values = false, has_transfer = false, has_d = false;
   PatchSet ps[2];
   // standard prolongation (scalar CSR, fine nodes x coarse nodes) and its transpose
-  int p_rows = 0, p_cols = 0;
+  int p_rows = 0, p_cols = 0, p_bs = 0;     // p_bs = bs: scalar CSR per node; 1: dof-level CSR
   DBuf<int32_t> p_rowptr, p_colidx, pt_rowptr, pt_colidx;
   DBuf<double> p_vals, pt_vals;
   // block rows [row_start[r], row_start[r+1]) of every BSR operator on this level belong to rank r

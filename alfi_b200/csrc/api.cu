@@ -520,13 +520,17 @@ int alfib_get_patch_inverse(alfib_ctx* c, int level, int which, int32_t patch, d
 // ---- transfer ---------------------------------------------------------------------------------
 int alfib_transfer_set(alfib_ctx* c, int level, int32_t n_fine_nodes, int32_t n_coarse_nodes,
                        const int32_t* P_rowptr, const int32_t* P_colidx, const double* P_vals, int32_t ncb,
-                       const int32_t* cb_dofs) {
+                       const int32_t* cb_dofs, int dof_level) {
   return guarded(c, [&] {
     cycle_graph_invalidate(c);
     Level& L = get_level(c, level);
     ALFIB_REQUIRE(level >= 1, "transfers live on levels >= 1");
     Level& Lc = get_level(c, level - 1);
-    ALFIB_REQUIRE(n_fine_nodes == L.n_nodes && n_coarse_nodes == Lc.n_nodes, "P shape does not match the levels");
+    if (dof_level)
+      ALFIB_REQUIRE(n_fine_nodes == L.n && n_coarse_nodes == Lc.n, "dof-level P shape does not match the levels");
+    else
+      ALFIB_REQUIRE(n_fine_nodes == L.n_nodes && n_coarse_nodes == Lc.n_nodes, "P shape does not match the levels");
+    L.p_bs = dof_level ? 1 : L.bs;
     ALFIB_REQUIRE(P_rowptr && P_colidx && P_vals && P_rowptr[0] == 0, "bad prolongation matrix");
     const int64_t nnz = P_rowptr[n_fine_nodes];
     for (int64_t k = 0; k < nnz; ++k) ALFIB_REQUIRE(P_colidx[k] >= 0 && P_colidx[k] < n_coarse_nodes, "P column out of range");

@@ -130,12 +130,14 @@ void launch_csr_apply(alfib_ctx* c, int nrows, int bs, const int32_t* rowptr, co
   const int threads = 256;
   const int blocks = cdiv(nrows, threads);
   if (blocks == 0) return;
-  if (bs == 2)
+  if (bs == 1)
+    csr_apply_kernel<1><<<blocks, threads, 0, c->stream>>>(nrows, rowptr, colidx, vals, x, y);
+  else if (bs == 2)
     csr_apply_kernel<2><<<blocks, threads, 0, c->stream>>>(nrows, rowptr, colidx, vals, x, y);
   else if (bs == 3)
     csr_apply_kernel<3><<<blocks, threads, 0, c->stream>>>(nrows, rowptr, colidx, vals, x, y);
   else
-    throw DeviceError{ALFIB_EINVAL, "block size must be 2 or 3"};
+    throw DeviceError{ALFIB_EINVAL, "block size must be 1, 2 or 3"};
   c->launches++;
   CUDA_TRY(cudaGetLastError());
 }

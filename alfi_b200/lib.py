@@ -57,7 +57,7 @@ SIGNATURES = {
     "alfib_get_colours": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i32p]),
     "alfib_get_patch_inverse": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int32, _f64p]),
     "alfib_transfer_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, C.c_int32, _i32p, _i32p, _f64p, C.c_int32,
-                                     _i32p]),
+                                     _i32p, C.c_int]),
     "alfib_transfer_update": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p, C.c_int]),
     "alfib_prolong": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
     "alfib_restrict": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
@@ -276,15 +276,16 @@ class Context:
         return out
 
     # -- transfer
-    def set_transfer(self, level, P, cb_dofs):
-        """P: scipy CSR (fine nodes x coarse nodes), scalar."""
+    def set_transfer(self, level, P, cb_dofs, dof_level=False):
+        """P: scipy CSR, scalar per node (fine nodes x coarse nodes) or, with dof_level, on scalar dofs."""
         P = P.tocsr()
         P.sort_indices()
         rp, ci = _i32(P.indptr), _i32(P.indices)
         pv = np.ascontiguousarray(P.data, dtype=np.float64)
         cb = _i32(cb_dofs)
         self._check(self.lib.alfib_transfer_set(self.h, level, P.shape[0], P.shape[1], _ptr(rp, C.c_int32),
-                                                _ptr(ci, C.c_int32), pv.ctypes.data, cb.size, _ptr(cb, C.c_int32)))
+                                                _ptr(ci, C.c_int32), pv.ctypes.data, cb.size, _ptr(cb, C.c_int32),
+                                                int(dof_level)))
 
     def transfer_update(self, level, a0_vals, d_vals, block_col_major=False):
         a0 = _Vec(a0_vals) if a0_vals is not None else None

@@ -29,7 +29,8 @@ class LevelInput:
     patch_dofs: np.ndarray | None = None
     patch_order: np.ndarray | None = None
     patch_colours: np.ndarray | None = None
-    P: object | None = None               # scipy CSR, scalar
+    P: object | None = None               # scipy CSR: scalar per node, or on dofs if P_dof_level
+    P_dof_level: bool = False
     cell_offsets: np.ndarray | None = None
     cell_dofs: np.ndarray | None = None
     cb_dofs: np.ndarray | None = None
@@ -45,6 +46,7 @@ def level_input_from_synth(ld) -> LevelInput:
         li.patch_offsets, li.patch_dofs, li.patch_order, li.patch_colours = ps.offsets, ps.dofs, ps.order, ps.colours
     if ld.P is not None:
         li.P = ld.P
+        li.P_dof_level = bool(getattr(ld, "P_dof_level", False))
         if ld.cell_patches is not None:
             li.cell_offsets, li.cell_dofs = ld.cell_patches.offsets, ld.cell_patches.dofs
             li.cb_dofs = ld.cb_dofs
@@ -90,7 +92,7 @@ class DeviceMultigrid:
                 if torch_storage:
                     self._bind(l, PATCHES_SMOOTHER)
                 cb = li.cb_dofs if li.cb_dofs is not None else np.empty(0, np.int32)
-                c.set_transfer(l, li.P, cb)
+                c.set_transfer(l, li.P, cb, li.P_dof_level)
                 if li.cell_offsets is not None:
                     off, dofs = li.cell_offsets, li.cell_dofs
                     cols = np.zeros(off.size - 1, np.int32)

@@ -25,7 +25,8 @@ from scipy.special import roots_jacobi
 
 from .mesh import LOCAL_EDGES, LOCAL_FACES, SimplexMesh
 
-__all__ = ["LagrangeElement", "VectorSpace", "assemble_velocity_block", "BSR", "reference_tensors"]
+__all__ = ["LagrangeElement", "P1FBElement", "make_element", "VectorSpace", "assemble_velocity_block", "BSR",
+           "reference_tensors"]
 
 
 # --------------------------------------------------------------------------- reference element
@@ -147,15 +148,75 @@ def _coeffs(dim, k):
     return np.linalg.inv(V)             # column i = monomial coefficients of basis function i
 
 
+@dataclass(frozen=True)
+class P1FBElement:
+    """P1 enriched with facet bubbles on a tetrahedron, nodal basis at the 4 vertices and the 4
+    face centroids: Firedrake's ``NodalEnrichedElement(P1, FacetBubble)`` of the [P1+FB]^3-P0
+    scheme (alfi/solver.py:574-584).  With b_f = 27 lambda_a lambda_b lambda_c the bubble of face f
+    (opposite vertex f):  phi_vertex_i = lambda_i - (1/3) sum_{f != i} b_f,  phi_face_f = b_f —
+    the change of basis hard-wired in alfi/bubble.py:58-147.  Every basis function is a cubic, so
+    it is tabulated through the P3 Lagrange basis."""
+    dim: int = 3
+    degree: int = 3                      # polynomial degree (for quadrature)
+
+    @property
+    def nnodes(self):
+        return 8
+
+    @property
+    def nodes_bary(self):
+        pts = [np.eye(4)[i] for i in range(4)]
+        for f in range(4):                                   # face f is opposite vertex f
+            lam = np.full(4, 1.0 / 3.0)
+            lam[f] = 0.0
+            pts.append(lam)
+        return np.array(pts)
+
+    @property
+    def nodes_ref(self):
+        return self.nodes_bary[:, 1:]
+
+    @property
+    def entities(self):
+        return [(0, v, 1) for v in range(4)] + [(2, f, 1) for f in range(4)]
+
+    def _to_p3(self):
+        """C[i, j] = phi_i(x_j) at the 20 P3 lattice points x_j."""
+        lam = _lattice(3, 3)[0]                              # (20, 4) barycentric
+        bub = np.stack([27.0 * np.prod(np.delete(lam, f, axis=1), axis=1) for f in range(4)], axis=0)
+        C = np.zeros((8, lam.shape[0]))
+        for i in range(4):
+            C[i] = lam[:, i] - sum(bub[f] for f in range(4) if f != i) / 3.0
+            C[4 + i] = bub[i]
+        return C
+
+    def tabulate(self, x):
+        return LagrangeElement(3, 3).tabulate(x) @ self._to_p3().T
+
+    def tabulate_grad(self, x):
+        g = LagrangeElement(3, 3).tabulate_grad(x)           # (q, 20, 3)
+        return np.einsum("qja,ij->qia", g, self._to_p3())
+
+
+def make_element(dim: int, k: int, kind: str = "lagrange"):
+    if kind == "lagrange":
+        return LagrangeElement(dim, k)
+    if kind == "p1fb":
+        if dim != 3:
+            raise NotImplementedError("P1+FacetBubble is the 3-D element of alfi (solver.py:576-579)")
+        return P1FBElement()
+    raise ValueError(kind)
+
+
 @lru_cache(maxsize=None)
-def reference_tensors(dim: int, k: int):
+def reference_tensors(el):
     """Exact reference integrals used by the assembly (see module docstring).
 
     K[a,b,i,j] = ∫ d_a phi_i d_b phi_j          T1[k,a,i,j] = ∫ phi_k phi_i d_a phi_j
     T2[k,a,i,j] = ∫ d_a phi_k phi_i phi_j       Dv[a,i] = ∫ d_a phi_i       M[i,j] = ∫ phi_i phi_j
     """
-    el = LagrangeElement(dim, k)
-    x, w = simplex_quadrature(dim, 3 * k)
+    dim = el.dim
+    x, w = simplex_quadrature(dim, 3 * el.degree)
     phi = el.tabulate(x)                # (q, n)
     dphi = el.tabulate_grad(x)          # (q, n, dim)
     K = np.einsum("q,qia,qjb->abij", w, dphi, dphi)
@@ -172,7 +233,8 @@ class VectorSpace:
     """[Pk]^d on a SimplexMesh; node numbering = first encounter walking cells in order."""
     mesh: SimplexMesh
     degree: int
-    element: LagrangeElement = field(init=False)
+    kind: str = "lagrange"               # "lagrange" | "p1fb"
+    element: object = field(init=False)
     cell_nodes: np.ndarray = field(init=False, repr=False)      # (nc, nnodes_local)
     nnodes: int = field(init=False)
     node_coords: np.ndarray = field(init=False, repr=False)
@@ -185,11 +247,18 @@ class VectorSpace:
     def __post_init__(self):
         m, k = self.mesh, self.degree
         d = m.dim
-        self.element = el = LagrangeElement(d, k)
+        self.element = el = make_element(d, k, self.kind)
         nv, ne, nf, nc = m.nv, m.ne, m.nf, m.nc
         cols = [m.cells]                                    # provisional ids, entity blocks
         off = nv
-        per_edge = k - 1
+        p1fb = self.kind == "p1fb"
+        per_edge = 0 if p1fb else k - 1
+        if p1fb:
+            # local face f of the element is opposite vertex f; mesh.cell_faces lists faces in
+            # lexicographic vertex order (0,1,2),(0,1,3),(0,2,3),(1,2,3) = opposite 3,2,1,0
+            cols.append(off + m.cell_faces[:, ::-1])
+            off += nf
+            k = 1                                           # no further Lagrange entities
         if per_edge:
             ce = m.cell_edges
             cols.append((off + ce[:, :, None] * per_edge + np.arange(per_edge)[None, None, :]).reshape(nc, -1))
@@ -213,7 +282,10 @@ class VectorSpace:
         o = nv
         self.edge_nodes = new[o:o + ne * per_edge].reshape(ne, per_edge)
         o += ne * per_edge
-        if k == 3 and d == 3:
+        if p1fb:
+            self.face_nodes = new[o:o + nf].reshape(nf, 1)
+            self.cell_int_nodes = np.empty((nc, 0), dtype=np.int64)
+        elif k == 3 and d == 3:
             self.face_nodes = new[o:o + nf].reshape(nf, 1)
             self.cell_int_nodes = np.empty((nc, 0), dtype=np.int64)
         elif k == 3 and d == 2:
@@ -311,8 +383,8 @@ def cell_geometry(mesh: SimplexMesh):
 def element_matrices(V: VectorSpace, nu: float, gamma: float, wind=None, advect: float = 1.0,
                      divform: str = "sv", cells=slice(None), parts=("visc", "div", "adv")):
     """Dense element tensors E[c, i, r, j, s] (test node i comp r, trial node j comp s)."""
-    mesh, d, k = V.mesh, V.mesh.dim, V.degree
-    rt = reference_tensors(d, k)
+    mesh, d = V.mesh, V.mesh.dim
+    rt = reference_tensors(V.element)
     G, det = cell_geometry(mesh)
     G, det = G[cells], det[cells]
     nc = G.shape[0]
@@ -386,11 +458,11 @@ def assemble_divergence(V: VectorSpace, kq: int):
     (alfi/solver.py:564-571, 615-622: ``- p*div(v) - div(u)*q``), and the block-diagonal inverse
     of the pressure mass matrix used by DGMassInv (alfi/solver.py:15-38).  Pressure dofs are
     numbered cell by cell."""
-    mesh, d, k = V.mesh, V.mesh.dim, V.degree
+    mesh, d = V.mesh, V.mesh.dim
     G, det = cell_geometry(mesh)
     el = V.element
     nc, nl = mesh.nc, el.nnodes
-    x, w = simplex_quadrature(d, k + kq)
+    x, w = simplex_quadrature(d, el.degree + kq)
     dphi = el.tabulate_grad(x)                                   # (q, nl, d)
     if kq == 0:
         psi = np.ones((x.shape[0], 1))

@@ -129,7 +129,7 @@ def prolongation_matrix(Vc: VectorSpace, Vf: VectorSpace, c2f: np.ndarray, drop_
     sel = order[first]
     assert sel.size == Vf.nnodes, "every fine node needs a candidate coarse cell"
     assert score[sel].min() > -1e-8, "fine node outside all candidate coarse cells"
-    el = LagrangeElement(d, Vc.degree)
+    el = Vc.element
     vals = el.tabulate(xi[sel])                                   # (nf, nlc)
     cols = Vc.cell_nodes[cc[sel]]
     rows = np.repeat(fn[sel], vals.shape[1])

@@ -39,6 +39,7 @@ class Config:
     macro_expand: str = "vertices"
     sort_order: str | None = None
     length: float = 2.0
+    element: str = "lagrange"    # "lagrange" | "p1fb" ([P1+FacetBubble]^3, alfi/solver.py:576-579)
 
     @property
     def m(self):
@@ -54,10 +55,13 @@ CONFIGS = {
     "ldc2d-sv-k2": Config("ldc2d-sv-k2", 2, 10, 1, "sv", 2, "macro", True, re=1000.0),
     "ldc2d-pkp0": Config("ldc2d-pkp0", 2, 16, 3, "pkp0", 2, "star", False, re=10000.0),
     "ldc3d-sv-k3": Config("ldc3d-sv-k3", 3, 4, 2, "sv", 3, "macro", True, re=5000.0),
+    "ldc3d-pkp0": Config("ldc3d-pkp0", 3, 16, 2, "pkp0", 1, "star", False, re=5000.0, element="p1fb"),
     # scaled-down members of the same families (tests, smoke, CPU-baseline sample)
     "ldc2d-sv-k2-tiny": Config("ldc2d-sv-k2-tiny", 2, 2, 1, "sv", 2, "macro", True, re=100.0),
     "ldc2d-pkp0-tiny": Config("ldc2d-pkp0-tiny", 2, 2, 2, "pkp0", 2, "star", False, re=100.0),
     "ldc3d-sv-k3-tiny": Config("ldc3d-sv-k3-tiny", 3, 1, 1, "sv", 3, "macro", True, re=100.0),
+    "ldc3d-pkp0-tiny": Config("ldc3d-pkp0-tiny", 3, 1, 2, "pkp0", 1, "star", False, re=100.0, element="p1fb"),
+    "ldc3d-pkp0-small": Config("ldc3d-pkp0-small", 3, 4, 2, "pkp0", 1, "star", False, re=1000.0, element="p1fb"),
     "ldc3d-sv-k3-small": Config("ldc3d-sv-k3-small", 3, 2, 1, "sv", 3, "macro", True, re=5000.0),
     "ldc3d-sv-k3-half": Config("ldc3d-sv-k3-half", 3, 2, 2, "sv", 3, "macro", True, re=5000.0),
 }
@@ -86,6 +90,7 @@ class LevelData:
     P: object | None = None              # scalar CSR prolongation from level index-1
     cell_patches: PatchSet | None = None
     cb_nodes: np.ndarray | None = None   # coarse-boundary nodes of the transfer (T2)
+    P_dof_level: bool = False            # P acts on scalar dofs (BubbleTransfer) instead of per node
     A0: BSR | None = None                # nu*visc + gamma*div  (transfer patch operator)
     D: BSR | None = None                 # gamma * div-div form  (transfer rhs operator)
 
@@ -161,12 +166,18 @@ def build_problem(cfg: Config | str, nu: float | None = None, with_transfer: boo
     hier = build_hierarchy(cfg.dim, cfg.N, cfg.nref, cfg.bary, cfg.length)
     levels = []
     for lev in hier:
-        V = VectorSpace(lev.mesh, cfg.k)
+        V = VectorSpace(lev.mesh, cfg.k, cfg.element)
         ld = LevelData(lev.index, lev, V, BlockPattern(V), V.boundary_nodes().astype(np.int32))
         assemble_level(cfg, ld, nu, cfg.gamma)
         if lev.index > 0:
             ld.patches = smoother_patches(cfg, ld)
-            ld.P = prolongation_matrix(levels[-1].V, V, hier[lev.index - 1].c2f)
+            if cfg.element == "p1fb":
+                # PkP0SchoeberlTransfer.standard_transfer -> BubbleTransfer (alfi/transfer.py:334-356)
+                from ..bubble import bubble_transfer_matrix
+                ld.P = bubble_transfer_matrix(levels[-1].V, V, hier[lev.index - 1].c2f)
+                ld.P_dof_level = True
+            else:
+                ld.P = prolongation_matrix(levels[-1].V, V, hier[lev.index - 1].c2f)
             if with_transfer:
                 ld.cell_patches, ld.cb_nodes = cell_patch_set(hier, lev.index, V, cfg.bary)
                 assemble_transfer(cfg, ld, nu, cfg.gamma)

@@ -134,12 +134,15 @@ int alfib_get_patch_inverse(alfib_ctx* ctx, int level, int which, int32_t patch,
 
 /* ---- robust transfer: replaces AutoSchoeberlTransfer.prolong/restrict (transfer.py:186-275)
  *      between `level-1` and `level`.  P is the scalar CSR of the standard prolongation
- *      (firedrake prolong, transfer.py:284-290) acting per component; cell patches come through
+ *      (firedrake prolong, transfer.py:284-290) acting per component — or, with dof_level = 1,
+ *      a CSR on scalar dofs (n_fine_nodes / n_coarse_nodes are then dof counts), which is what
+ *      BubbleTransfer's flux-corrected prolongation of [P1+FB]^3 needs because it mixes the
+ *      components on every facet (bubble.py:10-265, transfer.py:334-356); cell patches come through
  *      alfib_level_set_patches(which = TRANSFER); cb_dofs are the coarse-boundary dofs of
  *      fix_coarse_boundaries (transfer.py:121-158).                                            */
 int alfib_transfer_set(alfib_ctx* ctx, int level, int32_t n_fine_nodes, int32_t n_coarse_nodes,
                        const int32_t* P_rowptr, const int32_t* P_colidx, const double* P_vals,
-                       int32_t ncb, const int32_t* cb_dofs);
+                       int32_t ncb, const int32_t* cb_dofs, int dof_level);
 /* once per (nu, gamma) (transfer.py:173-184, 238-244): BSR values, on the level's pattern, of
  * A0 = nu(2 sym grad u, grad v) + gamma(div u, div v) and of gamma*D = gamma(div u, div v)
  * (transfer.py:295-309 / 319-332); gathers + inverts the cell patches.  A0_vals may be NULL to

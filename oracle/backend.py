@@ -22,7 +22,10 @@ class OracleBackend:
             lv.offsets, lv.dofs, lv.order = li.patch_offsets, li.patch_dofs, li.patch_order
             lv.factors = hp.factor_patches(hp.patch_matrices(A, lv.offsets, lv.dofs), self.mode)
         if li.P is not None:
-            lv.P = sp.kron(li.P, sp.identity(li.bs), format="csr") if old is None else old.P
+            if old is not None:
+                lv.P = old.P
+            else:
+                lv.P = li.P.tocsr() if li.P_dof_level else sp.kron(li.P, sp.identity(li.bs), format="csr")
             if old is not None:
                 lv.D, lv.cb_dofs, lv.c_offsets, lv.c_dofs, lv.c_factors = old.D, old.cb_dofs, old.c_offsets, old.c_dofs, old.c_factors
         if l == 0:

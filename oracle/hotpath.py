@@ -138,7 +138,7 @@ def level_from_host(ld, mode="inverse", with_transfer=True, transfer_mode="lu"):
         lv.offsets, lv.dofs, lv.order = ps.offsets, ps.dofs, ps.order
         lv.factors = factor_patches(patch_matrices(A, ps.offsets, ps.dofs), mode)
     if ld.P is not None:
-        lv.P = sp.kron(ld.P, sp.identity(bs), format="csr")
+        lv.P = ld.P.tocsr() if getattr(ld, "P_dof_level", False) else sp.kron(ld.P, sp.identity(bs), format="csr")
         if with_transfer and ld.cell_patches is not None:
             cp = ld.cell_patches
             lv.D = ld.D.to_csr()

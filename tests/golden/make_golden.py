@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 from alfi_b200.synth.problem import build_problem  # noqa: E402
 from oracle import hotpath as hp  # noqa: E402
 
-NAMES = ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny"]
+NAMES = ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny", "ldc3d-pkp0-tiny"]
 
 
 def make(name):
@@ -55,7 +55,7 @@ def make(name):
 
 
 if __name__ == "__main__":
-    for name in NAMES:
+    for name in (sys.argv[1:] or NAMES):
         path = os.path.join(os.path.dirname(os.path.abspath(__file__)), name + ".npz")
         np.savez_compressed(path, **make(name))
         print(path, os.path.getsize(path))

@@ -10,7 +10,7 @@ import pytest
 from oracle import hotpath as hp
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-NAMES = ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny"]
+NAMES = ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny", "ldc3d-pkp0-tiny"]
 TOL = 1e-11
 
 

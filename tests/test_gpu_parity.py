@@ -16,7 +16,7 @@ EPS = np.finfo(np.float64).eps
 # With gamma/nu ~ 1e6 the patch matrices have kappa ~ 1e6..1e8 and two backward-stable solvers
 # legitimately differ by ~kappa*eps; there the bar is 1e-11 * max(1, kappa_max*eps/1e-12)
 # and the conditioning-free backward error is asserted instead.
-BASE = ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny"]
+BASE = ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny", "ldc3d-pkp0-tiny"]
 SMALL = BASE + [b + "@mild" for b in BASE]
 
 

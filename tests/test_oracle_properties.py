@@ -5,7 +5,7 @@ import scipy.sparse as sp
 
 from oracle import hotpath as hp
 
-NAMES = ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny"]
+NAMES = ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny", "ldc3d-pkp0-tiny"]
 
 
 @pytest.fixture(scope="module")
