@@ -61,6 +61,7 @@ CONFIGS = {
     "ldc2d-pkp0-tiny": Config("ldc2d-pkp0-tiny", 2, 2, 2, "pkp0", 2, "star", False, re=100.0),
     "ldc3d-sv-k3-tiny": Config("ldc3d-sv-k3-tiny", 3, 1, 1, "sv", 3, "macro", True, re=100.0),
     "ldc3d-pkp0-tiny": Config("ldc3d-pkp0-tiny", 3, 1, 2, "pkp0", 1, "star", False, re=100.0, element="p1fb"),
+    "ldc3d-pkp0-mid": Config("ldc3d-pkp0-mid", 3, 8, 2, "pkp0", 1, "star", False, re=5000.0, element="p1fb"),
     "ldc3d-pkp0-small": Config("ldc3d-pkp0-small", 3, 4, 2, "pkp0", 1, "star", False, re=1000.0, element="p1fb"),
     "ldc3d-sv-k3-small": Config("ldc3d-sv-k3-small", 3, 2, 1, "sv", 3, "macro", True, re=5000.0),
     "ldc3d-sv-k3-half": Config("ldc3d-sv-k3-half", 3, 2, 2, "sv", 3, "macro", True, re=5000.0),
