@@ -423,6 +423,68 @@ def element_matrices(V: VectorSpace, nu: float, gamma: float, wind=None, advect:
     return E
 
 
+def element_parts(V: VectorSpace, wind=None, divform: str = "sv", cells=slice(None), want=("visc", "div", "adv1", "adv2")):
+    """Element tensors per form, component-major: part -> E[r, s, c, i, j] (test comp r node i, trial
+    comp s node j), each for unit coefficient:
+      visc  (2 sym grad u, grad v)      div   (div u, div v) or (cell_avg(div u), div v)
+      adv1  (w.grad u, v)               adv2  (u.grad w, v)
+    The operator is linear in (nu, gamma) and only the adv parts depend on the wind, so a
+    continuation run re-assembles only those per Newton step."""
+    mesh, d = V.mesh, V.mesh.dim
+    rt = reference_tensors(V.element)
+    G, det = cell_geometry(mesh)
+    G, det = G[cells], det[cells]
+    nc, nl = G.shape[0], V.element.nnodes
+    out = {}
+    need_K = "visc" in want or ("div" in want and divform == "sv")
+    if need_K:
+        Kp = np.einsum("c,cax,cby,abij->xycij", det, G, G, rt["K"], optimize=True)       # [x, y, c, i, j]
+        if "visc" in want:
+            E = np.ascontiguousarray(np.swapaxes(Kp, 0, 1))           # d_r phi_j d_s phi_i = Kp[s, r, i, j]
+            lap = np.einsum("xxcij->cij", Kp)
+            for r in range(d):
+                E[r, r] += lap
+            out["visc"] = E
+        if "div" in want and divform == "sv":
+            out["div"] = Kp
+    if "div" in want and divform == "pkp0":
+        dv = np.einsum("c,car,ai->cri", det, G, rt["Dv"])              # ∫ d_r phi_i
+        vol = det / (2.0 if d == 2 else 6.0)
+        out["div"] = np.einsum("c,cri,csj->rscij", 1.0 / vol, dv, dv)
+    if wind is not None and ("adv1" in want or "adv2" in want):
+        W = wind[V.cell_nodes[cells]]                                   # W[c, k, b]
+        if "adv1" in want:
+            cw = np.einsum("ckb,cab->cka", W, G)
+            A1 = np.einsum("c,cka,kaij->cij", det, cw, rt["T1"], optimize=True)
+            E = np.zeros((d, d, nc, nl, nl))
+            for r in range(d):
+                E[r, r] = A1
+            out["adv1"] = E
+        if "adv2" in want:
+            out["adv2"] = np.einsum("c,ckr,cas,kaij->rscij", det, W, G, rt["T2"], optimize=True)
+    return out
+
+
+def assemble_parts(V: VectorSpace, pattern: "BlockPattern", wind=None, divform: str = "sv",
+                   want=("visc", "div", "adv1", "adv2"), chunk: int = 16384):
+    """part -> block values (nnzb, d, d) on `pattern`, no boundary conditions applied."""
+    d, nc = V.bs, V.mesh.nc
+    want = tuple(w for w in want if wind is not None or not w.startswith("adv"))
+    vals = {w: np.zeros((pattern.nnzb, d, d)) for w in want}
+    nl = V.element.nnodes
+    buf = {w: np.empty((d, d, nc, nl, nl)) for w in want}
+    for c0 in range(0, nc, chunk):
+        sl = slice(c0, min(nc, c0 + chunk))
+        E = element_parts(V, wind, divform, sl, want)
+        for w in want:
+            buf[w][:, :, sl] = E[w]
+    for w in want:
+        for r in range(d):
+            for s_ in range(d):
+                vals[w][:, r, s_] = pattern.scatter(buf[w][r, s_])
+    return vals
+
+
 def assemble_velocity_block(V: VectorSpace, nu: float, gamma: float, wind=None, advect: float = 1.0,
                             divform: str = "sv", bc_nodes=None, pattern: BlockPattern | None = None,
                             parts=("visc", "div", "adv"), chunk: int = 8192) -> BSR:

@@ -23,7 +23,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from ..multigrid import level_input_from_synth
-from .fem import apply_dirichlet, assemble_divergence, assemble_velocity_block
+from .fem import assemble_divergence
 from .hierarchy import prolongation_matrix
 from .problem import Problem, assemble_transfer, build_problem, lid_wind
 
@@ -135,19 +135,20 @@ class ContinuationSolver:
         return w
 
     def _assemble(self, nu, gamma, advect):
+        """Jacobian velocity block on every level (wind injected) and, on the finest level, the
+        operator K + N1(u) of the residual.  Only the advection parts depend on u."""
+        from .problem import _bsr, _linear_parts, assemble_level
         cfg = self.config
         winds = self._winds()
+        nl = len(self.prob.levels)
         for l, ld in enumerate(self.prob.levels):
-            M1 = assemble_velocity_block(ld.V, nu, gamma, wind=winds[l], advect=advect, divform=cfg.discretisation,
-                                         pattern=ld.pattern, parts=("visc", "div", "adv1"))
-            N2 = assemble_velocity_block(ld.V, 0.0, 0.0, wind=winds[l], advect=advect, divform=cfg.discretisation,
-                                         pattern=ld.pattern, parts=("adv2",))
-            if l == len(self.prob.levels) - 1:
-                self.M1 = M1.to_csr()
-            A = M1
-            A.vals = M1.vals + N2.vals
-            apply_dirichlet(A, ld.bc_nodes, ld.pattern.rows)
-            ld.A = A
+            assemble_level(cfg, ld, nu, gamma, advect, wind=winds[l])
+            if l == nl - 1:
+                lin = _linear_parts(cfg, ld)
+                vals = nu * lin["visc"] + gamma * lin["div"]
+                if advect != 0.0:
+                    vals = vals + advect * ld.adv1
+                self.M1 = _bsr(ld, vals).to_csr()
         self.Afine = self.prob.finest.A.to_csr()
 
     def _residual(self):

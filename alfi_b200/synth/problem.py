@@ -17,7 +17,7 @@ import numpy as np
 from ..patches import PatchSet, greedy_colouring, patch_dofs_from_points
 from ..relaxation import macro_star_points, star_points, iteration_order
 from ..transfer import cell_patch_set
-from .fem import BSR, BlockPattern, VectorSpace, assemble_velocity_block
+from .fem import BSR, BlockPattern, VectorSpace, apply_dirichlet, assemble_parts, assemble_velocity_block
 from .hierarchy import Level, build_hierarchy, prolongation_matrix
 
 __all__ = ["Config", "CONFIGS", "LevelData", "Problem", "build_problem", "lid_wind"]
@@ -93,6 +93,7 @@ class LevelData:
     cb_nodes: np.ndarray | None = None   # coarse-boundary nodes of the transfer (T2)
     P_dof_level: bool = False            # P acts on scalar dofs (BubbleTransfer) instead of per node
     A0: BSR | None = None                # nu*visc + gamma*div  (transfer patch operator)
+    parts: dict | None = None            # unit-coefficient block values of the visc / div forms (cached)
     D: BSR | None = None                 # gamma * div-div form  (transfer rhs operator)
 
     @property
@@ -137,20 +138,35 @@ def smoother_patches(cfg: Config, ld: LevelData) -> PatchSet:
     return ps
 
 
-def assemble_level(cfg: Config, ld: LevelData, nu: float, gamma: float, advect: float = 1.0):
-    """(Re)assemble the level operator — the once-per-Newton-step hand-over."""
-    wind = ld.V.interpolate(lid_wind)
-    ld.A = assemble_velocity_block(ld.V, nu, gamma, wind=wind, advect=advect,
-                                   divform=cfg.discretisation, bc_nodes=ld.bc_nodes, pattern=ld.pattern)
+def _linear_parts(cfg: Config, ld: LevelData):
+    if ld.parts is None:
+        ld.parts = assemble_parts(ld.V, ld.pattern, None, cfg.discretisation, want=("visc", "div"))
+    return ld.parts
+
+
+def _bsr(ld: LevelData, vals):
+    return BSR(ld.V.nnodes, ld.V.bs, ld.pattern.rowptr, ld.pattern.colidx, vals)
+
+
+def assemble_level(cfg: Config, ld: LevelData, nu: float, gamma: float, advect: float = 1.0, wind=None):
+    """(Re)assemble the level operator — the once-per-Newton-step hand-over.  The viscous and
+    div-div parts are linear in (nu, gamma) and cached; only the advection parts are re-assembled."""
+    lin = _linear_parts(cfg, ld)
+    vals = nu * lin["visc"] + gamma * lin["div"]
+    if advect != 0.0:
+        wind = ld.V.interpolate(lid_wind) if wind is None else wind
+        adv = assemble_parts(ld.V, ld.pattern, wind, cfg.discretisation, want=("adv1", "adv2"))
+        ld.adv1 = adv["adv1"]
+        vals += advect * (adv["adv1"] + adv["adv2"])
+    ld.A = apply_dirichlet(_bsr(ld, vals), ld.bc_nodes, ld.pattern.rows)
     return ld.A
 
 
 def assemble_transfer(cfg: Config, ld: LevelData, nu: float, gamma: float):
     """(Re)assemble the Schöberl transfer operators — once per (nu, gamma), transfer.py:238-244."""
-    ld.A0 = assemble_velocity_block(ld.V, nu, gamma, wind=None, divform=cfg.discretisation,
-                                    pattern=ld.pattern, parts=("visc", "div"))
-    ld.D = assemble_velocity_block(ld.V, 0.0, gamma, wind=None, divform=cfg.discretisation,
-                                   pattern=ld.pattern, parts=("div",))
+    lin = _linear_parts(cfg, ld)
+    ld.A0 = _bsr(ld, nu * lin["visc"] + gamma * lin["div"])
+    ld.D = _bsr(ld, gamma * lin["div"])
     return ld.A0, ld.D
 
 
