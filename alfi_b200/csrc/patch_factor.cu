@@ -15,9 +15,10 @@
 //          columns *of the outer block only* (one row per thread, N[r, 0:NB] in registers);
 //     far update, all columns outside KO                                   [the O(n^3) part]
 //       3. all NBO row swaps in order, R = W[KO, far] set aside (k-major), W[KO, far] zeroed;
-//       4. W[:, far] += N * R with N = W[:, KO]: a rank-64 FP64 GEMM, 256 x 64 tiles of W per
-//          CTA iteration, 8 x 4 accumulators per thread, N and R tiles staged in shared memory
-//          (128 + 32 KB), W read and written once per outer block with 128-bit accesses.
+//       4. W[:, far] += N * R with N = W[:, KO]: a rank-64 FP64 GEMM on the tensor cores
+//          (mma.sync.m8n8k4.f64, DMMA): 256 x 64 tiles of W per CTA iteration, a 32 x 32 sub-tile
+//          per warp, N tile (135 KB) and double-buffered cp.async R tiles (2 x 37 KB) in shared
+//          memory, W read and written once per outer block with 128-bit accesses.
 //   A^{-1} = W with the column swaps undone in reverse order; that permutation is folded into
 //   the final pass that writes the 64-row-tiled apply layout (patch_apply.cu).
 //
@@ -41,6 +42,8 @@ constexpr int FT = 512;        // threads per CTA
 constexpr int NBO = 64;        // outer block (rank of the far update)
 constexpr int TR = 256;        // rows of W per far tile
 constexpr int TC = 64;         // columns of W per far tile
+constexpr int NS_LD = TR + 8;  // padded shared-memory rows: fragment loads (4 k x 8 indices) hit every bank pair twice
+constexpr int RS_LD = TC + 8;
 constexpr int UC = 8;          // columns whose loads are issued together in the in-block update
 
 struct FactorArgs {
@@ -107,7 +110,7 @@ __host__ __device__ inline size_t front_doubles(int maxn, int NB) {
   // the front region holds either the inner panel (+ its R staging) or the far tiles
   const size_t ldp = (size_t)((maxn + 1) & ~1);
   const size_t inner = ldp * NB + (size_t)NBO * NB;
-  const size_t far = (size_t)NBO * TR + 2 * (size_t)NBO * TC;      // N tile + double-buffered R tiles
+  const size_t far = (size_t)NBO * NS_LD + 2 * (size_t)NBO * RS_LD;   // N tile + double-buffered R tiles
   return inner > far ? inner : far;
 }
 
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(FT, 1) patch_factor_kernel(FactorArgs a) {
   double* panel = front;                                               // ldp_max * NB
   double* Rs = panel + (size_t)ldp_max * NB;                           // NBO * NB (in-block R)
   double* Ns = front;                                                  // NBO * TR   (far phase)
-  double* Rsm = Ns + (size_t)NBO * TR;                                 // 2 x NBO * TC (far phase)
+  double* Rsm = Ns + (size_t)NBO * NS_LD;                              // 2 x NBO * RS_LD (far phase)
   double* pr = front + front_doubles(a.maxn, NB);                      // NB
   double* red_v = pr + NB;                                             // 34
   int* red_i = reinterpret_cast<int*>(red_v + 34);                     // 34
@@ -368,18 +371,22 @@ __global__ void __launch_bounds__(FT, 1) patch_factor_kernel(FactorArgs a) {
           }
         }
         pc.mark(PH_FAR_SWAP);
-        // 4. W[:, far] += W[:, KO] * R : 256 x 64 tiles, 8 x 4 accumulators per thread
-        const int tx = tid & 31, ty = tid >> 5;
+        // 4. W[:, far] += W[:, KO] * R on the FP64 tensor cores: 256 x 64 tiles of W per CTA
+        //    iteration, one 32 x 32 sub-tile per warp = 4 x 4 mma.m8n8k4 tiles, accumulators
+        //    (32 doubles per lane) in registers.  The product is formed transposed, D[c][r] =
+        //    sum_k R[k][c] N[r][k], so that a lane's two accumulator entries are two consecutive
+        //    rows of one column of the column-major W (one 128-bit access).  Shared-memory rows
+        //    are padded by 8 doubles: the 4 k x 8 index pattern of a fragment load is then
+        //    conflict free.
+        const int lane = tid & 31, warp = tid >> 5;
+        const int g = lane >> 2, t4 = lane & 3;
+        const int wr = warp & 7, wc = warp >> 3;           // 8 row blocks x 2 column blocks of 32
         for (int rt0 = 0; rt0 < n; rt0 += TR) {
           __syncthreads();                           // previous tile's readers are done with Ns
           for (int idx = tid; idx < NBO * TR; idx += FT) {
             const int k = idx / TR, r = idx - k * TR;
-            Ns[idx] = (k < nbo && rt0 + r < n) ? W[rt0 + r + (size_t)(k0 + k) * ld] : 0.0;
+            Ns[k * NS_LD + r] = (k < nbo && rt0 + r < n) ? W[rt0 + r + (size_t)(k0 + k) * ld] : 0.0;
           }
-          // thread (tx, ty) owns rows rt0 + 64*i2 + 2*tx + {0,1} (i2 < 4) and columns fc0 + 4*ty + j:
-          // a warp reads 512 contiguous bytes of Ns per 128-bit shared load (no bank conflicts) and
-          // of W per 128-bit global access; the R values of a warp are broadcasts
-          const int row = rt0 + 2 * tx;
           pc.mark(PH_FAR_NS);
           // R tiles are double-buffered: chunk c+1 is fetched with cp.async while chunk c is used
           auto fetch_r = [&](double* dst, int fc) {
@@ -387,68 +394,64 @@ __global__ void __launch_bounds__(FT, 1) patch_factor_kernel(FactorArgs a) {
             for (int it = 0; it < NBO * TC / 2 / FT; ++it) {
               const int idx = tid + it * FT;
               const int k = idx / (TC / 2), c2 = idx - k * (TC / 2);
-              __pipeline_memcpy_async(dst + k * TC + 2 * c2, Rg + (size_t)k * ldr + fc + 2 * c2, 16);
+              __pipeline_memcpy_async(dst + k * RS_LD + 2 * c2, Rg + (size_t)k * ldr + fc + 2 * c2, 16);
             }
             __pipeline_commit();
           };
           fetch_r(Rsm, 0);
           int buf = 0;
+          const int row_w = rt0 + wr * 32 + 2 * t4;          // + 8 * nb
           for (int fc0 = 0; fc0 < nfar; fc0 += TC, buf ^= 1) {
             __pipeline_wait_prior(0);                // this thread's part of the current chunk landed
             __syncthreads();                         // everyone's did; Ns written; old readers done
             pc.mark(PH_FAR_RS);
-            if (fc0 + TC < nfar) fetch_r(Rsm + (buf ^ 1) * NBO * TC, fc0 + TC);
-            double acc[8][4];
+            if (fc0 + TC < nfar) fetch_r(Rsm + (buf ^ 1) * NBO * RS_LD, fc0 + TC);
+            double acc[4][4][2];
             double* cptr[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int f = fc0 + ty * 4 + j;
-              cptr[j] = (f < nfar) ? W + (size_t)(f < k0 ? f : f + nbo) * ld + row : nullptr;
+            for (int mb = 0; mb < 4; ++mb) {
+              const int f = fc0 + wc * 32 + mb * 8 + g;
+              cptr[mb] = (f < nfar) ? W + (size_t)(f < k0 ? f : f + nbo) * ld + row_w : nullptr;
 #pragma unroll
-              for (int i2 = 0; i2 < 4; ++i2) {
-                const int r = row + 64 * i2;
-                if (cptr[j] && r + 1 < n) {
-                  const double2 v = *reinterpret_cast<const double2*>(cptr[j] + 64 * i2);
-                  acc[2 * i2][j] = v.x;
-                  acc[2 * i2 + 1][j] = v.y;
+              for (int nb4 = 0; nb4 < 4; ++nb4) {
+                const int r = row_w + 8 * nb4;
+                if (cptr[mb] && r + 1 < n) {
+                  const double2 v = *reinterpret_cast<const double2*>(cptr[mb] + 8 * nb4);
+                  acc[mb][nb4][0] = v.x;
+                  acc[mb][nb4][1] = v.y;
                 } else {
-                  acc[2 * i2][j] = (cptr[j] && r < n) ? cptr[j][64 * i2] : 0.0;
-                  acc[2 * i2 + 1][j] = 0.0;
+                  acc[mb][nb4][0] = (cptr[mb] && r < n) ? cptr[mb][8 * nb4] : 0.0;
+                  acc[mb][nb4][1] = 0.0;
                 }
               }
             }
-            const double2* __restrict__ ap = reinterpret_cast<const double2*>(Ns) + tx;
-            const double2* __restrict__ bp = reinterpret_cast<const double2*>(Rsm + buf * NBO * TC + ty * 4);
-#pragma unroll 4
-            for (int k = 0; k < NBO; ++k) {
-              double av[8], bv[4];
+            const double* __restrict__ rs = Rsm + buf * NBO * RS_LD + t4 * RS_LD + wc * 32 + g;
+            const double* __restrict__ ns = Ns + t4 * NS_LD + wr * 32 + g;
+#pragma unroll 2
+            for (int kk = 0; kk < NBO; kk += 4) {
+              double af[4], bf[4];
 #pragma unroll
-              for (int i2 = 0; i2 < 4; ++i2) {
-                const double2 t = ap[k * (TR / 2) + 32 * i2];
-                av[2 * i2] = t.x;
-                av[2 * i2 + 1] = t.y;
-              }
+              for (int mb = 0; mb < 4; ++mb) af[mb] = rs[kk * RS_LD + mb * 8];       // R[kk + t4][col]
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const double2 t = bp[k * (TC / 2) + j];
-                bv[2 * j] = t.x;
-                bv[2 * j + 1] = t.y;
-              }
+              for (int nb4 = 0; nb4 < 4; ++nb4) bf[nb4] = ns[kk * NS_LD + nb4 * 8];  // N[row][kk + t4]
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
+              for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+                for (int nb4 = 0; nb4 < 4; ++nb4)
+                  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                               : "+d"(acc[mb][nb4][0]), "+d"(acc[mb][nb4][1])
+                               : "d"(af[mb]), "d"(bf[nb4]));
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (!cptr[j]) continue;
+            for (int mb = 0; mb < 4; ++mb) {
+              if (!cptr[mb]) continue;
 #pragma unroll
-              for (int i2 = 0; i2 < 4; ++i2) {
-                const int r = row + 64 * i2;
+              for (int nb4 = 0; nb4 < 4; ++nb4) {
+                const int r = row_w + 8 * nb4;
                 if (r + 1 < n)
-                  *reinterpret_cast<double2*>(cptr[j] + 64 * i2) = make_double2(acc[2 * i2][j], acc[2 * i2 + 1][j]);
+                  *reinterpret_cast<double2*>(cptr[mb] + 8 * nb4) = make_double2(acc[mb][nb4][0], acc[mb][nb4][1]);
                 else if (r < n)
-                  cptr[j][64 * i2] = acc[2 * i2][j];
+                  cptr[mb][8 * nb4] = acc[mb][nb4][0];
               }
             }
             pc.mark(PH_FAR_MMA);
