@@ -425,6 +425,16 @@ __global__ void __launch_bounds__(FT, 1) patch_factor_kernel(FactorArgs a) {
                 }
               }
             }
+            // pull the next chunk's W tile towards L2 while this one is multiplied: the update sits at
+            // the ridge of the roofline and its loads are otherwise exposed after the barrier
+            if (fc0 + TC < nfar) {
+              const int f = fc0 + TC + wc * 32 + lane;
+              if (f < nfar) {
+                const double* nxt = W + (size_t)(f < k0 ? f : f + nbo) * ld + rt0 + wr * 32;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 16));
+              }
+            }
             const double* __restrict__ rs = Rsm + buf * NBO * RS_LD + t4 * RS_LD + wc * 32 + g;
             const double* __restrict__ ns = Ns + t4 * NS_LD + wr * 32 + g;
 #pragma unroll 2
