@@ -15,6 +15,25 @@ from .pc import HostAdapter
 __all__ = ["FiredrakeAdapter", "attach", "transfer_backend"]
 
 
+def baij_csr_to_blocks(indptr, indices, data, bs):
+    """Scalar CSR of a BAIJ matrix (every block fully stored, as MatGetValuesCSR returns it) ->
+    (block rowptr, block colidx, values (nnzb, bs, bs) row-major blocks, block_col_major=False)."""
+    n = indptr.size - 1
+    counts = np.diff(indptr)
+    assert n % bs == 0 and (counts % bs == 0).all(), "not a fully stored block matrix"
+    bcount = counts[::bs] // bs
+    rowptr = np.concatenate(([0], np.cumsum(bcount))).astype(np.int32)
+    first = indptr[:-1:bs]                                     # first scalar row of every block row
+    lead = np.repeat(first, bcount * bs) + np.concatenate([np.arange(c * bs) for c in bcount]) if n else np.empty(0, int)
+    colidx = (indices[lead][::bs] // bs).astype(np.int32)
+    row_of = np.repeat(np.arange(n), counts)                   # scalar row of every stored entry
+    pos = np.arange(indices.size) - indptr[row_of]             # position inside its row
+    blk = rowptr[row_of // bs] + pos // bs
+    vals = np.empty((colidx.size, bs, bs))
+    vals[blk, row_of % bs, pos % bs] = data
+    return rowptr, colidx, vals, False
+
+
 class _Space:
     """The view of a Firedrake FunctionSpace the patch builders need."""
 
@@ -48,19 +67,8 @@ class FiredrakeAdapter(HostAdapter):
         _, P = pc.getOperators()
         bs = P.getBlockSize()
         indptr, indices, data = P.getValuesCSR()          # scalar CSR of the BAIJ matrix
-        n = indptr.size - 1
-        # block pattern from the scalar rows 0, bs, 2bs, ... (BAIJ stores full blocks)
-        rowptr = (indptr[::bs] // bs).astype(np.int32)
-        first = indptr[:-1:bs]
-        counts = np.diff(indptr)[::bs] // bs
-        colidx = np.concatenate([indices[s:s + c * bs:bs] // bs for s, c in zip(first, counts)]).astype(np.int32)
-        # values: scalar row r of block row i holds its blocks' r-th rows back to back
-        vals = np.empty((colidx.size, bs, bs))
-        for r in range(bs):
-            rows = np.arange(r, n, bs)
-            seg = np.concatenate([data[indptr[i]:indptr[i + 1]] for i in rows])
-            vals[:, r, :] = seg.reshape(-1, bs)
-        return rowptr, colidx, vals, False
+        return baij_csr_to_blocks(np.asarray(indptr), np.asarray(indices), np.asarray(data), bs)
+
 
     def function_space(self, pc):
         from firedrake import dmhooks
