@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "alfib.h"
+#include "condense_host.h"
 
 #define ALFIB_MAX_LEVELS 16
 #define ALFIB_TILE_ROWS 64          // rows per apply tile (one warp, double2 per lane)
@@ -82,6 +83,22 @@ struct DBuf {                       // device buffer owned by the library
   }
 };
 
+// ---- condensed ("statically condensed") patch sets: condense.cu / condense_host.h ----------------
+struct Condensed {
+  bool on = false;
+  CondensedHost h;                      // layout, index lists and op lists (host copies)
+  DBuf<int64_t> sepoff, ssoff;
+  DBuf<int32_t> seplocal, sepdofs, cidx, bdofs, bkeys, bperm, cptr, cg1;
+  DBuf<BlockDesc> blocks;
+  DBuf<TileOp> opsV, opsS, opsDW;
+  DBuf<double> g1, rs, us;              // per-block V outputs, per-patch separator rhs / solution
+  void release() {
+    sepoff.release(); ssoff.release(); seplocal.release(); sepdofs.release(); cidx.release();
+    bdofs.release(); bkeys.release(); bperm.release(); cptr.release(); cg1.release(); blocks.release();
+    opsV.release(); opsS.release(); opsDW.release(); g1.release(); rs.release(); us.release();
+  }
+};
+
 // One set of patches (the smoother's vertex/macro stars or the transfer's cell patches):
 // index sets, colouring, inverse factors in the tiled apply layout, and the warp work list.
 struct PatchSet {
@@ -103,12 +120,14 @@ struct PatchSet {
   int64_t store_elems = 0;
   bool store_owned = false;
   DBuf<double> store_buf;
+  Condensed cond;                   // block/separator form of the inverses (alfib_level_set_patch_blocks)
 };
 
 struct Level {
   int n_nodes = 0, bs = 0, n = 0;
   int64_t nnzb = 0;
   DBuf<int32_t> rowptr, colidx, bc, cb;
+  std::vector<int32_t> h_rowptr, h_colidx;   // host copy of the pattern (block structure checks)
   DBuf<double> vals, dvals, a0vals;
   int nbc = 0, ncb = 0;
   bool has_values = false, has_transfer = false, has_d = false;
@@ -237,6 +256,11 @@ void comm_peer_reduce(alfib_ctx* c, int64_t n, int hdr_slot, const long long* lo
 void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, PeerOut y);
 // y = sum over ranks of this rank's patch contributions (zeroing, exchange included)
 void patch_apply_sum(alfib_ctx* c, Level& L, int level, int which, const double* x, double* y);
+// condense.cu
+void condense_setup(alfib_ctx* c, Level& L, PatchSet& ps, const int32_t* block_of_dof);
+void launch_condense_blocks(alfib_ctx* c, const Level& L, PatchSet& ps, const double* vals);
+void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, PeerOut y);
+void condensed_extract_inverse(alfib_ctx* c, const PatchSet& ps, int patch, double* host_out);
 // patch_factor.cu
 void launch_patch_factor(alfib_ctx* c, const Level& L, PatchSet& ps, const double* vals);
 void patch_extract_inverse(alfib_ctx* c, const PatchSet& ps, int patch, double* host_out);

@@ -48,6 +48,7 @@ void release_patchset(PatchSet& ps) {
   ps.forder.release();
   ps.work.release();
   ps.store_buf.release();
+  ps.cond.release();
 }
 
 // equal split of the block rows across ranks (contiguous ranges)
@@ -294,6 +295,8 @@ int alfib_level_set_bsr_pattern(alfib_ctx* c, int level, int64_t nnzb, const int
     ALFIB_REQUIRE(rowptr[0] == 0 && rowptr[L.n_nodes] == nnzb, "rowptr does not match nnzb");
     for (int64_t k = 0; k < nnzb; ++k) ALFIB_REQUIRE(colidx[k] >= 0 && colidx[k] < L.n_nodes, "column index out of range");
     L.nnzb = nnzb;
+    L.h_rowptr.assign(rowptr, rowptr + L.n_nodes + 1);
+    L.h_colidx.assign(colidx, colidx + nnzb);
     L.rowptr.upload(rowptr, L.n_nodes + 1, c->stream);
     L.colidx.upload(colidx, nnzb, c->stream);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -443,6 +446,37 @@ int alfib_level_set_patches(alfib_ctx* c, int level, int which, int32_t npatch, 
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     comm_peer_publish_ranges(c);
   });
+}
+
+int alfib_level_set_patch_blocks(alfib_ctx* c, int level, int which, const int32_t* block_of_dof) {
+  return guarded(c, [&] {
+    cycle_graph_invalidate(c);
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(which == 0 || which == 1, "which must be 0 or 1");
+    PatchSet& ps = L.ps[which];
+    ALFIB_REQUIRE(ps.npatch > 0 || ps.h_off.size() == 1, "alfib_level_set_patches first");
+    if (!block_of_dof) {                       // back to dense inverses
+      if (ps.cond.on) {
+        ps.cond.release();
+        ps.cond = Condensed();
+        ps.store_elems = ps.h_soff.empty() ? 0 : ps.h_soff.back();
+        ps.store = nullptr;
+        ps.store_buf.release();
+        ps.store_owned = false;
+        ps.factored = false;
+      }
+      return;
+    }
+    condense_setup(c, L, ps, block_of_dof);
+  });
+}
+
+int64_t alfib_patch_apply_bytes(alfib_ctx* c, int level, int which) {
+  if (!c || level < 0 || level >= ALFIB_MAX_LEVELS || !c->levels[level] || which < 0 || which > 1) return -1;
+  const Level& L = *c->levels[level];
+  const PatchSet& ps = L.ps[which];
+  const int64_t index = ps.cond.on ? ps.cond.h.index_bytes : (int64_t)sizeof(int32_t) * (int64_t)ps.h_dofs.size();
+  return ps.store_elems * (int64_t)sizeof(double) + index + 16 * (int64_t)L.n;
 }
 
 int64_t alfib_patch_storage_bytes(alfib_ctx* c, int level, int which) {

@@ -1,0 +1,474 @@
+// Condensed patch inverses: the block/separator ("static condensation") form of A_i^{-1}.
+//
+// A macro-star patch of the Scott-Vogelius discretisation on a barycentrically refined mesh
+// (alfi/relaxation.py:168-177, alfi/bary.py) is mostly *interior* dofs of its macro cells: in 3-D
+// (k = 3) 24 cells x 45 dofs = 1080 of the 1275 patch dofs, and the interiors of different macro
+// cells do not couple.  With the patch dofs split into decoupled blocks B_k and a separator S
+// (everything else), and N_k the separator dofs block k couples to,
+//
+//     A^{-1} = blockdiag(D_k) + [-W; I] X_SS [-V, I],   D_k = A_kk^{-1}, W_k = D_k A_kN, V_k = A_Nk D_k,
+//
+// where X_SS = (A^{-1})[S, S] is the inverse of the Schur complement.  Stored per patch:
+// X_SS (|S|^2), and per block V_k (|N_k| x |B_k|) and [D_k | -W_k] (|B_k| x (|B_k| + |N_k|)):
+// 153 k doubles instead of 1.63 M for the interior 3-D patch.  PCApply_PATCH streams the factors
+// once per application, so the apply is ~10x fewer HBM bytes.
+//
+// Numerics (measured in numpy before this was written): forming the Schur
+// complement A_SS - sum_k A_Sk D_k A_kS in FP64 is *not* accurate enough for augmented-Lagrangian
+// patch matrices (kappa(A_kk) ~ gamma/nu: 1e-3 relative error at gamma = 1e4, Re = 5000), whereas
+// X_SS taken from the pivoted dense inverse of the whole patch together with FP64 D_k, V_k, W_k
+// reproduces the dense-inverse apply to its own accuracy (~kappa * eps).  So the per-Newton-step
+// setup still inverts the whole patch with the blocked Gauss-Jordan kernel (patch_factor.cu) in
+// its workspace, but keeps only X_SS; the block factors are computed by `condense_blocks_kernel`.
+//
+// Apply = four flat kernels over all patches of the set (no CTA barriers, warps independent):
+//   K1  tile ops   g1[q]   = V_q x[B_q]                              (one warp per block)
+//   K2  sep rhs    rs[p,s] = x[S_p[s]] - sum_{q, j: N_q[j] = s} g1[q][j]   (fixed order)
+//   K3  tile ops   us[p]   = X_SS rs[p];  y[S_p] += us[p]            (one warp per 64-row tile)
+//   K4  tile ops   y[B_q] += [D_q | -W_q] [x[B_q]; us[p][N_q]]       (one warp per block)
+// K3 and K4 scatter into y with atomics, or colour by colour with plain stores in deterministic
+// mode, exactly like patch_apply.cu.  Roofline: HBM; algorithmic bytes = stored factors + indices.
+#include <algorithm>
+#include <climits>
+#include <numeric>
+
+#include "alfib_internal.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// generic tile op:  dst[rows] (+)= M * src[cols],  M column-major with roundup2(nrows) rows per column
+// Lanes own row pairs (double2 loads); when a tile has <= 32 (<= 16) rows the warp is split into
+// 2 (4) column groups so that all lanes carry loads, and the groups are summed with shuffles.
+__device__ __forceinline__ double fetch_src(const int32_t* __restrict__ ci, int cpos, int n,
+                                            const double* __restrict__ srcA, const double* __restrict__ srcB) {
+  if (cpos >= n) return 0.0;
+  const int e = __ldg(ci + cpos);
+  return e >= 0 ? __ldg(srcA + e) : __ldg(srcB + (~e));
+}
+
+template <int G, bool ATOMIC>
+__device__ __forceinline__ void tile_op_body(const double* __restrict__ mat, const int32_t* __restrict__ ci,
+                                             const int32_t* __restrict__ ri, double* __restrict__ priv,
+                                             const int nrows, const int n, const double* __restrict__ srcA,
+                                             const double* __restrict__ srcB, double* __restrict__ y, int lane) {
+  constexpr int LPG = 32 / G;                       // lanes per column group
+  const int half = (nrows + 1) >> 1;                // double2 per column
+  const int grp = lane / LPG, l = lane - grp * LPG;
+  const bool active = l < half;
+  const double2* __restrict__ T = reinterpret_cast<const double2*>(mat) + (active ? l : 0);
+  double acc0 = 0.0, acc1 = 0.0;
+  double xv = fetch_src(ci, lane, n, srcA, srcB);
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const double xnext = fetch_src(ci, c0 + 32 + lane, n, srcA, srcB);
+    const int cnt = (n - c0) < 32 ? (n - c0) : 32;
+    const double2* __restrict__ Tc = T + (int64_t)c0 * half;
+    if (cnt == 32) {
+#pragma unroll 8
+      for (int jj = 0; jj < LPG; ++jj) {
+        const int j = jj * G + grp;
+        const double xc = __shfl_sync(0xffffffffu, xv, j);
+        if (active) {
+          const double2 a = __ldcs(Tc + (int64_t)j * half);
+          acc0 = fma(a.x, xc, acc0);
+          acc1 = fma(a.y, xc, acc1);
+        }
+      }
+    } else {
+      for (int jj = 0; jj * G < cnt; ++jj) {
+        const int j = jj * G + grp;
+        const double xc = __shfl_sync(0xffffffffu, xv, j & 31);
+        if (active && j < cnt) {
+          const double2 a = __ldcs(Tc + (int64_t)j * half);
+          acc0 = fma(a.x, xc, acc0);
+          acc1 = fma(a.y, xc, acc1);
+        }
+      }
+    }
+    xv = xnext;
+  }
+#pragma unroll
+  for (int off = 16; off >= LPG; off >>= 1) {       // sum the column groups (fixed order)
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, off);
+  }
+  if (grp == 0 && active) {
+    const int r = 2 * l;
+    if (priv) {
+      priv[r] = acc0;
+      if (r + 1 < nrows) priv[r + 1] = acc1;
+    }
+    if (ri) {
+      if (ATOMIC) {
+        atomicAdd(y + ri[r], acc0);
+        if (r + 1 < nrows) atomicAdd(y + ri[r + 1], acc1);
+      } else {
+        y[ri[r]] += acc0;
+        if (r + 1 < nrows) y[ri[r + 1]] += acc1;
+      }
+    }
+  }
+}
+
+template <bool ATOMIC>
+__global__ void __launch_bounds__(128) tile_ops_kernel(const TileOp* __restrict__ ops, int nops,
+                                                       const int32_t* __restrict__ cidx,
+                                                       const double* __restrict__ store,
+                                                       const double* __restrict__ srcA,
+                                                       const double* __restrict__ srcB, PeerOut yout,
+                                                       double* __restrict__ dstB) {
+  double* __restrict__ y = resolve(yout);
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nops) return;
+  const TileOp* __restrict__ op = ops + w;
+  const double* __restrict__ mat = store + op->mat;
+  const int32_t* __restrict__ ci = cidx + op->col;
+  const long long row = op->row, pv = op->priv;
+  const int32_t* __restrict__ ri = row >= 0 ? cidx + row : nullptr;
+  double* __restrict__ priv = pv >= 0 ? dstB + pv : nullptr;
+  const int nrows = op->nrows, ncols = op->ncols;
+  const int half = (nrows + 1) >> 1;
+  if (half <= 8)
+    tile_op_body<4, ATOMIC>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+  else if (half <= 16)
+    tile_op_body<2, ATOMIC>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+  else
+    tile_op_body<1, ATOMIC>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+}
+
+// K2: separator right-hand sides, rs[e] = x[sepdofs[e]] - sum_j g1[cg1[j]], j in [cptr[e], cptr[e+1])
+__global__ void sep_rhs_kernel(int64_t nsep, const int32_t* __restrict__ sepdofs, const int32_t* __restrict__ cptr,
+                               const int32_t* __restrict__ cg1, const double* __restrict__ x,
+                               const double* __restrict__ g1, double* __restrict__ rs) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nsep) return;
+  double v = __ldg(x + sepdofs[e]);
+  for (int j = cptr[e]; j < cptr[e + 1]; ++j) v -= g1[cg1[j]];
+  rs[e] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-Newton-step block setup: one CTA per (patch, block).  Gathers A_kk, A_kN, A_Nk from the BSR
+// values, inverts A_kk in shared memory by Gauss-Jordan with partial (row) pivoting (first-max
+// rule, like the patch kernel and LAPACK idamax) and writes the V and [D | -W] tiles.
+constexpr int CT = 128;
+
+struct CondenseArgs {
+  int64_t nblocks;
+  const BlockDesc* blocks;
+  const int32_t* bdofs;
+  const int32_t* bkeys;
+  const int32_t* bperm;
+  int bs;
+  const int32_t* rowptr;
+  const int32_t* colidx;
+  const double* vals;
+  double* store;
+  int maxb, maxm;
+  int* info;
+};
+
+__device__ __forceinline__ int bsearch_i32(const int32_t* a, int n, int key) {
+  int lo = 0, hi = n - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const int v = a[mid];
+    if (v == key) return mid;
+    if (v < key) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(CT) condense_blocks_kernel(CondenseArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ldk_max = a.maxb + 1;
+  double* Akk = reinterpret_cast<double*>(smem_raw);          // b x b, column-major, ld = b + 1
+  double* AkN = Akk + (size_t)a.maxb * ldk_max;               // b x m, column-major, ld = b
+  double* ANk = AkN + (size_t)a.maxb * a.maxm;                // m x b, column-major, ld = m
+  double* prow = ANk + (size_t)a.maxb * a.maxm;               // b
+  double* fcol = prow + a.maxb;                               // b
+  int* piv = reinterpret_cast<int*>(fcol + a.maxb);           // b
+  int* src = piv + a.maxb;                                    // b
+  int* keys = src + a.maxb;                                   // b + m
+  int* perm = keys + a.maxb + a.maxm;                         // b + m
+  int* s_flag = perm + a.maxb + a.maxm;                       // [0] pivot row, [1] singular
+
+  for (int64_t q = blockIdx.x; q < a.nblocks; q += gridDim.x) {
+    const BlockDesc d = a.blocks[q];
+    const int b = d.b, m = d.m, ld = b + 1, bm = b + m;
+    const int32_t* dofs = a.bdofs + d.dofs;
+    __syncthreads();                                         // previous block's readers are done
+    for (int i = tid; i < b * ld; i += CT) Akk[i] = 0.0;
+    for (int i = tid; i < b * m; i += CT) { AkN[i] = 0.0; ANk[i] = 0.0; }
+    for (int i = tid; i < bm; i += CT) { keys[i] = a.bkeys[d.keys + i]; perm[i] = a.bperm[d.keys + i]; }
+    __syncthreads();
+    // ---- gather: one warp per row of [B; N], lanes over the BSR row's blocks ------------------
+    {
+      const int bs = a.bs, b2 = bs * bs;
+      for (int rp = warp; rp < bm; rp += CT / 32) {
+        const int g = dofs[rp];
+        const int node = g / bs, comp = g - node * bs;
+        const int k1 = a.rowptr[node + 1];
+        for (int k = a.rowptr[node] + lane; k < k1; k += 32) {
+          const int cn = a.colidx[k];
+          for (int c2 = 0; c2 < bs; ++c2) {
+            const int hit = bsearch_i32(keys, bm, cn * bs + c2);
+            if (hit < 0) continue;
+            const int cp = perm[hit];
+            const double v = a.vals[(int64_t)k * b2 + comp * bs + c2];
+            if (rp < b) {
+              if (cp < b) Akk[rp + cp * ld] = v; else AkN[rp + (cp - b) * b] = v;
+            } else if (cp < b) {
+              ANk[(rp - b) + cp * m] = v;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- in-place Gauss-Jordan inversion of Akk with partial pivoting --------------------------
+    for (int j = 0; j < b; ++j) {
+      if (warp == 0) {
+        double best = -1.0;
+        int bi = INT_MAX;
+        for (int r = j + lane; r < b; r += 32) {
+          const double v = fabs(Akk[r + j * ld]);
+          if (v > best) { best = v; bi = r; }
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+          const double ov = __shfl_down_sync(0xffffffffu, best, off);
+          const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+          if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) {
+          const bool singular = !(best > 0.0);
+          if (singular) { bi = j; atomicCAS(a.info, 0, (int)(q % INT_MAX) + 1); }
+          piv[j] = bi;
+          s_flag[0] = bi;
+          s_flag[1] = singular ? 1 : 0;
+        }
+      }
+      __syncthreads();
+      const int pv = s_flag[0];
+      const bool singular = s_flag[1] != 0;
+      if (pv != j && tid < b) {
+        const double t0 = Akk[j + tid * ld];
+        Akk[j + tid * ld] = Akk[pv + tid * ld];
+        Akk[pv + tid * ld] = t0;
+      }
+      __syncthreads();
+      const double dinv = singular ? 0.0 : 1.0 / Akk[j + j * ld];
+      if (tid < b) {
+        prow[tid] = (tid == j) ? 0.0 : Akk[j + tid * ld] * dinv;
+        fcol[tid] = Akk[tid + j * ld];
+      }
+      __syncthreads();
+      for (int i = tid; i < b * b; i += CT) {
+        const int cc = i / b, r = i - cc * b;
+        double v;
+        if (r == j)
+          v = (cc == j) ? dinv : prow[cc];
+        else if (cc == j)
+          v = -fcol[r] * dinv;
+        else
+          v = fma(-fcol[r], prow[cc], Akk[r + cc * ld]);
+        Akk[r + cc * ld] = v;
+      }
+      __syncthreads();
+    }
+    // undo the row pivoting: A^-1 = M with the column swaps applied in reverse order
+    if (tid == 0) {
+      for (int cc = 0; cc < b; ++cc) src[cc] = cc;
+      for (int k = b - 1; k >= 0; --k) {
+        const int pv = piv[k];
+        if (pv != k) { const int t0 = src[k]; src[k] = src[pv]; src[pv] = t0; }
+      }
+    }
+    __syncthreads();
+    // D[r][c] = Akk[r + src[c] * ld]
+    // ---- V = A_Nk D  (m x b), tile with roundup2(m) rows per column ------------------------------
+    {
+      const int mr = (m + 1) & ~1;
+      double* Vt = a.store + d.voff;
+      for (int i = tid; i < mr * b; i += CT) {
+        const int cc = i / mr, r = i - cc * mr;
+        double v = 0.0;
+        if (r < m) {
+          const double* Dc = Akk + (size_t)src[cc] * ld;
+          for (int k = 0; k < b; ++k) v = fma(ANk[r + k * m], Dc[k], v);
+        }
+        Vt[i] = v;
+      }
+    }
+    // ---- [D | -W], W = D A_kN  (b x m), tile with roundup2(b) rows per column ---------------------
+    {
+      const int br = (b + 1) & ~1;
+      double* Dt = a.store + d.dwoff;
+      for (int i = tid; i < br * b; i += CT) {
+        const int cc = i / br, r = i - cc * br;
+        Dt[i] = (r < b) ? Akk[r + (size_t)src[cc] * ld] : 0.0;
+      }
+      double* Wt = Dt + (size_t)br * b;
+      for (int i = tid; i < br * m; i += CT) {
+        const int cc = i / br, r = i - cc * br;
+        double v = 0.0;
+        if (r < b) {
+          const double* Ac = AkN + (size_t)cc * b;
+          for (int k = 0; k < b; ++k) v = fma(Akk[r + (size_t)src[k] * ld], Ac[k], v);
+        }
+        Wt[i] = -v;
+      }
+    }
+  }
+}
+
+size_t condense_smem_bytes(int maxb, int maxm) {
+  const size_t doubles = (size_t)maxb * (maxb + 1) + 2 * (size_t)maxb * maxm + 2 * (size_t)maxb;
+  const size_t ints = 2 * (size_t)maxb + 2 * (size_t)(maxb + maxm) + 4;
+  return doubles * sizeof(double) + ints * sizeof(int) + 16;
+}
+
+}  // namespace
+
+// ---- host: block structure -> op lists (condense_host.h), uploaded here ----------------------------
+void condense_setup(alfib_ctx* c, Level& L, PatchSet& ps, const int32_t* block_of_dof) {
+  ALFIB_REQUIRE(!L.h_rowptr.empty(), "set the BSR pattern before the patch blocks");
+  Condensed& cd = ps.cond;
+  cd.release();
+  cd.on = false;
+  PatchView pv;
+  pv.npatch = ps.npatch;
+  pv.ncolour = ps.ncolour;
+  pv.bs = L.bs;
+  pv.ndofs = L.n;
+  pv.off = ps.h_off.data();
+  pv.dofs = ps.h_dofs.data();
+  pv.order = &ps.h_order;
+  pv.colour = ps.h_colour.data();
+  pv.rowptr = L.h_rowptr.data();
+  pv.colidx = L.h_colidx.data();
+  try {
+    build_condensed_host(pv, block_of_dof, cd.h);
+  } catch (const std::runtime_error& e) {
+    cd.h = CondensedHost();
+    throw DeviceError{ALFIB_EINVAL, e.what()};
+  }
+  const CondensedHost& h = cd.h;
+  ps.store_elems = h.store_elems;
+  ps.store = nullptr;                 // storage requirement changed: (re)allocated on the next factor
+  ps.store_buf.release();
+  ps.store_owned = false;
+  ps.factored = false;
+  cd.sepoff.upload(h.sepoff.data(), h.sepoff.size(), c->stream);
+  cd.ssoff.upload(h.ssoff.data(), h.ssoff.size(), c->stream);
+  cd.seplocal.upload(h.seplocal.data(), h.seplocal.size(), c->stream);
+  cd.sepdofs.upload(h.sepdofs.data(), h.sepdofs.size(), c->stream);
+  cd.cidx.upload(h.cidx.data(), h.cidx.size(), c->stream);
+  cd.bdofs.upload(h.bdofs.data(), h.bdofs.size(), c->stream);
+  cd.bkeys.upload(h.bkeys.data(), h.bkeys.size(), c->stream);
+  cd.bperm.upload(h.bperm.data(), h.bperm.size(), c->stream);
+  cd.cptr.upload(h.cptr.data(), h.cptr.size(), c->stream);
+  cd.cg1.upload(h.cg1.data(), h.cg1.size(), c->stream);
+  cd.blocks.upload(h.blocks.data(), h.blocks.size(), c->stream);
+  cd.opsV.upload(h.opsV.data(), h.opsV.size(), c->stream);
+  cd.opsS.upload(h.opsS.data(), h.opsS.size(), c->stream);
+  cd.opsDW.upload(h.opsDW.data(), h.opsDW.size(), c->stream);
+  cd.g1.alloc((size_t)std::max<int64_t>(h.g1_total, 1));
+  cd.rs.alloc((size_t)std::max<int64_t>(h.nsep_total, 1));
+  cd.us.alloc((size_t)std::max<int64_t>(h.nsep_total, 1));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  cd.on = true;
+}
+
+// D, V, W of every block from the current operator values (X_SS is written by patch_factor.cu)
+void launch_condense_blocks(alfib_ctx* c, const Level& L, PatchSet& ps, const double* vals) {
+  Condensed& cd = ps.cond;
+  if (cd.h.nblocks == 0) return;
+  CondenseArgs a;
+  a.nblocks = cd.h.nblocks;
+  a.blocks = cd.blocks.p;
+  a.bdofs = cd.bdofs.p;
+  a.bkeys = cd.bkeys.p;
+  a.bperm = cd.bperm.p;
+  a.bs = L.bs;
+  a.rowptr = L.rowptr.p;
+  a.colidx = L.colidx.p;
+  a.vals = vals;
+  a.store = ps.store;
+  a.maxb = cd.h.maxb;
+  a.maxm = std::max(cd.h.maxm, 1);
+  c->finfo.alloc(2);
+  CUDA_TRY(cudaMemsetAsync(c->finfo.p, 0, 2 * sizeof(int), c->stream));
+  a.info = c->finfo.p;
+  const size_t smem = condense_smem_bytes(a.maxb, a.maxm);
+  CUDA_TRY(cudaFuncSetAttribute(condense_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<int64_t>(cd.h.nblocks, (int64_t)c->num_sms * 16);
+  condense_blocks_kernel<<<grid, CT, smem, c->stream>>>(a);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  int info = 0;
+  CUDA_TRY(cudaMemcpyAsync(&info, c->finfo.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (info != 0)
+    throw DeviceError{ALFIB_ESINGULAR, "interior block " + std::to_string(info - 1) + " of a condensed patch is singular"};
+}
+
+void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, PeerOut y) {
+  const Condensed& cd = ps.cond;
+  const CondensedHost& h = cd.h;
+  const int threads = 128, wpb = threads / 32;
+  const int nV = (int)h.opsV.size(), nS = (int)h.opsS.size(), nDW = (int)h.opsDW.size();
+  // K1: V ops, all patches, plain private stores
+  if (nV) {
+    tile_ops_kernel<false><<<cdiv(nV, wpb), threads, 0, c->stream>>>(cd.opsV.p, nV, cd.cidx.p, ps.store, x, nullptr,
+                                                                      plain_out(nullptr), cd.g1.p);
+    c->launches++;
+  }
+  // K2: separator right-hand sides
+  if (h.nsep_total) {
+    sep_rhs_kernel<<<cdiv(h.nsep_total, 256), 256, 0, c->stream>>>(h.nsep_total, cd.sepdofs.p, cd.cptr.p, cd.cg1.p, x,
+                                                                    cd.g1.p, cd.rs.p);
+    c->launches++;
+  }
+  // K3 (separator solve + scatter), K4 (block back-substitution + scatter)
+  const bool coloured = c->deterministic && !ps.repeated;
+  auto run = [&](const TileOp* ops, int nops, const double* srcA, const double* srcB, double* dstB, bool atomic) {
+    if (nops <= 0) return;
+    if (atomic)
+      tile_ops_kernel<true><<<cdiv(nops, wpb), threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB);
+    else
+      tile_ops_kernel<false><<<cdiv(nops, wpb), threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB);
+    c->launches++;
+  };
+  if (!coloured && ps.ncolour > 1) {
+    run(cd.opsS.p, nS, cd.rs.p, nullptr, cd.us.p, true);
+    run(cd.opsDW.p, nDW, x, cd.us.p, nullptr, true);
+  } else {
+    for (int col = 0; col < ps.ncolour; ++col) {
+      const int s = h.s_colour_start[col], e = h.s_colour_start[col + 1];
+      run(cd.opsS.p + s, e - s, cd.rs.p, nullptr, cd.us.p, ps.repeated);
+    }
+    for (int col = 0; col < ps.ncolour; ++col) {
+      const int s = h.dw_colour_start[col], e = h.dw_colour_start[col + 1];
+      run(cd.opsDW.p + s, e - s, x, cd.us.p, nullptr, ps.repeated);
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+}
+
+// tests / debugging: dense inverse of one patch rebuilt on the host from its condensed factors
+void condensed_extract_inverse(alfib_ctx* c, const PatchSet& ps, int patch, double* host_out) {
+  ALFIB_REQUIRE(patch >= 0 && patch < ps.npatch, "patch index out of range");
+  ALFIB_REQUIRE(ps.factored, "patches not factored");
+  const int n = (int)(ps.h_off[patch + 1] - ps.h_off[patch]);
+  auto download = [&](int64_t off, int64_t count) {
+    std::vector<double> t((size_t)std::max<int64_t>(count, 1));
+    if (count) CUDA_TRY(cudaMemcpyAsync(t.data(), ps.store + off, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return t;
+  };
+  condensed_inverse_host(ps.cond.h, patch, n, download, host_out);
+}

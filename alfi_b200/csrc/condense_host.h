@@ -1,0 +1,354 @@
+// Host side of the condensed patch sets (see condense.cu for the method): block structure ->
+// storage layout, index lists and tile-op lists.  CUDA-free on purpose, so that the same code is
+// compiled into libalfib.so (condense.cu) and into the CPU-only checker tests/condense_host_shim.cpp,
+// which executes the op lists on the host against dense patch solves (tests/test_condense_host.py).
+#pragma once
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#ifndef ALFIB_TILE_ROWS
+#define ALFIB_TILE_ROWS 64
+#endif
+
+// One dense tile operation of the condensed apply: dst[rows] (+)= M * src[cols].
+struct TileOp {
+  long long mat;    // element offset of the tile in the store: column-major, roundup2(nrows) rows per column
+  long long col;    // offset into cidx of the ncols source indices (i >= 0: srcA[i]; i < 0: srcB[~i])
+  long long row;    // offset into cidx of the nrows global destination dofs, or -1
+  long long priv;   // offset into the private destination buffer (plain store), or -1
+  int nrows, ncols; // nrows <= ALFIB_TILE_ROWS
+};
+
+// Per (patch, block) descriptor of the per-Newton-step block setup (D = A_kk^-1, V = A_Nk D, W = D A_kN)
+struct BlockDesc {
+  long long dofs;   // offset into bdofs: b block dofs, then m neighbour (separator) dofs, global numbers
+  long long keys;   // offset into bkeys / bperm: the same b+m dofs sorted ascending + their positions
+  long long voff;   // store offset of the V tile   (roundup2(m) x b)
+  long long dwoff;  // store offset of the [D | -W] tile (roundup2(b) x (b+m))
+  int b, m;
+};
+
+// what the builder needs to know about a patch set and its level (all host memory, borrowed)
+struct PatchView {
+  int npatch, ncolour, bs, ndofs;
+  const int64_t* off;          // npatch+1
+  const int32_t* dofs;
+  const std::vector<int32_t>* order;
+  const int32_t* colour;       // npatch
+  const int32_t* rowptr;       // BSR pattern of the level (block rows)
+  const int32_t* colidx;
+};
+
+struct CondensedHost {
+  int maxb = 0, maxm = 0, maxsep = 0;
+  int64_t nblocks = 0, nsep_total = 0, g1_total = 0, store_elems = 0;
+  std::vector<int64_t> sepoff;          // npatch+1: separator dofs per patch ...
+  std::vector<int32_t> seplocal;        // ... as patch-local indices
+  std::vector<int32_t> sepdofs;         // ... and as global dofs
+  std::vector<int64_t> ssoff;           // npatch+1: store offsets of the X_SS tiles
+  std::vector<int64_t> blk_start;       // npatch+1: blocks of patch p are [blk_start[p], blk_start[p+1])
+  std::vector<BlockDesc> blocks;
+  std::vector<int64_t> bl_off;          // nblocks+1 into bl_local
+  std::vector<int32_t> bl_local;        // patch-local indices of the block dofs
+  std::vector<int64_t> nb_off;          // nblocks+1 into nb_pos
+  std::vector<int32_t> nb_pos;          // positions of the neighbour dofs in the patch's separator list
+  std::vector<int64_t> g1off;           // nblocks+1: private slots of the V outputs
+  std::vector<int32_t> cidx, bdofs, bkeys, bperm, cptr, cg1;
+  std::vector<TileOp> opsV, opsS, opsDW;
+  std::vector<int> s_colour_start, dw_colour_start;   // ncolour+1 ranges of opsS / opsDW
+  int64_t index_bytes = 0;              // bytes of index data one apply reads (roofline accounting)
+};
+
+inline int ch_roundup2(int n) { return (n + 1) & ~1; }
+
+// block_of_dof[k] for every entry of the patch dof list: < 0 separator, otherwise a block label
+// (any non-negative integer, local to the patch).  Blocks must be pairwise decoupled in the BSR
+// pattern; this is checked here, so a wrong hint is an error, never a wrong answer.
+inline void build_condensed_host(const PatchView& pv, const int32_t* block_of_dof, CondensedHost& cd) {
+  cd = CondensedHost();
+  const int npatch = pv.npatch, bs = pv.bs;
+  cd.sepoff.assign(npatch + 1, 0);
+  cd.ssoff.assign(npatch + 1, 0);
+  cd.blk_start.assign(npatch + 1, 0);
+  cd.bl_off.assign(1, 0);
+  cd.nb_off.assign(1, 0);
+  std::vector<int32_t> mark(pv.ndofs, 0);             // 0: not in patch; k+1: block k; -(s+1): separator position s
+  std::vector<int32_t> nbstamp;
+  std::vector<std::vector<int32_t>> blk_local, blk_nb;
+
+  for (int p = 0; p < npatch; ++p) {
+    const int64_t o = pv.off[p];
+    const int n = (int)(pv.off[p + 1] - o);
+    const int32_t* I = pv.dofs + o;
+    const int32_t* B = block_of_dof + o;
+    blk_local.clear();
+    std::vector<std::pair<int32_t, int32_t>> labels;   // (label, block index), first-appearance order
+    int nsep = 0;
+    for (int l = 0; l < n; ++l) {
+      if (B[l] < 0) {
+        mark[I[l]] = -(nsep + 1);
+        cd.seplocal.push_back(l);
+        cd.sepdofs.push_back(I[l]);
+        ++nsep;
+      } else {
+        int kk = -1;
+        for (auto& lb : labels)
+          if (lb.first == B[l]) { kk = lb.second; break; }
+        if (kk < 0) {
+          kk = (int)labels.size();
+          labels.push_back({B[l], kk});
+          blk_local.emplace_back();
+        }
+        blk_local[kk].push_back(l);
+        mark[I[l]] = kk + 1;
+      }
+    }
+    const int nblk = (int)blk_local.size();
+    blk_nb.assign(nblk, {});
+    nbstamp.assign((size_t)nblk * std::max(nsep, 1), 0);
+    auto add_nb = [&](int kk, int s) {
+      int32_t& st = nbstamp[(size_t)kk * nsep + s];
+      if (!st) { st = 1; blk_nb[kk].push_back(s); }
+    };
+    // structural check + neighbour sets (rows of block dofs and rows of separator dofs)
+    int prev_node = -1, prev_mark = 0;
+    std::string problem;
+    for (int l = 0; l < n && problem.empty(); ++l) {
+      const int g = I[l], node = g / bs, mk = mark[g];
+      if (node == prev_node && mk == prev_mark) continue;      // same node, same role: same scan
+      prev_node = node;
+      prev_mark = mk;
+      for (int k = pv.rowptr[node]; k < pv.rowptr[node + 1] && problem.empty(); ++k) {
+        const int cn = pv.colidx[k];
+        for (int c2 = 0; c2 < bs; ++c2) {
+          const int mk2 = mark[cn * bs + c2];
+          if (mk2 == 0) continue;
+          if (mk > 0) {
+            if (mk2 > 0) {
+              if (mk2 != mk) {
+                problem = "patch " + std::to_string(p) + ": blocks " + std::to_string(mk - 1) + " and " +
+                          std::to_string(mk2 - 1) + " are coupled in the operator";
+                break;
+              }
+            } else {
+              add_nb(mk - 1, -mk2 - 1);
+            }
+          } else if (mk2 > 0) {
+            add_nb(mk2 - 1, -mk - 1);
+          }
+        }
+      }
+    }
+    for (int t = 0; t < n; ++t) mark[I[t]] = 0;
+    if (!problem.empty()) throw std::runtime_error(problem);
+    cd.sepoff[p + 1] = cd.sepoff[p] + nsep;
+    cd.maxsep = std::max(cd.maxsep, nsep);
+    cd.blk_start[p + 1] = cd.blk_start[p] + nblk;
+    for (int kk = 0; kk < nblk; ++kk) {
+      std::sort(blk_nb[kk].begin(), blk_nb[kk].end());
+      const int b = (int)blk_local[kk].size(), m = (int)blk_nb[kk].size();
+      if (b > ALFIB_TILE_ROWS || m > ALFIB_TILE_ROWS)
+        throw std::runtime_error("condensation block (or its separator neighbourhood) has more than 64 dofs");
+      cd.maxb = std::max(cd.maxb, b);
+      cd.maxm = std::max(cd.maxm, m);
+      cd.bl_local.insert(cd.bl_local.end(), blk_local[kk].begin(), blk_local[kk].end());
+      cd.nb_pos.insert(cd.nb_pos.end(), blk_nb[kk].begin(), blk_nb[kk].end());
+      cd.bl_off.push_back((int64_t)cd.bl_local.size());
+      cd.nb_off.push_back((int64_t)cd.nb_pos.size());
+    }
+  }
+  cd.nblocks = cd.blk_start[npatch];
+  cd.nsep_total = cd.sepoff[npatch];
+  if (cd.nsep_total >= INT_MAX / 2 || (int64_t)cd.nb_pos.size() >= INT_MAX / 2)
+    throw std::runtime_error("condensed set too large for int32 indices");
+
+  // ---- store layout: X_SS tiles of every patch, then V and [D | -W] of every block ------------------
+  int64_t cur = 0;
+  for (int p = 0; p < npatch; ++p) {
+    const int ns = (int)(cd.sepoff[p + 1] - cd.sepoff[p]);
+    cd.ssoff[p] = cur;
+    cur += (int64_t)ns * ch_roundup2(ns);
+  }
+  cd.ssoff[npatch] = cur;
+  cd.blocks.resize(cd.nblocks);
+  cd.g1off.assign(cd.nblocks + 1, 0);
+  // cidx = per patch [rs positions (ns)] [global separator dofs (ns)], then per block
+  //        [global block dofs (b)] [~(us position) of the neighbours (m)]
+  std::vector<int64_t> rs_list(npatch), sg_list(npatch), blk_list(cd.nblocks);
+  for (int p = 0; p < npatch; ++p) {
+    const int64_t so = cd.sepoff[p];
+    const int ns = (int)(cd.sepoff[p + 1] - so);
+    rs_list[p] = (int64_t)cd.cidx.size();
+    for (int s = 0; s < ns; ++s) cd.cidx.push_back((int32_t)(so + s));
+    sg_list[p] = (int64_t)cd.cidx.size();
+    for (int s = 0; s < ns; ++s) cd.cidx.push_back(cd.sepdofs[so + s]);
+  }
+  std::vector<int32_t> idx;
+  for (int p = 0; p < npatch; ++p) {
+    const int64_t o = pv.off[p], so = cd.sepoff[p];
+    for (int64_t q = cd.blk_start[p]; q < cd.blk_start[p + 1]; ++q) {
+      const int b = (int)(cd.bl_off[q + 1] - cd.bl_off[q]), m = (int)(cd.nb_off[q + 1] - cd.nb_off[q]);
+      BlockDesc& d = cd.blocks[q];
+      d.b = b;
+      d.m = m;
+      d.voff = cur;
+      cur += (int64_t)ch_roundup2(m) * b;
+      d.dwoff = cur;
+      cur += (int64_t)ch_roundup2(b) * (b + m);
+      d.dofs = (int64_t)cd.bdofs.size();
+      d.keys = d.dofs;
+      blk_list[q] = (int64_t)cd.cidx.size();
+      for (int i = 0; i < b; ++i) {
+        const int32_t g = pv.dofs[o + cd.bl_local[cd.bl_off[q] + i]];
+        cd.cidx.push_back(g);
+        cd.bdofs.push_back(g);
+      }
+      for (int j = 0; j < m; ++j) {
+        const int32_t s = cd.nb_pos[cd.nb_off[q] + j];
+        cd.cidx.push_back(~(int32_t)(so + s));
+        cd.bdofs.push_back(cd.sepdofs[so + s]);
+      }
+      idx.resize(b + m);
+      std::iota(idx.begin(), idx.end(), 0);
+      const int32_t* gd = cd.bdofs.data() + d.dofs;
+      std::sort(idx.begin(), idx.end(), [&](int x, int y) { return gd[x] < gd[y]; });
+      for (int i = 0; i < b + m; ++i) {
+        cd.bkeys.push_back(gd[idx[i]]);
+        cd.bperm.push_back(idx[i]);
+      }
+      cd.g1off[q + 1] = cd.g1off[q] + m;
+    }
+  }
+  cd.g1_total = cd.g1off[cd.nblocks];
+  cd.store_elems = cur;
+
+  // ---- K2: contributions to every separator entry, in block order -----------------------------------
+  cd.cptr.assign(cd.nsep_total + 1, 0);
+  cd.cg1.assign(cd.g1_total, 0);
+  for (int p = 0; p < npatch; ++p)
+    for (int64_t q = cd.blk_start[p]; q < cd.blk_start[p + 1]; ++q)
+      for (int64_t j = cd.nb_off[q]; j < cd.nb_off[q + 1]; ++j) cd.cptr[cd.sepoff[p] + cd.nb_pos[j] + 1]++;
+  for (int64_t e = 0; e < cd.nsep_total; ++e) cd.cptr[e + 1] += cd.cptr[e];
+  {
+    std::vector<int32_t> cursor(cd.cptr.begin(), cd.cptr.end() - 1);
+    for (int p = 0; p < npatch; ++p)
+      for (int64_t q = cd.blk_start[p]; q < cd.blk_start[p + 1]; ++q)
+        for (int64_t j = cd.nb_off[q]; j < cd.nb_off[q + 1]; ++j)
+          cd.cg1[cursor[cd.sepoff[p] + cd.nb_pos[j]]++] = (int32_t)(cd.g1off[q] + (j - cd.nb_off[q]));
+  }
+
+  // ---- op lists: V ops of every block; S and DW ops colour-major in iteration order ------------------
+  for (int64_t q = 0; q < cd.nblocks; ++q) {
+    const BlockDesc& d = cd.blocks[q];
+    if (d.m == 0) continue;
+    cd.opsV.push_back(TileOp{d.voff, blk_list[q], -1, cd.g1off[q], d.m, d.b});
+  }
+  cd.s_colour_start.assign(pv.ncolour + 1, 0);
+  cd.dw_colour_start.assign(pv.ncolour + 1, 0);
+  for (int col = 0; col < pv.ncolour; ++col) {
+    cd.s_colour_start[col] = (int)cd.opsS.size();
+    cd.dw_colour_start[col] = (int)cd.opsDW.size();
+    for (int32_t p : *pv.order) {
+      if (pv.colour[p] != col) continue;
+      const int64_t so = cd.sepoff[p];
+      const int ns = (int)(cd.sepoff[p + 1] - so);
+      for (int row0 = 0; row0 < ns; row0 += ALFIB_TILE_ROWS) {
+        const int rows = std::min(ns - row0, ALFIB_TILE_ROWS);
+        cd.opsS.push_back(TileOp{cd.ssoff[p] + (int64_t)row0 * ns, rs_list[p], sg_list[p] + row0, so + row0, rows, ns});
+      }
+      for (int64_t q = cd.blk_start[p]; q < cd.blk_start[p + 1]; ++q) {
+        const BlockDesc& d = cd.blocks[q];
+        cd.opsDW.push_back(TileOp{d.dwoff, blk_list[q], blk_list[q], -1, d.b, d.b + d.m});
+      }
+    }
+  }
+  if (pv.ncolour) {
+    cd.s_colour_start[pv.ncolour] = (int)cd.opsS.size();
+    cd.dw_colour_start[pv.ncolour] = (int)cd.opsDW.size();
+  }
+  cd.index_bytes = (int64_t)sizeof(int32_t) * (int64_t)(cd.cidx.size() + cd.sepdofs.size() + cd.cptr.size() + cd.cg1.size()) +
+                   (int64_t)sizeof(TileOp) * (int64_t)(cd.opsV.size() + cd.opsS.size() + cd.opsDW.size());
+}
+
+// Dense inverse (row-major n x n) of one patch rebuilt from its condensed factors.  `fetch(off,
+// count)` returns `count` doubles of the store starting at element `off` (device download in the
+// library, a plain copy in the host checker).
+template <class Fetch>
+inline void condensed_inverse_host(const CondensedHost& cd, int patch, int n, Fetch&& fetch, double* out) {
+  if (n == 0) return;
+  const int64_t so = cd.sepoff[patch];
+  const int ns = (int)(cd.sepoff[patch + 1] - so);
+  std::vector<double> XS((size_t)ns * ns, 0.0);        // X_SS row-major, from its 64-row tiles
+  {
+    const std::vector<double> t = fetch(cd.ssoff[patch], (int64_t)ns * ch_roundup2(ns));
+    for (int row0 = 0; row0 < ns; row0 += ALFIB_TILE_ROWS) {
+      const int rows = std::min(ns - row0, ALFIB_TILE_ROWS), rt = ch_roundup2(rows);
+      const double* tile = t.data() + (int64_t)row0 * ns;
+      for (int cc = 0; cc < ns; ++cc)
+        for (int r = 0; r < rows; ++r) XS[(size_t)(row0 + r) * ns + cc] = tile[(size_t)cc * rt + r];
+    }
+  }
+  std::fill(out, out + (size_t)n * n, 0.0);
+  const int32_t* sl = cd.seplocal.data() + so;
+  for (int r = 0; r < ns; ++r)
+    for (int cc = 0; cc < ns; ++cc) out[(size_t)sl[r] * n + sl[cc]] = XS[(size_t)r * ns + cc];
+  struct Blk {
+    int b, m;
+    std::vector<double> V, D, W;
+    const int32_t* loc;
+    const int32_t* nb;
+  };
+  std::vector<Blk> blks;
+  for (int64_t q = cd.blk_start[patch]; q < cd.blk_start[patch + 1]; ++q) {
+    const BlockDesc& d = cd.blocks[q];
+    Blk k;
+    k.b = d.b;
+    k.m = d.m;
+    k.loc = cd.bl_local.data() + cd.bl_off[q];
+    k.nb = cd.nb_pos.data() + cd.nb_off[q];
+    const int mr = ch_roundup2(d.m), br = ch_roundup2(d.b);
+    const std::vector<double> tv = fetch(d.voff, (int64_t)mr * d.b);
+    const std::vector<double> td = fetch(d.dwoff, (int64_t)br * (d.b + d.m));
+    k.V.assign((size_t)d.m * d.b, 0.0);
+    k.D.assign((size_t)d.b * d.b, 0.0);
+    k.W.assign((size_t)d.b * d.m, 0.0);
+    for (int cc = 0; cc < d.b; ++cc)
+      for (int r = 0; r < d.m; ++r) k.V[(size_t)r * d.b + cc] = tv[(size_t)cc * mr + r];
+    for (int cc = 0; cc < d.b; ++cc)
+      for (int r = 0; r < d.b; ++r) k.D[(size_t)r * d.b + cc] = td[(size_t)cc * br + r];
+    for (int cc = 0; cc < d.m; ++cc)
+      for (int r = 0; r < d.b; ++r) k.W[(size_t)r * d.m + cc] = -td[(size_t)(d.b + cc) * br + r];
+    blks.push_back(std::move(k));
+  }
+  // X[S, B_l] = -X_SS[:, N_l] V_l ;  X[B_k, B_l] = delta_kl D_k + W_k X_SS[N_k, N_l] V_l ;  X[B_k, S] = -W_k X_SS[N_k, :]
+  for (const Blk& l : blks) {
+    std::vector<double> XV((size_t)std::max(ns, 1) * l.b, 0.0);     // X_SS[:, N_l] V_l
+    for (int r = 0; r < ns; ++r)
+      for (int j = 0; j < l.m; ++j) {
+        const double xs = XS[(size_t)r * ns + l.nb[j]];
+        for (int cc = 0; cc < l.b; ++cc) XV[(size_t)r * l.b + cc] += xs * l.V[(size_t)j * l.b + cc];
+      }
+    for (int r = 0; r < ns; ++r)
+      for (int cc = 0; cc < l.b; ++cc) out[(size_t)sl[r] * n + l.loc[cc]] = -XV[(size_t)r * l.b + cc];
+    for (const Blk& k : blks)
+      for (int r = 0; r < k.b; ++r)
+        for (int cc = 0; cc < l.b; ++cc) {
+          double v = (&k == &l) ? k.D[(size_t)r * k.b + cc] : 0.0;
+          for (int j = 0; j < k.m; ++j) v += k.W[(size_t)r * k.m + j] * XV[(size_t)k.nb[j] * l.b + cc];
+          out[(size_t)k.loc[r] * n + l.loc[cc]] = v;
+        }
+  }
+  for (const Blk& k : blks)
+    for (int r = 0; r < k.b; ++r)
+      for (int cc = 0; cc < ns; ++cc) {
+        double v = 0.0;
+        for (int j = 0; j < k.m; ++j) v += k.W[(size_t)r * k.m + j] * XS[(size_t)k.nb[j] * ns + cc];
+        out[(size_t)k.loc[r] * n + sl[cc]] = -v;
+      }
+}

@@ -86,6 +86,10 @@ __global__ void __launch_bounds__(128) patch_apply_kernel(const int2* __restrict
 
 void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, PeerOut y) {
   if (ps.nwork == 0) return;
+  if (ps.cond.on) {                   // block/separator form of the inverses (condense.cu)
+    launch_condensed_apply(c, ps, x, y);
+    return;
+  }
   const int threads = 128, wpb = threads / 32;
   const bool coloured = c->deterministic && !ps.repeated;
   if (!coloured && ps.ncolour > 1) {

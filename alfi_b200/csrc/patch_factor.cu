@@ -55,6 +55,9 @@ struct FactorArgs {
   const int32_t* sperm;        // ... and their local indices
   const int64_t* soff;
   double* store;
+  // condensed sets (condense.cu): keep only X[S, S], S = separator dofs (patch-local indices); else null
+  const int64_t* sepoff;
+  const int32_t* seplocal;
   // level operator
   int bs;
   const int32_t* rowptr;
@@ -482,7 +485,23 @@ __global__ void __launch_bounds__(FT, 1) patch_factor_kernel(FactorArgs a) {
       }
     }
     __syncthreads();
-    {
+    if (a.sepoff) {
+      // condensed set: only the separator block of the inverse is kept, in the same tiled layout
+      const int64_t so = a.sepoff[p];
+      const int ns = (int)(a.sepoff[p + 1] - so);
+      const int32_t* __restrict__ sl = a.seplocal + so;
+      double* out = a.store + a.soff[p];
+      for (int row0 = 0; row0 < ns; row0 += ALFIB_TILE_ROWS) {
+        int rows = ns - row0;
+        rows = rows > ALFIB_TILE_ROWS ? ALFIB_TILE_ROWS : ((rows + 1) & ~1);
+        double* tile = out + (size_t)row0 * ns;
+        for (int64_t i = tid; i < (int64_t)rows * ns; i += FT) {
+          const int c = (int)(i / rows), rr = (int)(i - (int64_t)c * rows);
+          const int r = row0 + rr;
+          tile[i] = (r < ns) ? W[sl[r] + (size_t)src[sl[c]] * ld] : 0.0;
+        }
+      }
+    } else {
       double* out = a.store + a.soff[p];
       const int ntile = (n + ALFIB_TILE_ROWS - 1) / ALFIB_TILE_ROWS;
       for (int t = 0; t < ntile; ++t) {
@@ -547,8 +566,10 @@ void launch_patch_factor(alfib_ctx* c, const Level& L, PatchSet& ps, const doubl
   a.pdofs = ps.dofs.p;
   a.sorted = ps.sorted.p;
   a.sperm = ps.sperm.p;
-  a.soff = ps.soff.p;
+  a.soff = ps.cond.on ? ps.cond.ssoff.p : ps.soff.p;
   a.store = ps.store;
+  a.sepoff = ps.cond.on ? ps.cond.sepoff.p : nullptr;
+  a.seplocal = ps.cond.on ? ps.cond.seplocal.p : nullptr;
   a.bs = L.bs;
   a.rowptr = L.rowptr.p;
   a.colidx = L.colidx.p;
@@ -588,10 +609,15 @@ void launch_patch_factor(alfib_ctx* c, const Level& L, PatchSet& ps, const doubl
   }
   if (info[0] != 0)
     throw DeviceError{ALFIB_ESINGULAR, "patch " + std::to_string(info[0] - 1) + " is singular"};
+  if (ps.cond.on) launch_condense_blocks(c, L, ps, vals);
   ps.factored = true;
 }
 
 void patch_extract_inverse(alfib_ctx* c, const PatchSet& ps, int patch, double* host_out) {
+  if (ps.cond.on) {
+    condensed_extract_inverse(c, ps, patch, host_out);
+    return;
+  }
   ALFIB_REQUIRE(patch >= 0 && patch < ps.npatch, "patch index out of range");
   ALFIB_REQUIRE(ps.factored, "patches not factored");
   const int n = (int)(ps.h_off[patch + 1] - ps.h_off[patch]);

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["partition_patches", "shard_patch_arrays", "bootstrap_unique_id"]
+__all__ = ["partition_patches", "shard_patch_arrays", "shard_dof_array", "bootstrap_unique_id"]
 
 
 def partition_patches(offsets, dofs, nranks: int) -> np.ndarray:
@@ -53,6 +53,15 @@ def shard_patch_arrays(offsets, dofs, order, colours, owner, rank):
     new_order = local[order[owner[order] == rank]].astype(np.int32)
     new_col = None if colours is None else np.asarray(colours)[mine].astype(np.int32)
     return new_off, new_dofs, new_order, new_col, mine
+
+
+def shard_dof_array(offsets, arr, mine):
+    """Entries of a per-patch-dof array (e.g. the condensation block labels) of the patches `mine`."""
+    if arr is None:
+        return None
+    offsets = np.asarray(offsets, dtype=np.int64)
+    idx = np.concatenate([np.arange(offsets[p], offsets[p + 1]) for p in mine]) if len(mine) else np.empty(0, np.int64)
+    return np.asarray(arr)[idx]
 
 
 def bootstrap_unique_id(rank: int):

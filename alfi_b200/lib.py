@@ -50,6 +50,8 @@ SIGNATURES = {
     "alfib_residual": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p, _f64p]),
     "alfib_level_set_patches": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int32, _i64p, _i32p, C.c_int32,
                                           _i32p, _i32p]),
+    "alfib_level_set_patch_blocks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i32p]),
+    "alfib_patch_apply_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int]),
     "alfib_patch_storage_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int]),
     "alfib_patch_bind_storage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
     "alfib_level_factor": (C.c_int, [C.c_void_p, C.c_int]),
@@ -246,6 +248,19 @@ class Context:
             0 if order_a is None else order_a.size,
             None if order_a is None else _ptr(order_a, C.c_int32),
             None if col_a is None else _ptr(col_a, C.c_int32)))
+
+    def set_patch_blocks(self, level, blocks, which=PATCHES_SMOOTHER):
+        """Block/separator structure of the patches set with set_patches (one int32 per patch dof:
+        < 0 separator, else a block label); None returns to dense inverses.  See include/alfib.h."""
+        if blocks is None:
+            self._check(self.lib.alfib_level_set_patch_blocks(self.h, level, which, None))
+            return
+        b = _i32(blocks)
+        self._check(self.lib.alfib_level_set_patch_blocks(self.h, level, which, _ptr(b, C.c_int32)))
+
+    def patch_apply_bytes(self, level, which=PATCHES_SMOOTHER):
+        """Algorithmic bytes of one application of the patch set (factors + indices + 16 N)."""
+        return int(self.lib.alfib_patch_apply_bytes(self.h, level, which))
 
     def patch_storage_bytes(self, level, which=PATCHES_SMOOTHER):
         return int(self.lib.alfib_patch_storage_bytes(self.h, level, which))

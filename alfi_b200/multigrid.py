@@ -29,10 +29,12 @@ class LevelInput:
     patch_dofs: np.ndarray | None = None
     patch_order: np.ndarray | None = None
     patch_colours: np.ndarray | None = None
+    patch_blocks: np.ndarray | None = None   # condensed form: block label per patch dof, -1 = separator
     P: object | None = None               # scipy CSR: scalar per node, or on dofs if P_dof_level
     P_dof_level: bool = False
     cell_offsets: np.ndarray | None = None
     cell_dofs: np.ndarray | None = None
+    cell_blocks: np.ndarray | None = None
     cb_dofs: np.ndarray | None = None
     a0_vals: np.ndarray | None = None
     d_vals: np.ndarray | None = None
@@ -44,11 +46,13 @@ def level_input_from_synth(ld) -> LevelInput:
     if ld.patches is not None:
         ps = ld.patches
         li.patch_offsets, li.patch_dofs, li.patch_order, li.patch_colours = ps.offsets, ps.dofs, ps.order, ps.colours
+        li.patch_blocks = ps.blocks
     if ld.P is not None:
         li.P = ld.P
         li.P_dof_level = bool(getattr(ld, "P_dof_level", False))
         if ld.cell_patches is not None:
             li.cell_offsets, li.cell_dofs = ld.cell_patches.offsets, ld.cell_patches.dofs
+            li.cell_blocks = ld.cell_patches.blocks
             li.cb_dofs = ld.cb_dofs
             li.a0_vals, li.d_vals = ld.A0.vals, ld.D.vals
     return li
@@ -60,13 +64,16 @@ class DeviceMultigrid:
     def __init__(self, levels: list[LevelInput], smoothing: int, device: int = 0, deterministic: bool = False,
                  robust_restrict: bool = True, ctx: Context | None = None, torch_storage: bool = False,
                  rank: int = 0, nranks: int = 1, unique_id: bytes | None = None,
-                 peer_memory: bool = False):
+                 peer_memory: bool = False, condense: bool = True):
         """With nranks > 1 every rank passes the same global `levels`; this rank keeps the patches
         `alfi_b200.dist.partition_patches` assigns to it (in a deployment each rank would only
         ever see its own) and the library adds the exchange steps: NCCL collectives by default,
         NVLink peer-memory pull-reductions with ``peer_memory=True`` (measured equal within 2 % at
-        2/4/8 GPUs in round 1, so the simpler NCCL path is the default)."""
-        from .dist import partition_patches, shard_patch_arrays
+        2/4/8 GPUs in round 1, so the simpler NCCL path is the default).
+
+        ``condense``: use the block/separator form of the patch inverses (csrc/condense.cu) for the
+        patch sets whose LevelInput carries block labels; False keeps dense inverses everywhere."""
+        from .dist import partition_patches, shard_dof_array, shard_patch_arrays
         self.ctx = ctx or Context(device, deterministic)
         self.nlevels = len(levels)
         self.smoothing = smoothing
@@ -84,11 +91,16 @@ class DeviceMultigrid:
             c.set_bc(l, li.bc_dofs)
             if l > 0:
                 off, dofs, order, cols = li.patch_offsets, li.patch_dofs, li.patch_order, li.patch_colours
+                blocks = li.patch_blocks if condense else None
                 if nranks > 1:
                     owner = partition_patches(off, dofs, nranks)
+                    goff = off
                     off, dofs, order, cols, mine = shard_patch_arrays(off, dofs, order, cols, owner, rank)
+                    blocks = shard_dof_array(goff, blocks, mine)
                     self.local_patches[(l, PATCHES_SMOOTHER)] = mine
                 c.set_patches(l, off, dofs, order, cols, PATCHES_SMOOTHER)
+                if blocks is not None:
+                    c.set_patch_blocks(l, blocks, PATCHES_SMOOTHER)
                 if torch_storage:
                     self._bind(l, PATCHES_SMOOTHER)
                 cb = li.cb_dofs if li.cb_dofs is not None else np.empty(0, np.int32)
@@ -97,11 +109,16 @@ class DeviceMultigrid:
                     off, dofs = li.cell_offsets, li.cell_dofs
                     cols = np.zeros(off.size - 1, np.int32)
                     order = None
+                    blocks = li.cell_blocks if condense else None
                     if nranks > 1:
                         owner = partition_patches(off, dofs, nranks)
+                        goff = off
                         off, dofs, order, cols, mine = shard_patch_arrays(off, dofs, None, cols, owner, rank)
+                        blocks = shard_dof_array(goff, blocks, mine)
                         self.local_patches[(l, PATCHES_TRANSFER)] = mine
                     c.set_patches(l, off, dofs, order, cols, PATCHES_TRANSFER)
+                    if blocks is not None:
+                        c.set_patch_blocks(l, blocks, PATCHES_TRANSFER)
                     if torch_storage:
                         self._bind(l, PATCHES_TRANSFER)
         if nranks > 1 and peer_memory:

@@ -22,7 +22,10 @@ from dataclasses import dataclass
 import numpy as np
 import scipy.sparse as sp
 
-__all__ = ["PatchSet", "patch_dofs_from_points", "points_to_csr", "greedy_colouring"]
+__all__ = ["PatchSet", "patch_dofs_from_points", "points_to_csr", "greedy_colouring", "macro_interior_blocks",
+           "MAX_BLOCK_DOFS"]
+
+MAX_BLOCK_DOFS = 64        # limit of the condensed form (csrc/condense.cu: one warp tile per block)
 
 
 @dataclass
@@ -32,6 +35,7 @@ class PatchSet:
     order: np.ndarray          # int32 iteration set (indices into patches)
     bs: int
     colours: np.ndarray | None = None     # int32 (npatch,), greedy colouring in iteration order
+    blocks: np.ndarray | None = None      # int32 per dof entry: -1 separator, else block label (condensed form)
 
     @property
     def npatch(self):
@@ -128,3 +132,41 @@ def greedy_colouring(ps: PatchSet, ndofs: int) -> np.ndarray:
         used[d] |= one << np.uint64(c)
     ps.colours = colours
     return colours
+
+
+def macro_interior_blocks(plex, V, ps: PatchSet, label: str = "MacroVertices") -> np.ndarray | None:
+    """Block/separator structure of patches on a barycentrically refined mesh, for the condensed
+    form of the patch inverses (``alfib_level_set_patch_blocks``, csrc/condense.cu).
+
+    A point lies in the interior of a macro cell iff it is in the star of that cell's barycentre,
+    i.e. of a vertex *not* carrying the ``MacroVertices`` label that alfi/bary.py:16-27 sets and
+    ``MacroStar`` already relies on (alfi/relaxation.py:168-177).  Dofs attached to such points
+    couple only to dofs of the same macro cell, so per patch they form decoupled blocks (label =
+    the barycentre's point number); every other dof is separator (-1).  Returns None when the mesh
+    has no macro structure or a block would exceed the 64-dof limit of the condensed kernels (the
+    caller then keeps dense inverses).  The library re-checks decoupling against the operator's
+    sparsity pattern, so this is a hint that cannot change results.
+    """
+    lab = plex.labels.get(label) if hasattr(plex, "labels") else None
+    if lab is None or ps.dofs.size == 0:
+        return None
+    verts = np.arange(plex.vStart, plex.vEnd)
+    bary = verts[lab[verts] != 1]
+    if bary.size == 0:
+        return None
+    star = plex.star
+    block_of_point = np.full(plex.npoints, -1, dtype=np.int64)
+    counts = np.diff(star.indptr)[bary]
+    pts = np.concatenate([star.indices[star.indptr[b]:star.indptr[b + 1]] for b in bary])
+    block_of_point[pts] = np.repeat(bary, counts)
+    block_of_node = block_of_point[plex.node_points(V)]
+    blocks = block_of_node[ps.dofs // ps.bs].astype(np.int32)
+    # size limit: dofs per (patch, label)
+    patch_of = np.repeat(np.arange(ps.npatch, dtype=np.int64), np.diff(ps.offsets))
+    inb = blocks >= 0
+    if inb.any():
+        key = patch_of[inb] * np.int64(plex.npoints) + blocks[inb]
+        _, cnt = np.unique(key, return_counts=True)
+        if cnt.max() > MAX_BLOCK_DOFS:
+            return None
+    return blocks

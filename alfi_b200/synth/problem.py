@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from ..patches import PatchSet, greedy_colouring, patch_dofs_from_points
+from ..patches import PatchSet, greedy_colouring, macro_interior_blocks, patch_dofs_from_points
 from ..relaxation import macro_star_points, star_points, iteration_order
 from ..transfer import cell_patch_set
 from .fem import BSR, BlockPattern, VectorSpace, apply_dirichlet, assemble_parts, assemble_velocity_block
@@ -135,6 +135,8 @@ def smoother_patches(cfg: Config, ld: LevelData) -> PatchSet:
         order = iteration_order(coords, cfg.sort_order)
     ps = patch_dofs_from_points(plex, ld.V, H, bc_nodes=ld.bc_nodes, order=order)
     greedy_colouring(ps, ld.V.ndofs)
+    if cfg.bary:
+        ps.blocks = macro_interior_blocks(plex, ld.V, ps)
     return ps
 
 
@@ -197,6 +199,8 @@ def build_problem(cfg: Config | str, nu: float | None = None, with_transfer: boo
                 ld.P = prolongation_matrix(levels[-1].V, V, hier[lev.index - 1].c2f)
             if with_transfer:
                 ld.cell_patches, ld.cb_nodes = cell_patch_set(hier, lev.index, V, cfg.bary)
+                if cfg.bary:
+                    ld.cell_patches.blocks = macro_interior_blocks(lev.plex, V, ld.cell_patches)
                 assemble_transfer(cfg, ld, nu, cfg.gamma)
         levels.append(ld)
         if verbose:

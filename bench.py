@@ -4,8 +4,8 @@
 A "step" is one application of `fieldsplit_0` (richardson(1) + PCMG-full F-cycle with
 FGMRES(m)/patch smoothing, Schoeberl transfers, direct coarse solve — alfi/solver.py:359-379)
 on the ldc3d Scott-Vogelius k=3 barycentric workload (BASELINE.json configs[4] at the size that
-fits one GPU: baseN 4, nref 2 — 1 458 867 velocity dofs, 4 913 macro-star patches, 48 GB of
-patch inverses).  `value` = finest-level velocity dofs / time of one step, inputs resident in
+fits one GPU: baseN 4, nref 2 — 1 458 867 velocity dofs, 4 913 macro-star patches; their inverses
+are 48 GB dense, ~6 GB in the condensed block/separator form the library uses by default).  `value` = finest-level velocity dofs / time of one step, inputs resident in
 HBM; `e2e` = the same through the C-ABI with pinned host vectors (H2D + D2H inside the timed
 region).  The JSON line also carries the roofline of the dominant kernel (finest-level patch
 apply), the CPU baseline (oracle restatement timed on a bounded sample) and the clocks seen.
@@ -185,7 +185,8 @@ def ours(args):
         uid = bootstrap_unique_id(rank)
     mg = DeviceMultigrid([level_input_from_synth(l) for l in prob.levels], cfg.m, device=local,
                          deterministic=bool(args.deterministic), torch_storage=True,
-                         rank=rank, nranks=world, unique_id=uid, peer_memory=bool(args.peer_memory))
+                         rank=rank, nranks=world, unique_id=uid, peer_memory=bool(args.peer_memory),
+                         condense=bool(args.condense))
     mg.ctx.synchronize()
     setup_s = time.time() - t0
     log("rank %d: device setup (upload + factor) %.1fs" % (rank, setup_s))
@@ -229,6 +230,8 @@ def ours(args):
     prof_fine = mg.ctx.profile_get(len(prob.levels) - 1)
     prof_all = mg.ctx.profile_get(-1)
     mg.ctx.profile(False)
+    patch_apply_bytes = mg.ctx.patch_apply_bytes(len(prob.levels) - 1)
+    factor_bytes = mg.ctx.patch_storage_bytes(len(prob.levels) - 1)
 
     # ---- end to end through the C-ABI with host buffers --------------------------------------
     bhn, xhn = bh.numpy(), xh.numpy()
@@ -262,22 +265,22 @@ def ours(args):
     except Exception:       # noqa: BLE001
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     fine = prob.finest
-    bs_bytes = smoother_bytes(fine)
-    if world > 1:       # this rank streams only its own patches
-        from alfi_b200.lib import PATCHES_SMOOTHER
-        mine = mg.local_patches[(len(prob.levels) - 1, PATCHES_SMOOTHER)]
-        nloc = fine.patches.sizes[mine].astype(np.float64)
-        bs_bytes = float((8 * nloc * nloc + 4 * nloc).sum() + 16 * fine.ndofs)
+    # algorithmic bytes of one finest-level PCApply_PATCH on this rank: stored factors
+    # (dense: 8 n_i^2; condensed: X_SS + per-block V and [D | -W]) + index data + 16 N
+    condensed = bool(args.condense) and fine.patches.blocks is not None
+    bs_bytes = float(patch_apply_bytes)
     app_ms, app_calls = prof_fine["PCPATCHApply"]
     achieved = bs_bytes / (app_ms / max(app_calls, 1) * 1e-3) / 1e9 if app_calls else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "patch_apply_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.config)
+            traffic = json.load(open(tpath)).get(args.config + (":condensed" if condensed else ""))
         except Exception:   # noqa: BLE001
             traffic = None
-    roofline = {"kernel": "patch_apply_kernel (finest-level PCApply_PATCH: memset + colour launches + bc fix-up)",
+    roofline = {"kernel": ("tile_ops_kernel x3 + sep_rhs_kernel (finest-level PCApply_PATCH, condensed inverses: memset, "
+                           "V ops, separator rhs, X_SS ops, [D|-W] ops, bc fix-up)") if condensed else
+                "patch_apply_kernel (finest-level PCApply_PATCH: memset + colour launches + bc fix-up)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bs_bytes, "launches_timed": app_calls,
@@ -322,8 +325,11 @@ def ours(args):
         "config": {"workload": args.config, "mesh": "Kuhn %d^%d x 2^%d, Alfeld split" % (cfg.N, cfg.dim, cfg.nref),
                    "velocity_dofs": n, "levels": len(prob.levels), "smoothing": cfg.m, "re": cfg.re, "gamma": cfg.gamma,
                    "patches_finest": int(fine.patches.npatch), "max_patch_dofs": int(fine.patches.sizes.max()),
-                   "factor_bytes_finest": float((fine.patches.sizes.astype(float) ** 2).sum() * 8),
-                   "l2_policy": "inputs larger than L2 (48 GB of patch inverses streamed per smoother application)",
+                   "factor_bytes_finest": float(factor_bytes),
+                   "dense_factor_bytes_finest": float((fine.patches.sizes.astype(float) ** 2).sum() * 8),
+                   "patch_inverses": "condensed (block/separator form, csrc/condense.cu)" if condensed else "dense",
+                   "l2_policy": "inputs larger than L2 (%.1f GB of patch inverses streamed per finest-level smoother "
+                                "application, 126 MB L2)" % (factor_bytes / 1e9),
                    "deterministic": bool(args.deterministic), "parallelism": "1 GPU" if world == 1 else
                    "patches + operator rows sharded over %d GPUs, level vectors replicated; ncclAllReduce after "
                    "every patch apply, grouped ncclBroadcast after every SpMV" % world},
@@ -357,6 +363,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-continuation", action="store_true")
     ap.add_argument("--peer-memory", type=int, default=0, help="N > 1: NVLink peer-memory exchanges instead of NCCL")
+    ap.add_argument("--condense", type=int, default=1,
+                    help="1 (default): condensed block/separator patch inverses where the mesh has macro structure; 0: dense")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

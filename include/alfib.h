@@ -115,6 +115,20 @@ int alfib_residual(alfib_ctx* ctx, int level, const double* b, const double* x, 
 int alfib_level_set_patches(alfib_ctx* ctx, int level, int which, int32_t npatch,
                             const int64_t* offsets, const int32_t* dofs, int32_t norder,
                             const int32_t* order, const int32_t* colours);
+/* Optional, after alfib_level_set_patches and before the first factorisation: the block/separator
+ * structure of every patch (csrc/condense.cu).  block_of_dof has one entry per entry of `dofs`:
+ * < 0 for separator dofs, otherwise a block label local to the patch.  Blocks must be pairwise
+ * decoupled in the level's BSR pattern (checked: a wrong hint is ALFIB_EINVAL, never a wrong
+ * result) and have <= 64 dofs and <= 64 coupled separator dofs.  The inverse of patch i is then
+ * held as X_SS (the separator block of A_i^-1) plus D_k = A_kk^-1, A_Nk D_k and D_k A_kN per block:
+ * for the macro-star patches of Scott-Vogelius elements on barycentrically refined meshes
+ * (relaxation.py:168-177, bary.py) — interiors of the macro cells = blocks — that is ~10x fewer
+ * bytes to store and to stream per PCApply_PATCH than the dense inverse PETSc's
+ * `patch_pc_patch_dense_inverse` (solver.py:602) keeps; the result is the same A_i^-1 r_i.
+ * NULL returns the set to dense inverses.                                                      */
+int alfib_level_set_patch_blocks(alfib_ctx* ctx, int level, int which, const int32_t* block_of_dof);
+/* algorithmic bytes of one application of that patch set: stored factors + index data + 16 N   */
+int64_t alfib_patch_apply_bytes(alfib_ctx* ctx, int level, int which);
 /* bytes of device storage the inverse factors of that patch set need                          */
 int64_t alfib_patch_storage_bytes(alfib_ctx* ctx, int level, int which);
 /* optional: caller-owned device buffer (a torch tensor's data_ptr()) for the factors; if never

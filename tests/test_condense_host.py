@@ -1,0 +1,214 @@
+"""CPU check of the condensed (block/separator) patch sets.
+
+`alfi_b200/csrc/condense_host.h` is the code libalfib.so uses to turn the block labels of
+`alfi_b200.patches.macro_interior_blocks` into storage layout, index lists and tile-op lists;
+`tests/condense_host_shim.cpp` compiles it with g++ together with a host restatement of the CUDA
+kernels that consume those lists.  Here the result is compared with dense patch solves, i.e. with
+the definition of PCApply_PATCH, y = sum_i R_i^T A_i^-1 R_i x.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import hotpath as hp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_i32p, _i64p, _f64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def shim():
+    out = os.path.join(ROOT, "oracle", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libcondense_host_shim.so")
+    src = os.path.join(ROOT, "tests", "condense_host_shim.cpp")
+    hdr = os.path.join(ROOT, "alfi_b200", "csrc", "condense_host.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.dirname(hdr), src, "-o", so])
+    lib = C.CDLL(so)
+    lib.ch_create.restype = C.c_void_p
+    lib.ch_create.argtypes = [C.c_int, C.c_int, _i32p, _i32p, C.c_int, _i64p, _i32p, C.c_int, _i32p, _i32p, C.c_int,
+                              _i32p, C.c_char_p, C.c_int]
+    lib.ch_destroy.argtypes = [C.c_void_p]
+    lib.ch_stats.argtypes = [C.c_void_p, _i64p]
+    lib.ch_factor.argtypes = [C.c_void_p, _f64p]
+    lib.ch_apply.argtypes = [C.c_void_p, _f64p, _f64p]
+    lib.ch_inverse.argtypes = [C.c_void_p, C.c_int, _f64p]
+    lib.ch_check_disjoint.argtypes = [C.c_void_p]
+    return lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Host:
+    def __init__(self, lib, ld, ps, blocks):
+        self.lib = lib
+        A = ld.A
+        self.keep = [np.ascontiguousarray(a, dtype=t) for a, t in (
+            (A.rowptr, np.int32), (A.colidx, np.int32), (ps.offsets, np.int64), (ps.dofs, np.int32),
+            (ps.order, np.int32), (ps.colours if ps.colours is not None else np.zeros(ps.npatch), np.int32),
+            (blocks, np.int32))]
+        rp, ci, off, dofs, order, col, blk = self.keep
+        err = C.create_string_buffer(512)
+        ncol = int(col.max()) + 1 if col.size else 0
+        self.h = lib.ch_create(ld.V.nnodes, ld.V.bs, _p(rp, C.c_int32), _p(ci, C.c_int32), ps.npatch, _p(off, C.c_int64),
+                               _p(dofs, C.c_int32), order.size, _p(order, C.c_int32), _p(col, C.c_int32), ncol,
+                               _p(blk, C.c_int32), err, 512)
+        self.err = err.value.decode()
+
+    def stats(self):
+        s = np.zeros(8, np.int64)
+        self.lib.ch_stats(self.h, _p(s, C.c_int64))
+        return dict(zip(["store_elems", "index_bytes", "nblocks", "nsep_total", "maxb", "maxm", "maxsep", "nops"], s.tolist()))
+
+    def factor(self, vals):
+        v = np.ascontiguousarray(vals, dtype=np.float64)
+        return self.lib.ch_factor(self.h, _p(v, C.c_double))
+
+    def apply(self, x):
+        y = np.zeros_like(x)
+        self.lib.ch_apply(self.h, _p(np.ascontiguousarray(x), C.c_double), _p(y, C.c_double))
+        return y
+
+    def inverse(self, p, n):
+        out = np.empty((n, n))
+        self.lib.ch_inverse(self.h, p, _p(out, C.c_double))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.ch_destroy(self.h)
+            self.h = None
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+BACKWARD_TOL = 1e-11
+CASES = [("ldc2d-sv-k2-tiny", {}), ("ldc3d-sv-k3-tiny", {}), ("ldc3d-sv-k3-tiny", dict(gamma=10.0, nu=0.2)),
+         ("ldc2d-sv-k2", dict(gamma=10.0, nu=0.2))]
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+@pytest.mark.parametrize("which", ["smoother", "cell"])
+def test_condensed_apply_equals_dense_patch_solves(shim, problems, name, kw, which):
+    prob = problems(name, **kw)
+    mild = bool(kw)
+    for ld in prob.levels[1:]:
+        ps = ld.patches if which == "smoother" else ld.cell_patches
+        A = ld.A if which == "smoother" else ld.A0
+        assert ps.blocks is not None and (ps.blocks >= 0).any()
+        if ps.colours is None:
+            ps.colours = np.zeros(ps.npatch, np.int32)
+        host = Host(shim, ld, ps, ps.blocks)
+        assert host.h, host.err
+        st = host.stats()
+        dense = int((ps.sizes.astype(np.int64) ** 2).sum())
+        assert st["store_elems"] < dense                       # fewer bytes than the dense inverses
+        assert st["maxb"] <= 64 and st["maxm"] <= 64
+        assert shim.ch_check_disjoint(host.h) == 0
+        assert host.factor(A.vals) == 0
+        csr = A.to_csr()
+        mats = hp.patch_matrices(csr, ps.offsets, ps.dofs)
+        x = np.random.default_rng(5).standard_normal(ld.V.ndofs)
+        y = host.apply(x)
+        yo = np.zeros_like(x)
+        for p in ps.order:
+            I = ps.patch(p)
+            if I.size:
+                yo[I] += np.linalg.solve(mats[p], x[I])
+        kappa = max(np.linalg.cond(M) for M in mats if M.size)
+        tol = 1e-11 * max(1.0, kappa * np.finfo(float).eps / 1e-12)
+        assert rel(y, yo) <= tol, (rel(y, yo), kappa)
+        if mild:
+            assert tol == 1e-11
+        # the inverse rebuilt from the condensed pieces is the inverse (normwise backward error)
+        worst = 0.0
+        for p in list(range(0, ps.npatch, max(1, ps.npatch // 6))):
+            n = int(ps.sizes[p])
+            if n == 0:
+                continue
+            X = host.inverse(p, n)
+            resid = np.linalg.norm(X @ mats[p] - np.eye(n)) / (np.linalg.norm(X) * np.linalg.norm(mats[p]))
+            worst = max(worst, resid)
+        # dense Gauss-Jordan inverses reach ~1e-15 here; the rebuilt product form D + W X_SS V carries the
+        # rounding of its three factors (|W||X_SS||V| >> |X| for augmented-Lagrangian blocks)
+        assert worst < BACKWARD_TOL, worst
+        host.close()
+        print("%s level %d %s: %d patches, store %.2f MB vs dense %.2f MB (x%.1f), rel diff %.1e (kappa %.1e)" % (
+            name, ld.index, which, ps.npatch, st["store_elems"] * 8e-6, dense * 8e-6, dense / st["store_elems"],
+            rel(y, yo), kappa) + ", inverse backward error %.1e" % worst)
+
+
+def test_coupled_blocks_are_rejected(shim, problems):
+    """A wrong hint must be an error, never a wrong answer: put two coupled dofs into different blocks."""
+    prob = problems("ldc2d-sv-k2-tiny")
+    ld = prob.levels[1]
+    ps = ld.patches
+    blocks = ps.blocks.copy()
+    p = int(np.argmax(ps.sizes))
+    o = ps.offsets[p]
+    sep = np.flatnonzero(blocks[o:ps.offsets[p + 1]] < 0)
+    blocks[o + sep[0]] = 10 ** 6            # the patch's vertex dof couples to every block
+    host = Host(shim, ld, ps, blocks)
+    assert not host.h and "coupled" in host.err
+
+
+def test_all_separator_is_the_dense_inverse(shim, problems):
+    """No blocks at all: the condensed form degenerates to the dense tiled inverse."""
+    prob = problems("ldc2d-sv-k2-tiny")
+    ld = prob.levels[1]
+    ps = ld.patches
+    host = Host(shim, ld, ps, np.full(ps.dofs.size, -1, np.int32))
+    assert host.h, host.err
+    st = host.stats()
+    assert st["nblocks"] == 0 and st["store_elems"] == int((ps.sizes * ((ps.sizes + 1) // 2 * 2)).sum())
+    assert host.factor(ld.A.vals) == 0
+    mats = hp.patch_matrices(ld.A.to_csr(), ps.offsets, ps.dofs)
+    x = np.random.default_rng(6).standard_normal(ld.V.ndofs)
+    yo = np.zeros_like(x)
+    for p in ps.order:
+        I = ps.patch(p)
+        if I.size:
+            yo[I] += np.linalg.solve(mats[p], x[I])
+    assert rel(host.apply(x), yo) <= 1e-9
+    host.close()
+
+
+@pytest.mark.parametrize("bs", [2, 3])
+@pytest.mark.parametrize("order", [None, [7, 3, 3, 6, 5, 4, 1, 2]])
+def test_edge_cases_on_clustered_operator(shim, bs, order):
+    """Empty / separator-only / block-only patches, m = 0 blocks, 64-dof limits, repeated visits."""
+    from tests.condense_cases import clustered_problem, dense_reference, greedy_colours
+
+    class LD:                       # the two attributes Host() reads
+        pass
+
+    case = clustered_problem(bs, seed=bs)
+    order = np.arange(len(case["patches"]), dtype=np.int32) if order is None else np.asarray(order, np.int32)
+    ld = LD()
+    ld.A = type("A", (), dict(rowptr=case["rowptr"], colidx=case["colidx"]))
+    ld.V = type("V", (), dict(nnodes=case["n_nodes"], bs=bs))
+    ps = type("PS", (), dict(offsets=case["offsets"], dofs=case["dofs"], order=order, npatch=len(case["patches"]),
+                             colours=greedy_colours(case, order.tolist())))
+    host = Host(shim, ld, ps, case["blocks"])
+    assert host.h, host.err
+    st = host.stats()
+    assert st["maxb"] == 64 - (64 % bs) and st["maxm"] >= 60 and st["maxsep"] > 64
+    repeated = len(set(order.tolist())) < order.size
+    if not repeated:
+        assert shim.ch_check_disjoint(host.h) == 0
+    assert host.factor(case["vals"]) == 0
+    x = np.random.default_rng(9).standard_normal(case["n_nodes"] * bs)
+    assert rel(host.apply(x), dense_reference(case, order, x)) < 1e-12
+    for p, I in enumerate(case["patches"]):
+        if I.size:
+            X = host.inverse(p, I.size)
+            assert np.abs(X @ case["A"][I][:, I].toarray() - np.eye(I.size)).max() < 1e-10
+    host.close()

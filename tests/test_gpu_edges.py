@@ -84,6 +84,52 @@ def test_ragged_empty_and_repeated_patches(bs):
             ctx.close()
 
 
+@pytest.mark.parametrize("bs", [2, 3])
+def test_condensed_edge_cases(bs):
+    """Condensed (block/separator) patch sets on a synthetic clustered operator: empty, separator-only
+    and block-only patches, blocks without separator neighbours, blocks and neighbourhoods at the
+    64-dof limit, > 64 separator dofs (several tiles), overlapping patches, a repeated visit."""
+    from alfi_b200.lib import Context
+    from tests.condense_cases import clustered_problem, dense_reference
+    case = clustered_problem(bs, seed=bs)
+    n = case["n_nodes"] * bs
+    bc = np.array([1, n - 2], dtype=np.int32)
+    x = np.random.default_rng(11).standard_normal(n)
+    npatch = len(case["patches"])
+    for order in (np.arange(npatch), np.array([7, 3, 3, 6, 5, 4, 1, 2])):
+        for det in (False, True):
+            ctx = Context(deterministic=det)
+            ctx.level_create(0, case["n_nodes"], bs)
+            ctx.set_bsr_pattern(0, case["rowptr"], case["colidx"])
+            ctx.set_bsr_values(0, case["vals"])
+            ctx.set_bc(0, bc)
+            ctx.set_patches(0, case["offsets"], case["dofs"], order.astype(np.int32), None)
+            dense_bytes = ctx.patch_storage_bytes(0)
+            ctx.set_patch_blocks(0, case["blocks"])
+            assert ctx.patch_storage_bytes(0) < dense_bytes
+            ctx.factor(0)
+            y = ctx.smoother_apply(0, x, np.empty(n))
+            assert rel(y, dense_reference(case, order, x, bc)) < 1e-12, (order, det)
+            if det:
+                assert np.array_equal(y, ctx.smoother_apply(0, x, np.empty(n)))
+            for p, I in enumerate(case["patches"]):
+                if I.size:
+                    inv = ctx.patch_inverse(0, p, I.size)
+                    assert np.abs(inv @ case["A"][I][:, I].toarray() - np.eye(I.size)).max() < 1e-10
+            # new values, same structure: the per-Newton-step path
+            ctx.set_bsr_values(0, 2.0 * case["vals"])
+            ctx.factor(0)
+            y2 = ctx.smoother_apply(0, x, np.empty(n))
+            want = 0.5 * dense_reference(case, order, x)
+            want[bc] = x[bc]
+            assert rel(y2, want) < 1e-12
+            # back to dense inverses on the same context
+            ctx.set_patch_blocks(0, None)
+            ctx.factor(0)
+            assert rel(ctx.smoother_apply(0, x, np.empty(n)), want) < 1e-12
+            ctx.close()
+
+
 def test_singular_patch_is_reported():
     from alfi_b200.lib import AlfibError, Context
     n_nodes, bs = 10, 2

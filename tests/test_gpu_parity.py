@@ -38,13 +38,13 @@ def loaded(problems):
     from oracle import hotpath as hp
     cache = {}
 
-    def get(name, deterministic=False):
-        key = (name, deterministic)
+    def get(name, deterministic=False, condense=True):
+        key = (name, deterministic, condense)
         if key not in cache:
             base, _, regime = name.partition("@")
             prob = problems(base, gamma=10.0, nu=0.2) if regime == "mild" else problems(base)
             mg = DeviceMultigrid([level_input_from_synth(l) for l in prob.levels], prob.config.m,
-                                 deterministic=deterministic)
+                                 deterministic=deterministic, condense=condense)
             if name not in cache:
                 cache[name] = [hp.level_from_host(l) for l in prob.levels]
             cache[key] = (prob, mg, cache[name])
@@ -84,10 +84,21 @@ def test_colourings_bit_exact(loaded, name):
         ctx.close()
 
 
-@pytest.mark.parametrize("name", SMALL)
+# Scott-Vogelius configurations carry block labels (alfi_b200.patches.macro_interior_blocks), so the
+# default DeviceMultigrid holds their patch inverses in the condensed block/separator form
+# (csrc/condense.cu); condense=False keeps the dense tiled inverses for the same index sets.
+SV = [n for n in SMALL if "-sv-" in n]
+# normwise backward error |X A - I| / (|X||A|) of an explicit inverse: ~1e-15 for the dense
+# Gauss-Jordan inverses; the condensed product form D + W X_SS V carries the rounding of its three
+# factors (measured 3e-13 on the 3-D patches at gamma = 1e4, tests/test_condense_host.py)
+BACKWARD_DENSE, BACKWARD_CONDENSED = 100 * EPS, 1e-11
+
+
+@pytest.mark.parametrize("name", SMALL + [n + "/dense" for n in SV])
 def test_patch_inverses(loaded, name):
     from oracle import hotpath as hp
-    prob, mg, olv = loaded(name)
+    name, _, mode = name.partition("/")
+    prob, mg, olv = loaded(name, condense=(mode != "dense"))
     for l, ld in enumerate(prob.levels):
         if ld.patches is None:
             continue
@@ -102,14 +113,16 @@ def test_patch_inverses(loaded, name):
             # conditioning-free check: |X A - I| <= c n eps |X| |A|  (normwise backward error)
             resid = np.linalg.norm(inv @ mats[p] - np.eye(n)) / (np.linalg.norm(inv) * np.linalg.norm(mats[p]))
             worst = max(worst, resid)
-        assert worst < 100 * EPS, worst
+        condensed = mode != "dense" and ps.blocks is not None
+        assert worst < (BACKWARD_CONDENSED if condensed else BACKWARD_DENSE), (worst, condensed)
 
 
-@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("name", SMALL + [n + "/dense" for n in SV])
 @pytest.mark.parametrize("deterministic", [False, True])
 def test_smoother_apply(loaded, name, deterministic):
     from oracle import hotpath as hp
-    prob, mg, olv = loaded(name, deterministic)
+    name, _, mode = name.partition("/")
+    prob, mg, olv = loaded(name, deterministic, condense=(mode != "dense"))
     for l, lv in enumerate(olv):
         if lv.offsets is None:
             continue
@@ -124,6 +137,62 @@ def test_smoother_apply(loaded, name, deterministic):
         if deterministic:
             y2 = mg.ctx.smoother_apply(l, x, np.empty_like(x))
             assert np.array_equal(y, y2)
+
+
+@pytest.mark.parametrize("name", SV)
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_condensed_against_dense_inverses(loaded, name, deterministic):
+    """The condensed form is the same operator as the dense inverses: smoother apply, transfer block
+    solves (through prolong / restrict) and the whole F-cycle, condensed vs dense on the device."""
+    from oracle import hotpath as hp
+    prob, mgc, olv = loaded(name, deterministic, True)
+    _, mgd, _ = loaded(name, deterministic, False)
+    for l in range(1, len(olv)):
+        lv, lc = olv[l], olv[l - 1]
+        assert prob.levels[l].patches.blocks is not None and prob.levels[l].cell_patches.blocks is not None
+        assert mgc.ctx.patch_storage_bytes(l) < mgd.ctx.patch_storage_bytes(l)
+        assert mgc.ctx.patch_storage_bytes(l, 1) < mgd.ctx.patch_storage_bytes(l, 1)
+        kappa = _kappa(hp.patch_matrices(lv.A, lv.offsets, lv.dofs))
+        x = _vec(lv, 80 + l)
+        yc = mgc.ctx.smoother_apply(l, x, np.empty_like(x))
+        yd = mgd.ctx.smoother_apply(l, x, np.empty_like(x))
+        assert rel(yc, yd) <= _tol(kappa), (l, rel(yc, yd), kappa)
+        if deterministic:
+            assert np.array_equal(yc, mgc.ctx.smoother_apply(l, x, np.empty_like(x)))
+        kc = _kappa(hp.patch_matrices(prob.levels[l].A0.to_csr(), lv.c_offsets, lv.c_dofs))
+        c, f = _vec(lc, 81 + l), _vec(lv, 82 + l)
+        pc, pd = mgc.ctx.prolong(l, c, np.empty(lv.n)), mgd.ctx.prolong(l, c, np.empty(lv.n))
+        assert rel(pc, pd) <= _tol(kc), (l, rel(pc, pd), kc)
+        rc, rd = mgc.ctx.restrict(l, f, np.empty(lc.n)), mgd.ctx.restrict(l, f, np.empty(lc.n))
+        assert rel(rc, rd) <= _tol(kc), (l, rel(rc, rd), kc)
+    b = _vec(olv[-1], 83)
+    xc, xd = mgc.apply(b, np.empty_like(b)), mgd.apply(b, np.empty_like(b))
+    kappa = max(_kappa(hp.patch_matrices(lv.A, lv.offsets, lv.dofs)) for lv in olv[1:])
+    assert rel(xc, xd) <= _tol(kappa), (rel(xc, xd), kappa)
+    if deterministic:
+        for _ in range(3):                                   # eager, captured, replayed
+            assert np.array_equal(mgc.apply(b, np.empty_like(b)), xc)
+
+
+def test_wrong_block_hint_is_an_error(problems):
+    """Blocks that are coupled in the operator are rejected (never a wrong answer)."""
+    from alfi_b200.lib import AlfibError, Context
+    prob = problems("ldc2d-sv-k2-tiny")
+    ld = prob.levels[1]
+    ps = ld.patches
+    ctx = Context()
+    ctx.level_create(0, ld.V.nnodes, ld.V.bs)
+    ctx.set_bsr_pattern(0, ld.A.rowptr, ld.A.colidx)
+    ctx.set_patches(0, ps.offsets, ps.dofs, ps.order, ps.colours)
+    blocks = ps.blocks.copy()
+    p = int(np.argmax(ps.sizes))
+    o = ps.offsets[p]
+    blocks[o + np.flatnonzero(blocks[o:ps.offsets[p + 1]] < 0)[0]] = 10 ** 6
+    with pytest.raises(AlfibError, match="coupled"):
+        ctx.set_patch_blocks(0, blocks)
+    ctx.set_patch_blocks(0, ps.blocks)                       # the right hint is accepted afterwards
+    ctx.set_patch_blocks(0, None)                            # and can be dropped again (dense inverses)
+    ctx.close()
 
 
 @pytest.mark.parametrize("name", SMALL)
