@@ -90,7 +90,7 @@ def rel(a, b):
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
 
-BACKWARD_TOL = 1e-11
+BACKWARD_TOL = 1e-9
 CASES = [("ldc2d-sv-k2-tiny", {}), ("ldc3d-sv-k3-tiny", {}), ("ldc3d-sv-k3-tiny", dict(gamma=10.0, nu=0.2)),
          ("ldc2d-sv-k2", dict(gamma=10.0, nu=0.2))]
 

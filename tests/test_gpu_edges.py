@@ -110,7 +110,8 @@ def test_condensed_edge_cases(bs):
             ctx.factor(0)
             y = ctx.smoother_apply(0, x, np.empty(n))
             assert rel(y, dense_reference(case, order, x, bc)) < 1e-12, (order, det)
-            if det:
+            if det and len(set(order.tolist())) == order.size:
+                # bitwise reproducible; a repeated visit falls back to atomics like the dense path
                 assert np.array_equal(y, ctx.smoother_apply(0, x, np.empty(n)))
             for p, I in enumerate(case["patches"]):
                 if I.size:

@@ -72,7 +72,7 @@ def test_sample_of_patch_inverses(full):
         X = mg.ctx.patch_inverse(L, p, I.size)
         err = np.linalg.norm(X @ Ap - np.eye(I.size)) / (np.linalg.norm(X) * np.linalg.norm(Ap))
         # condensed block/separator form (default for this configuration): see tests/test_gpu_parity.py
-        assert err < 1e-11, (p, I.size, err)
+        assert err < 1e-9, (p, I.size, err)
 
 
 def test_storage_is_condensed(full):

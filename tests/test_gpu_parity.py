@@ -90,8 +90,9 @@ def test_colourings_bit_exact(loaded, name):
 SV = [n for n in SMALL if "-sv-" in n]
 # normwise backward error |X A - I| / (|X||A|) of an explicit inverse: ~1e-15 for the dense
 # Gauss-Jordan inverses; the condensed product form D + W X_SS V carries the rounding of its three
-# factors (measured 3e-13 on the 3-D patches at gamma = 1e4, tests/test_condense_host.py)
-BACKWARD_DENSE, BACKWARD_CONDENSED = 100 * EPS, 1e-11
+# factors (measured 3e-13 at Re = 100 and 2e-11 at Re = 5000 on the 3-D patches with gamma = 1e4; for
+# scale, numpy's LAPACK getri inverse has 7e-11 in the same measure on those matrices)
+BACKWARD_DENSE, BACKWARD_CONDENSED = 100 * EPS, 1e-9
 
 
 @pytest.mark.parametrize("name", SMALL + [n + "/dense" for n in SV])
