@@ -88,13 +88,14 @@ struct Condensed {
   bool on = false;
   CondensedHost h;                      // layout, index lists and op lists (host copies)
   DBuf<int64_t> sepoff, ssoff;
-  DBuf<int32_t> seplocal, sepdofs, cidx, bdofs, bkeys, bperm, cptr, cg1;
-  DBuf<BlockDesc> blocks;
+  DBuf<int32_t> seplocal, sepdofs, cidx, bdofs, bkeys, bperm, cptr, cg1, zptr, zsrc;
+  DBuf<BlockDesc> blocks;               // what the block setup kernel runs over: instances, or distinct blocks (shared form)
   DBuf<TileOp> opsV, opsS, opsDW;
-  DBuf<double> g1, rs, us;              // per-block V outputs, per-patch separator rhs / solution
+  DBuf<double> g1, rs, us, z;           // V outputs, per-patch separator rhs / solution, shared form: summed us per block
   void release() {
     sepoff.release(); ssoff.release(); seplocal.release(); sepdofs.release(); cidx.release();
     bdofs.release(); bkeys.release(); bperm.release(); cptr.release(); cg1.release(); blocks.release();
+    zptr.release(); zsrc.release(); z.release();
     opsV.release(); opsS.release(); opsDW.release(); g1.release(); rs.release(); us.release();
   }
 };

@@ -484,6 +484,12 @@ int64_t alfib_patch_storage_bytes(alfib_ctx* c, int level, int which) {
   return c->levels[level]->ps[which].store_elems * (int64_t)sizeof(double);
 }
 
+int alfib_patch_storage_form(alfib_ctx* c, int level, int which) {
+  if (!c || level < 0 || level >= ALFIB_MAX_LEVELS || !c->levels[level] || which < 0 || which > 1) return -1;
+  const PatchSet& ps = c->levels[level]->ps[which];
+  return !ps.cond.on ? 0 : (ps.cond.h.shared ? 2 : 1);
+}
+
 int alfib_patch_bind_storage(alfib_ctx* c, int level, int which, void* dev_ptr, int64_t bytes) {
   return guarded(c, [&] {
     cycle_graph_invalidate(c);

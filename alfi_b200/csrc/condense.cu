@@ -30,6 +30,7 @@
 // mode, exactly like patch_apply.cu.  Roofline: HBM; algorithmic bytes = stored factors + indices.
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <numeric>
 
 #include "alfib_internal.h"
@@ -110,6 +111,106 @@ __device__ __forceinline__ void tile_op_body(const double* __restrict__ mat, con
   }
 }
 
+// Second version of the tile op (default; ALFIB_TILE_V1=1 selects the first).  The ops are small (a few
+// KB to 40 KB), so what counts is how soon the matrix stream starts and that it never waits on a
+// dependent load.  Each lane keeps a ring of UB column loads in flight: a slot is refilled with the
+// column UB*G further on as soon as it has been consumed, so the first UB columns are requested before
+// the gathered source has arrived, a partial last batch is just predicated loads, and there is no
+// drain between batches.  The source index list is read two 32-column chunks ahead and the source
+// values one chunk ahead (no dependent wait at a chunk switch).
+template <int G, bool ATOMIC>
+__device__ __forceinline__ void tile_op_body_v2(const double* __restrict__ mat, const int32_t* __restrict__ ci,
+                                                const int32_t* __restrict__ ri, double* __restrict__ priv,
+                                                const int nrows, const int n, const double* __restrict__ srcA,
+                                                const double* __restrict__ srcB, double* __restrict__ y, int lane) {
+  constexpr int LPG = 32 / G, UB = 8, CPB = UB * G;   // lanes per column group; ring slots; columns per round
+  const int half = (nrows + 1) >> 1;
+  const int grp = lane / LPG, l = lane - grp * LPG;
+  const bool active = l < half;
+  const double2* __restrict__ T = reinterpret_cast<const double2*>(mat) + (active ? l : 0);
+  auto column = [&](int c) { return (active && c < n) ? __ldcs(T + c * half) : make_double2(0.0, 0.0); };
+  auto index_at = [&](int pos) { return pos < n ? __ldg(ci + pos) : 0; };
+  auto value_at = [&](int e, int pos) { return pos < n ? (e >= 0 ? __ldg(srcA + e) : __ldg(srcB + (~e))) : 0.0; };
+  const int e0 = index_at(lane), e1 = index_at(32 + lane);
+  double2 a[UB];
+#pragma unroll
+  for (int u = 0; u < UB; ++u) a[u] = column(u * G + grp);
+  double xv = value_at(e0, lane);
+  double xnext = value_at(e1, 32 + lane);
+  int enext = index_at(64 + lane);
+  double acc0 = 0.0, acc1 = 0.0, bcc0 = 0.0, bcc1 = 0.0;   // even / odd slots: two independent FMA chains
+  for (int cb = 0; cb < n; cb += CPB) {               // CPB divides 32: a round never straddles a chunk
+    if (cb > 0 && (cb & 31) == 0) {
+      xv = xnext;
+      xnext = value_at(enext, cb + 32 + lane);
+      enext = index_at(cb + 64 + lane);
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int c = cb + u * G + grp;
+      const double xc = __shfl_sync(0xffffffffu, xv, c & 31);
+      if (u & 1) {
+        bcc0 = fma(a[u].x, xc, bcc0);
+        bcc1 = fma(a[u].y, xc, bcc1);
+      } else {
+        acc0 = fma(a[u].x, xc, acc0);
+        acc1 = fma(a[u].y, xc, acc1);
+      }
+      a[u] = column(c + CPB);                         // predicated off behind the last column
+    }
+  }
+  acc0 += bcc0;
+  acc1 += bcc1;
+#pragma unroll
+  for (int off = 16; off >= LPG; off >>= 1) {       // sum the column groups (fixed order)
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, off);
+  }
+  if (grp == 0 && active) {
+    const int r = 2 * l;
+    if (priv) {
+      priv[r] = acc0;
+      if (r + 1 < nrows) priv[r + 1] = acc1;
+    }
+    if (ri) {
+      if (ATOMIC) {
+        atomicAdd(y + ri[r], acc0);
+        if (r + 1 < nrows) atomicAdd(y + ri[r + 1], acc1);
+      } else {
+        y[ri[r]] += acc0;
+        if (r + 1 < nrows) y[ri[r + 1]] += acc1;
+      }
+    }
+  }
+}
+
+template <bool ATOMIC>
+__global__ void __launch_bounds__(128) tile_ops_kernel_v2(const TileOp* __restrict__ ops, int nops,
+                                                          const int32_t* __restrict__ cidx,
+                                                          const double* __restrict__ store,
+                                                          const double* __restrict__ srcA,
+                                                          const double* __restrict__ srcB, PeerOut yout,
+                                                          double* __restrict__ dstB) {
+  double* __restrict__ y = resolve(yout);
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nops) return;
+  const TileOp* __restrict__ op = ops + w;
+  const double* __restrict__ mat = store + op->mat;
+  const int32_t* __restrict__ ci = cidx + op->col;
+  const long long row = op->row, pv = op->priv;
+  const int32_t* __restrict__ ri = row >= 0 ? cidx + row : nullptr;
+  double* __restrict__ priv = pv >= 0 ? dstB + pv : nullptr;
+  const int nrows = op->nrows, ncols = op->ncols;
+  const int half = (nrows + 1) >> 1;
+  if (half <= 8)
+    tile_op_body_v2<4, ATOMIC>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+  else if (half <= 16)
+    tile_op_body_v2<2, ATOMIC>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+  else
+    tile_op_body_v2<1, ATOMIC>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+}
+
 template <bool ATOMIC>
 __global__ void __launch_bounds__(128) tile_ops_kernel(const TileOp* __restrict__ ops, int nops,
                                                        const int32_t* __restrict__ cidx,
@@ -146,6 +247,17 @@ __global__ void sep_rhs_kernel(int64_t nsep, const int32_t* __restrict__ sepdofs
   double v = __ldg(x + sepdofs[e]);
   for (int j = cptr[e]; j < cptr[e + 1]; ++j) v -= g1[cg1[j]];
   rs[e] = v;
+}
+
+// K3b (shared form): z[e] = sum_j us[zsrc[j]], j in [zptr[e], zptr[e+1]) — the separator solutions of the
+// visited patches gathered to the positions of each distinct block's neighbourhood U_k, fixed order
+__global__ void slot_sum_kernel(int64_t nslots, const int32_t* __restrict__ zptr, const int32_t* __restrict__ zsrc,
+                                const double* __restrict__ us, double* __restrict__ z) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nslots) return;
+  double v = 0.0;
+  for (int j = zptr[e]; j < zptr[e + 1]; ++j) v += us[zsrc[j]];
+  z[e] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -309,7 +421,7 @@ __global__ void __launch_bounds__(CT) condense_blocks_kernel(CondenseArgs a) {
       double* Dt = a.store + d.dwoff;
       for (int i = tid; i < br * b; i += CT) {
         const int cc = i / br, r = i - cc * br;
-        Dt[i] = (r < b) ? Akk[r + (size_t)src[cc] * ld] : 0.0;
+        Dt[i] = (r < b) ? Akk[r + (size_t)src[cc] * ld] * d.dscale : 0.0;
       }
       double* Wt = Dt + (size_t)br * b;
       for (int i = tid; i < br * m; i += CT) {
@@ -350,8 +462,11 @@ void condense_setup(alfib_ctx* c, Level& L, PatchSet& ps, const int32_t* block_o
   pv.colour = ps.h_colour.data();
   pv.rowptr = L.h_rowptr.data();
   pv.colidx = L.h_colidx.data();
+  // ALFIB_CONDENSE_SHARED=0 keeps one V / [D | -W] pair per (patch, block) even where blocks could be shared
+  const char* env_shared = std::getenv("ALFIB_CONDENSE_SHARED");
+  const bool allow_shared = !(env_shared && env_shared[0] == '0');
   try {
-    build_condensed_host(pv, block_of_dof, cd.h);
+    build_condensed_host(pv, block_of_dof, cd.h, allow_shared);
   } catch (const std::runtime_error& e) {
     cd.h = CondensedHost();
     throw DeviceError{ALFIB_EINVAL, e.what()};
@@ -367,18 +482,32 @@ void condense_setup(alfib_ctx* c, Level& L, PatchSet& ps, const int32_t* block_o
   cd.seplocal.upload(h.seplocal.data(), h.seplocal.size(), c->stream);
   cd.sepdofs.upload(h.sepdofs.data(), h.sepdofs.size(), c->stream);
   cd.cidx.upload(h.cidx.data(), h.cidx.size(), c->stream);
-  cd.bdofs.upload(h.bdofs.data(), h.bdofs.size(), c->stream);
-  cd.bkeys.upload(h.bkeys.data(), h.bkeys.size(), c->stream);
-  cd.bperm.upload(h.bperm.data(), h.bperm.size(), c->stream);
+  if (h.shared) {                       // block setup over the distinct blocks
+    cd.bdofs.upload(h.sdofs.data(), h.sdofs.size(), c->stream);
+    cd.bkeys.upload(h.skeys.data(), h.skeys.size(), c->stream);
+    cd.bperm.upload(h.sperm.data(), h.sperm.size(), c->stream);
+    cd.blocks.upload(h.sblocks.data(), h.sblocks.size(), c->stream);
+    cd.zptr.upload(h.zptr.data(), h.zptr.size(), c->stream);
+    cd.zsrc.upload(h.zsrc.data(), h.zsrc.size(), c->stream);
+    cd.z.alloc((size_t)std::max<int64_t>(h.g1_total, 1));
+  } else {
+    cd.bdofs.upload(h.bdofs.data(), h.bdofs.size(), c->stream);
+    cd.bkeys.upload(h.bkeys.data(), h.bkeys.size(), c->stream);
+    cd.bperm.upload(h.bperm.data(), h.bperm.size(), c->stream);
+    cd.blocks.upload(h.blocks.data(), h.blocks.size(), c->stream);
+  }
   cd.cptr.upload(h.cptr.data(), h.cptr.size(), c->stream);
   cd.cg1.upload(h.cg1.data(), h.cg1.size(), c->stream);
-  cd.blocks.upload(h.blocks.data(), h.blocks.size(), c->stream);
   cd.opsV.upload(h.opsV.data(), h.opsV.size(), c->stream);
   cd.opsS.upload(h.opsS.data(), h.opsS.size(), c->stream);
   cd.opsDW.upload(h.opsDW.data(), h.opsDW.size(), c->stream);
   cd.g1.alloc((size_t)std::max<int64_t>(h.g1_total, 1));
   cd.rs.alloc((size_t)std::max<int64_t>(h.nsep_total, 1));
   cd.us.alloc((size_t)std::max<int64_t>(h.nsep_total, 1));
+  // slots of blocks / patches outside the iteration set are read (K2, K3b) but never written
+  CUDA_TRY(cudaMemsetAsync(cd.g1.p, 0, cd.g1.n * sizeof(double), c->stream));
+  CUDA_TRY(cudaMemsetAsync(cd.us.p, 0, cd.us.n * sizeof(double), c->stream));
+  if (cd.z.p) CUDA_TRY(cudaMemsetAsync(cd.z.p, 0, cd.z.n * sizeof(double), c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   cd.on = true;
 }
@@ -388,7 +517,7 @@ void launch_condense_blocks(alfib_ctx* c, const Level& L, PatchSet& ps, const do
   Condensed& cd = ps.cond;
   if (cd.h.nblocks == 0) return;
   CondenseArgs a;
-  a.nblocks = cd.h.nblocks;
+  a.nblocks = cd.h.shared ? cd.h.ndist : cd.h.nblocks;
   a.blocks = cd.blocks.p;
   a.bdofs = cd.bdofs.p;
   a.bkeys = cd.bkeys.p;
@@ -405,7 +534,7 @@ void launch_condense_blocks(alfib_ctx* c, const Level& L, PatchSet& ps, const do
   a.info = c->finfo.p;
   const size_t smem = condense_smem_bytes(a.maxb, a.maxm);
   CUDA_TRY(cudaFuncSetAttribute(condense_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)std::min<int64_t>(cd.h.nblocks, (int64_t)c->num_sms * 16);
+  const int grid = (int)std::min<int64_t>(a.nblocks, (int64_t)c->num_sms * 16);
   condense_blocks_kernel<<<grid, CT, smem, c->stream>>>(a);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -421,10 +550,16 @@ void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, P
   const CondensedHost& h = cd.h;
   const int threads = 128, wpb = threads / 32;
   const int nV = (int)h.opsV.size(), nS = (int)h.opsS.size(), nDW = (int)h.opsDW.size();
+  const char* env_v1 = std::getenv("ALFIB_TILE_V1");
+  const bool v1 = env_v1 && env_v1[0] == '1';
   // K1: V ops, all patches, plain private stores
   if (nV) {
-    tile_ops_kernel<false><<<cdiv(nV, wpb), threads, 0, c->stream>>>(cd.opsV.p, nV, cd.cidx.p, ps.store, x, nullptr,
-                                                                      plain_out(nullptr), cd.g1.p);
+    if (v1)
+      tile_ops_kernel<false><<<cdiv(nV, wpb), threads, 0, c->stream>>>(cd.opsV.p, nV, cd.cidx.p, ps.store, x, nullptr,
+                                                                        plain_out(nullptr), cd.g1.p);
+    else
+      tile_ops_kernel_v2<false><<<cdiv(nV, wpb), threads, 0, c->stream>>>(cd.opsV.p, nV, cd.cidx.p, ps.store, x, nullptr,
+                                                                           plain_out(nullptr), cd.g1.p);
     c->launches++;
   }
   // K2: separator right-hand sides
@@ -437,13 +572,36 @@ void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, P
   const bool coloured = c->deterministic && !ps.repeated;
   auto run = [&](const TileOp* ops, int nops, const double* srcA, const double* srcB, double* dstB, bool atomic) {
     if (nops <= 0) return;
-    if (atomic)
-      tile_ops_kernel<true><<<cdiv(nops, wpb), threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB);
-    else
-      tile_ops_kernel<false><<<cdiv(nops, wpb), threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB);
+    if (v1) {
+      if (atomic)
+        tile_ops_kernel<true><<<cdiv(nops, wpb), threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB);
+      else
+        tile_ops_kernel<false><<<cdiv(nops, wpb), threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB);
+    } else {
+      if (atomic)
+        tile_ops_kernel_v2<true><<<cdiv(nops, wpb), threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB);
+      else
+        tile_ops_kernel_v2<false><<<cdiv(nops, wpb), threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB);
+    }
     c->launches++;
   };
-  if (!coloured && ps.ncolour > 1) {
+  if (h.shared) {
+    // shared blocks: K3 as below; K3b sums the separator solutions per distinct block; K4 is one launch
+    // over the distinct blocks, which are pairwise disjoint (plain stores, deterministic in every mode)
+    if (!coloured && ps.ncolour > 1) {
+      run(cd.opsS.p, nS, cd.rs.p, nullptr, cd.us.p, true);
+    } else {
+      for (int col = 0; col < ps.ncolour; ++col) {
+        const int s = h.s_colour_start[col], e = h.s_colour_start[col + 1];
+        run(cd.opsS.p + s, e - s, cd.rs.p, nullptr, cd.us.p, ps.repeated);
+      }
+    }
+    if (h.g1_total) {
+      slot_sum_kernel<<<cdiv(h.g1_total, 256), 256, 0, c->stream>>>(h.g1_total, cd.zptr.p, cd.zsrc.p, cd.us.p, cd.z.p);
+      c->launches++;
+    }
+    run(cd.opsDW.p, nDW, x, cd.z.p, nullptr, false);
+  } else if (!coloured && ps.ncolour > 1) {
     run(cd.opsS.p, nS, cd.rs.p, nullptr, cd.us.p, true);
     run(cd.opsDW.p, nDW, x, cd.us.p, nullptr, true);
   } else {

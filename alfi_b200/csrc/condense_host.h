@@ -7,6 +7,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdint>
+#include <map>
 #include <numeric>
 #include <stdexcept>
 #include <string>
@@ -32,6 +33,7 @@ struct BlockDesc {
   long long voff;   // store offset of the V tile   (roundup2(m) x b)
   long long dwoff;  // store offset of the [D | -W] tile (roundup2(b) x (b+m))
   int b, m;
+  double dscale;    // the D part of the tile is stored multiplied by this (1 unless the block is shared)
 };
 
 // what the builder needs to know about a patch set and its level (all host memory, borrowed)
@@ -63,14 +65,193 @@ struct CondensedHost {
   std::vector<TileOp> opsV, opsS, opsDW;
   std::vector<int> s_colour_start, dw_colour_start;   // ncolour+1 ranges of opsS / opsDW
   int64_t index_bytes = 0;              // bytes of index data one apply reads (roofline accounting)
+
+  // ---- shared blocks -----------------------------------------------------------------------------------
+  // A block with a given dof set occurs in several patches (a macro cell lies in the macro stars of all
+  // its vertices) and D_k = A_kk^-1 is the same matrix in all of them.  With U_k the union of the
+  // separator neighbourhoods N_q of its instances q, V_q / W_q are row / column subsets of
+  //     Vf_k = A_Uk D_k  (|U_k| x |B_k|),     Wf_k = D_k A_kU  (|B_k| x |U_k|),
+  // so the additive sum over the patches can be taken block by block instead of instance by instance:
+  //     g[k]    = Vf_k x[B_k]                                          (one op per distinct block)
+  //     rs[p,s] = x[S_p[s]] - sum over the instances q of p with s in N_q of g[k(q)][pos of s in U_k]
+  //     us[p]   = X_SS rs[p],  y[S_p] += us[p]                         (unchanged)
+  //     z[k]    = sum over the visited instances q of k of us[p(q)] scattered to U_k positions
+  //     y[B_k] += [visits_k D_k | -Wf_k] [x[B_k]; z[k]]                (one op per distinct block)
+  // which stores and streams Vf, Wf and D once per distinct block (3-D SV k=3: 60x45, 45x60, 45x45 per
+  // macro cell instead of 4 x (30x45 + 45x30 + 45x45)).  Used when the distinct blocks are pairwise
+  // disjoint and every |U_k| <= ALFIB_TILE_ROWS; otherwise the per-instance form above is kept.
+  bool shared = false;
+  int64_t ndist = 0;
+  std::vector<int64_t> inst_dist;       // nblocks: distinct block of each instance
+  std::vector<int32_t> inst_opos;       // parallel to bl_local: position of the dof in the owner's block order
+  std::vector<int32_t> inst_upos;       // parallel to nb_pos: position of the neighbour in U_k
+  std::vector<BlockDesc> sblocks;       // ndist descriptors, dofs = [B_k (owner order); U_k (ascending)]
+  std::vector<int32_t> sdofs, skeys, sperm, svisits;
+  std::vector<int64_t> uoff;            // ndist+1: slots of g[k] / z[k] in the private buffers
+  std::vector<int32_t> zptr, zsrc;      // CSR: z slot -> positions in us, in iteration order
 };
 
 inline int ch_roundup2(int n) { return (n + 1) & ~1; }
 
+// Shared-block form (see CondensedHost): rewrites the V / [D | -W] op lists, the K2 lists, the store
+// layout behind the X_SS tiles and the private-buffer sizes of a finished per-instance build.  Leaves
+// `cd` untouched (shared = false) when the structure does not allow it.
+inline void build_shared_blocks(const PatchView& pv, CondensedHost& cd) {
+  if (cd.nblocks == 0) return;
+  const int npatch = pv.npatch;
+  // ---- distinct blocks: instances with the same dof set; the first instance is the owner ---------------
+  std::vector<int64_t> inst_dist(cd.nblocks, -1), owner;
+  {
+    std::map<std::vector<int32_t>, int64_t> seen;
+    std::vector<int32_t> key;
+    for (int64_t q = 0; q < cd.nblocks; ++q) {
+      const BlockDesc& d = cd.blocks[q];
+      key.assign(cd.bdofs.begin() + d.dofs, cd.bdofs.begin() + d.dofs + d.b);
+      std::sort(key.begin(), key.end());
+      auto it = seen.find(key);
+      if (it == seen.end()) {
+        it = seen.emplace(key, (int64_t)owner.size()).first;
+        owner.push_back(q);
+      }
+      inst_dist[q] = it->second;
+    }
+  }
+  const int64_t nd = (int64_t)owner.size();
+  // the ops of different distinct blocks run in one launch with plain stores: they must not overlap
+  std::vector<int32_t> opos_of_dof(pv.ndofs, -1);
+  for (int64_t k = 0; k < nd; ++k) {
+    const BlockDesc& d = cd.blocks[owner[k]];
+    for (int i = 0; i < d.b; ++i) {
+      int32_t& st = opos_of_dof[cd.bdofs[d.dofs + i]];
+      if (st >= 0) return;
+      st = i;
+    }
+  }
+  // ---- U_k: union of the instances' separator neighbourhoods, global dofs ascending ---------------------
+  std::vector<std::vector<int32_t>> U(nd);
+  for (int64_t q = 0; q < cd.nblocks; ++q) {
+    const BlockDesc& d = cd.blocks[q];
+    std::vector<int32_t>& u = U[inst_dist[q]];
+    u.insert(u.end(), cd.bdofs.begin() + d.dofs + d.b, cd.bdofs.begin() + d.dofs + d.b + d.m);
+  }
+  int64_t utotal = 0;
+  for (int64_t k = 0; k < nd; ++k) {
+    std::sort(U[k].begin(), U[k].end());
+    U[k].erase(std::unique(U[k].begin(), U[k].end()), U[k].end());
+    if ((int)U[k].size() > ALFIB_TILE_ROWS) return;
+    utotal += (int64_t)U[k].size();
+  }
+  if (utotal >= INT_MAX / 2) return;
+
+  // ---- from here on the shared form is used ------------------------------------------------------------
+  cd.shared = true;
+  cd.ndist = nd;
+  cd.inst_dist = inst_dist;
+  cd.inst_opos.resize(cd.bl_local.size());
+  cd.inst_upos.resize(cd.nb_pos.size());
+  for (int64_t q = 0; q < cd.nblocks; ++q) {
+    const BlockDesc& d = cd.blocks[q];
+    const std::vector<int32_t>& u = U[inst_dist[q]];
+    for (int i = 0; i < d.b; ++i) cd.inst_opos[cd.bl_off[q] + i] = opos_of_dof[cd.bdofs[d.dofs + i]];
+    for (int j = 0; j < d.m; ++j)
+      cd.inst_upos[cd.nb_off[q] + j] =
+          (int32_t)(std::lower_bound(u.begin(), u.end(), cd.bdofs[d.dofs + d.b + j]) - u.begin());
+  }
+  cd.svisits.assign(nd, 0);
+  for (int32_t p : *pv.order)
+    for (int64_t q = cd.blk_start[p]; q < cd.blk_start[p + 1]; ++q) cd.svisits[inst_dist[q]]++;
+
+  // store: X_SS tiles (unchanged), then Vf and [visits D | -Wf] of every distinct block
+  int64_t cur = cd.ssoff[npatch];
+  cd.sblocks.resize(nd);
+  cd.uoff.assign(nd + 1, 0);
+  cd.maxm = 0;
+  std::vector<int64_t> sblk_list(nd);
+  std::vector<int32_t> idx;
+  int64_t list_entries = 0;
+  for (int64_t k = 0; k < nd; ++k) {
+    const BlockDesc& od = cd.blocks[owner[k]];
+    const int b = od.b, m = (int)U[k].size();
+    BlockDesc& d = cd.sblocks[k];
+    d.b = b;
+    d.m = m;
+    d.voff = cur;
+    cur += (int64_t)ch_roundup2(m) * b;
+    d.dwoff = cur;
+    cur += (int64_t)ch_roundup2(b) * (b + m);
+    d.dscale = (double)std::max(cd.svisits[k], 1);
+    d.dofs = (int64_t)cd.sdofs.size();
+    d.keys = d.dofs;
+    cd.uoff[k + 1] = cd.uoff[k] + m;
+    cd.maxm = std::max(cd.maxm, m);
+    sblk_list[k] = (int64_t)cd.cidx.size();
+    for (int i = 0; i < b; ++i) {
+      const int32_t g = cd.bdofs[od.dofs + i];
+      cd.cidx.push_back(g);
+      cd.sdofs.push_back(g);
+    }
+    for (int t = 0; t < m; ++t) {
+      cd.cidx.push_back(~(int32_t)(cd.uoff[k] + t));
+      cd.sdofs.push_back(U[k][t]);
+    }
+    list_entries += b + m;
+    idx.resize(b + m);
+    std::iota(idx.begin(), idx.end(), 0);
+    const int32_t* gd = cd.sdofs.data() + d.dofs;
+    std::sort(idx.begin(), idx.end(), [&](int x, int y) { return gd[x] < gd[y]; });
+    for (int i = 0; i < b + m; ++i) {
+      cd.skeys.push_back(gd[idx[i]]);
+      cd.sperm.push_back(idx[i]);
+    }
+  }
+  cd.g1_total = cd.uoff[nd];
+  cd.store_elems = cur;
+
+  // K2: contributions to every separator entry, now slots of g[k]
+  {
+    std::vector<int32_t> cursor(cd.cptr.begin(), cd.cptr.end() - 1);
+    for (int p = 0; p < npatch; ++p)
+      for (int64_t q = cd.blk_start[p]; q < cd.blk_start[p + 1]; ++q)
+        for (int64_t j = cd.nb_off[q]; j < cd.nb_off[q + 1]; ++j)
+          cd.cg1[cursor[cd.sepoff[p] + cd.nb_pos[j]]++] = (int32_t)(cd.uoff[inst_dist[q]] + cd.inst_upos[j]);
+  }
+  // z[k]: for every slot the us entries of the visited instances, in iteration order
+  cd.zptr.assign(cd.g1_total + 1, 0);
+  for (int32_t p : *pv.order)
+    for (int64_t q = cd.blk_start[p]; q < cd.blk_start[p + 1]; ++q)
+      for (int64_t j = cd.nb_off[q]; j < cd.nb_off[q + 1]; ++j) cd.zptr[cd.uoff[inst_dist[q]] + cd.inst_upos[j] + 1]++;
+  for (int64_t e = 0; e < cd.g1_total; ++e) cd.zptr[e + 1] += cd.zptr[e];
+  cd.zsrc.assign((size_t)cd.zptr[cd.g1_total], 0);
+  {
+    std::vector<int32_t> cursor(cd.zptr.begin(), cd.zptr.end() - 1);
+    for (int32_t p : *pv.order)
+      for (int64_t q = cd.blk_start[p]; q < cd.blk_start[p + 1]; ++q)
+        for (int64_t j = cd.nb_off[q]; j < cd.nb_off[q + 1]; ++j)
+          cd.zsrc[cursor[cd.uoff[inst_dist[q]] + cd.inst_upos[j]]++] = (int32_t)(cd.sepoff[p] + cd.nb_pos[j]);
+  }
+  // op lists: one V op and one [D | -W] op per visited distinct block; the S ops stay as they are.
+  // All [D | -W] ops sit in the range of colour 0 (they are pairwise disjoint: one launch, plain stores).
+  cd.opsV.clear();
+  cd.opsDW.clear();
+  for (int64_t k = 0; k < nd; ++k) {
+    const BlockDesc& d = cd.sblocks[k];
+    if (cd.svisits[k] == 0) continue;
+    if (d.m > 0) cd.opsV.push_back(TileOp{d.voff, sblk_list[k], -1, cd.uoff[k], d.m, d.b});
+    cd.opsDW.push_back(TileOp{d.dwoff, sblk_list[k], sblk_list[k], -1, d.b, d.b + d.m});
+  }
+  cd.dw_colour_start.assign(pv.ncolour + 1, (int)cd.opsDW.size());
+  if (pv.ncolour) cd.dw_colour_start[0] = 0;
+  cd.index_bytes = (int64_t)sizeof(int32_t) * (2 * cd.nsep_total + 2 * list_entries + (int64_t)cd.sepdofs.size() +
+                                              (int64_t)cd.cptr.size() + (int64_t)cd.cg1.size() +
+                                              (int64_t)cd.zptr.size() + (int64_t)cd.zsrc.size()) +
+                   (int64_t)sizeof(TileOp) * (int64_t)(cd.opsV.size() + cd.opsS.size() + cd.opsDW.size());
+}
+
 // block_of_dof[k] for every entry of the patch dof list: < 0 separator, otherwise a block label
 // (any non-negative integer, local to the patch).  Blocks must be pairwise decoupled in the BSR
 // pattern; this is checked here, so a wrong hint is an error, never a wrong answer.
-inline void build_condensed_host(const PatchView& pv, const int32_t* block_of_dof, CondensedHost& cd) {
+inline void build_condensed_host(const PatchView& pv, const int32_t* block_of_dof, CondensedHost& cd,
+                                 bool allow_shared = true) {
   cd = CondensedHost();
   const int npatch = pv.npatch, bs = pv.bs;
   cd.sepoff.assign(npatch + 1, 0);
@@ -201,6 +382,7 @@ inline void build_condensed_host(const PatchView& pv, const int32_t* block_of_do
       cur += (int64_t)ch_roundup2(m) * b;
       d.dwoff = cur;
       cur += (int64_t)ch_roundup2(b) * (b + m);
+      d.dscale = 1.0;
       d.dofs = (int64_t)cd.bdofs.size();
       d.keys = d.dofs;
       blk_list[q] = (int64_t)cd.cidx.size();
@@ -274,6 +456,7 @@ inline void build_condensed_host(const PatchView& pv, const int32_t* block_of_do
   }
   cd.index_bytes = (int64_t)sizeof(int32_t) * (int64_t)(cd.cidx.size() + cd.sepdofs.size() + cd.cptr.size() + cd.cg1.size()) +
                    (int64_t)sizeof(TileOp) * (int64_t)(cd.opsV.size() + cd.opsS.size() + cd.opsDW.size());
+  if (allow_shared) build_shared_blocks(pv, cd);
 }
 
 // Dense inverse (row-major n x n) of one patch rebuilt from its condensed factors.  `fetch(off,
@@ -312,18 +495,35 @@ inline void condensed_inverse_host(const CondensedHost& cd, int patch, int n, Fe
     k.m = d.m;
     k.loc = cd.bl_local.data() + cd.bl_off[q];
     k.nb = cd.nb_pos.data() + cd.nb_off[q];
-    const int mr = ch_roundup2(d.m), br = ch_roundup2(d.b);
-    const std::vector<double> tv = fetch(d.voff, (int64_t)mr * d.b);
-    const std::vector<double> td = fetch(d.dwoff, (int64_t)br * (d.b + d.m));
     k.V.assign((size_t)d.m * d.b, 0.0);
     k.D.assign((size_t)d.b * d.b, 0.0);
     k.W.assign((size_t)d.b * d.m, 0.0);
-    for (int cc = 0; cc < d.b; ++cc)
-      for (int r = 0; r < d.m; ++r) k.V[(size_t)r * d.b + cc] = tv[(size_t)cc * mr + r];
-    for (int cc = 0; cc < d.b; ++cc)
-      for (int r = 0; r < d.b; ++r) k.D[(size_t)r * d.b + cc] = td[(size_t)cc * br + r];
-    for (int cc = 0; cc < d.m; ++cc)
-      for (int r = 0; r < d.b; ++r) k.W[(size_t)r * d.m + cc] = -td[(size_t)(d.b + cc) * br + r];
+    if (cd.shared) {
+      // rows / columns of the distinct block's tiles: block dofs in the owner's order (opos), the
+      // neighbours at their positions in U_k (upos); the D part is stored times dscale
+      const BlockDesc& sd = cd.sblocks[cd.inst_dist[q]];
+      const int32_t* opos = cd.inst_opos.data() + cd.bl_off[q];
+      const int32_t* upos = cd.inst_upos.data() + cd.nb_off[q];
+      const int mr = ch_roundup2(sd.m), br = ch_roundup2(sd.b);
+      const std::vector<double> tv = fetch(sd.voff, (int64_t)mr * sd.b);
+      const std::vector<double> td = fetch(sd.dwoff, (int64_t)br * (sd.b + sd.m));
+      for (int cc = 0; cc < d.b; ++cc)
+        for (int r = 0; r < d.m; ++r) k.V[(size_t)r * d.b + cc] = tv[(size_t)opos[cc] * mr + upos[r]];
+      for (int cc = 0; cc < d.b; ++cc)
+        for (int r = 0; r < d.b; ++r) k.D[(size_t)r * d.b + cc] = td[(size_t)opos[cc] * br + opos[r]] / sd.dscale;
+      for (int cc = 0; cc < d.m; ++cc)
+        for (int r = 0; r < d.b; ++r) k.W[(size_t)r * d.m + cc] = -td[(size_t)(sd.b + upos[cc]) * br + opos[r]];
+    } else {
+      const int mr = ch_roundup2(d.m), br = ch_roundup2(d.b);
+      const std::vector<double> tv = fetch(d.voff, (int64_t)mr * d.b);
+      const std::vector<double> td = fetch(d.dwoff, (int64_t)br * (d.b + d.m));
+      for (int cc = 0; cc < d.b; ++cc)
+        for (int r = 0; r < d.m; ++r) k.V[(size_t)r * d.b + cc] = tv[(size_t)cc * mr + r];
+      for (int cc = 0; cc < d.b; ++cc)
+        for (int r = 0; r < d.b; ++r) k.D[(size_t)r * d.b + cc] = td[(size_t)cc * br + r];
+      for (int cc = 0; cc < d.m; ++cc)
+        for (int r = 0; r < d.b; ++r) k.W[(size_t)r * d.m + cc] = -td[(size_t)(d.b + cc) * br + r];
+    }
     blks.push_back(std::move(k));
   }
   // X[S, B_l] = -X_SS[:, N_l] V_l ;  X[B_k, B_l] = delta_kl D_k + W_k X_SS[N_k, N_l] V_l ;  X[B_k, S] = -W_k X_SS[N_k, :]

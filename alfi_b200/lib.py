@@ -53,6 +53,7 @@ SIGNATURES = {
     "alfib_level_set_patch_blocks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i32p]),
     "alfib_patch_apply_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int]),
     "alfib_patch_storage_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int]),
+    "alfib_patch_storage_form": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "alfib_patch_bind_storage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
     "alfib_level_factor": (C.c_int, [C.c_void_p, C.c_int]),
     "alfib_smoother_apply": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
@@ -261,6 +262,10 @@ class Context:
     def patch_apply_bytes(self, level, which=PATCHES_SMOOTHER):
         """Algorithmic bytes of one application of the patch set (factors + indices + 16 N)."""
         return int(self.lib.alfib_patch_apply_bytes(self.h, level, which))
+
+    def patch_storage_form(self, level, which=PATCHES_SMOOTHER):
+        """0 dense, 1 condensed per (patch, block), 2 condensed with shared blocks."""
+        return int(self.lib.alfib_patch_storage_form(self.h, level, which))
 
     def patch_storage_bytes(self, level, which=PATCHES_SMOOTHER):
         return int(self.lib.alfib_patch_storage_bytes(self.h, level, which))

@@ -238,6 +238,7 @@ def ours(args):
     prof_all = mg.ctx.profile_get(-1)
     mg.ctx.profile(False)
     patch_apply_bytes = mg.ctx.patch_apply_bytes(len(prob.levels) - 1)
+    mg_form = mg.ctx.patch_storage_form(len(prob.levels) - 1)
     factor_bytes = mg.ctx.patch_storage_bytes(len(prob.levels) - 1)
 
     # ---- end to end through the C-ABI with host buffers --------------------------------------
@@ -278,15 +279,21 @@ def ours(args):
     bs_bytes = float(patch_apply_bytes)
     app_ms, app_calls = prof_fine["PCPATCHApply"]
     achieved = bs_bytes / (app_ms / max(app_calls, 1) * 1e-3) / 1e9 if app_calls else None
+    form = mg_form
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "patch_apply_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.config + (":condensed" if condensed else ""))
+            traffic = json.load(open(tpath)).get(args.config + ((":condensed-shared" if form == 2 else ":condensed")
+                                                                if condensed else ""))
         except Exception:   # noqa: BLE001
             traffic = None
-    roofline = {"kernel": ("tile_ops_kernel x3 + sep_rhs_kernel (finest-level PCApply_PATCH, condensed inverses: memset, "
-                           "V ops, separator rhs, X_SS ops, [D|-W] ops, bc fix-up)") if condensed else
+    tile = "tile_ops_kernel" if os.environ.get("ALFIB_TILE_V1", "0")[:1] == "1" else "tile_ops_kernel_v2"
+    roofline = {"kernel": ("%s x3 + sep_rhs_kernel + slot_sum_kernel (finest-level PCApply_PATCH, condensed inverses with "
+                           "shared blocks: memset, Vf ops, separator rhs, X_SS ops, z sums, [D|-Wf] ops, bc fix-up)" % tile)
+                if form == 2 else
+                ("%s x3 + sep_rhs_kernel (finest-level PCApply_PATCH, condensed inverses: memset, "
+                 "V ops, separator rhs, X_SS ops, [D|-W] ops, bc fix-up)" % tile) if condensed else
                 "patch_apply_kernel (finest-level PCApply_PATCH: memset + colour launches + bc fix-up)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
@@ -334,7 +341,9 @@ def ours(args):
                    "patches_finest": int(fine.patches.npatch), "max_patch_dofs": int(fine.patches.sizes.max()),
                    "factor_bytes_finest": float(factor_bytes),
                    "dense_factor_bytes_finest": float((fine.patches.sizes.astype(float) ** 2).sum() * 8),
-                   "patch_inverses": "condensed (block/separator form, csrc/condense.cu)" if condensed else "dense",
+                   "patch_inverses": ("condensed (block/separator form, blocks shared between patches, csrc/condense.cu)"
+                                      if mg_form == 2 else "condensed (block/separator form, csrc/condense.cu)")
+                   if condensed else "dense",
                    "l2_policy": "inputs larger than L2 (%.1f GB of patch inverses streamed per finest-level smoother "
                                 "application, 126 MB L2)" % (factor_bytes / 1e9),
                    "deterministic": bool(args.deterministic), "parallelism": "1 GPU" if world == 1 else

@@ -125,12 +125,20 @@ int alfib_level_set_patches(alfib_ctx* ctx, int level, int which, int32_t npatch
  * (relaxation.py:168-177, bary.py) — interiors of the macro cells = blocks — that is ~10x fewer
  * bytes to store and to stream per PCApply_PATCH than the dense inverse PETSc's
  * `patch_pc_patch_dense_inverse` (solver.py:602) keeps; the result is the same A_i^-1 r_i.
+ * Blocks with the same dof set in several patches (a macro cell is in the macro stars of all its
+ * vertices) are stored and applied once (D_k, A_Uk D_k, D_k A_kU with U_k the union of their
+ * separator neighbourhoods) when they are pairwise disjoint and |U_k| <= 64; environment
+ * ALFIB_CONDENSE_SHARED=0 keeps one copy per (patch, block).
  * NULL returns the set to dense inverses.                                                      */
 int alfib_level_set_patch_blocks(alfib_ctx* ctx, int level, int which, const int32_t* block_of_dof);
 /* algorithmic bytes of one application of that patch set: stored factors + index data + 16 N   */
 int64_t alfib_patch_apply_bytes(alfib_ctx* ctx, int level, int which);
 /* bytes of device storage the inverse factors of that patch set need                          */
 int64_t alfib_patch_storage_bytes(alfib_ctx* ctx, int level, int which);
+/* how that patch set holds its inverses: 0 dense tiles, 1 condensed with one V / [D | -W] pair per
+ * (patch, block), 2 condensed with the blocks shared between the patches that contain them
+ * (alfib_level_set_patch_blocks; csrc/condense.cu); negative on a bad handle                      */
+int alfib_patch_storage_form(alfib_ctx* ctx, int level, int which);
 /* optional: caller-owned device buffer (a torch tensor's data_ptr()) for the factors; if never
  * called the library allocates.                                                               */
 int alfib_patch_bind_storage(alfib_ctx* ctx, int level, int which, void* dev_ptr, int64_t bytes);

@@ -5,7 +5,7 @@
 // restatement of what the CUDA kernels of condense.cu / patch_factor.cu do with them:
 //   ch_factor : X_SS from a pivoted Gauss-Jordan inverse of the whole patch; per block the gather
 //               through the sorted key tables, Gauss-Jordan inverse of A_kk, V = A_Nk D, [D | -W]
-//   ch_apply  : K1 (V ops) -> K2 (separator rhs) -> K3 (X_SS ops) -> K4 ([D | -W] ops)
+//   ch_apply  : K1 (V ops) -> K2 (separator rhs) -> K3 (X_SS ops) [-> K3b (z sums, shared form)] -> K4 ([D | -W] ops)
 // tests/test_condense_host.py drives it through ctypes and compares with dense patch solves.
 #include <cstring>
 
@@ -18,7 +18,7 @@ struct Shim {
   int npatch, ncolour, bs, ndofs;
   std::vector<int64_t> off;
   std::vector<int32_t> dofs, order, colour, rowptr, colidx;
-  std::vector<double> store, g1, rs, us;
+  std::vector<double> store, g1, rs, us, z;
   std::string err;
 };
 
@@ -85,7 +85,7 @@ extern "C" {
 
 void* ch_create(int n_nodes, int bs, const int32_t* rowptr, const int32_t* colidx, int npatch, const int64_t* off,
                 const int32_t* dofs, int norder, const int32_t* order, const int32_t* colour, int ncolour,
-                const int32_t* blocks, char* err, int errlen) {
+                const int32_t* blocks, int allow_shared, char* err, int errlen) {
   Shim* s = new Shim();
   s->npatch = npatch;
   s->ncolour = ncolour;
@@ -100,7 +100,7 @@ void* ch_create(int n_nodes, int bs, const int32_t* rowptr, const int32_t* colid
   PatchView pv{npatch, ncolour, bs, s->ndofs, s->off.data(), s->dofs.data(), &s->order, s->colour.data(),
                s->rowptr.data(), s->colidx.data()};
   try {
-    build_condensed_host(pv, blocks, s->cd);
+    build_condensed_host(pv, blocks, s->cd, allow_shared != 0);
   } catch (const std::exception& e) {
     std::strncpy(err, e.what(), errlen - 1);
     err[errlen - 1] = 0;
@@ -111,12 +111,13 @@ void* ch_create(int n_nodes, int bs, const int32_t* rowptr, const int32_t* colid
   s->g1.assign((size_t)std::max<int64_t>(s->cd.g1_total, 1), 0.0);
   s->rs.assign((size_t)std::max<int64_t>(s->cd.nsep_total, 1), 0.0);
   s->us.assign((size_t)std::max<int64_t>(s->cd.nsep_total, 1), 0.0);
+  s->z.assign((size_t)std::max<int64_t>(s->cd.g1_total, 1), 0.0);
   return s;
 }
 
 void ch_destroy(void* h) { delete static_cast<Shim*>(h); }
 
-// stats[0..7] = store_elems, index_bytes, nblocks, nsep_total, maxb, maxm, maxsep, #ops
+// stats[0..9] = store_elems, index_bytes, nblocks, nsep_total, maxb, maxm, maxsep, #ops, shared, ndist
 void ch_stats(void* h, int64_t* stats) {
   const CondensedHost& cd = static_cast<Shim*>(h)->cd;
   stats[0] = cd.store_elems;
@@ -127,6 +128,8 @@ void ch_stats(void* h, int64_t* stats) {
   stats[5] = cd.maxm;
   stats[6] = cd.maxsep;
   stats[7] = (int64_t)(cd.opsV.size() + cd.opsS.size() + cd.opsDW.size());
+  stats[8] = cd.shared ? 1 : 0;
+  stats[9] = cd.ndist;
 }
 
 // vals: nnzb x bs x bs row-major blocks.  Returns 0, or 1 + index of a singular patch / block.
@@ -163,12 +166,17 @@ int ch_factor(void* h, const double* vals) {
         for (int r = 0; r < rt; ++r) tile[(size_t)c * rt + r] = r < rows ? W[sl[row0 + r] + (size_t)sl[c] * n] : 0.0;
     }
   }
-  for (int64_t q = 0; q < cd.nblocks; ++q) {
-    const BlockDesc& d = cd.blocks[q];
+  // what condense_blocks_kernel is launched over: the instances, or the distinct blocks in shared form
+  const std::vector<BlockDesc>& fblocks = cd.shared ? cd.sblocks : cd.blocks;
+  const std::vector<int32_t>& fdofs = cd.shared ? cd.sdofs : cd.bdofs;
+  const std::vector<int32_t>& fkeys = cd.shared ? cd.skeys : cd.bkeys;
+  const std::vector<int32_t>& fperm = cd.shared ? cd.sperm : cd.bperm;
+  for (int64_t q = 0; q < (int64_t)fblocks.size(); ++q) {
+    const BlockDesc& d = fblocks[q];
     const int b = d.b, m = d.m, bm = b + m;
-    const int32_t* gd = cd.bdofs.data() + d.dofs;
-    const int32_t* keys = cd.bkeys.data() + d.keys;
-    const int32_t* perm = cd.bperm.data() + d.keys;
+    const int32_t* gd = fdofs.data() + d.dofs;
+    const int32_t* keys = fkeys.data() + d.keys;
+    const int32_t* perm = fperm.data() + d.keys;
     std::vector<double> Akk((size_t)b * b, 0.0), AkN((size_t)b * std::max(m, 1), 0.0), ANk((size_t)std::max(m, 1) * b, 0.0);
     for (int rp = 0; rp < bm; ++rp) {
       const int node = gd[rp] / bs, comp = gd[rp] % bs;
@@ -197,7 +205,7 @@ int ch_factor(void* h, const double* vals) {
       }
     double* Dt = s.store.data() + d.dwoff;
     for (int c = 0; c < b; ++c)
-      for (int r = 0; r < br; ++r) Dt[(size_t)c * br + r] = r < b ? Akk[r + (size_t)c * b] : 0.0;
+      for (int r = 0; r < br; ++r) Dt[(size_t)c * br + r] = r < b ? Akk[r + (size_t)c * b] * d.dscale : 0.0;
     double* Wt = Dt + (size_t)br * b;
     for (int c = 0; c < m; ++c)
       for (int r = 0; r < br; ++r) {
@@ -223,6 +231,16 @@ void ch_apply(void* h, const double* x, double* y) {
   for (int col = 0; col < s.ncolour; ++col)
     for (int i = cd.s_colour_start[col]; i < cd.s_colour_start[col + 1]; ++i)
       run_op(s, cd.opsS[i], s.rs.data(), nullptr, y, s.us.data());
+  if (cd.shared) {
+    // K3b: z[k] = sum of the visited instances' us entries; K4: one [visits D | -Wf] op per distinct block
+    for (int64_t e = 0; e < cd.g1_total; ++e) {
+      double v = 0.0;
+      for (int j = cd.zptr[e]; j < cd.zptr[e + 1]; ++j) v += s.us[cd.zsrc[j]];
+      s.z[e] = v;
+    }
+    for (const TileOp& op : cd.opsDW) run_op(s, op, x, s.z.data(), y, nullptr);
+    return;
+  }
   for (int col = 0; col < s.ncolour; ++col)
     for (int i = cd.dw_colour_start[col]; i < cd.dw_colour_start[col + 1]; ++i)
       run_op(s, cd.opsDW[i], x, s.us.data(), y, nullptr);

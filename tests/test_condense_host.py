@@ -31,7 +31,7 @@ def shim():
     lib = C.CDLL(so)
     lib.ch_create.restype = C.c_void_p
     lib.ch_create.argtypes = [C.c_int, C.c_int, _i32p, _i32p, C.c_int, _i64p, _i32p, C.c_int, _i32p, _i32p, C.c_int,
-                              _i32p, C.c_char_p, C.c_int]
+                              _i32p, C.c_int, C.c_char_p, C.c_int]
     lib.ch_destroy.argtypes = [C.c_void_p]
     lib.ch_stats.argtypes = [C.c_void_p, _i64p]
     lib.ch_factor.argtypes = [C.c_void_p, _f64p]
@@ -46,7 +46,7 @@ def _p(a, t):
 
 
 class Host:
-    def __init__(self, lib, ld, ps, blocks):
+    def __init__(self, lib, ld, ps, blocks, shared=True):
         self.lib = lib
         A = ld.A
         self.keep = [np.ascontiguousarray(a, dtype=t) for a, t in (
@@ -58,13 +58,13 @@ class Host:
         ncol = int(col.max()) + 1 if col.size else 0
         self.h = lib.ch_create(ld.V.nnodes, ld.V.bs, _p(rp, C.c_int32), _p(ci, C.c_int32), ps.npatch, _p(off, C.c_int64),
                                _p(dofs, C.c_int32), order.size, _p(order, C.c_int32), _p(col, C.c_int32), ncol,
-                               _p(blk, C.c_int32), err, 512)
+                               _p(blk, C.c_int32), int(shared), err, 512)
         self.err = err.value.decode()
 
     def stats(self):
-        s = np.zeros(8, np.int64)
+        s = np.zeros(10, np.int64)
         self.lib.ch_stats(self.h, _p(s, C.c_int64))
-        return dict(zip(["store_elems", "index_bytes", "nblocks", "nsep_total", "maxb", "maxm", "maxsep", "nops"], s.tolist()))
+        return dict(zip(["store_elems", "index_bytes", "nblocks", "nsep_total", "maxb", "maxm", "maxsep", "nops", "shared", "ndist"], s.tolist()))
 
     def factor(self, vals):
         v = np.ascontiguousarray(vals, dtype=np.float64)
@@ -97,7 +97,8 @@ CASES = [("ldc2d-sv-k2-tiny", {}), ("ldc3d-sv-k3-tiny", {}), ("ldc3d-sv-k3-tiny"
 
 @pytest.mark.parametrize("name,kw", CASES)
 @pytest.mark.parametrize("which", ["smoother", "cell"])
-def test_condensed_apply_equals_dense_patch_solves(shim, problems, name, kw, which):
+@pytest.mark.parametrize("shared", [True, False])
+def test_condensed_apply_equals_dense_patch_solves(shim, problems, name, kw, which, shared):
     prob = problems(name, **kw)
     mild = bool(kw)
     for ld in prob.levels[1:]:
@@ -106,9 +107,16 @@ def test_condensed_apply_equals_dense_patch_solves(shim, problems, name, kw, whi
         assert ps.blocks is not None and (ps.blocks >= 0).any()
         if ps.colours is None:
             ps.colours = np.zeros(ps.npatch, np.int32)
-        host = Host(shim, ld, ps, ps.blocks)
+        host = Host(shim, ld, ps, ps.blocks, shared)
         assert host.h, host.err
         st = host.stats()
+        # macro-cell interiors are pairwise disjoint and their boundary has <= 60 dofs: the shared form applies
+        assert st["shared"] == int(shared)
+        if shared:
+            assert st["ndist"] == np.unique(ps.blocks[ps.blocks >= 0]).size <= st["nblocks"]
+            per_instance = Host(shim, ld, ps, ps.blocks, False)
+            assert st["store_elems"] <= per_instance.stats()["store_elems"]
+            per_instance.close()
         dense = int((ps.sizes.astype(np.int64) ** 2).sum())
         assert st["store_elems"] < dense                       # fewer bytes than the dense inverses
         assert st["maxb"] <= 64 and st["maxm"] <= 64
@@ -141,8 +149,8 @@ def test_condensed_apply_equals_dense_patch_solves(shim, problems, name, kw, whi
         # rounding of its three factors (|W||X_SS||V| >> |X| for augmented-Lagrangian blocks)
         assert worst < BACKWARD_TOL, worst
         host.close()
-        print("%s level %d %s: %d patches, store %.2f MB vs dense %.2f MB (x%.1f), rel diff %.1e (kappa %.1e)" % (
-            name, ld.index, which, ps.npatch, st["store_elems"] * 8e-6, dense * 8e-6, dense / st["store_elems"],
+        print("%s level %d %s shared=%d: %d patches, store %.2f MB vs dense %.2f MB (x%.1f), rel diff %.1e (kappa %.1e)" % (
+            name, ld.index, which, shared, ps.npatch, st["store_elems"] * 8e-6, dense * 8e-6, dense / st["store_elems"],
             rel(y, yo), kappa) + ", inverse backward error %.1e" % worst)
 
 
@@ -158,6 +166,34 @@ def test_coupled_blocks_are_rejected(shim, problems):
     blocks[o + sep[0]] = 10 ** 6            # the patch's vertex dof couples to every block
     host = Host(shim, ld, ps, blocks)
     assert not host.h and "coupled" in host.err
+
+
+def test_partially_overlapping_blocks_fall_back_to_the_per_instance_form(shim, problems):
+    """Sharing needs the distinct blocks to be pairwise disjoint: demote part of one instance to the separator."""
+    prob = problems("ldc2d-sv-k2-tiny")
+    ld = prob.levels[1]
+    ps = ld.patches
+    blocks = ps.blocks.copy()
+    p = int(np.argmax(ps.sizes))
+    o = ps.offsets[p]
+    lab = blocks[o:ps.offsets[p + 1]]
+    first = np.flatnonzero(lab == lab[lab >= 0][0])
+    assert first.size >= 2
+    blocks[o + first[: first.size // 2]] = -1
+    host = Host(shim, ld, ps, blocks, True)
+    assert host.h, host.err
+    st = host.stats()
+    assert st["shared"] == 0 and shim.ch_check_disjoint(host.h) == 0
+    assert host.factor(ld.A.vals) == 0
+    mats = hp.patch_matrices(ld.A.to_csr(), ps.offsets, ps.dofs)
+    x = np.random.default_rng(8).standard_normal(ld.V.ndofs)
+    yo = np.zeros_like(x)
+    for q in ps.order:
+        I = ps.patch(q)
+        if I.size:
+            yo[I] += np.linalg.solve(mats[q], x[I])
+    assert rel(host.apply(x), yo) <= 1e-9
+    host.close()
 
 
 def test_all_separator_is_the_dense_inverse(shim, problems):
@@ -183,7 +219,8 @@ def test_all_separator_is_the_dense_inverse(shim, problems):
 
 @pytest.mark.parametrize("bs", [2, 3])
 @pytest.mark.parametrize("order", [None, [7, 3, 3, 6, 5, 4, 1, 2]])
-def test_edge_cases_on_clustered_operator(shim, bs, order):
+@pytest.mark.parametrize("shared", [True, False])
+def test_edge_cases_on_clustered_operator(shim, bs, order, shared):
     """Empty / separator-only / block-only patches, m = 0 blocks, 64-dof limits, repeated visits."""
     from tests.condense_cases import clustered_problem, dense_reference, greedy_colours
 
@@ -197,9 +234,10 @@ def test_edge_cases_on_clustered_operator(shim, bs, order):
     ld.V = type("V", (), dict(nnodes=case["n_nodes"], bs=bs))
     ps = type("PS", (), dict(offsets=case["offsets"], dofs=case["dofs"], order=order, npatch=len(case["patches"]),
                              colours=greedy_colours(case, order.tolist())))
-    host = Host(shim, ld, ps, case["blocks"])
+    host = Host(shim, ld, ps, case["blocks"], shared)
     assert host.h, host.err
     st = host.stats()
+    print("clustered bs=%d shared requested %d used %d: %d instances, %d distinct" % (bs, shared, st["shared"], st["nblocks"], st["ndist"]))
     assert st["maxb"] == 64 - (64 % bs) and st["maxm"] >= 60 and st["maxsep"] > 64
     repeated = len(set(order.tolist())) < order.size
     if not repeated:

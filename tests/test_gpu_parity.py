@@ -175,6 +175,53 @@ def test_condensed_against_dense_inverses(loaded, name, deterministic):
             assert np.array_equal(mgc.apply(b, np.empty_like(b)), xc)
 
 
+# (ALFIB_CONDENSE_SHARED, ALFIB_TILE_V1): shared blocks + tile op v2 is the default; per-instance blocks and
+# the first tile op stay selectable (csrc/condense.cu) and must be the same operator
+VARIANTS = [("1", "0"), ("1", "1"), ("0", "0"), ("0", "1")]
+
+
+@pytest.mark.parametrize("name", SV)
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_condensed_variants_agree(problems, monkeypatch, name, deterministic):
+    from alfi_b200.multigrid import DeviceMultigrid, level_input_from_synth
+    from oracle import hotpath as hp
+    base, _, regime = name.partition("@")
+    prob = problems(base, gamma=10.0, nu=0.2) if regime == "mild" else problems(base)
+    olv = [hp.level_from_host(l) for l in prob.levels]
+    out, store = {}, {}
+    for shared, v1 in VARIANTS:
+        monkeypatch.setenv("ALFIB_CONDENSE_SHARED", shared)
+        monkeypatch.setenv("ALFIB_TILE_V1", v1)
+        mg = DeviceMultigrid([level_input_from_synth(l) for l in prob.levels], prob.config.m,
+                             deterministic=deterministic, condense=True)
+        res = []
+        for l in range(1, len(olv)):
+            lv, lc = olv[l], olv[l - 1]
+            x = _vec(lv, 90 + l)
+            y = mg.ctx.smoother_apply(l, x, np.empty_like(x)).copy()
+            if deterministic:
+                assert np.array_equal(y, mg.ctx.smoother_apply(l, x, np.empty_like(x)))
+            res.append(y)
+            res.append(mg.ctx.prolong(l, _vec(lc, 91 + l), np.empty(lv.n)).copy())
+            res.append(mg.ctx.restrict(l, _vec(lv, 92 + l), np.empty(lc.n)).copy())
+            store[(shared, v1, l)] = mg.ctx.patch_storage_bytes(l)
+        b = _vec(olv[-1], 93)
+        res.append(mg.apply(b, np.empty_like(b)).copy())
+        if deterministic:
+            for _ in range(3):                               # eager, captured, replayed
+                assert np.array_equal(mg.apply(b, np.empty_like(b)), res[-1])
+        out[(shared, v1)] = res
+        mg.ctx.close()
+    kappa = max(_kappa(hp.patch_matrices(lv.A, lv.offsets, lv.dofs)) for lv in olv[1:])
+    ref = out[("0", "1")]                                    # the version validated first
+    for key, res in out.items():
+        for a, r in zip(res, ref):
+            assert rel(a, r) <= _tol(kappa), (key, rel(a, r), kappa)
+    for l in range(1, len(olv)):                             # macro stars share their macro cells
+        assert store[("1", "0", l)] < store[("0", "0", l)]
+        assert store[("1", "0", l)] == store[("1", "1", l)]
+
+
 def test_wrong_block_hint_is_an_error(problems):
     """Blocks that are coupled in the operator are rejected (never a wrong answer)."""
     from alfi_b200.lib import AlfibError, Context
