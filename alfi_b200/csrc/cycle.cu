@@ -213,8 +213,12 @@ void coarse_factor_device(alfib_ctx* c) {
   CUSOLVER_TRY(cusolverDnDgetrs(c->cusolver, CUBLAS_OP_N, n, n, c->coarse_lu.p, n, c->coarse_piv.p, c->coarse_inv.p,
                                 (int)ld, c->coarse_info.p));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  c->coarse_work.release();
-  c->coarse_lu.release();
+  // the LU and its workspace are transient; small ones are kept for the next Newton step (cudaFree /
+  // cudaMalloc per call cost more than the factorisation of a small coarse level)
+  if ((size_t)n * n * sizeof(double) > ((size_t)256 << 20)) {
+    c->coarse_work.release();
+    c->coarse_lu.release();
+  }
   c->coarse_factored = true;
 }
 

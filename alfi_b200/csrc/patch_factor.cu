@@ -555,7 +555,7 @@ void launch_patch_factor(alfib_ctx* c, const Level& L, PatchSet& ps, const doubl
   const int ldmax = roundup2(maxn);
   const int64_t slot = (int64_t)maxn * ldmax + (int64_t)NBO * ((maxn + TC - 1) & ~(TC - 1));
   const int grid = std::min(ps.npatch, c->num_sms);          // >= 160 KB of shared memory: one CTA per SM
-  c->fwork.alloc((size_t)grid * slot);
+  if (c->fwork.n < (size_t)grid * slot) c->fwork.alloc((size_t)grid * slot);   // grow-only: shared by all patch sets
   c->finfo.alloc(2);
   CUDA_TRY(cudaMemsetAsync(c->finfo.p, 0, 2 * sizeof(int), c->stream));
 
