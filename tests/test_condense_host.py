@@ -154,6 +154,43 @@ def test_condensed_apply_equals_dense_patch_solves(shim, problems, name, kw, whi
             rel(y, yo), kappa) + ", inverse backward error %.1e" % worst)
 
 
+@pytest.mark.parametrize("nranks", [2, 4])
+@pytest.mark.parametrize("shared", [True, False])
+def test_sharded_patch_sets_sum_to_the_global_apply(shim, problems, nranks, shared):
+    """Multi-GPU (alfi_b200/dist.py): every rank condenses only its own patches — a macro cell whose
+    vertex patches live on different ranks is a (shared) block on each of them, with local visit counts —
+    and the rank results are summed (ncclAllReduce in the library).  Same lists, executed on the host."""
+    from alfi_b200.dist import partition_patches, shard_dof_array, shard_patch_arrays
+    prob = problems("ldc3d-sv-k3-tiny", gamma=10.0, nu=0.2)
+    ld = prob.levels[1]
+    ps = ld.patches
+    owner = partition_patches(ps.offsets, ps.dofs, nranks)
+    x = np.random.default_rng(7).standard_normal(ld.V.ndofs)
+    total = np.zeros_like(x)
+    nblocks = 0
+    for rank in range(nranks):
+        off, dofs, order, cols, mine = shard_patch_arrays(ps.offsets, ps.dofs, ps.order, ps.colours, owner, rank)
+        blocks = shard_dof_array(ps.offsets, ps.blocks, mine)
+        local = type("PS", (), dict(offsets=off, dofs=dofs, order=order, npatch=mine.size, colours=cols))
+        host = Host(shim, ld, local, blocks, shared)
+        assert host.h, host.err
+        st = host.stats()
+        assert st["shared"] == int(shared) and shim.ch_check_disjoint(host.h) == 0
+        nblocks += st["nblocks"]
+        assert host.factor(ld.A.vals) == 0
+        total += host.apply(x)
+        host.close()
+    assert nblocks == np.unique(np.stack([np.repeat(np.arange(ps.npatch), ps.sizes)[ps.blocks >= 0],
+                                          ps.blocks[ps.blocks >= 0]]), axis=1).shape[1]
+    mats = hp.patch_matrices(ld.A.to_csr(), ps.offsets, ps.dofs)
+    want = np.zeros_like(x)
+    for p in ps.order:
+        I = ps.patch(p)
+        if I.size:
+            want[I] += np.linalg.solve(mats[p], x[I])
+    assert rel(total, want) <= 1e-11
+
+
 def test_coupled_blocks_are_rejected(shim, problems):
     """A wrong hint must be an error, never a wrong answer: put two coupled dofs into different blocks."""
     prob = problems("ldc2d-sv-k2-tiny")
