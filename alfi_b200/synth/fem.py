@@ -311,6 +311,16 @@ class VectorSpace:
         x, L = self.node_coords, self.mesh.length
         return np.flatnonzero(np.any((np.abs(x) < tol) | (np.abs(x - L) < tol), axis=1))
 
+    def tagged_boundary_nodes(self, tags):
+        """Nodes in the closure of the boundary facets carrying one of the physical `tags` — what
+        `DirichletBC(V, g, tag).nodes` is for a Gmsh mesh (examples/bfs2d/bfs2d.py:25-27).  2-D."""
+        m = self.mesh
+        if m.dim != 2 or m.facet_tag is None:
+            raise NotImplementedError("tagged boundaries are implemented for 2-D meshes with boundary markers")
+        e = np.flatnonzero(np.isin(m.facet_tag, np.asarray(tags)))
+        nodes = [self.vertex_nodes[m.edges[e].ravel()].ravel(), self.edge_nodes[e].ravel()]
+        return np.unique(np.concatenate(nodes))
+
     def interpolate(self, fn):
         """Nodal interpolant of fn(x)->(n, d); returns (nnodes, d)."""
         return np.asarray(fn(self.node_coords), dtype=np.float64)

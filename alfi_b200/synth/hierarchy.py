@@ -23,10 +23,10 @@ import numpy as np
 import scipy.sparse as sp
 
 from .fem import LagrangeElement, VectorSpace
-from .mesh import SimplexMesh, alfeld_split, kuhn_mesh, locate_in_kuhn
+from .mesh import SimplexMesh, alfeld_split, kuhn_mesh, locate_in_kuhn, refine_uniform
 from .plex import SynthPlex
 
-__all__ = ["Level", "build_hierarchy", "prolongation_matrix"]
+__all__ = ["Level", "build_hierarchy", "build_hierarchy_from", "prolongation_matrix"]
 
 
 @dataclass
@@ -96,6 +96,31 @@ def build_hierarchy(dim: int, N: int, nref: int, bary: bool, length: float = 2.0
             c.c2f = np.repeat(fine, d + 1, axis=0)          # same list for the d+1 sub-cells
         else:
             c.c2f = c.macro_c2f
+    for i, lev in enumerate(levels):
+        _label_prolongation(lev, levels[i - 1] if i else None)
+    return levels
+
+
+def build_hierarchy_from(base: SimplexMesh, nref: int, bary: bool) -> list[Level]:
+    """The same hierarchy over a general base mesh (a Gmsh file, examples/bfs2d/bfs2d.py:14-17): `nref`
+    uniform refinements (alfi/problem.py:10-24), every level Alfeld-split for `bary` (alfi/bary.py:89)."""
+    d = base.dim
+    macros, c2fs = [base], []
+    for _ in range(nref):
+        fine, c2f = refine_uniform(macros[-1])
+        macros.append(fine)
+        c2fs.append(c2f)
+    levels = []
+    for l, macro in enumerate(macros):
+        mesh = alfeld_split(macro) if bary else macro
+        levels.append(Level(l, macro, mesh, SynthPlex(mesh), bary))
+    for c, c2f in zip(levels[:-1], c2fs):
+        c.macro_c2f = c2f
+        if bary:
+            fine = (c2f[:, :, None] * (d + 1) + np.arange(d + 1)[None, None, :]).reshape(c.macro.nc, -1)
+            c.c2f = np.repeat(fine, d + 1, axis=0)
+        else:
+            c.c2f = c2f
     for i, lev in enumerate(levels):
         _label_prolongation(lev, levels[i - 1] if i else None)
     return levels

@@ -23,7 +23,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-__all__ = ["SimplexMesh", "kuhn_mesh", "alfeld_split", "LOCAL_EDGES", "LOCAL_FACES"]
+__all__ = ["SimplexMesh", "kuhn_mesh", "alfeld_split", "refine_uniform", "LOCAL_EDGES", "LOCAL_FACES"]
 
 # local sub-entity -> local vertices, lexicographic
 LOCAL_EDGES = {2: [(0, 1), (0, 2), (1, 2)],
@@ -46,6 +46,11 @@ class SimplexMesh:
     macro: "SimplexMesh | None" = None       # the mesh this one is the Alfeld split of
     length: float = 2.0
     M: int = 0                               # cells per side of the underlying Kuhn grid
+    # boundary markers of general (Gmsh) meshes: (nb, dim) vertex tuples of tagged boundary facets, rows
+    # ascending, and their physical tags; `facet_tag` (per facet id, 0 = untagged) is derived from them
+    boundary_facets: np.ndarray | None = None
+    boundary_tags: np.ndarray | None = None
+    facet_tag: np.ndarray = field(default=None, repr=False)
     # derived topology
     edges: np.ndarray = field(default=None, repr=False)       # (ne, 2)
     faces: np.ndarray = field(default=None, repr=False)       # (nf, 3) (3-D only)
@@ -82,7 +87,30 @@ class SimplexMesh:
             uniq, inv = _unique_rows(fk.ravel())
             self.faces = np.stack([uniq // (nv * nv), (uniq // nv) % nv, uniq % nv], axis=1)
             self.cell_faces = inv.reshape(c.shape[0], 4)
+        if self.boundary_facets is not None:
+            self.facet_tag = self._tags_of_facets()
         return self
+
+    def _facet_keys(self, f):
+        nv = np.int64(self.nv)
+        key = f[:, 0].astype(np.int64)
+        for j in range(1, f.shape[1]):
+            key = key * nv + f[:, j]
+        return key
+
+    def _tags_of_facets(self):
+        """Physical tag of every facet (0 where none): match the tagged vertex tuples to facet ids."""
+        fac = self.facets
+        tag = np.zeros(fac.shape[0], dtype=np.int64)
+        if self.boundary_facets.size:
+            keys = self._facet_keys(fac)                     # ascending: facets come out of np.unique
+            want = self._facet_keys(np.sort(self.boundary_facets, axis=1))
+            pos = np.searchsorted(keys, want)
+            ok = (pos < keys.size) & (keys[np.minimum(pos, keys.size - 1)] == want)
+            if not ok.all():
+                raise ValueError("a tagged boundary facet is not a facet of the mesh")
+            tag[pos] = self.boundary_tags
+        return tag
 
     # ---- facets (codim 1): edges in 2-D, faces in 3-D ----
     @property
@@ -154,9 +182,38 @@ def alfeld_split(macro: SimplexMesh) -> SimplexMesh:
     cells = np.sort(np.stack(sub, axis=1).reshape(-1, d + 1), axis=1)
     mv = np.zeros(nvm + ncm, dtype=bool)
     mv[:nvm] = True
+    # macro vertices keep their ids, so tagged boundary facets of the macro mesh are facets of the split
     m = SimplexMesh(dim=d, coords=coords, cells=cells, macro_vertex=mv, macro=macro,
-                    length=macro.length, M=macro.M)
+                    length=macro.length, M=macro.M, boundary_facets=macro.boundary_facets,
+                    boundary_tags=macro.boundary_tags)
     return m.build_topology()
+
+
+def refine_uniform(mesh: SimplexMesh):
+    """Red refinement of a general triangle mesh (Firedrake ``MeshHierarchy`` / DMPlex uniform refinement,
+    alfi/problem.py:10-24): a new vertex on every edge (id ``nv + edge id``), four children per cell.
+
+    Returns ``(fine, c2f)`` with ``c2f[c] = [4c, 4c+1, 4c+2, 4c+3]`` (three corner children in the
+    parent's vertex order, then the middle one).  Tagged boundary facets are split with their tag."""
+    if mesh.dim != 2:
+        raise NotImplementedError("general uniform refinement is implemented for triangles (Kuhn hierarchies "
+                                  "cover the 3-D configurations)")
+    nv = mesh.nv
+    c, ce = mesh.cells, mesh.cell_edges                      # local edges (0,1), (0,2), (1,2)
+    m01, m02, m12 = nv + ce[:, 0], nv + ce[:, 1], nv + ce[:, 2]
+    kids = np.stack([np.stack([c[:, 0], m01, m02], 1), np.stack([c[:, 1], m01, m12], 1),
+                     np.stack([c[:, 2], m02, m12], 1), np.stack([m01, m02, m12], 1)], axis=1).reshape(-1, 3)
+    coords = np.concatenate([mesh.coords, mesh.coords[mesh.edges].mean(axis=1)], axis=0)
+    bf = bt = None
+    if mesh.boundary_facets is not None:
+        tagged = np.flatnonzero(mesh.facet_tag)
+        e = mesh.edges[tagged]
+        mid = nv + tagged
+        bf = np.sort(np.concatenate([np.stack([e[:, 0], mid], 1), np.stack([e[:, 1], mid], 1)], axis=0), axis=1)
+        bt = np.concatenate([mesh.facet_tag[tagged], mesh.facet_tag[tagged]])
+    fine = SimplexMesh(dim=2, coords=coords, cells=np.sort(kids.astype(np.int64), axis=1), length=mesh.length,
+                       M=0, boundary_facets=bf, boundary_tags=bt)
+    return fine.build_topology(), np.arange(4 * mesh.nc, dtype=np.int64).reshape(mesh.nc, 4)
 
 
 def locate_in_kuhn(mesh: SimplexMesh, pts: np.ndarray) -> np.ndarray:

@@ -18,7 +18,7 @@ from ..patches import PatchSet, greedy_colouring, macro_interior_blocks, patch_d
 from ..relaxation import macro_star_points, star_points, iteration_order
 from ..transfer import cell_patch_set
 from .fem import BSR, BlockPattern, VectorSpace, apply_dirichlet, assemble_parts, assemble_velocity_block
-from .hierarchy import Level, build_hierarchy, prolongation_matrix
+from .hierarchy import Level, build_hierarchy, build_hierarchy_from, prolongation_matrix
 
 __all__ = ["Config", "CONFIGS", "LevelData", "Problem", "build_problem", "lid_wind"]
 
@@ -40,6 +40,9 @@ class Config:
     sort_order: str | None = None
     length: float = 2.0
     element: str = "lagrange"    # "lagrange" | "p1fb" ([P1+FacetBubble]^3, alfi/solver.py:576-579)
+    domain: str = "ldc"          # "ldc": lid-driven cavity on [0, length]^d | "bfs": backward-facing step (2-D)
+    mesh_file: str | None = None  # bfs: a Gmsh 2.2 file (examples/bfs2d/coarse*.msh); None = synth.gmsh.step_mesh(N)
+    dirichlet_tags: tuple = (1, 2)  # bfs: Inflow + NoSlip (examples/bfs2d/bfs2d.py:25-27); Outflow stays natural
 
     @property
     def m(self):
@@ -65,6 +68,15 @@ CONFIGS = {
     "ldc3d-pkp0-small": Config("ldc3d-pkp0-small", 3, 4, 2, "pkp0", 1, "star", False, re=1000.0, element="p1fb"),
     "ldc3d-sv-k3-small": Config("ldc3d-sv-k3-small", 3, 2, 1, "sv", 3, "macro", True, re=5000.0),
     "ldc3d-sv-k3-half": Config("ldc3d-sv-k3-half", 3, 2, 2, "sv", 3, "macro", True, re=5000.0),
+    # BASELINE.json configs[2]: backward-facing step, SV k=2, relaxation direction "0+:1-" (bfs2d.py:32),
+    # char_length 1 (alfi/problem.py:43).  The reference meshes are Gmsh files (coarse09.msh: 2979 vertices);
+    # N = 12 cells per unit length gives a base mesh of that size without them; pass mesh_file to use one.
+    "bfs2d-sv-k2": Config("bfs2d-sv-k2", 2, 12, 4, "sv", 2, "macro", True, re=5000.0, length=1.0, domain="bfs",
+                          sort_order="0+:1-"),
+    "bfs2d-sv-k2-small": Config("bfs2d-sv-k2-small", 2, 4, 2, "sv", 2, "macro", True, re=1000.0, length=1.0,
+                                domain="bfs", sort_order="0+:1-"),
+    "bfs2d-sv-k2-tiny": Config("bfs2d-sv-k2-tiny", 2, 1, 1, "sv", 2, "macro", True, re=100.0, length=1.0,
+                               domain="bfs", sort_order="0+:1-"),
 }
 
 
@@ -76,6 +88,14 @@ def lid_wind(x):
     if d == 3:
         prof = prof * x[:, 2] ** 2 * (2 - x[:, 2]) ** 2
     w[:, 0] = prof
+    return w
+
+
+def step_wind(x):
+    """Inflow profile of examples/bfs2d/bfs2d.py:20-22 extended along the channel (synthetic wind)."""
+    w = np.zeros_like(x)
+    y = x[:, 1]
+    w[:, 0] = 4.0 * (2.0 - y) * (y - 1.0) * (y > 1.0)
     return w
 
 
@@ -156,7 +176,7 @@ def assemble_level(cfg: Config, ld: LevelData, nu: float, gamma: float, advect: 
     lin = _linear_parts(cfg, ld)
     vals = nu * lin["visc"] + gamma * lin["div"]
     if advect != 0.0:
-        wind = ld.V.interpolate(lid_wind) if wind is None else wind
+        wind = ld.V.interpolate(step_wind if cfg.domain == "bfs" else lid_wind) if wind is None else wind
         adv = assemble_parts(ld.V, ld.pattern, wind, cfg.discretisation, want=("adv1", "adv2"))
         ld.adv1 = adv["adv1"]
         vals += advect * (adv["adv1"] + adv["adv2"])
@@ -182,11 +202,17 @@ def build_problem(cfg: Config | str, nu: float | None = None, with_transfer: boo
         cfg = dataclasses.replace(cfg, gamma=gamma)
     nu = cfg.nu if nu is None else nu
     t0 = time.time()
-    hier = build_hierarchy(cfg.dim, cfg.N, cfg.nref, cfg.bary, cfg.length)
+    if cfg.domain == "bfs":
+        from .gmsh import read_msh, step_mesh
+        base = read_msh(cfg.mesh_file) if cfg.mesh_file else step_mesh(cfg.N)
+        hier = build_hierarchy_from(base, cfg.nref, cfg.bary)
+    else:
+        hier = build_hierarchy(cfg.dim, cfg.N, cfg.nref, cfg.bary, cfg.length)
     levels = []
     for lev in hier:
         V = VectorSpace(lev.mesh, cfg.k, cfg.element)
-        ld = LevelData(lev.index, lev, V, BlockPattern(V), V.boundary_nodes().astype(np.int32))
+        bc = V.tagged_boundary_nodes(cfg.dirichlet_tags) if cfg.domain == "bfs" else V.boundary_nodes()
+        ld = LevelData(lev.index, lev, V, BlockPattern(V), bc.astype(np.int32))
         assemble_level(cfg, ld, nu, cfg.gamma)
         if lev.index > 0:
             ld.patches = smoother_patches(cfg, ld)

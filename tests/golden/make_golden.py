@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 from alfi_b200.synth.problem import build_problem  # noqa: E402
 from oracle import hotpath as hp  # noqa: E402
 
-NAMES = ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny", "ldc3d-pkp0-tiny"]
+NAMES = ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny", "ldc3d-pkp0-tiny", "bfs2d-sv-k2-tiny"]
 
 
 def make(name):

@@ -11,6 +11,9 @@ from oracle import hotpath as hp
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 NAMES = ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny", "ldc3d-pkp0-tiny"]
+# the backward-facing step (BASELINE configs[2]) joined after the last GPU run of round 1: its CUDA check
+# lives in tests/test_gpu_bfs.py until it has been run once on a B200
+CPU_NAMES = NAMES + ["bfs2d-sv-k2-tiny"]
 TOL = 1e-11
 
 
@@ -22,7 +25,7 @@ def load(name):
     return np.load(os.path.join(HERE, "golden", name + ".npz"))
 
 
-@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("name", CPU_NAMES)
 def test_index_sets_bit_exact(problems, name):
     g = load(name)
     prob = problems(name, gamma=10.0, nu=0.2)
@@ -35,7 +38,7 @@ def test_index_sets_bit_exact(problems, name):
             assert np.array_equal(g["l%d_%s" % (l, key)], val), (l, key)
 
 
-@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("name", CPU_NAMES)
 def test_oracle_reproduces_golden(problems, name):
     g = load(name)
     prob = problems(name, gamma=10.0, nu=0.2)

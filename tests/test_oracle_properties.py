@@ -5,7 +5,7 @@ import scipy.sparse as sp
 
 from oracle import hotpath as hp
 
-NAMES = ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny", "ldc3d-pkp0-tiny"]
+NAMES = ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny", "ldc3d-pkp0-tiny", "bfs2d-sv-k2-tiny"]
 
 
 @pytest.fixture(scope="module")
@@ -67,7 +67,7 @@ def test_restrict_is_prolong_transpose(olevels, name):
     assert abs(lhs - rhs) <= 1e-13 * max(abs(lhs), 1.0)
 
 
-@pytest.mark.parametrize("name", ["ldc2d-sv-k2-tiny", "ldc3d-sv-k3-tiny"])
+@pytest.mark.parametrize("name", ["ldc2d-sv-k2-tiny", "ldc3d-sv-k3-tiny", "bfs2d-sv-k2-tiny"])
 def test_schoeberl_prolongation_property(olevels, name):
     """Defining property of the robust transfer (transfer.py:246-259): the correction t solves
     A0 t = gamma D rhs on every coarse-cell interior with zero trace on the coarse facets; for
