@@ -29,7 +29,7 @@ from .multigrid import DeviceMultigrid, LevelInput
 from .patches import greedy_colouring, patch_dofs_from_points, points_to_csr
 from .relaxation import _Options, star_points
 
-__all__ = ["PatchPC", "VelocityMGPC", "HostAdapter"]
+__all__ = ["fieldsplit0_config", "PatchPC", "VelocityMGPC", "HostAdapter"]
 
 
 class HostAdapter:
@@ -158,6 +158,48 @@ class PatchPC:
         print("alfi_b200.PatchPC: %d patches, max %d dofs, %d colours, %.1f MB of inverses"
               % (ps.npatch, int(ps.sizes.max()), int(ps.colours.max()) + 1,
                  self.ctx.patch_storage_bytes(0) / 1e6))
+
+
+def fieldsplit0_config(fs0: dict) -> dict:
+    """Read the reference's own ``fieldsplit_0`` dictionary (alfi/solver.py:359-379 with ``mg_levels`` from
+    :313-344) and return what `VelocityMGPC` / `DeviceMultigrid` need: ``smoothing`` (FGMRES iterations per
+    level), the patch construction (``construct``: "star" or a python class name, ``sort_order``) and the
+    patch sub-matrix options.  The dictionary is taken unchanged; anything the device path does not implement
+    raises NotImplementedError instead of being silently ignored."""
+    def need(d, key, *allowed):
+        if d.get(key) not in allowed:
+            raise NotImplementedError("fieldsplit_0: %s = %r (supported: %s)" % (key, d.get(key), ", ".join(map(repr, allowed))))
+    need(fs0, "ksp_type", "richardson")
+    need(fs0, "ksp_max_it", 1)
+    need(fs0, "ksp_richardson_self_scale", False, None)
+    need(fs0, "pc_type", "mg")
+    need(fs0, "pc_mg_type", "full")
+    lv = fs0["mg_levels"]
+    need(lv, "ksp_type", "fgmres")
+    need(lv, "ksp_norm_type", "unpreconditioned")
+    need(lv, "ksp_convergence_test", "skip")
+    need(lv, "pc_type", "python")
+    need(lv, "pc_python_type", "firedrake.PatchPC", "alfi_b200.PatchPC")
+    need(lv, "patch_pc_patch_partition_of_unity", False, None)
+    need(lv, "patch_pc_patch_local_type", "additive")
+    need(lv, "patch_sub_ksp_type", "preonly")
+    need(lv, "patch_sub_pc_type", "lu")
+    ctype = lv.get("patch_pc_patch_construct_type", "star")
+    if ctype == "star":
+        need(lv, "patch_pc_patch_construct_dim", 0, None)
+        construct, sort_order = "star", None
+    elif ctype == "python":
+        construct = lv["patch_pc_patch_construct_python_type"]
+        name = construct.rpartition(".")[2]
+        sort_order = lv.get("patch_pc_patch_construction_%s_sort_order" % name)
+    else:
+        raise NotImplementedError("fieldsplit_0: patch construct_type %r" % ctype)
+    coarse = fs0.get("mg_coarse_assembled", {})
+    if coarse and coarse.get("telescope_pc_type", coarse.get("pc_type")) != "lu":
+        raise NotImplementedError("fieldsplit_0: the coarse solve must be a direct LU (solver.py:369-378)")
+    return {"smoothing": int(lv["ksp_max_it"]), "construct": construct, "sort_order": sort_order,
+            "sub_mat_type": lv.get("patch_pc_patch_sub_mat_type"), "dense_inverse": bool(lv.get("patch_pc_patch_dense_inverse", False)),
+            "patch_lu": lv.get("patch_sub_pc_factor_mat_solver_type")}
 
 
 class _PrefixedPC:

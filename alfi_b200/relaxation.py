@@ -85,13 +85,21 @@ def parse_sort_order(sortorders):
     return res
 
 
-def iteration_order(coords, sortorders):
+def iteration_order(coords, sortorders, literal=True):
     """Concatenated stable sorts of patch indices by signed coordinates
-    (alfi/relaxation.py:141-149); identity when no sort order is given."""
+    (alfi/relaxation.py:141-149); identity when no sort order is given.
+
+    ``literal=True`` (default) reproduces what the reference actually computes for several sweeps
+    ``"a|b"``: its key functions close over the loop variable ``sortdata`` (relaxation.py:96-107), so when
+    they are called every sweep sorts by the keys of the *last* sweep.  Found by running the reference's
+    own code (tests/test_reference_code.py); single-sweep orders — all the examples use "0+:1-" — are
+    unaffected.  ``literal=False`` gives each sweep its own keys, which is what the syntax suggests."""
     n = len(coords)
     sweeps = parse_sort_order(sortorders)
     if sweeps is None:
         return np.arange(n, dtype=np.int32)
+    if literal:
+        sweeps = [sweeps[-1]] * len(sweeps)
     coords = np.asarray(coords, dtype=np.float64).reshape(n, -1)
     out = []
     for sortdata in sweeps:

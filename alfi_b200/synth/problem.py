@@ -54,20 +54,22 @@ class Config:
 
 
 CONFIGS = {
-    # BASELINE.json configs[0..4]; sizes per SURVEY §8d
-    "ldc2d-sv-k2": Config("ldc2d-sv-k2", 2, 10, 1, "sv", 2, "macro", True, re=1000.0),
+    # BASELINE.json configs[0..4]; sizes per SURVEY §8d.  Macro-star patches are swept in the problem's
+    # relaxation direction "0+:1-" (ldc2d.py:39, ldc3d.py:31 -> solver.py:342; confirmed by running the
+    # reference's get_parameters, tests/test_reference_code.py); the builtin star construction has no order.
+    "ldc2d-sv-k2": Config("ldc2d-sv-k2", 2, 10, 1, "sv", 2, "macro", True, re=1000.0, sort_order="0+:1-"),
     "ldc2d-pkp0": Config("ldc2d-pkp0", 2, 16, 3, "pkp0", 2, "star", False, re=10000.0),
-    "ldc3d-sv-k3": Config("ldc3d-sv-k3", 3, 4, 2, "sv", 3, "macro", True, re=5000.0),
+    "ldc3d-sv-k3": Config("ldc3d-sv-k3", 3, 4, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
     "ldc3d-pkp0": Config("ldc3d-pkp0", 3, 16, 2, "pkp0", 1, "star", False, re=5000.0, element="p1fb"),
     # scaled-down members of the same families (tests, smoke, CPU-baseline sample)
-    "ldc2d-sv-k2-tiny": Config("ldc2d-sv-k2-tiny", 2, 2, 1, "sv", 2, "macro", True, re=100.0),
+    "ldc2d-sv-k2-tiny": Config("ldc2d-sv-k2-tiny", 2, 2, 1, "sv", 2, "macro", True, re=100.0, sort_order="0+:1-"),
     "ldc2d-pkp0-tiny": Config("ldc2d-pkp0-tiny", 2, 2, 2, "pkp0", 2, "star", False, re=100.0),
-    "ldc3d-sv-k3-tiny": Config("ldc3d-sv-k3-tiny", 3, 1, 1, "sv", 3, "macro", True, re=100.0),
+    "ldc3d-sv-k3-tiny": Config("ldc3d-sv-k3-tiny", 3, 1, 1, "sv", 3, "macro", True, re=100.0, sort_order="0+:1-"),
     "ldc3d-pkp0-tiny": Config("ldc3d-pkp0-tiny", 3, 1, 2, "pkp0", 1, "star", False, re=100.0, element="p1fb"),
     "ldc3d-pkp0-mid": Config("ldc3d-pkp0-mid", 3, 8, 2, "pkp0", 1, "star", False, re=5000.0, element="p1fb"),
     "ldc3d-pkp0-small": Config("ldc3d-pkp0-small", 3, 4, 2, "pkp0", 1, "star", False, re=1000.0, element="p1fb"),
-    "ldc3d-sv-k3-small": Config("ldc3d-sv-k3-small", 3, 2, 1, "sv", 3, "macro", True, re=5000.0),
-    "ldc3d-sv-k3-half": Config("ldc3d-sv-k3-half", 3, 2, 2, "sv", 3, "macro", True, re=5000.0),
+    "ldc3d-sv-k3-small": Config("ldc3d-sv-k3-small", 3, 2, 1, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
+    "ldc3d-sv-k3-half": Config("ldc3d-sv-k3-half", 3, 2, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
     # BASELINE.json configs[2]: backward-facing step, SV k=2, relaxation direction "0+:1-" (bfs2d.py:32),
     # char_length 1 (alfi/problem.py:43).  The reference meshes are Gmsh files (coarse09.msh: 2979 vertices);
     # N = 12 cells per unit length gives a base mesh of that size without them; pass mesh_file to use one.

@@ -121,8 +121,12 @@ def test_sort_order_semantics():
     # same as sorted(enumerate(coords), key=lambda z: (z[1][0], -z[1][1]))  (relaxation.py:104-107)
     want = [i for i, _ in sorted(enumerate(coords), key=lambda z: (z[1][0], -z[1][1]))]
     assert iteration_order(coords, "0+:1-").tolist() == want
-    two = iteration_order(coords, "0+:1-|1+")
+    two = iteration_order(coords, "0+:1-|1+", literal=False)
     assert two.size == 8 and two[:4].tolist() == want
+    # the reference's key functions all see the last sweep's keys (closure over the loop variable,
+    # relaxation.py:96-107; pinned by tests/test_reference_code.py): both sweeps sort by "1+"
+    lit = iteration_order(coords, "0+:1-|1+")
+    assert lit[:4].tolist() == lit[4:].tolist() == iteration_order(coords, "1+").tolist()
     plex = SynthPlex(alfeld_split(kuhn_mesh(2, 2)))
     patches, order = MacroStar()(FakePC(plex, {"pc_patch_construction_MacroStar_sort_order": "0+:1-"}))
     assert sorted(order.tolist()) == list(range(len(patches)))

@@ -1,0 +1,179 @@
+"""Patch index sets against the REFERENCE'S OWN CODE.
+
+tests/golden/reference_index_sets.npz holds what alfi/relaxation.py and alfi/transfer.py themselves produce
+(loaded from the reference tree by oracle/refshim.py over stand-ins for Firedrake / petsc4py, see
+tests/golden/make_reference_golden.py) on five synthetic hierarchies.  alfi_b200's plugin classes and its
+vectorised builders must reproduce them: patch point lists exactly (order and duplicates included) for the
+per-entity callbacks, as sets for the vectorised CSR builders (PCPATCH puts the points into a hash set),
+iteration sets and coarse-boundary node lists exactly.  Where the reference tree is present the fixture is also
+regenerated and must not have drifted.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from alfi_b200.patches import points_to_csr
+from alfi_b200.relaxation import MacroStar, Star, macro_star_points, star_points
+from alfi_b200.synth.fem import VectorSpace
+from alfi_b200.transfer import (CoarseCellMacroPatches, CoarseCellPatches, coarse_cell_points,
+                                fix_coarse_boundaries)
+from oracle import refshim
+from tests.test_patches import Ctx, FakePC
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_reference_golden as gen  # noqa: E402
+
+GOLD = np.load(os.path.join(HERE, "golden", "reference_index_sets.npz"))
+
+
+def unflatten(off, data):
+    return [data[off[i]:off[i + 1]] for i in range(off.size - 1)]
+
+
+def csr_of(sets, npoints):
+    return points_to_csr([np.asarray(s) for s in sets], npoints)
+
+
+@pytest.mark.parametrize("name", list(gen.CASES))
+def test_patch_constructors_reproduce_the_reference(name):
+    build, k, kind, sort = gen.CASES[name]
+    levels = build()
+    bary = levels[0].bary
+    g = {key.split("/", 1)[1]: GOLD[key] for key in GOLD.files if key.startswith(name + "/")}
+    for l, lev in enumerate(levels):
+        plex = lev.plex
+        # ---- Star (relaxation.py:153-160): callback class and vectorised builder
+        ref = unflatten(g["l%d_star_off" % l], g["l%d_star_pts" % l])
+        patches, order = Star()(FakePC(plex))
+        assert len(patches) == len(ref) and all(np.array_equal(a, b) for a, b in zip(patches, ref))
+        assert np.array_equal(order, g["l%d_star_iter" % l])
+        H, _ = star_points(plex)
+        assert (csr_of(ref, plex.npoints) != H).nnz == 0
+        # ---- MacroStar (relaxation.py:163-177) with the case's sort order
+        if bary:
+            ref = unflatten(g["l%d_macro_off" % l], g["l%d_macro_pts" % l])
+            opts = {} if sort is None else {"pc_patch_construction_MacroStar_sort_order": sort}
+            patches, order = MacroStar()(FakePC(plex, opts))
+            assert len(patches) == len(ref) and all(np.array_equal(a, b) for a, b in zip(patches, ref))
+            assert np.array_equal(order, g["l%d_macro_iter" % l])
+            H, _ = macro_star_points(plex, "all")
+            assert (csr_of(ref, plex.npoints) != H).nnz == 0
+        # ---- transfer patches and coarse-boundary nodes (transfer.py:13-88, 121-158)
+        if l > 0:
+            ref = unflatten(g["l%d_cell_off" % l], g["l%d_cell_pts" % l])
+            maker = CoarseCellMacroPatches() if bary else CoarseCellPatches()
+            patches, order = maker(FakePC(plex, ctx=Ctx(levels, l)))
+            assert len(patches) == len(ref) and all(np.array_equal(a, b) for a, b in zip(patches, ref))
+            assert np.array_equal(order, g["l%d_cell_iter" % l])
+            assert (csr_of(ref, plex.npoints) != coarse_cell_points(levels, l, bary)).nnz == 0
+            V = VectorSpace(lev.mesh, k, kind)
+            assert np.array_equal(fix_coarse_boundaries(plex, V, l), g["l%d_cb_nodes" % l])
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name", list(gen.CASES))
+def test_fixture_is_what_the_reference_code_produces_now(name):
+    """Re-run alfi's own relaxation.py / transfer.py and compare with the committed fixture."""
+    out = gen.run_reference(name)
+    keys = sorted(k.split("/", 1)[1] for k in GOLD.files if k.startswith(name + "/"))
+    assert sorted(out) == keys
+    for key in keys:
+        assert np.array_equal(out[key], GOLD[name + "/" + key]), key
+    assert "firedrake" not in sys.modules and "alfi" not in sys.modules        # the stand-ins do not leak
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present (GPU box)")
+def test_sort_order_parsing_is_the_reference_one():
+    """keyfuncs (relaxation.py:88-108) on the key syntax of the examples ("0+:1-", bfs2d.py:32) and sweeps ("|")."""
+    from alfi_b200.relaxation import iteration_order
+    rng = np.random.default_rng(0)
+    coords = rng.integers(0, 4, size=(40, 3)).astype(float)          # many ties: stability matters
+    with refshim.reference_modules() as (rel, _):
+        for spec in ("0+:1-", "1-", "2+:0-:1+", "0+:1-|1+:0-", "0", "None", ""):
+            refshim.set_options({"pc_patch_construction_MacroStar_sort_order": spec})
+            ms = rel.MacroStar()
+            ms.opts = refshim.Options("")
+            kf = ms.keyfuncs(list(enumerate(coords)))
+            # no key functions -> createStride(len(patches)) (relaxation.py:140-143), else concatenated sorts (:145-149)
+            want = list(range(len(coords))) if kf is None else \
+                sum(([i for i, _ in sorted(enumerate(coords), key=f)] for f in kf), [])
+            assert np.array_equal(iteration_order(coords, spec), want), spec
+    refshim.set_options({})
+
+
+# ------------------------------------------------------------------------------------ solver dictionaries
+import json  # noqa: E402
+
+import alfi_b200  # noqa: E402
+from alfi_b200 import pc as pcmod  # noqa: E402
+from alfi_b200.pc import fieldsplit0_config  # noqa: E402
+
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_reference_parameters as genp  # noqa: E402
+
+PARAMS = json.load(open(os.path.join(HERE, "golden", "reference_parameters.json")))
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name", list(genp.VARIANTS))
+def test_parameter_fixture_is_what_get_parameters_returns_now(name):
+    assert json.loads(json.dumps(genp.run(name), sort_keys=True)) == PARAMS[name]
+
+
+@pytest.mark.parametrize("name,m,construct,sort", [
+    ("ldc2d-sv-k2", 6, "alfi.MacroStar", "0+:1-"), ("bfs2d-sv-k2", 6, "alfi.MacroStar", "0+:1-"),
+    ("ldc3d-sv-k3", 10, "alfi.MacroStar", "0+:1-"), ("ldc2d-pkp0", 6, "star", None), ("ldc3d-pkp0", 10, "star", None)])
+def test_fieldsplit0_dictionary_is_accepted_unchanged(name, m, construct, sort):
+    """The reference's own fieldsplit_0 dictionary (solver.py:359-379) configures the device cycle."""
+    outer = PARAMS[name]["outer"]
+    assert outer["pc_fieldsplit_type"] == "schur" and outer["ksp_type"] == "fgmres"
+    cfg = fieldsplit0_config(outer["fieldsplit_0"])
+    assert cfg["smoothing"] == m == PARAMS[name]["smoothing"]
+    assert cfg["construct"] == construct and cfg["sort_order"] == sort
+    assert PARAMS[name]["firedrake_parameters"]["default_sub_matrix_type"] == "baij"      # solver.py:512 -> BSR on the device
+    from alfi_b200.synth.problem import CONFIGS
+    c = CONFIGS[name]
+    assert c.m == m and c.sort_order in (sort, None) and (c.patch == "macro") == (construct == "alfi.MacroStar")
+
+
+@pytest.mark.parametrize("name", ["ldc3d-sv-k3-multiplicative", "ldc2d-pkp0-star-multiplicative"])
+def test_unsupported_dictionaries_are_refused(name):
+    with pytest.raises(NotImplementedError, match="local_type"):
+        fieldsplit0_config(PARAMS[name]["outer"]["fieldsplit_0"])
+
+
+class _Recorder:
+    def __init__(self, *a, **k):
+        self.calls = []
+
+    def __getattr__(self, name):
+        def f(*a, **k):
+            self.calls.append((name, a, k))
+            return 0
+        return f
+
+
+@pytest.mark.parametrize("config,problem,level", [("ldc2d-sv-k2", "ldc2d-sv-k2-tiny", 1), ("ldc2d-pkp0", "ldc2d-pkp0-tiny", 2),
+                                                  ("bfs2d-sv-k2", "bfs2d-sv-k2-tiny", 1)])
+def test_patchpc_takes_the_reference_mg_levels_options(problems, monkeypatch, config, problem, level):
+    """mg_levels of the reference's dictionary, flattened to PETSc option names the way Firedrake does and
+    put under the level prefix, is all alfi_b200.PatchPC needs: it builds the problem's patch dof sets and
+    iteration order (the CUDA context is replaced by a recorder)."""
+    from alfi_b200.synth.fakepetsc import FakePC as SynthPC, SynthAdapter
+    monkeypatch.setattr(pcmod, "Context", _Recorder)
+    prefix = "fieldsplit_0_mg_levels_%d_" % level
+    opts = refshim.flatten_options(PARAMS[config]["outer"]["fieldsplit_0"]["mg_levels"], prefix)
+    assert opts[prefix + "pc_python_type"] == "firedrake.PatchPC"           # the one string a maintainer changes
+    prob = problems(problem, gamma=10.0, nu=0.2)
+    ad = SynthAdapter(prob, level)
+    pc = SynthPC(prob.levels[level].level.plex, options=opts, prefix=prefix, attrs={"alfi_b200_adapter": ad})
+    p = alfi_b200.PatchPC()
+    p.initialize(pc)
+    ref = prob.levels[level].patches
+    assert np.array_equal(p.patches.offsets, ref.offsets) and np.array_equal(p.patches.dofs, ref.dofs)
+    assert np.array_equal(p.patches.order, ref.order)
+    assert p.options_seen["pc_patch_sub_mat_type"] in ("seqaij", "seqdense")
+    assert [c[0] for c in p.ctx.calls] == ["level_create", "set_bsr_pattern", "set_bc", "set_patches", "set_bsr_values", "factor"]
