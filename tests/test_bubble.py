@@ -92,3 +92,92 @@ def test_flux_across_coarse_facets_is_preserved(pair):
         worst_std = max(worst_std, abs((sign * ff_std[inside]).sum() - fc[F]))
     assert worst < 1e-13
     assert worst_std > 1e-3                                               # the uncorrected transfer does not
+
+
+# ---------------------------------------------------------------- the reference's own C kernels (oracle/_ref)
+def _ref_kernels():
+    from oracle import build_ref
+    return build_ref.load()
+
+
+def _ptr(a):
+    import ctypes as C
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@pytest.mark.skipif(_ref_kernels() is None, reason="oracle/_ref not built and no reference tree to build it from")
+def test_kernel_tables_equal_the_compiled_reference_kernels():
+    """split / splitadj / combine / combineadj / count of alfi/bubble.py:57-185, compiled by oracle/build_ref.py
+    from the reference's own source strings, against the tables oracle/bubble.py restates them with."""
+    from oracle.bubble import A_COMB, A_SPLIT, B_COMB, B_SPLIT
+    lib = _ref_kernels()
+    rng = np.random.default_rng(4)
+    for _ in range(5):
+        both = rng.standard_normal((8, 3))
+        p1, fb = np.zeros((4, 3)), np.zeros((4, 3))
+        lib.split(_ptr(p1), _ptr(fb), _ptr(both))
+        assert np.array_equal(p1, A_SPLIT.T @ both) and np.allclose(fb, B_SPLIT.T @ both, rtol=0, atol=2e-16 * 8)
+        p1, fb = rng.standard_normal((4, 3)), rng.standard_normal((4, 3))
+        out = np.zeros((8, 3))
+        lib.splitadj(_ptr(p1), _ptr(fb), _ptr(out))
+        assert np.allclose(out, A_SPLIT @ p1 + B_SPLIT @ fb, rtol=0, atol=1e-15)
+        out = np.zeros((8, 3))
+        lib.combine(_ptr(p1), _ptr(fb), _ptr(out))
+        assert np.allclose(out, A_COMB.T @ p1 + B_COMB.T @ fb, rtol=0, atol=1e-15)
+        both = rng.standard_normal((8, 3))
+        p1, fb = np.zeros((4, 3)), np.zeros((4, 3))
+        lib.combineadj(_ptr(both), _ptr(p1), _ptr(fb))
+        assert np.allclose(p1, A_COMB @ both, rtol=0, atol=1e-15) and np.allclose(fb, B_COMB @ both, rtol=0, atol=1e-15)
+    both, fb, p1 = np.zeros((8, 3)), np.zeros((4, 3)), np.zeros((4, 3))
+    lib.count(_ptr(both), _ptr(fb), _ptr(p1))
+    assert (both == 1).all() and (fb == 1).all() and (p1 == 1).all()
+
+
+@pytest.mark.skipif(_ref_kernels() is None, reason="oracle/_ref not built and no reference tree to build it from")
+def test_matrix_form_equals_the_sequence_run_with_the_reference_kernels(pair):
+    """bubble.py:233-265 (prolong) with the cell loops executing the compiled reference kernels — the par_loops
+    of the reference, INC access = scatter-add — equals the dof-level CSR the library is given."""
+    lib = _ref_kernels()
+    lev, Vc, Vf = pair
+    lit = LiteralBubbleTransfer(Vc, Vf, lev[0].c2f)
+
+    def par_loop_split(V, both):
+        p1, fb = np.zeros_like(both), np.zeros_like(both)
+        for c in range(V.mesh.nc):
+            nodes = V.cell_nodes[c]
+            a, b = np.zeros((4, 3)), np.zeros((4, 3))
+            lib.split(_ptr(a), _ptr(b), _ptr(np.ascontiguousarray(both[nodes])))
+            p1[nodes[:4]] += a
+            fb[nodes[4:]] += b
+        return p1, fb
+
+    def par_loop_combine(V, p1, fb):
+        both = np.zeros_like(p1)
+        for c in range(V.mesh.nc):
+            nodes = V.cell_nodes[c]
+            out = np.zeros((8, 3))
+            lib.combine(_ptr(np.ascontiguousarray(p1[nodes[:4]])), _ptr(np.ascontiguousarray(fb[nodes[4:]])), _ptr(out))
+            both[nodes] += out
+        return both
+
+    def counts(V):
+        both = np.zeros((V.nnodes, 3))
+        for c in range(V.mesh.nc):
+            nodes = V.cell_nodes[c]
+            a, b, p = np.zeros((8, 3)), np.zeros((4, 3)), np.zeros((4, 3))
+            lib.count(_ptr(a), _ptr(b), _ptr(p))
+            both[nodes] += a
+        return both[:, 0]
+
+    assert np.array_equal(counts(Vc), lit.cnt["c"]) and np.array_equal(counts(Vf), lit.cnt["f"])
+    c = np.random.default_rng(5).standard_normal(Vc.ndofs)
+    coarse = c.reshape(Vc.nnodes, 3)
+    p1c, fbc = par_loop_split(Vc, coarse)
+    cv, cf = lit.cnt["c"], lit.cnt["f"]
+    p1c[Vc.vertex_nodes[:, 0]] /= cv[Vc.vertex_nodes[:, 0], None]
+    fbc[Vc.face_nodes[:, 0]] /= cv[Vc.face_nodes[:, 0], None]
+    fbc = lit.scale_normal(Vc, fbc)
+    fine = par_loop_combine(Vf, lit.point_prolong("p1", p1c), lit.point_prolong("fb", fbc)) / cf[:, None]
+    P = bubble_transfer_matrix(Vc, Vf, lev[0].c2f)
+    assert np.abs(P @ c - fine.ravel()).max() < 1e-13
+    assert np.abs(lit.prolong(c) - fine.ravel()).max() < 1e-13
