@@ -192,7 +192,7 @@ class FakeFunctionSpace:
         return types.SimpleNamespace(value_shape=lambda: (self.V.bs,))
 
 
-def _stub_modules():
+def _stub_modules(extra_firedrake=None):
     def mod(name, **attrs):
         m = types.ModuleType(name)
         m.__dict__.update(attrs)
@@ -201,6 +201,9 @@ def _stub_modules():
     class DirichletBC:                                   # transfer.py:146-153 subclasses it
         def __init__(self, V, g, sub_domain):
             self.V, self.g, self.sub_domain = V, g, sub_domain
+
+        def apply(self, fn):                             # transfer.py:266: impose g (= 0) on the bc nodes
+            fn.dat.data[np.asarray(self.nodes, dtype=np.int64)] = self.g
 
     class _cached_property:                              # firedrake.utils.cached_property
         def __init__(self, fn):
@@ -232,7 +235,8 @@ def _stub_modules():
     mg_utils = mod("firedrake.mg.utils", get_level=get_level)
     mods = {
         "firedrake": mod("firedrake", DirichletBC=DirichletBC, utils=utils, ufl=ufl, PCBase=PCBase,
-                         DistributedMeshOverlapType=DistributedMeshOverlapType, parameters={}),
+                         DistributedMeshOverlapType=DistributedMeshOverlapType, parameters={},
+                         **(extra_firedrake or {})),
         "firedrake.petsc": mod("firedrake.petsc", PETSc=petsc),
         "firedrake.dmhooks": mod("firedrake.dmhooks", get_appctx=lambda dm: None),
         "firedrake.mg": mod("firedrake.mg", utils=mg_utils),
@@ -259,13 +263,14 @@ def _stub_modules():
 
 
 @contextlib.contextmanager
-def reference_modules(with_solver=False):
+def reference_modules(with_solver=False, extra_firedrake=None, extra_modules=None):
     """Context manager yielding (relaxation, transfer[, solver]): the reference's modules loaded from their
     source files."""
     if not available():
         raise FileNotFoundError("reference tree not found at %s" % REFERENCE)
     saved = {}
-    stubs = _stub_modules()
+    stubs = _stub_modules(extra_firedrake)
+    stubs.update(extra_modules or {})
     for name, m in stubs.items():
         saved[name] = sys.modules.get(name)
         sys.modules[name] = m
