@@ -88,6 +88,12 @@ def fgmres_outer(Aop, Mop, b, rtol, atol, maxit=500, restart=30):
     return x, its, hist
 
 
+def dg_mass_inv_apply(Minv, nu, gamma, x):
+    """`alfi.solver.DGMassInv.apply` (solver.py:32-35): y = -(nu + gamma) M_p^-1 x, the Schur complement
+    approximation of the augmented-Lagrangian preconditioner (fieldsplit_1, solver.py:386-390)."""
+    return -(float(nu) + float(gamma)) * (Minv @ x)
+
+
 @dataclass
 class ContinuationSolver:
     """Lid-driven cavity continuation in Reynolds number around a pluggable velocity-block PC.
@@ -211,7 +217,7 @@ class ContinuationSolver:
                 y1 = self.backend.apply(ru)
                 y10 = y1.copy()
                 y10[nbc] = 0.0
-                yp = -(nu + gamma) * (Minv @ (rp - B @ y10))
+                yp = dg_mass_inv_apply(Minv, nu, gamma, rp - B @ y10)
                 yp -= yp.mean()                              # constant-pressure nullspace
                 t = B.T @ yp
                 t[nbc] = 0.0

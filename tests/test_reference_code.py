@@ -177,3 +177,35 @@ def test_patchpc_takes_the_reference_mg_levels_options(problems, monkeypatch, co
     assert np.array_equal(p.patches.order, ref.order)
     assert p.options_seen["pc_patch_sub_mat_type"] in ("seqaij", "seqdense")
     assert [c[0] for c in p.ctx.calls] == ["level_create", "set_bsr_pattern", "set_bc", "set_patches", "set_bsr_values", "factor"]
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present (GPU box)")
+def test_dg_mass_inv_is_the_reference_one():
+    """solver.py:15-38: the reference's DGMassInv.apply on stand-in Mat/Vec objects == the continuation stand-in's
+    Schur complement approximation (alfi_b200/synth/outer.py)."""
+    import types
+
+    import scipy.sparse as sp
+    from alfi_b200.synth.outer import dg_mass_inv_apply
+    rng = np.random.default_rng(0)
+    Minv = sp.random(30, 30, density=0.2, random_state=1, format="csr") + sp.identity(30)
+    x = rng.standard_normal(30)
+
+    class Vec:
+        def __init__(self, a):
+            self.array = np.array(a, dtype=float)
+
+        def scale(self, k):
+            self.array *= k
+
+    def mult(xv, yv):
+        yv.array[:] = Minv @ xv.array
+    with refshim.reference_modules(with_solver=True) as (_, _, sol):
+        pc = sol.DGMassInv.__new__(sol.DGMassInv)
+        pc.massinv = types.SimpleNamespace(mult=mult)
+        pc.nu, pc.gamma = 0.004, 1.0e4
+        y = Vec(np.zeros(30))
+        pc.apply(None, Vec(x), y)
+        with pytest.raises(NotImplementedError):
+            pc.applyTranspose(None, None, None)
+    assert np.array_equal(y.array, dg_mass_inv_apply(Minv, 0.004, 1.0e4, x))
