@@ -327,3 +327,9 @@ def flatten_options(params, prefix=""):
         else:
             out[prefix + key] = val
     return out
+
+
+def _module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    return m

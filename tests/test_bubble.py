@@ -1,6 +1,8 @@
 """[P1+FacetBubble]^3 (BASELINE configs[3]) and its flux-preserving BubbleTransfer (alfi/bubble.py):
 matrix form (product path) against the literal per-cell restatement of the reference's C kernels,
 plus the property the transfer exists for — the flux across every coarse facet is preserved."""
+import os
+
 import numpy as np
 import pytest
 
@@ -181,3 +183,23 @@ def test_matrix_form_equals_the_sequence_run_with_the_reference_kernels(pair):
     P = bubble_transfer_matrix(Vc, Vf, lev[0].c2f)
     assert np.abs(P @ c - fine.ravel()).max() < 1e-13
     assert np.abs(lit.prolong(c) - fine.ravel()).max() < 1e-13
+
+
+@pytest.mark.skipif(_ref_kernels() is None or not os.path.exists("/root/reference/alfi/bubble.py"),
+                    reason="needs the reference tree (build container)")
+def test_reference_bubble_transfer_methods_equal_the_matrix_form(pair):
+    """alfi/bubble.py:204-265 executed verbatim (oracle/refshim_bubble.py: par_loops run the reference's compiled
+    kernels) == the dof-level CSR handed to the library, and its restrict == the transpose."""
+    from oracle.refshim_bubble import Harness
+    lev, Vc, Vf = pair
+    h = Harness(Vc, Vf, lev[0].c2f)
+    P = bubble_transfer_matrix(Vc, Vf, lev[0].c2f)
+    rng = np.random.default_rng(6)
+    c, f = rng.standard_normal(Vc.ndofs), rng.standard_normal(Vf.ndofs)
+    with h.reference_class() as BubbleTransfer:
+        coarse, fine = h.full(Vc, c), h.full(Vf)
+        BubbleTransfer.prolong(h.me, coarse, fine)
+        assert np.abs(fine.dat.data.ravel() - P @ c).max() < 1e-13
+        fine2, coarse2 = h.full(Vf, f), h.full(Vc)
+        BubbleTransfer.restrict(h.me, fine2, coarse2)
+        assert np.abs(coarse2.dat.data.ravel() - P.T @ f).max() < 1e-12
