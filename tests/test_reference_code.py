@@ -209,3 +209,37 @@ def test_dg_mass_inv_is_the_reference_one():
         with pytest.raises(NotImplementedError):
             pc.applyTranspose(None, None, None)
     assert np.array_equal(y.array, dg_mass_inv_apply(Minv, 0.004, 1.0e4, x))
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("case", ["kuhn2d", "kuhn3d", "step"])
+def test_bary_hierarchy_cell_maps_are_the_reference_ones(case):
+    """alfi/bary.py:29-194 executed over stand-ins (oracle/refshim_bary.py): every level is Alfeld-split after
+    uniform refinement with all uniform vertices labelled MacroVertices, the hierarchy is not nested, and the
+    coarse-to-fine table of the barycentric meshes composed by the reference equals the synthetic one
+    (alfi_b200/synth/hierarchy.py) — the table CoarseCellMacroPatches and the standard prolongation consume."""
+    from fractions import Fraction
+
+    from alfi_b200.synth.gmsh import step_mesh
+    from alfi_b200.synth.hierarchy import build_hierarchy, build_hierarchy_from
+    from oracle.refshim_bary import World
+    levels = {"kuhn2d": lambda: build_hierarchy(2, 2, 2, True), "kuhn3d": lambda: build_hierarchy(3, 1, 1, True),
+              "step": lambda: build_hierarchy_from(step_mesh(1, seed=3), 2, True)}[case]()
+    nref = len(levels) - 1
+    w = World(levels)
+    with w.reference_function() as BaryMeshHierarchy:
+        mh = BaryMeshHierarchy(w.base_mesh(), nref)
+    d = levels[0].macro.dim
+    assert mh.nested is False and len(mh.meshes) == nref + 1 and w.alfeld_applied == list(range(nref + 1))
+    assert [m._topology_dm.refine_level for m in mh.meshes] == list(range(nref + 1))
+    for l in range(nref):
+        c2f = mh.coarse_to_fine_cells[Fraction(l, 1)]
+        assert c2f.shape == (levels[l].mesh.nc, (d + 1) * 2 ** d)
+        assert np.array_equal(c2f, levels[l].c2f)
+        f2c = mh.fine_to_coarse_cells[Fraction(l + 1, 1)]
+        assert f2c.shape == (levels[l + 1].mesh.nc, d + 1)
+        # every fine bary cell lists the d+1 bary cells of its coarse macro cell
+        parent = np.empty(levels[l + 1].macro.nc, dtype=np.int64)
+        parent[levels[l].macro_c2f.ravel()] = np.repeat(np.arange(levels[l].macro.nc), 2 ** d)
+        want = parent[np.arange(levels[l + 1].mesh.nc) // (d + 1)][:, None] * (d + 1) + np.arange(d + 1)[None, :]
+        assert np.array_equal(f2c, want)
