@@ -1,0 +1,147 @@
+"""Owned / ghost layout of a level for distributed vectors (host side, numpy).
+
+The library's multi-GPU path of round 1 replicates every level vector and pays an all-reduce of the whole
+vector after each patch application and an all-gather after each SpMV.  This module is the index
+machinery of the replacement SURVEY §8(e) asks for — the PetscSF pattern of the reference's PCPATCH / MatMult
+on a vertex-partitioned DMPlex (alfi/solver.py:604-605,661-662: overlap VERTEX,1 or VERTEX,2):
+
+* patches are the owned unit (`alfi_b200.dist.partition_patches`);
+* every dof has exactly one owner — the rank owning the first patch (in partition order) that contains it;
+  dofs outside every patch (Dirichlet dofs) follow the first dof they are coupled to in the operator pattern;
+* a rank's *local* vector = its owned dofs followed by its ghosts: every other dof touched by its patches or
+  by the operator rows of its owned dofs;
+* owner -> ghost update ("broadcast", before SpMV / patch gather) and ghost -> owner sum ("reduce", after the
+  patch scatter-add) move only the ghost entries, between the pairs of ranks that share them.
+
+`Layout.exchange_bytes()` is the traffic model quoted in DESIGN §6.  oracle/distributed.py executes a level
+smoother on these layouts rank by rank and checks it against the serial oracle; the gloo test does the same
+with real processes.  The device side (NCCL send/recv or NVLink peer stores driven by these lists) is the next
+step and is not part of the round-1 library.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+__all__ = ["Layout", "RankLayout", "build_layout"]
+
+
+@dataclass
+class RankLayout:
+    rank: int
+    owned: np.ndarray            # global dofs owned by this rank, ascending
+    ghost: np.ndarray            # global dofs held as ghosts, ascending
+    patches: np.ndarray          # global patch ids owned by this rank (iteration order preserved)
+    send: dict                   # peer -> positions in `owned` whose values the peer holds as ghosts
+    recv: dict                   # peer -> positions in `ghost` owned by the peer (same order as the peer's send)
+
+    @property
+    def local(self):
+        return np.concatenate([self.owned, self.ghost])
+
+    @property
+    def n_owned(self):
+        return self.owned.size
+
+    @property
+    def n_local(self):
+        return self.owned.size + self.ghost.size
+
+
+@dataclass
+class Layout:
+    nranks: int
+    ndofs: int
+    owner: np.ndarray            # owner rank of every dof
+    ranks: list
+
+    def exchange_bytes(self):
+        """(max, total) bytes one owner->ghost update (equivalently one ghost->owner reduce) moves per rank."""
+        per_rank = [8 * sum(v.size for v in r.recv.values()) for r in self.ranks]
+        return max(per_rank), sum(per_rank)
+
+    def neighbours(self):
+        return [sorted(r.recv) for r in self.ranks]
+
+    # ---- the two exchange steps, on a list of per-rank local arrays (reference implementation) ----
+    def update_ghosts(self, locs):
+        """owner -> ghost: every ghost entry takes its owner's value."""
+        for r in self.ranks:
+            for peer, pos in r.recv.items():
+                src = self.ranks[peer]
+                locs[r.rank][r.n_owned + pos] = locs[peer][src.send[r.rank]]
+
+    def reduce_ghosts(self, locs):
+        """ghost -> owner: ghost contributions are added to the owner's entry (peers in ascending rank order, so the
+        sum is reproducible) and the ghost copies are cleared."""
+        for r in self.ranks:
+            for peer in sorted(r.send):
+                src = self.ranks[peer]
+                locs[r.rank][r.send[peer]] += locs[peer][src.n_owned + src.recv[r.rank]]
+        for r in self.ranks:
+            locs[r.rank][r.n_owned:] = 0.0
+
+    def scatter(self, x):
+        """Global vector -> per-rank local arrays with consistent ghosts."""
+        return [x[r.local].copy() for r in self.ranks]
+
+    def gather(self, locs):
+        out = np.empty(self.ndofs)
+        for r in self.ranks:
+            out[r.owned] = locs[r.rank][:r.n_owned]
+        return out
+
+
+def build_layout(patch_offsets, patch_dofs, patch_order, patch_owner, rowptr, colidx, bs, ndofs) -> Layout:
+    """`patch_owner[p]` = rank of patch p (alfi_b200.dist.partition_patches); `rowptr/colidx` = the level's block
+    pattern (block rows of `bs` dofs)."""
+    patch_offsets = np.asarray(patch_offsets, dtype=np.int64)
+    patch_dofs = np.asarray(patch_dofs, dtype=np.int64)
+    patch_owner = np.asarray(patch_owner)
+    nranks = int(patch_owner.max()) + 1 if patch_owner.size else 1
+    npatch = patch_offsets.size - 1
+    order = np.arange(npatch) if patch_order is None else np.asarray(patch_order)
+    # ---- dof ownership: first containing patch in iteration order
+    owner = np.full(ndofs, -1, dtype=np.int64)
+    for p in order[::-1]:                                   # later writes win -> iterate backwards
+        owner[patch_dofs[patch_offsets[p]:patch_offsets[p + 1]]] = patch_owner[p]
+    nodes = rowptr.size - 1
+    node_of = np.arange(ndofs) // bs
+    # dofs in no patch: take the owner of the first coupled dof that has one (repeat until settled)
+    for _ in range(8):
+        missing = np.flatnonzero(owner < 0)
+        if missing.size == 0:
+            break
+        node_owner = np.full(nodes, -1, dtype=np.int64)
+        have = owner >= 0
+        np.maximum.at(node_owner, node_of[have], owner[have])
+        for g in missing:
+            nb = colidx[rowptr[node_of[g]]:rowptr[node_of[g] + 1]]
+            cand = node_owner[nb]
+            cand = cand[cand >= 0]
+            if cand.size:
+                owner[g] = cand[0]
+    owner[owner < 0] = 0
+    # ---- per rank: owned, ghosts (patch dofs + operator columns of owned rows)
+    ranks = []
+    for r in range(nranks):
+        owned = np.flatnonzero(owner == r)
+        mine = order[patch_owner[order] == r]
+        need = [patch_dofs[patch_offsets[p]:patch_offsets[p + 1]] for p in mine]
+        own_nodes = np.unique(node_of[owned])
+        cols = np.unique(np.concatenate([colidx[rowptr[n]:rowptr[n + 1]] for n in own_nodes])) if own_nodes.size else np.empty(0, np.int64)
+        need.append((cols[:, None] * bs + np.arange(bs)[None, :]).ravel())
+        need = np.unique(np.concatenate(need)) if need else np.empty(0, np.int64)
+        ghost = need[owner[need] != r]
+        ranks.append(RankLayout(r, owned, ghost, mine, {}, {}))
+    pos_in_owned = np.empty(ndofs, dtype=np.int64)
+    for r in ranks:
+        pos_in_owned[r.owned] = np.arange(r.owned.size)
+    for r in ranks:
+        go = owner[r.ghost]
+        for peer in np.unique(go):
+            sel = np.flatnonzero(go == peer)
+            r.recv[int(peer)] = sel
+            ranks[int(peer)].send[r.rank] = pos_in_owned[r.ghost[sel]]
+    return Layout(nranks, ndofs, owner, ranks)
