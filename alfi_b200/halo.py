@@ -24,7 +24,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-__all__ = ["Layout", "RankLayout", "build_layout"]
+__all__ = ["Layout", "RankLayout", "build_layout", "layout_from_owner", "transfer_halo"]
 
 
 @dataclass
@@ -55,6 +55,7 @@ class Layout:
     ndofs: int
     owner: np.ndarray            # owner rank of every dof
     ranks: list
+    extra_owner: np.ndarray | None = None   # owner rank of every extra set (cell patch), if any
 
     def exchange_bytes(self):
         """(max, total) bytes one owner->ghost update (equivalently one ghost->owner reduce) moves per rank."""
@@ -93,13 +94,49 @@ class Layout:
         return out
 
 
-def build_layout(patch_offsets, patch_dofs, patch_order, patch_owner, rowptr, colidx, bs, ndofs) -> Layout:
+def layout_from_owner(owner, needs, patches=None) -> Layout:
+    """Layout for a given dof ownership and, per rank, the set of dofs it must hold locally (`needs[r]`, any
+    order, owned entries allowed): ghosts = needs minus owned; exchange lists follow."""
+    owner = np.asarray(owner, dtype=np.int64)
+    ndofs = owner.size
+    nranks = len(needs)
+    ranks = []
+    for r in range(nranks):
+        owned = np.flatnonzero(owner == r)
+        need = np.unique(np.asarray(needs[r], dtype=np.int64)) if len(needs[r]) else np.empty(0, np.int64)
+        ghost = need[owner[need] != r]
+        mine = np.empty(0, np.int64) if patches is None else patches[r]
+        ranks.append(RankLayout(r, owned, ghost, mine, {}, {}))
+    pos_in_owned = np.empty(ndofs, dtype=np.int64)
+    for r in ranks:
+        pos_in_owned[r.owned] = np.arange(r.owned.size)
+    for r in ranks:
+        go = owner[r.ghost]
+        for peer in np.unique(go):
+            sel = np.flatnonzero(go == peer)
+            r.recv[int(peer)] = sel
+            ranks[int(peer)].send[r.rank] = pos_in_owned[r.ghost[sel]]
+    return Layout(nranks, ndofs, owner, ranks)
+
+
+def transfer_halo(P, fine: Layout, coarse_owner) -> Layout:
+    """Layout on the COARSE level for the standard prolongation `P` (fine dofs x coarse dofs, scipy CSR): a rank
+    needs the coarse dofs in the columns of its owned fine rows.  Owned sets are those of `coarse_owner`; prolong
+    uses `update_ghosts` on it, restrict (P^T) ends with `reduce_ghosts` on it."""
+    needs = [np.unique(P[r.owned].indices) for r in fine.ranks]
+    return layout_from_owner(coarse_owner, needs)
+
+
+def build_layout(patch_offsets, patch_dofs, patch_order, patch_owner, rowptr, colidx, bs, ndofs,
+                 extra_sets=None, nranks=None) -> Layout:
     """`patch_owner[p]` = rank of patch p (alfi_b200.dist.partition_patches); `rowptr/colidx` = the level's block
-    pattern (block rows of `bs` dofs)."""
+    pattern (block rows of `bs` dofs).  `extra_sets` = (offsets, dofs) of further index sets that must be local
+    to one rank each (the transfer's cell patches): a set goes to the owner of its first dof."""
     patch_offsets = np.asarray(patch_offsets, dtype=np.int64)
     patch_dofs = np.asarray(patch_dofs, dtype=np.int64)
     patch_owner = np.asarray(patch_owner)
-    nranks = int(patch_owner.max()) + 1 if patch_owner.size else 1
+    if nranks is None:
+        nranks = int(patch_owner.max()) + 1 if patch_owner.size else 1
     npatch = patch_offsets.size - 1
     order = np.arange(npatch) if patch_order is None else np.asarray(patch_order)
     # ---- dof ownership: first containing patch in iteration order
@@ -123,8 +160,13 @@ def build_layout(patch_offsets, patch_dofs, patch_order, patch_owner, rowptr, co
             if cand.size:
                 owner[g] = cand[0]
     owner[owner < 0] = 0
-    # ---- per rank: owned, ghosts (patch dofs + operator columns of owned rows)
-    ranks = []
+    # ---- per rank: what must be local (patch dofs + operator columns of owned rows + its extra sets)
+    needs, mine_all = [], []
+    extra_owner = None
+    if extra_sets is not None:
+        eoff, edofs = np.asarray(extra_sets[0], dtype=np.int64), np.asarray(extra_sets[1], dtype=np.int64)
+        first = edofs[np.minimum(eoff[:-1], max(edofs.size - 1, 0))] if edofs.size else np.empty(0, np.int64)
+        extra_owner = np.where(np.diff(eoff) > 0, owner[first], 0) if edofs.size else np.zeros(eoff.size - 1, np.int64)
     for r in range(nranks):
         owned = np.flatnonzero(owner == r)
         mine = order[patch_owner[order] == r]
@@ -132,16 +174,11 @@ def build_layout(patch_offsets, patch_dofs, patch_order, patch_owner, rowptr, co
         own_nodes = np.unique(node_of[owned])
         cols = np.unique(np.concatenate([colidx[rowptr[n]:rowptr[n + 1]] for n in own_nodes])) if own_nodes.size else np.empty(0, np.int64)
         need.append((cols[:, None] * bs + np.arange(bs)[None, :]).ravel())
-        need = np.unique(np.concatenate(need)) if need else np.empty(0, np.int64)
-        ghost = need[owner[need] != r]
-        ranks.append(RankLayout(r, owned, ghost, mine, {}, {}))
-    pos_in_owned = np.empty(ndofs, dtype=np.int64)
-    for r in ranks:
-        pos_in_owned[r.owned] = np.arange(r.owned.size)
-    for r in ranks:
-        go = owner[r.ghost]
-        for peer in np.unique(go):
-            sel = np.flatnonzero(go == peer)
-            r.recv[int(peer)] = sel
-            ranks[int(peer)].send[r.rank] = pos_in_owned[r.ghost[sel]]
-    return Layout(nranks, ndofs, owner, ranks)
+        if extra_owner is not None:
+            for q in np.flatnonzero(extra_owner == r):
+                need.append(edofs[eoff[q]:eoff[q + 1]])
+        needs.append(np.concatenate(need) if need else np.empty(0, np.int64))
+        mine_all.append(mine)
+    lay = layout_from_owner(owner, needs, mine_all)
+    lay.extra_owner = extra_owner
+    return lay

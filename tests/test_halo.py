@@ -160,3 +160,28 @@ def test_halo_exchange_world2_gloo():
     for r in range(world):
         ok, err, nghost, n = res[r]
         assert ok and err <= 1e-13 and 0 < nghost < n, res
+
+
+@pytest.mark.parametrize("name", ["ldc2d-sv-k2-tiny", "ldc2d-pkp0-tiny", "ldc3d-sv-k3-tiny", "bfs2d-sv-k2-tiny"])
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_distributed_fcycle_equals_serial(problems, name, nranks):
+    """The whole fieldsplit_0 application — F-cycle, FGMRES smoothers, robust prolongation / restriction with
+    their cell-patch solves, coarse solve — executed rank by rank on owned/ghost arrays (level 0 replicated,
+    intermediate levels with a transfer halo for P_H) equals oracle.hotpath.fcycle."""
+    prob = problems(name, gamma=10.0, nu=0.2)
+    lv = [hp.level_from_host(l) for l in prob.levels]
+    b = np.random.default_rng(2).standard_normal(lv[-1].n)
+    b[lv[-1].bc_dofs] = 0
+    want = hp.fcycle(lv, b, prob.config.m)
+    got, h = od.fcycle(prob, lv, b, prob.config.m, nranks)
+    assert np.linalg.norm(got - want) <= 1e-12 * np.linalg.norm(want)
+    assert h.exchanges > 0
+    for l in range(1, len(lv)):
+        lay = h.layouts[l]
+        cp = prob.levels[l].cell_patches
+        assert lay.extra_owner.shape == (cp.npatch,)
+        for q in range(cp.npatch):                                   # every cell patch is local to its owner
+            assert set(cp.patch(q).tolist()) <= set(lay.ranks[lay.extra_owner[q]].local.tolist())
+        if l > 1:
+            halo = h.halos[l]
+            assert all(np.array_equal(a.owned, b_.owned) for a, b_ in zip(halo.ranks, h.layouts[l - 1].ranks))
