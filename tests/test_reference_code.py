@@ -243,3 +243,32 @@ def test_bary_hierarchy_cell_maps_are_the_reference_ones(case):
         parent[levels[l].macro_c2f.ravel()] = np.repeat(np.arange(levels[l].macro.nc), 2 ** d)
         want = parent[np.arange(levels[l + 1].mesh.nc) // (d + 1)][:, None] * (d + 1) + np.arange(d + 1)[None, :]
         assert np.array_equal(f2c, want)
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name,solver", [("ldc2d-sv-k2-tiny", "ScottVogeliusSolver"), ("ldc2d-pkp0-tiny", "ConstantPressureSolver"),
+                                         ("ldc3d-sv-k3-tiny", "ScottVogeliusSolver"), ("ldc3d-pkp0-tiny", "ConstantPressureSolver"),
+                                         ("bfs2d-sv-k2-tiny", "ScottVogeliusSolver")])
+def test_velocity_operator_is_the_reference_form(problems, name, solver):
+    """Row M1's operator: the reference's `residual()` (solver.py:562-572, 613-623), evaluated numerically by
+    oracle/ufl_eval.py on the synthetic mesh and element, against the parts alfi_b200.synth.fem assembles and
+    hands to the library — nu (2 sym grad u, grad v) + gamma (div u, div v) [cell_avg(div u) for pkp0] exactly,
+    and the Newton linearisation of advect ((grad u) u, v) through N(u+d) - N(u) - N(d)."""
+    from alfi_b200.synth.fem import BSR, assemble_parts
+    from oracle.ufl_eval import reference_velocity_residual
+    prob = problems(name, gamma=10.0, nu=0.2)
+    ld = prob.finest
+    V = ld.V
+    rng = np.random.default_rng(0)
+    U, D = rng.standard_normal((V.nnodes, V.bs)), rng.standard_normal((V.nnodes, V.bs))
+    nu, gamma = 0.3, 7.0
+    mat = lambda vals: BSR(V.nnodes, V.bs, ld.pattern.rowptr, ld.pattern.colidx, vals).to_csr()      # noqa: E731
+    parts = assemble_parts(V, ld.pattern, None, prob.config.discretisation, want=("visc", "div"))
+    want = mat(nu * parts["visc"] + gamma * parts["div"]) @ U.ravel()
+    got = reference_velocity_residual(solver, V, U, nu, gamma, 0.0)
+    assert np.linalg.norm(got - want) <= 1e-13 * np.linalg.norm(want)
+    N = lambda W: reference_velocity_residual(solver, V, W, 0.0, 0.0, 1.0)                           # noqa: E731
+    adv = assemble_parts(V, ld.pattern, U, prob.config.discretisation, want=("adv1", "adv2"))
+    want = mat(adv["adv1"] + adv["adv2"]) @ D.ravel()
+    got = N(U + D) - N(U) - N(D)
+    assert np.linalg.norm(got - want) <= 1e-12 * np.linalg.norm(want)
