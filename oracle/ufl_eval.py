@@ -193,3 +193,27 @@ def reference_velocity_residual(solver_name, V, U, nu, gamma, advect):
         me = types.SimpleNamespace(z=None, Z=None, nu=nu, gamma=gamma, advect=advect)
         form = getattr(sol, solver_name).residual(me)
     return ev.scatter_v(form)
+
+
+def reference_residual(solver_name, V, kq, U, P, nu, gamma, advect):
+    """(F_u, F_p) of the reference's residual for velocity nodal values U (nnodes, d) and pressure dofs P of the
+    discontinuous P_kq space, numbered cell by cell like alfi_b200.synth.fem.assemble_divergence."""
+    import types
+
+    from alfi_b200.synth.fem import LagrangeElement
+
+    from . import refshim
+    ev = Evaluator(V)
+    d = ev.d
+    x, _ = simplex_quadrature(d, 3 * V.element.degree + 1)
+    psi = np.ones((x.shape[0], 1)) if kq == 0 else LagrangeElement(d, kq).tabulate(x)        # (q, nq)
+    nc, nqb = V.mesh.nc, psi.shape[1]
+    p = F(np.einsum("qj,cj->cq", psi, np.asarray(P).reshape(nc, nqb))[:, :, None], None)
+    q = F(np.broadcast_to(psi[None, :, :], (nc,) + psi.shape).copy(), "q")
+    names = ev.namespace()
+    u, v = ev.trial(U), ev.test()
+    names.update(split=lambda z: (u, p), TestFunctions=lambda Z: (v, q))
+    with refshim.reference_modules(with_solver=True, extra_firedrake=names) as (_, _, sol):
+        me = types.SimpleNamespace(z=None, Z=None, nu=nu, gamma=gamma, advect=advect)
+        form = getattr(sol, solver_name).residual(me)
+    return ev.scatter_v(form), form.parts["q"].reshape(-1)

@@ -272,3 +272,32 @@ def test_velocity_operator_is_the_reference_form(problems, name, solver):
     want = mat(adv["adv1"] + adv["adv2"]) @ D.ravel()
     got = N(U + D) - N(U) - N(D)
     assert np.linalg.norm(got - want) <= 1e-12 * np.linalg.norm(want)
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name,solver", [("ldc2d-sv-k2-tiny", "ScottVogeliusSolver"), ("ldc2d-pkp0-tiny", "ConstantPressureSolver"),
+                                         ("ldc3d-sv-k3-tiny", "ScottVogeliusSolver")])
+def test_saddle_point_residual_is_the_reference_form(problems, name, solver):
+    """The whole residual of solver.py:562-572 / 613-623 with a pressure: F_u = A(u) u + B^T p, F_p = B u with
+    B = -(div u, q) as alfi_b200.synth.fem.assemble_divergence builds it for the continuation stand-in
+    (alfi_b200/synth/outer.py), and the pressure mass matrix DGMassInv inverts."""
+    from alfi_b200.synth.fem import BSR, assemble_divergence, assemble_parts
+    from oracle.ufl_eval import reference_residual
+    prob = problems(name, gamma=10.0, nu=0.2)
+    cfg = prob.config
+    ld = prob.finest
+    V = ld.V
+    kq = cfg.k - 1 if cfg.discretisation == "sv" else 0
+    B, Minv = assemble_divergence(V, kq)
+    rng = np.random.default_rng(1)
+    U, P = rng.standard_normal((V.nnodes, V.bs)), rng.standard_normal(B.shape[0])
+    nu, gamma = 0.3, 7.0
+    Fu, Fp = reference_residual(solver, V, kq, U, P, nu, gamma, 1.0)
+    mat = lambda vals: BSR(V.nnodes, V.bs, ld.pattern.rowptr, ld.pattern.colidx, vals).to_csr()      # noqa: E731
+    parts = assemble_parts(V, ld.pattern, U, cfg.discretisation, want=("visc", "div", "adv1"))
+    want_u = mat(nu * parts["visc"] + gamma * parts["div"] + parts["adv1"]) @ U.ravel() + B.T @ P
+    assert np.linalg.norm(Fu - want_u) <= 1e-12 * np.linalg.norm(want_u)
+    assert np.linalg.norm(Fp - B @ U.ravel()) <= 1e-12 * np.linalg.norm(Fp)
+    # Minv is the inverse of (p, q): applying the mass form to Minv's columns gives the identity on a cell
+    _, Fq = reference_residual(solver, V, kq, np.zeros_like(U), P, 0.0, 0.0, 0.0)
+    assert np.abs(Fq).max() == 0.0                       # no (p, q) term in the residual: mass only enters DGMassInv
