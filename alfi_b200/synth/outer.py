@@ -88,6 +88,16 @@ def fgmres_outer(Aop, Mop, b, rtol, atol, maxit=500, restart=30):
     return x, its, hist
 
 
+SNES_MAX_IT, KSP_MAX_IT = 20, 500                 # outer_base / outer_fieldsplit, alfi/solver.py:450-474
+
+
+def tolerances(tdim):
+    """Newton / Krylov tolerances of `get_parameters` without --high-accuracy (alfi/solver.py:484-499)."""
+    if tdim == 2:
+        return dict(ksp_rtol=1e-9, ksp_atol=1e-10, snes_rtol=1e-9, snes_atol=1e-8)
+    return dict(ksp_rtol=1e-8, ksp_atol=1e-8, snes_rtol=1e-8, snes_atol=1e-8)
+
+
 def dg_mass_inv_apply(Minv, nu, gamma, x):
     """`alfi.solver.DGMassInv.apply` (solver.py:32-35): y = -(nu + gamma) M_p^-1 x, the Schur complement
     approximation of the augmented-Lagrangian preconditioner (fieldsplit_1, solver.py:386-390)."""
@@ -168,8 +178,7 @@ class ContinuationSolver:
     def solve(self, re):
         cfg = self.config
         tdim = self.d
-        tol = dict(ksp_rtol=1e-9, ksp_atol=1e-10, snes_rtol=1e-9, snes_atol=1e-8) if tdim == 2 else \
-            dict(ksp_rtol=1e-8, ksp_atol=1e-8, snes_rtol=1e-8, snes_atol=1e-8)
+        tol = tolerances(tdim)
         nu = cfg.length * 1.0 / re if re > 0 else cfg.length
         advect = 1.0 if re > 0 else 0.0
         gamma = cfg.gamma
@@ -180,14 +189,14 @@ class ContinuationSolver:
         lin_its, newton = 0, 0
         fnorm0 = None
         nbc = fine.bc_dofs
-        for newton in range(21):
+        for newton in range(SNES_MAX_IT + 1):
             self._assemble(nu, gamma, advect)
             Fu, Fp = self._residual()
             fnorm = np.sqrt(Fu @ Fu + Fp @ Fp)
             fnorm0 = fnorm if fnorm0 is None else fnorm0
             if self.verbose:
                 print("  Re %g  SNES %d  |F| = %.6e" % (re, newton, fnorm), flush=True)
-            if fnorm <= max(tol["snes_atol"], tol["snes_rtol"] * fnorm0) or newton == 20:
+            if fnorm <= max(tol["snes_atol"], tol["snes_rtol"] * fnorm0) or newton == SNES_MAX_IT:
                 break
             levels = [level_input_from_synth(l) for l in self.prob.levels]
             if not self._setup_done:

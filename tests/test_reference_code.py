@@ -301,3 +301,17 @@ def test_saddle_point_residual_is_the_reference_form(problems, name, solver):
     # Minv is the inverse of (p, q): applying the mass form to Minv's columns gives the identity on a cell
     _, Fq = reference_residual(solver, V, kq, np.zeros_like(U), P, 0.0, 0.0, 0.0)
     assert np.abs(Fq).max() == 0.0                       # no (p, q) term in the residual: mass only enters DGMassInv
+
+
+@pytest.mark.parametrize("name,tdim", [("ldc2d-sv-k2", 2), ("ldc2d-pkp0", 2), ("ldc3d-sv-k3", 3), ("ldc3d-pkp0", 3)])
+def test_continuation_tolerances_are_the_reference_ones(name, tdim):
+    """The outer Newton / FGMRES settings of the continuation stand-in == the reference's dictionary."""
+    from alfi_b200.synth import outer
+    ref = PARAMS[name]["outer"]
+    tol = outer.tolerances(tdim)
+    for key in ("ksp_rtol", "ksp_atol", "snes_rtol", "snes_atol"):
+        assert tol[key] == ref[key], key
+    assert ref["snes_max_it"] == outer.SNES_MAX_IT and ref["ksp_max_it"] == outer.KSP_MAX_IT
+    assert ref["ksp_type"] == "fgmres" and ref["snes_type"] == "newtonls" and ref["snes_linesearch_type"] == "basic"
+    assert ref["pc_fieldsplit_schur_factorization_type"] == "full" and ref["pc_fieldsplit_schur_precondition"] == "user"
+    assert ref["fieldsplit_1"] == {"ksp_type": "preonly", "pc_type": "python", "pc_python_type": "alfi.solver.DGMassInv"}
