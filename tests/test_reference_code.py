@@ -315,3 +315,45 @@ def test_continuation_tolerances_are_the_reference_ones(name, tdim):
     assert ref["ksp_type"] == "fgmres" and ref["snes_type"] == "newtonls" and ref["snes_linesearch_type"] == "basic"
     assert ref["pc_fieldsplit_schur_factorization_type"] == "full" and ref["pc_fieldsplit_schur_precondition"] == "user"
     assert ref["fieldsplit_1"] == {"ksp_type": "preonly", "pc_type": "python", "pc_python_type": "alfi.solver.DGMassInv"}
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present (GPU box)")
+def test_driver_defaults_and_reynolds_rule():
+    """driver.get_default_parser (driver.py:9-51) and NavierStokesSolver.solve's parameter update (solver.py:257-268)
+    executed from the reference tree: gamma, composition, smoothing defaults and nu = L U / Re, advect = [Re > 0]."""
+    import importlib.util
+    import types
+
+    from alfi_b200.synth.problem import CONFIGS
+    extra = {"alfi.solver": refshim._module("alfi.solver", ConstantPressureSolver=None, ScottVogeliusSolver=None)}
+    with refshim.reference_modules(with_solver=True, extra_modules=extra) as (_, _, sol):
+        spec = importlib.util.spec_from_file_location("_alfi_reference_driver", os.path.join(refshim.REFERENCE, "alfi", "driver.py"))
+        drv = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(drv)
+        args = drv.get_default_parser().parse_args(["--discretisation", "sv"])
+        assert args.gamma == CONFIGS["ldc3d-sv-k3"].gamma == 1e4
+        assert args.patch_composition == "additive" and args.solver_type == "almg" and args.smoothing is None
+        assert args.restriction is False and args.high_accuracy is False
+
+        class Const:
+            def __init__(self):
+                self.v = None
+
+            def assign(self, v):
+                self.v = float(v)
+
+            def values(self):
+                return [self.v]
+        for re in (0, 10, 5000):
+            me = types.SimpleNamespace(
+                z_last=types.SimpleNamespace(assign=lambda z: None), z=None, message=lambda m: None,
+                advect=Const(), nu=Const(), char_L=2.0, char_U=1.0, stabilisation=None, nsp=None,
+                check_nograddiv_residual=False,
+                solver=types.SimpleNamespace(solve=lambda: None, snes=types.SimpleNamespace(
+                    getLinearSolveIterations=lambda: 7, getIterationNumber=lambda: 2)))
+            sol.GREEN = "%s"
+            _, info = sol.NavierStokesSolver.solve(me, re)
+            cfg = CONFIGS["ldc2d-sv-k2"]
+            want_nu = cfg.length * 1.0 / re if re > 0 else cfg.length          # alfi_b200/synth/outer.py
+            assert me.nu.v == want_nu == info["nu"] and me.advect.v == (1.0 if re > 0 else 0.0)
+            assert info["linear_iter"] == 7 and info["nonlinear_iter"] == 2 and info["Re"] == re
