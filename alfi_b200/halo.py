@@ -24,7 +24,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-__all__ = ["Layout", "RankLayout", "build_layout", "layout_from_owner", "transfer_halo"]
+__all__ = ["Layout", "RankLayout", "LocalLevel", "build_layout", "layout_from_owner", "transfer_halo", "local_level"]
 
 
 @dataclass
@@ -182,3 +182,123 @@ def build_layout(patch_offsets, patch_dofs, patch_order, patch_owner, rowptr, co
     lay = layout_from_owner(owner, needs, mine_all)
     lay.extra_owner = extra_owner
     return lay
+
+
+# ------------------------------------------------------------------------------------------ rank-local inputs
+@dataclass
+class LocalLevel:
+    """One rank's share of a level in LOCAL numbering (owned nodes first, then ghosts) — what a distributed-vector
+    library instance is handed instead of the global `alfi_b200.multigrid.LevelInput`.
+
+    Block rows exist for every local node — complete for the owned ones (SpMV runs over the first `n_owned_nodes`
+    rows), restricted to local columns for the ghosts (read only by the patch gathers); columns, patch dofs,
+    Dirichlet lists and the transfer's index sets are local ids.  `P` has one row per owned fine dof; its columns are local ids of the coarser level's transfer
+    halo (`coarse_local`, global coarse dofs in that order) or global coarse dofs when the coarser level is
+    replicated.  `send` / `recv` are the two exchange lists in local DOF ids per peer rank."""
+    rank: int
+    bs: int
+    n_owned_nodes: int
+    n_local_nodes: int
+    local_dofs: np.ndarray            # global dof of every local dof
+    rowptr: np.ndarray
+    colidx: np.ndarray
+    vals: np.ndarray
+    bc_dofs: np.ndarray
+    patch_offsets: np.ndarray
+    patch_dofs: np.ndarray
+    patch_order: np.ndarray
+    patch_colours: np.ndarray | None
+    patch_blocks: np.ndarray | None
+    patch_ids: np.ndarray             # global ids of the owned patches
+    send: dict
+    recv: dict
+    P: object | None = None
+    coarse_local: np.ndarray | None = None
+    cell_offsets: np.ndarray | None = None
+    cell_dofs: np.ndarray | None = None
+    cell_blocks: np.ndarray | None = None
+    cell_ids: np.ndarray | None = None
+    cb_dofs: np.ndarray | None = None
+    a0_vals: np.ndarray | None = None
+    d_vals: np.ndarray | None = None
+
+    @property
+    def n_owned(self):
+        return self.n_owned_nodes * self.bs
+
+    @property
+    def n_local(self):
+        return self.n_local_nodes * self.bs
+
+
+def _subset_ragged(offsets, data, ids):
+    n = np.diff(offsets)[ids]
+    off = np.concatenate(([0], np.cumsum(n))).astype(np.int64)
+    idx = np.concatenate([np.arange(offsets[p], offsets[p + 1]) for p in ids]) if len(ids) else np.empty(0, np.int64)
+    return off, idx
+
+
+def local_level(li, layout: Layout, rank: int, halo: Layout | None = None) -> LocalLevel:
+    """Rank `rank`'s LocalLevel of the global LevelInput `li` (alfi_b200.multigrid.LevelInput) for `layout`
+    (built with `extra_sets` = the level's cell patches when it has a transfer).  `halo` = `transfer_halo` on the
+    coarser level, or None when that level is replicated."""
+    import scipy.sparse as sp
+    r = layout.ranks[rank]
+    bs = li.bs
+    loc = r.local
+    assert (loc.reshape(-1, bs)[:, 0] % bs == 0).all() and (np.diff(loc.reshape(-1, bs), axis=1) == 1).all(), \
+        "ownership and ghosts must be node-wise"
+    g2l = np.full(layout.ndofs, -1, dtype=np.int64)
+    g2l[loc] = np.arange(loc.size)
+    nodes = loc[::bs] // bs                                        # global node of every local node
+    n_owned_nodes = r.n_owned // bs
+    node_g2l = np.full(li.n_nodes, -1, dtype=np.int64)
+    node_g2l[nodes] = np.arange(nodes.size)
+    # operator rows of ALL local nodes (the patch gather needs the rows of ghost patch dofs too), columns restricted
+    # to local nodes: complete for the owned rows (SpMV), truncated for ghost rows (only read inside patches)
+    sel_all = np.concatenate([np.arange(li.rowptr[n], li.rowptr[n + 1]) for n in nodes]) if nodes.size else np.empty(0, np.int64)
+    row_of = np.repeat(np.arange(nodes.size), (li.rowptr[nodes + 1] - li.rowptr[nodes]).astype(np.int64))
+    col_all = node_g2l[li.colidx[sel_all]]
+    assert (col_all[row_of < n_owned_nodes] >= 0).all(), "an operator column of an owned row is not local"
+    keep = col_all >= 0
+    sel, colidx = sel_all[keep], col_all[keep]
+    rowptr = np.concatenate(([0], np.cumsum(np.bincount(row_of[keep], minlength=nodes.size)))).astype(np.int32)
+    bc = g2l[np.asarray(li.bc_dofs, dtype=np.int64)]
+    # owned patches, local dofs, iteration order re-indexed
+    mine = r.patches
+    poff, pidx = _subset_ragged(np.asarray(li.patch_offsets, dtype=np.int64), li.patch_dofs, mine)
+    pdofs = g2l[np.asarray(li.patch_dofs, dtype=np.int64)[pidx]]
+    assert (pdofs >= 0).all()
+    out = LocalLevel(
+        rank=rank, bs=bs, n_owned_nodes=n_owned_nodes, n_local_nodes=nodes.size, local_dofs=loc,
+        rowptr=rowptr, colidx=colidx.astype(np.int32), vals=np.asarray(li.vals)[sel], bc_dofs=np.sort(bc[bc >= 0]).astype(np.int32),
+        patch_offsets=poff, patch_dofs=pdofs.astype(np.int32), patch_order=np.arange(mine.size, dtype=np.int32),
+        patch_colours=None if li.patch_colours is None else np.asarray(li.patch_colours)[mine].astype(np.int32),
+        patch_blocks=None if li.patch_blocks is None else np.asarray(li.patch_blocks)[pidx],
+        patch_ids=mine,
+        send={p: v.copy() for p, v in r.send.items()},
+        recv={p: r.n_owned + v for p, v in r.recv.items()})
+    if li.P is not None:
+        P = li.P.tocsr() if li.P_dof_level else sp.kron(li.P, sp.identity(bs), format="csr")
+        Pr = P[r.owned]
+        if halo is None:
+            out.P = Pr.tocsr()
+        else:
+            hl = halo.ranks[rank].local
+            c2l = np.full(halo.ndofs, -1, dtype=np.int64)
+            c2l[hl] = np.arange(hl.size)
+            Pc = Pr.tocoo()
+            assert (c2l[Pc.col] >= 0).all()
+            out.P = sp.csr_matrix((Pc.data, (Pc.row, c2l[Pc.col])), shape=(r.n_owned, hl.size))
+            out.coarse_local = hl
+        if li.cell_offsets is not None:
+            cells = np.flatnonzero(layout.extra_owner == rank)
+            coff, cidx = _subset_ragged(np.asarray(li.cell_offsets, dtype=np.int64), li.cell_dofs, cells)
+            cd = g2l[np.asarray(li.cell_dofs, dtype=np.int64)[cidx]]
+            assert (cd >= 0).all(), "a cell patch of this rank has a dof that is not local"
+            out.cell_offsets, out.cell_dofs, out.cell_ids = coff, cd.astype(np.int32), cells
+            out.cell_blocks = None if li.cell_blocks is None else np.asarray(li.cell_blocks)[cidx]
+            cb = g2l[np.asarray(li.cb_dofs, dtype=np.int64)]
+            out.cb_dofs = np.sort(cb[cb >= 0]).astype(np.int32)
+            out.a0_vals, out.d_vals = np.asarray(li.a0_vals)[sel], np.asarray(li.d_vals)[sel]
+    return out

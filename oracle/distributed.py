@@ -304,3 +304,58 @@ def fcycle(prob, levels, b, m, nranks):
     layouts, halos = build_hierarchy_layouts(prob, nranks)
     h = DistHierarchy(levels, layouts, halos)
     return h.fcycle(b, m), h
+
+
+# ------------------------------------------------------------------------------------------ from LocalLevel data only
+class LocalRankData:
+    """What one rank computes with, rebuilt from an alfi_b200.halo.LocalLevel alone (no global arrays): the check
+    that the rank-local inputs are self-sufficient."""
+
+    def __init__(self, ll):
+        import scipy.sparse as sp
+        self.ll = ll
+        bs = ll.bs
+        n = ll.n_local_nodes
+
+        def mat(vals):
+            return sp.bsr_matrix((vals, ll.colidx, ll.rowptr), shape=(n * bs, n * bs)).tocsr()
+        self.A = mat(ll.vals)
+        self.patches = []
+        for p in range(ll.patch_offsets.size - 1):
+            I = ll.patch_dofs[ll.patch_offsets[p]:ll.patch_offsets[p + 1]].astype(np.int64)
+            self.patches.append((I, np.linalg.inv(self.A[I][:, I].toarray()) if I.size else np.empty((0, 0))))
+        self.cells = []
+        if ll.cell_offsets is not None:
+            A0 = mat(ll.a0_vals)
+            self.D = mat(ll.d_vals)
+            for q in range(ll.cell_offsets.size - 1):
+                I = ll.cell_dofs[ll.cell_offsets[q]:ll.cell_offsets[q + 1]].astype(np.int64)
+                self.cells.append((I, np.linalg.inv(A0[I][:, I].toarray()) if I.size else np.empty((0, 0))))
+
+
+def local_smoother_apply(layout, locals_, data, xs):
+    """PCApply_PATCH on LocalLevel data: per rank gather/solve/scatter in local numbering, then the two exchanges."""
+    out = []
+    for ll, d, x in zip(locals_, data, xs):
+        y = np.zeros(ll.n_local)
+        for p in ll.patch_order:
+            I, X = d.patches[p]
+            if I.size:
+                y[I] += X @ x[I]
+        out.append(y)
+    layout.reduce_ghosts(out)
+    for ll, y, x in zip(locals_, out, xs):
+        bc = ll.bc_dofs[ll.bc_dofs < ll.n_owned]
+        y[bc] = x[bc]
+    layout.update_ghosts(out)
+    return out
+
+
+def local_spmv(layout, locals_, data, xs):
+    out = []
+    for ll, d, x in zip(locals_, data, xs):
+        y = np.zeros(ll.n_local)
+        y[:ll.n_owned] = (d.A @ x)[:ll.n_owned]
+        out.append(y)
+    layout.update_ghosts(out)
+    return out

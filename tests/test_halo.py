@@ -185,3 +185,49 @@ def test_distributed_fcycle_equals_serial(problems, name, nranks):
         if l > 1:
             halo = h.halos[l]
             assert all(np.array_equal(a.owned, b_.owned) for a, b_ in zip(halo.ranks, h.layouts[l - 1].ranks))
+
+
+@pytest.mark.parametrize("name", ["ldc2d-sv-k2-tiny", "ldc3d-sv-k3-tiny", "ldc2d-pkp0-tiny"])
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_rank_local_inputs_are_self_sufficient(problems, name, nranks):
+    """alfi_b200.halo.local_level: every rank's LocalLevel (local numbering, operator rows of its local nodes,
+    its patches / cell patches / Dirichlet lists / transfer columns) is enough to reproduce the global smoother
+    application, SpMV and the transfer's operators — nothing global is consulted."""
+    import scipy.sparse as sp
+    from alfi_b200.halo import local_level, transfer_halo
+    from alfi_b200.multigrid import level_input_from_synth
+    prob = problems(name, gamma=10.0, nu=0.2)
+    layouts, halos = od.build_hierarchy_layouts(prob, nranks)
+    rng = np.random.default_rng(4)
+    for l in range(1, len(prob.levels)):
+        ld = prob.levels[l]
+        li = level_input_from_synth(ld)
+        lv = hp.level_from_host(ld)
+        lay, halo = layouts[l], halos[l]
+        locs = [local_level(li, lay, r, halo) for r in range(nranks)]
+        data = [od.LocalRankData(ll) for ll in locs]
+        x = rng.standard_normal(lv.n)
+        x[lv.bc_dofs] = 0
+        xs = lay.scatter(x)
+        for ll, r in zip(locs, lay.ranks):
+            assert np.array_equal(ll.local_dofs, r.local) and ll.n_owned == r.n_owned
+            assert ll.rowptr.size == ll.n_local_nodes + 1 and ll.colidx.max() < ll.n_local_nodes
+        got = lay.gather(od.local_spmv(lay, locs, data, xs))
+        assert np.linalg.norm(got - lv.A @ x) <= 1e-13 * np.linalg.norm(lv.A @ x)
+        want = hp.smoother_apply(x, lv.offsets, lv.dofs, lv.order, lv.factors, lv.bc_dofs)
+        got = lay.gather(od.local_smoother_apply(lay, locs, data, xs))
+        assert np.linalg.norm(got - want) <= 1e-12 * np.linalg.norm(want)
+        # transfer pieces: P rows of the owned dofs in the coarse numbering of this rank; cell patches local and owned once
+        P = ld.P.tocsr() if ld.P_dof_level else sp.kron(ld.P, sp.identity(ld.V.bs), format="csr")
+        c = rng.standard_normal(P.shape[1])
+        for ll, r in zip(locs, lay.ranks):
+            cl = c if ll.coarse_local is None else c[ll.coarse_local]
+            assert np.allclose(ll.P @ cl, (P @ c)[r.owned], rtol=0, atol=1e-13)
+            for q, (I, X) in zip(ll.cell_ids, data[ll.rank].cells):
+                assert np.array_equal(ll.local_dofs[I], ld.cell_patches.patch(q))
+                A0 = ld.A0.to_csr()
+                G = ld.cell_patches.patch(q)
+                assert np.allclose(X @ A0[G][:, G].toarray(), np.eye(G.size), atol=1e-9)
+            assert np.array_equal(np.sort(ll.local_dofs[ll.cb_dofs]), np.intersect1d(ld.cb_dofs, ll.local_dofs))
+        assert sorted(np.concatenate([ll.cell_ids for ll in locs]).tolist()) == list(range(ld.cell_patches.npatch))
+        assert sorted(np.concatenate([ll.patch_ids for ll in locs]).tolist()) == sorted(set(ld.patches.order.tolist()))
