@@ -13,11 +13,31 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["partition_patches", "shard_patch_arrays", "shard_dof_array", "bootstrap_unique_id"]
+__all__ = ["partition_patches", "condensed_cost", "shard_patch_arrays", "shard_dof_array", "bootstrap_unique_id"]
 
 
-def partition_patches(offsets, dofs, nranks: int) -> np.ndarray:
-    """owner[p] in [0, nranks): contiguous in the patches' mean dof index, balanced by n_p^2."""
+def condensed_cost(offsets, blocks) -> np.ndarray:
+    """Per-patch estimate of the bytes a condensed patch streams per application (csrc/condense.cu): the
+    separator inverse |S|^2 plus, per block, D and the two coupling tiles (~3 b_k^2).  Only used to balance
+    the partition, so a proxy is enough."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    blocks = np.asarray(blocks)
+    npatch = offsets.size - 1
+    patch_of = np.repeat(np.arange(npatch), np.diff(offsets))
+    sep = np.bincount(patch_of[blocks < 0], minlength=npatch).astype(np.float64)
+    cost = sep ** 2
+    inb = blocks >= 0
+    if inb.any():
+        key = patch_of[inb].astype(np.int64) * (int(blocks.max()) + 1) + blocks[inb]
+        uniq, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
+        per_block_patch = (uniq // (int(blocks.max()) + 1)).astype(np.int64)
+        cost += np.bincount(per_block_patch, weights=3.0 * cnt.astype(np.float64) ** 2, minlength=npatch)
+    return cost
+
+
+def partition_patches(offsets, dofs, nranks: int, cost=None) -> np.ndarray:
+    """owner[p] in [0, nranks): contiguous in the patches' mean dof index, balanced by `cost` per patch
+    (default n_p^2, the bytes of a dense inverse; pass `condensed_cost` for condensed sets)."""
     offsets = np.asarray(offsets, dtype=np.int64)
     npatch = offsets.size - 1
     n = np.diff(offsets)
@@ -26,7 +46,7 @@ def partition_patches(offsets, dofs, nranks: int) -> np.ndarray:
     csum = np.concatenate(([0.0], np.cumsum(np.asarray(dofs, dtype=np.float64))))
     mean = (csum[offsets[1:]] - csum[offsets[:-1]]) / np.maximum(n, 1)
     order = np.argsort(mean, kind="stable")
-    cost = (n[order].astype(np.float64)) ** 2
+    cost = (n[order].astype(np.float64)) ** 2 if cost is None else np.asarray(cost, dtype=np.float64)[order]
     cum = np.cumsum(cost)
     total = cum[-1] if cum.size else 0.0
     # patch k goes to the rank whose share contains the midpoint of its cost interval

@@ -73,7 +73,7 @@ class DeviceMultigrid:
 
         ``condense``: use the block/separator form of the patch inverses (csrc/condense.cu) for the
         patch sets whose LevelInput carries block labels; False keeps dense inverses everywhere."""
-        from .dist import partition_patches, shard_dof_array, shard_patch_arrays
+        from .dist import condensed_cost, partition_patches, shard_dof_array, shard_patch_arrays
         self.ctx = ctx or Context(device, deterministic)
         self.nlevels = len(levels)
         self.smoothing = smoothing
@@ -93,7 +93,9 @@ class DeviceMultigrid:
                 off, dofs, order, cols = li.patch_offsets, li.patch_dofs, li.patch_order, li.patch_colours
                 blocks = li.patch_blocks if condense else None
                 if nranks > 1:
-                    owner = partition_patches(off, dofs, nranks)
+                    # balance what is streamed per application: condensed bytes where blocks are given
+                    cost = condensed_cost(off, blocks) if blocks is not None else None
+                    owner = partition_patches(off, dofs, nranks, cost)
                     goff = off
                     off, dofs, order, cols, mine = shard_patch_arrays(off, dofs, order, cols, owner, rank)
                     blocks = shard_dof_array(goff, blocks, mine)

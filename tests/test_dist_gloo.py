@@ -75,3 +75,20 @@ def test_sharded_apply_world2_gloo():
     for r in range(world):
         assert res[r] <= 1e-13, res
         assert res[world + r] == 0.0, res
+
+
+def test_condensed_cost_balances_condensed_bytes(problems):
+    """With condensed inverses the partition balances what is streamed per application, not n^2."""
+    from alfi_b200.dist import condensed_cost
+    prob = problems("ldc3d-sv-k3-tiny", gamma=10.0, nu=0.2)
+    ps = prob.levels[1].patches
+    cost = condensed_cost(ps.offsets, ps.blocks)
+    assert cost.shape == (ps.npatch,) and (cost > 0).all()
+    # interior patch: 195 separator dofs and 24 blocks of 45 dofs
+    p = int(np.argmax(ps.sizes))
+    assert cost[p] == 195.0 ** 2 + 24 * 3 * 45.0 ** 2
+    for nranks in (2, 4):
+        owner = partition_patches(ps.offsets, ps.dofs, nranks, cost)
+        share = np.bincount(owner, weights=cost, minlength=nranks)
+        assert share.max() <= 2.0 * cost.sum() / nranks + cost.max()
+        assert np.array_equal(np.sort(np.unique(owner)), np.arange(nranks))
