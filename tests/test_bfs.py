@@ -22,7 +22,7 @@ from tests.test_patches import FakePC
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FIXTURE = os.path.join(ROOT, "tests", "golden", "step_n2.msh")
-REFERENCE_MSH = "/root/reference/examples/bfs2d/coarse09.msh"
+REFERENCE_MSH = os.path.join(os.environ.get("ALFI_REFERENCE", "/root/reference"), "examples", "bfs2d", "coarse09.msh")
 
 
 def areas(m):

@@ -185,7 +185,7 @@ def test_matrix_form_equals_the_sequence_run_with_the_reference_kernels(pair):
     assert np.abs(lit.prolong(c) - fine.ravel()).max() < 1e-13
 
 
-@pytest.mark.skipif(_ref_kernels() is None or not os.path.exists("/root/reference/alfi/bubble.py"),
+@pytest.mark.skipif(_ref_kernels() is None or not os.path.exists(os.path.join(os.environ.get("ALFI_REFERENCE", "/root/reference"), "alfi", "bubble.py")),
                     reason="needs the reference tree (build container)")
 def test_reference_bubble_transfer_methods_equal_the_matrix_form(pair):
     """alfi/bubble.py:204-265 executed verbatim (oracle/refshim_bubble.py: par_loops run the reference's compiled
