@@ -357,3 +357,50 @@ def test_driver_defaults_and_reynolds_rule():
             want_nu = cfg.length * 1.0 / re if re > 0 else cfg.length          # alfi_b200/synth/outer.py
             assert me.nu.v == want_nu == info["nu"] and me.advect.v == (1.0 if re > 0 else 0.0)
             assert info["linear_iter"] == 7 and info["nonlinear_iter"] == 2 and info["Re"] == re
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present (GPU box)")
+def test_transfer_wiring_is_the_reference_one():
+    """Row W1: ScottVogeliusSolver.get_transfers (solver.py:632-653) and NullTransfer (transfer.py:359-366)
+    executed from the reference tree — which callables go to the TransferManager for the velocity and the pressure
+    element, with and without --restriction — against alfi_b200's drop-in classes."""
+    import types
+
+    import alfi_b200
+    prolong, restrict, inject = object(), object(), object()
+    with refshim.reference_modules(with_solver=True, extra_firedrake=dict(prolong=prolong, restrict=restrict, inject=inject)) as (_, tr, sol):
+        for restriction in (True, False):
+            V = types.SimpleNamespace(ufl_element=lambda: "V-element")
+            Q = types.SimpleNamespace(ufl_element=lambda: "Q-element")
+            me = types.SimpleNamespace(Z=types.SimpleNamespace(sub=lambda i: (V, Q)[i]), stabilisation_type=None,
+                                       hierarchy="bary", nu=0.1, gamma=1e4, tdim=3, restriction=restriction)
+            transfers = sol.ScottVogeliusSolver.get_transfers(me)
+            vp, vr, vi = transfers["V-element"]
+            assert isinstance(me.vtransfer, sol.SVSchoeberlTransfer) and me.vtransfer.parameters == (0.1, 1e4)
+            assert vp == me.vtransfer.prolong and vi is inject
+            assert (vr == me.vtransfer.restrict) if restriction else (vr is restrict)
+            qp, qr, qi = transfers["Q-element"]
+            assert qp is prolong and qr is restrict and isinstance(me.qtransfer, tr.NullTransfer) and qi == me.qtransfer.inject
+            # the patch solver of the transfer: same option dictionary as alfi_b200 honours
+            pp = me.vtransfer.patchparams
+            assert pp["patch_pc_patch_construct_python_type"] == "alfi.transfer.CoarseCellMacroPatches"
+            assert pp["patch_pc_patch_partition_of_unity"] is False and pp["patch_sub_pc_type"] == "lu"
+            assert pp["patch_pc_patch_sub_mat_type"] == "seqaij"
+
+        class Vec:
+            def __init__(self):
+                self.a = np.zeros(4)
+
+            def set(self, v):
+                self.a[:] = v
+        dest = types.SimpleNamespace(dat=types.SimpleNamespace(vec_wo=None))
+        import contextlib
+        v = Vec()
+        dest.dat.vec_wo = contextlib.nullcontext(v)
+        tr.NullTransfer().inject(None, dest)
+        assert np.isnan(v.a).all()
+    ours = np.zeros(4)
+    alfi_b200.NullTransfer().inject(None, ours)
+    assert np.isnan(ours).all()
+    for name in ("prolong", "restrict", "inject"):
+        assert callable(getattr(alfi_b200.NullTransfer(), name)) and callable(getattr(alfi_b200.SVSchoeberlTransfer, name, None) or getattr(alfi_b200.AutoSchoeberlTransfer, name, None) or (lambda: 0))
