@@ -123,20 +123,55 @@ CONT_CONFIG = "ldc2d-sv-k2"                      # BASELINE.json configs[0]: Re 
 CONT_RES = [10, 100] + list(range(200, 1001, 100))
 
 
-def run_continuation(backend, label):
-    """Full Newton continuation (alfi/driver.py:95-129) of BASELINE configs[0] around `backend` as the
-    fieldsplit_0 preconditioner; assembly and the outer FGMRES/Schur loop run on the host."""
+class TimedBackend:
+    """Wraps a fieldsplit_0 backend and accumulates the wall time spent inside it (setup / per-Newton refresh /
+    applications), so a continuation's time splits into library time and host assembly + outer loop."""
+
+    def __init__(self, inner):
+        self.inner = inner
+        self.t = {"setup": 0.0, "update_operators": 0.0, "update_transfers": 0.0, "apply": 0.0}
+        self.n = {k: 0 for k in self.t}
+
+    def _timed(self, key, fn, *a):
+        t0 = time.perf_counter()
+        out = fn(*a)
+        self.t[key] += time.perf_counter() - t0
+        self.n[key] += 1
+        return out
+
+    def setup(self, levels):
+        return self._timed("setup", self.inner.setup, levels)
+
+    def update_operators(self, levels):
+        return self._timed("update_operators", self.inner.update_operators, levels)
+
+    def update_transfers(self, levels):
+        return self._timed("update_transfers", self.inner.update_transfers, levels)
+
+    def apply(self, b):
+        return self._timed("apply", self.inner.apply, b)
+
+
+def run_continuation(backend, label, config=None, res=None):
+    """Full Newton continuation (alfi/driver.py:95-129) of BASELINE configs[0] (or `config`) around `backend` as
+    the fieldsplit_0 preconditioner; assembly and the outer FGMRES/Schur loop run on the host."""
     from alfi_b200.synth.outer import ContinuationSolver
     from alfi_b200.synth.problem import CONFIGS
-    cfg = CONFIGS[CONT_CONFIG]
-    solver = ContinuationSolver(cfg, backend)
+    config = config or CONT_CONFIG
+    res = list(res or CONT_RES)
+    cfg = CONFIGS[config]
+    timed = TimedBackend(backend)
+    solver = ContinuationSolver(cfg, timed)
     t0 = time.perf_counter()
-    infos = [solver.solve(re) for re in CONT_RES]
+    infos = [solver.solve(re) for re in res]
     dt = time.perf_counter() - t0
-    return {"config": CONT_CONFIG, "velocity_dofs": solver.nu_dofs, "pressure_dofs": solver.np_dofs, "re": CONT_RES,
+    return {"config": config, "velocity_dofs": solver.nu_dofs, "pressure_dofs": solver.np_dofs, "re": res,
             "time_s": dt, "nonlinear_iter": [i["nonlinear_iter"] for i in infos],
             "linear_iter": [i["linear_iter"] for i in infos], "final_residual": float(infos[-1]["residual"]),
-            "fieldsplit_0": label}, solver
+            "fieldsplit_0": label,
+            "time_in_fieldsplit_0_s": {k: round(v, 4) for k, v in timed.t.items()},
+            "calls_of_fieldsplit_0": dict(timed.n),
+            "time_on_host_s": round(dt - sum(timed.t.values()), 4)}, solver
 
 
 def reference_arm(args):
@@ -378,6 +413,19 @@ def ours(args):
                 continuation["pressure_rel_diff_vs_cpu"] = float(np.linalg.norm(sdev.p - sref.p) / np.linalg.norm(sref.p))
         except Exception as e:      # noqa: BLE001
             continuation = {"error": repr(e)}
+        if args.continuation_3d and isinstance(continuation, dict) and "error" not in continuation:
+            # opt-in: the same continuation on a 3-D Scott-Vogelius k=3 mesh (the family BASELINE's metric names).  The
+            # host stand-in assembles in numpy (~4 s per Newton step at 185 k dofs, ~30 s at cfg5's size), which is not the
+            # library's job, so the line splits the time into library and host parts.
+            try:
+                from alfi_b200.multigrid import DeviceBackend
+                from alfi_b200.synth.problem import CONFIGS as _C3
+                name3 = args.continuation_3d
+                res3 = [int(r) for r in args.continuation_3d_re.split(",")]
+                c3, _ = run_continuation(DeviceBackend(_C3[name3].m, device=local), "CUDA library (alfib_cycle_apply)", name3, res3)
+                continuation["three_d"] = c3
+            except Exception as e:      # noqa: BLE001
+                continuation["three_d"] = {"error": repr(e)}
 
     total = n            # N > 1: the same problem sharded over the ranks (strong scaling)
     line = {
@@ -427,6 +475,9 @@ def main():
     ap.add_argument("--deterministic", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-continuation", action="store_true")
+    ap.add_argument("--continuation-3d", default="", metavar="CONFIG",
+                    help="also run the Newton continuation on this 3-D config (e.g. ldc3d-sv-k3-half); minutes of host assembly")
+    ap.add_argument("--continuation-3d-re", default="10,100,200,300,400,500", help="Reynolds numbers of --continuation-3d")
     ap.add_argument("--peer-memory", type=int, default=0, help="N > 1: NVLink peer-memory exchanges instead of NCCL")
     ap.add_argument("--condense", type=int, default=1,
                     help="1 (default): condensed block/separator patch inverses where the mesh has macro structure; 0: dense")
