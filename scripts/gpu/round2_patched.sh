@@ -24,6 +24,8 @@ for f in ("r2_bench_default", "r2_bench_schur"):
     except Exception as e:
         print(f, "unreadable:", e)
 PY
+timeout 200 python -m pytest tests/test_gpu_fused_index.py -q -m gpu > gpurun_out/r2_t_fused.log 2>&1; el fused-index $?; tail -2 gpurun_out/r2_t_fused.log
+ALFIB_FUSE_INDEX=1 timeout 200 python scripts/kernel_bench.py ldc3d-sv-k3 2>&1 | tail -2 | sed "s/^/[fused index] /"
 # 3. sweep of the X_SS column-chunk width (patch 3) on the finest-level smoother application
 for w in 256 96 64; do ALFIB_SPLIT_COLS=$w timeout 200 python scripts/kernel_bench.py ldc3d-sv-k3 2>&1 | tail -2 | sed "s/^/[split $w] /"; done
 el done 0
