@@ -61,6 +61,12 @@ CONFIGS = {
     "ldc2d-pkp0": Config("ldc2d-pkp0", 2, 16, 3, "pkp0", 2, "star", False, re=10000.0),
     "ldc3d-sv-k3": Config("ldc3d-sv-k3", 3, 4, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
     "ldc3d-pkp0": Config("ldc3d-pkp0", 3, 16, 2, "pkp0", 1, "star", False, re=5000.0, element="p1fb"),
+    # larger members of configs[4]'s family: baseN 6 is the reference's own choice for ldc3d (generate_submission:75;
+    # 4 899 531 dofs, 15 625 patches: its dense coarse inverse (78.9 k dofs) does not fit — needs the condensed coarse
+    # inverse of scripts/r2_prep), baseN 5 (2 840 943 dofs, 9 261 patches, coarse 46 038 dofs) runs as is.  The host
+    # generator needs ~33 / ~57 GB of RAM and minutes for them (cfg5: 17 GB, 73 s).
+    "ldc3d-sv-k3-n5": Config("ldc3d-sv-k3-n5", 3, 5, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
+    "ldc3d-sv-k3-n6": Config("ldc3d-sv-k3-n6", 3, 6, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
     # scaled-down members of the same families (tests, smoke, CPU-baseline sample)
     "ldc2d-sv-k2-tiny": Config("ldc2d-sv-k2-tiny", 2, 2, 1, "sv", 2, "macro", True, re=100.0, sort_order="0+:1-"),
     "ldc2d-pkp0-tiny": Config("ldc2d-pkp0-tiny", 2, 2, 2, "pkp0", 2, "star", False, re=100.0),

@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DEFAULT_CONFIG = "ldc3d-sv-k3"
-CPU_SAMPLE_CONFIG = {"ldc3d-sv-k3": "ldc3d-sv-k3-half", "ldc2d-sv-k2": "ldc2d-sv-k2", "ldc2d-pkp0": "ldc2d-pkp0"}
+CPU_SAMPLE_CONFIG = {"ldc3d-sv-k3": "ldc3d-sv-k3-half", "ldc3d-sv-k3-n5": "ldc3d-sv-k3-half", "ldc3d-sv-k3-n6": "ldc3d-sv-k3-half", "ldc2d-sv-k2": "ldc2d-sv-k2", "ldc2d-pkp0": "ldc2d-pkp0"}
 METRIC = "V-cycle DoF/s (finest-level velocity dofs per second of one fieldsplit_0 PCMG-full application)"
 
 
