@@ -308,8 +308,8 @@ class VectorSpace:
         return self.nnodes * self.bs
 
     def boundary_nodes(self, tol=1e-12):
-        x, L = self.node_coords, self.mesh.length
-        return np.flatnonzero(np.any((np.abs(x) < tol) | (np.abs(x - L) < tol), axis=1))
+        x, L = self.node_coords, self.mesh.extent
+        return np.flatnonzero(np.any((np.abs(x) < tol) | (np.abs(x - L[None, :]) < tol), axis=1))
 
     def tagged_boundary_nodes(self, tags):
         """Nodes in the closure of the boundary facets carrying one of the physical `tags` — what

@@ -78,10 +78,10 @@ def _label_prolongation(level: Level, coarse: Level | None):
     plex.labels["prolongation"] = lab
 
 
-def build_hierarchy(dim: int, N: int, nref: int, bary: bool, length: float = 2.0) -> list[Level]:
+def build_hierarchy(dim: int, N: int, nref: int, bary: bool, length: float = 2.0, shape: tuple = ()) -> list[Level]:
     levels: list[Level] = []
     for l in range(nref + 1):
-        macro = kuhn_mesh(dim, N * 2 ** l, length)
+        macro = kuhn_mesh(dim, N * 2 ** l, length, shape)
         mesh = alfeld_split(macro) if bary else macro
         levels.append(Level(l, macro, mesh, SynthPlex(mesh), bary))
     d = dim

@@ -46,6 +46,9 @@ class SimplexMesh:
     macro: "SimplexMesh | None" = None       # the mesh this one is the Alfeld split of
     length: float = 2.0
     M: int = 0                               # cells per side of the underlying Kuhn grid
+    # box-shaped Kuhn grids (weak-scaling family): axis a has M * shape[a] cells and extent length * shape[a];
+    # () = the cube
+    shape: tuple = ()
     # boundary markers of general (Gmsh) meshes: (nb, dim) vertex tuples of tagged boundary facets, rows
     # ascending, and their physical tags; `facet_tag` (per facet id, 0 = untagged) is derived from them
     boundary_facets: np.ndarray | None = None
@@ -121,37 +124,51 @@ class SimplexMesh:
     def cell_facets(self):
         return self.cell_edges if self.dim == 2 else self.cell_faces
 
+    @property
+    def axis_shape(self):
+        return tuple(self.shape) if self.shape else (1,) * self.dim
+
+    @property
+    def extent(self):
+        """Upper corner of the Kuhn box [0, extent]."""
+        return self.length * np.asarray(self.axis_shape, dtype=np.float64)
+
     def boundary_vertex_mask(self, tol=1e-12):
         x = self.coords
-        return np.any((np.abs(x) < tol) | (np.abs(x - self.length) < tol), axis=1)
+        return np.any((np.abs(x) < tol) | (np.abs(x - self.extent[None, :]) < tol), axis=1)
 
 
-def kuhn_mesh(dim: int, M: int, length: float = 2.0) -> SimplexMesh:
-    """Kuhn triangulation of [0, length]^dim with M cells per side.
+def kuhn_mesh(dim: int, M: int, length: float = 2.0, shape: tuple = ()) -> SimplexMesh:
+    """Kuhn triangulation of [0, length]^dim with M cells per side — or, with `shape`, of the box
+    [0, length * shape[a]] with M * shape[a] cells along axis a (same cell size; the weak-scaling family).
 
     2-D: each square (ll, lr, ur, ul) is cut along lr–ul (Firedrake ``diagonal="left"``,
     examples/ldc2d/ldc2d.py:11-12).  3-D: six tetrahedra per cube sharing the main diagonal
     (Firedrake ``BoxMesh``, examples/ldc3d/ldc3d.py:13-15).
     """
-    n1 = M + 1
-    ax = np.arange(n1)
+    shp = tuple(int(v) for v in shape) if shape else (1,) * dim
+    if len(shp) != dim or min(shp) < 1:
+        raise ValueError("shape must have one positive integer per axis")
+    Ma = [M * v for v in shp]
+    n1 = [m + 1 for m in Ma]
+    h = length / M
     if dim == 2:
-        # vertex id = i + n1*j  (x fastest)
-        J, I = np.meshgrid(ax, ax, indexing="ij")
-        coords = np.stack([I.ravel(), J.ravel()], axis=1) * (length / M)
-        j, i = np.meshgrid(np.arange(M), np.arange(M), indexing="ij")
+        # vertex id = i + n1x*j  (x fastest)
+        J, I = np.meshgrid(np.arange(n1[1]), np.arange(n1[0]), indexing="ij")
+        coords = np.stack([I.ravel(), J.ravel()], axis=1) * h
+        j, i = np.meshgrid(np.arange(Ma[1]), np.arange(Ma[0]), indexing="ij")
         i, j = i.ravel(), j.ravel()
-        ll = i + n1 * j
+        ll = i + n1[0] * j
         lr = ll + 1
-        ul = ll + n1
+        ul = ll + n1[0]
         ur = ul + 1
         cells = np.stack([np.stack([ll, lr, ul], 1), np.stack([lr, ur, ul], 1)], axis=1).reshape(-1, 3)
     elif dim == 3:
-        K, J, I = np.meshgrid(ax, ax, ax, indexing="ij")
-        coords = np.stack([I.ravel(), J.ravel(), K.ravel()], axis=1) * (length / M)
-        k, j, i = np.meshgrid(np.arange(M), np.arange(M), np.arange(M), indexing="ij")
-        base = (i + n1 * (j + n1 * k)).ravel()
-        step = np.array([1, n1, n1 * n1])
+        K, J, I = np.meshgrid(np.arange(n1[2]), np.arange(n1[1]), np.arange(n1[0]), indexing="ij")
+        coords = np.stack([I.ravel(), J.ravel(), K.ravel()], axis=1) * h
+        k, j, i = np.meshgrid(np.arange(Ma[2]), np.arange(Ma[1]), np.arange(Ma[0]), indexing="ij")
+        base = (i + n1[0] * (j + n1[1] * k)).ravel()
+        step = np.array([1, n1[0], n1[0] * n1[1]])
         tets = []
         for perm in itertools.permutations(range(3)):
             v0 = base
@@ -163,7 +180,8 @@ def kuhn_mesh(dim: int, M: int, length: float = 2.0) -> SimplexMesh:
     else:
         raise ValueError("dim must be 2 or 3")
     cells = np.sort(cells.astype(np.int64), axis=1)
-    m = SimplexMesh(dim=dim, coords=coords.astype(np.float64), cells=cells, length=length, M=M)
+    m = SimplexMesh(dim=dim, coords=coords.astype(np.float64), cells=cells, length=length, M=M,
+                    shape=shp if any(v != 1 for v in shp) else ())
     return m.build_topology()
 
 
@@ -184,7 +202,7 @@ def alfeld_split(macro: SimplexMesh) -> SimplexMesh:
     mv[:nvm] = True
     # macro vertices keep their ids, so tagged boundary facets of the macro mesh are facets of the split
     m = SimplexMesh(dim=d, coords=coords, cells=cells, macro_vertex=mv, macro=macro,
-                    length=macro.length, M=macro.M, boundary_facets=macro.boundary_facets,
+                    length=macro.length, M=macro.M, shape=macro.shape, boundary_facets=macro.boundary_facets,
                     boundary_tags=macro.boundary_tags)
     return m.build_topology()
 
@@ -222,16 +240,17 @@ def locate_in_kuhn(mesh: SimplexMesh, pts: np.ndarray) -> np.ndarray:
     Used to build ``coarse_to_fine_cells`` of the uniform hierarchy by locating fine-cell
     centroids (strictly interior, so there are no ties).
     """
-    d, M, h = mesh.dim, mesh.M, mesh.length / mesh.M
+    d, h = mesh.dim, mesh.length / mesh.M
+    Ma = np.asarray([mesh.M * v for v in mesh.axis_shape], dtype=np.int64)
     g = pts / h
-    ijk = np.clip(np.floor(g).astype(np.int64), 0, M - 1)
+    ijk = np.clip(np.floor(g).astype(np.int64), 0, Ma[None, :] - 1)
     frac = g - ijk
     if d == 2:
-        cube = ijk[:, 0] + M * ijk[:, 1]
+        cube = ijk[:, 0] + Ma[0] * ijk[:, 1]
         # cell 0 = (ll, lr, ul): x + y <= 1 ; cell 1 = (lr, ur, ul)
         which = (frac.sum(axis=1) > 1.0).astype(np.int64)
         return cube * 2 + which
-    cube = ijk[:, 0] + M * (ijk[:, 1] + M * ijk[:, 2])
+    cube = ijk[:, 0] + Ma[0] * (ijk[:, 1] + Ma[1] * ijk[:, 2])
     # tet for permutation perm: frac[perm0] >= frac[perm1] >= frac[perm2]
     order = np.argsort(-frac, axis=1, kind="stable")
     perms = list(itertools.permutations(range(3)))

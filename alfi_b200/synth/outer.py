@@ -137,7 +137,7 @@ class ContinuationSolver:
                         fill[f] += 1
             self.inject[l - 1] = prolongation_matrix(self.prob.levels[l].V, self.prob.levels[l - 1].V, f2c)
         self.u = np.zeros((fine.V.nnodes, self.d))
-        bcv = lid_wind(fine.V.node_coords)
+        bcv = lid_wind(fine.V.node_coords, fine.V.mesh.extent)
         self.u[fine.bc_nodes] = bcv[fine.bc_nodes]
         self.p = np.zeros(self.np_dofs)
         self._setup_done = False

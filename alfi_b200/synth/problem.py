@@ -43,6 +43,7 @@ class Config:
     domain: str = "ldc"          # "ldc": lid-driven cavity on [0, length]^d | "bfs": backward-facing step (2-D)
     mesh_file: str | None = None  # bfs: a Gmsh 2.2 file (examples/bfs2d/coarse*.msh); None = synth.gmsh.step_mesh(N)
     dirichlet_tags: tuple = (1, 2)  # bfs: Inflow + NoSlip (examples/bfs2d/bfs2d.py:25-27); Outflow stays natural
+    shape: tuple = ()            # ldc: box [0, length * shape[a]] with N * shape[a] base cells per axis (() = cube)
 
     @property
     def m(self):
@@ -67,6 +68,15 @@ CONFIGS = {
     # generator needs ~33 / ~57 GB of RAM and minutes for them (cfg5: 17 GB, 73 s).
     "ldc3d-sv-k3-n5": Config("ldc3d-sv-k3-n5", 3, 5, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
     "ldc3d-sv-k3-n6": Config("ldc3d-sv-k3-n6", 3, 6, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
+    # weak-scaling family of configs[4]: rank r of an sx x sy x sz rank grid gets one 16^3-cell brick (cfg5's
+    # finest mesh: 1.46 M dofs per rank); four levels from a base of 2 cells per brick edge, so that the coarsest
+    # level stays at cfg5's size (4^3 base cells, 23 871 dofs) on 8 ranks instead of growing with the rank count
+    "ldc3d-sv-k3-w1": Config("ldc3d-sv-k3-w1", 3, 2, 3, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
+    "ldc3d-sv-k3-w2": Config("ldc3d-sv-k3-w2", 3, 2, 3, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-", shape=(2, 1, 1)),
+    "ldc3d-sv-k3-w4": Config("ldc3d-sv-k3-w4", 3, 2, 3, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-", shape=(2, 2, 1)),
+    "ldc3d-sv-k3-w8": Config("ldc3d-sv-k3-w8", 3, 2, 3, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-", shape=(2, 2, 2)),
+    # the same family at test size (one 4^3-cell brick per rank, three levels)
+    "ldc3d-sv-k3-wtiny2": Config("ldc3d-sv-k3-wtiny2", 3, 1, 2, "sv", 3, "macro", True, re=100.0, sort_order="0+:1-", shape=(2, 1, 1)),
     # scaled-down members of the same families (tests, smoke, CPU-baseline sample)
     "ldc2d-sv-k2-tiny": Config("ldc2d-sv-k2-tiny", 2, 2, 1, "sv", 2, "macro", True, re=100.0, sort_order="0+:1-"),
     "ldc2d-pkp0-tiny": Config("ldc2d-pkp0-tiny", 2, 2, 2, "pkp0", 2, "star", False, re=100.0),
@@ -88,9 +98,12 @@ CONFIGS = {
 }
 
 
-def lid_wind(x):
-    """Lid profile of examples/ldc2d/ldc2d.py:32 / ldc3d/ldc3d.py:26 extended to the interior."""
+def lid_wind(x, extent=None):
+    """Lid profile of examples/ldc2d/ldc2d.py:32 / ldc3d/ldc3d.py:26 extended to the interior; on a box
+    [0, extent] the profile of the [0, 2]^d cavity is stretched axis by axis."""
     d = x.shape[1]
+    if extent is not None:
+        x = x * (2.0 / np.asarray(extent, dtype=np.float64))[None, :]
     w = np.zeros_like(x)
     prof = x[:, 0] ** 2 * (2 - x[:, 0]) ** 2 * (0.25 * x[:, 1] ** 2)
     if d == 3:
@@ -184,7 +197,9 @@ def assemble_level(cfg: Config, ld: LevelData, nu: float, gamma: float, advect: 
     lin = _linear_parts(cfg, ld)
     vals = nu * lin["visc"] + gamma * lin["div"]
     if advect != 0.0:
-        wind = ld.V.interpolate(step_wind if cfg.domain == "bfs" else lid_wind) if wind is None else wind
+        if wind is None:
+            ext = ld.V.mesh.extent
+            wind = ld.V.interpolate(step_wind if cfg.domain == "bfs" else (lambda xx: lid_wind(xx, ext)))
         adv = assemble_parts(ld.V, ld.pattern, wind, cfg.discretisation, want=("adv1", "adv2"))
         ld.adv1 = adv["adv1"]
         vals += advect * (adv["adv1"] + adv["adv2"])
@@ -215,7 +230,7 @@ def build_problem(cfg: Config | str, nu: float | None = None, with_transfer: boo
         base = read_msh(cfg.mesh_file) if cfg.mesh_file else step_mesh(cfg.N)
         hier = build_hierarchy_from(base, cfg.nref, cfg.bary)
     else:
-        hier = build_hierarchy(cfg.dim, cfg.N, cfg.nref, cfg.bary, cfg.length)
+        hier = build_hierarchy(cfg.dim, cfg.N, cfg.nref, cfg.bary, cfg.length, cfg.shape)
     levels = []
     for lev in hier:
         V = VectorSpace(lev.mesh, cfg.k, cfg.element)
