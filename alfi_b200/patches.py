@@ -36,6 +36,7 @@ class PatchSet:
     bs: int
     colours: np.ndarray | None = None     # int32 (npatch,), greedy colouring in iteration order
     blocks: np.ndarray | None = None      # int32 per dof entry: -1 separator, else block label (condensed form)
+    centres: np.ndarray | None = None     # (npatch, dim) coordinates of the patches' entities (partitioning only)
 
     @property
     def npatch(self):

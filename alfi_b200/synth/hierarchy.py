@@ -78,10 +78,12 @@ def _label_prolongation(level: Level, coarse: Level | None):
     plex.labels["prolongation"] = lab
 
 
-def build_hierarchy(dim: int, N: int, nref: int, bary: bool, length: float = 2.0, shape: tuple = ()) -> list[Level]:
+def build_hierarchy(dim: int, N: int, nref: int, bary: bool, length: float = 2.0, shape: tuple = (),
+                    counts: tuple = (), origin: tuple = ()) -> list[Level]:
+    """`counts` / `origin` (cells of the coarsest level, size length / N): the hierarchy over a sub-box of the grid."""
     levels: list[Level] = []
     for l in range(nref + 1):
-        macro = kuhn_mesh(dim, N * 2 ** l, length, shape)
+        macro = kuhn_mesh(dim, N * 2 ** l, length, shape, tuple(c * 2 ** l for c in counts), tuple(o * 2 ** l for o in origin))
         mesh = alfeld_split(macro) if bary else macro
         levels.append(Level(l, macro, mesh, SynthPlex(mesh), bary))
     d = dim

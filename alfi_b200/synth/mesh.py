@@ -49,6 +49,10 @@ class SimplexMesh:
     # box-shaped Kuhn grids (weak-scaling family): axis a has M * shape[a] cells and extent length * shape[a];
     # () = the cube
     shape: tuple = ()
+    # sub-boxes of a Kuhn grid (rank-local generation, synth/bricks.py): explicit cells per axis and the lower corner
+    # in cells of this grid; () = derived from M and shape, origin 0
+    counts: tuple = ()
+    origin: tuple = ()
     # boundary markers of general (Gmsh) meshes: (nb, dim) vertex tuples of tagged boundary facets, rows
     # ascending, and their physical tags; `facet_tag` (per facet id, 0 = untagged) is derived from them
     boundary_facets: np.ndarray | None = None
@@ -129,16 +133,27 @@ class SimplexMesh:
         return tuple(self.shape) if self.shape else (1,) * self.dim
 
     @property
+    def axis_counts(self):
+        """Cells per axis of the underlying Kuhn grid."""
+        return tuple(self.counts) if self.counts else tuple(self.M * v for v in self.axis_shape)
+
+    @property
+    def lower(self):
+        """Lower corner of the Kuhn box."""
+        h = self.length / self.M
+        return h * np.asarray(self.origin if self.origin else (0,) * self.dim, dtype=np.float64)
+
+    @property
     def extent(self):
-        """Upper corner of the Kuhn box [0, extent]."""
-        return self.length * np.asarray(self.axis_shape, dtype=np.float64)
+        """Upper corner of the Kuhn box (lower corner: `lower`, the origin unless this is a sub-box)."""
+        return self.lower + (self.length / self.M) * np.asarray(self.axis_counts, dtype=np.float64)
 
     def boundary_vertex_mask(self, tol=1e-12):
         x = self.coords
         return np.any((np.abs(x) < tol) | (np.abs(x - self.extent[None, :]) < tol), axis=1)
 
 
-def kuhn_mesh(dim: int, M: int, length: float = 2.0, shape: tuple = ()) -> SimplexMesh:
+def kuhn_mesh(dim: int, M: int, length: float = 2.0, shape: tuple = (), counts: tuple = (), origin: tuple = ()) -> SimplexMesh:
     """Kuhn triangulation of [0, length]^dim with M cells per side — or, with `shape`, of the box
     [0, length * shape[a]] with M * shape[a] cells along axis a (same cell size; the weak-scaling family).
 
@@ -149,13 +164,17 @@ def kuhn_mesh(dim: int, M: int, length: float = 2.0, shape: tuple = ()) -> Simpl
     shp = tuple(int(v) for v in shape) if shape else (1,) * dim
     if len(shp) != dim or min(shp) < 1:
         raise ValueError("shape must have one positive integer per axis")
-    Ma = [M * v for v in shp]
+    # `counts` / `origin` (in cells of size length / M): an arbitrary sub-box of the grid, same cut directions
+    Ma = [int(v) for v in counts] if counts else [M * v for v in shp]
+    org = np.asarray([int(v) for v in origin] if origin else [0] * dim, dtype=np.float64)
+    if len(Ma) != dim or min(Ma) < 1:
+        raise ValueError("counts must have one positive integer per axis")
     n1 = [m + 1 for m in Ma]
     h = length / M
     if dim == 2:
         # vertex id = i + n1x*j  (x fastest)
         J, I = np.meshgrid(np.arange(n1[1]), np.arange(n1[0]), indexing="ij")
-        coords = np.stack([I.ravel(), J.ravel()], axis=1) * h
+        coords = (np.stack([I.ravel(), J.ravel()], axis=1) + org[None, :]) * h
         j, i = np.meshgrid(np.arange(Ma[1]), np.arange(Ma[0]), indexing="ij")
         i, j = i.ravel(), j.ravel()
         ll = i + n1[0] * j
@@ -165,7 +184,7 @@ def kuhn_mesh(dim: int, M: int, length: float = 2.0, shape: tuple = ()) -> Simpl
         cells = np.stack([np.stack([ll, lr, ul], 1), np.stack([lr, ur, ul], 1)], axis=1).reshape(-1, 3)
     elif dim == 3:
         K, J, I = np.meshgrid(np.arange(n1[2]), np.arange(n1[1]), np.arange(n1[0]), indexing="ij")
-        coords = np.stack([I.ravel(), J.ravel(), K.ravel()], axis=1) * h
+        coords = (np.stack([I.ravel(), J.ravel(), K.ravel()], axis=1) + org[None, :]) * h
         k, j, i = np.meshgrid(np.arange(Ma[2]), np.arange(Ma[1]), np.arange(Ma[0]), indexing="ij")
         base = (i + n1[0] * (j + n1[1] * k)).ravel()
         step = np.array([1, n1[0], n1[0] * n1[1]])
@@ -181,7 +200,8 @@ def kuhn_mesh(dim: int, M: int, length: float = 2.0, shape: tuple = ()) -> Simpl
         raise ValueError("dim must be 2 or 3")
     cells = np.sort(cells.astype(np.int64), axis=1)
     m = SimplexMesh(dim=dim, coords=coords.astype(np.float64), cells=cells, length=length, M=M,
-                    shape=shp if any(v != 1 for v in shp) else ())
+                    shape=shp if any(v != 1 for v in shp) else (), counts=tuple(Ma) if counts else (),
+                    origin=tuple(int(v) for v in origin) if origin else ())
     return m.build_topology()
 
 
@@ -202,7 +222,8 @@ def alfeld_split(macro: SimplexMesh) -> SimplexMesh:
     mv[:nvm] = True
     # macro vertices keep their ids, so tagged boundary facets of the macro mesh are facets of the split
     m = SimplexMesh(dim=d, coords=coords, cells=cells, macro_vertex=mv, macro=macro,
-                    length=macro.length, M=macro.M, shape=macro.shape, boundary_facets=macro.boundary_facets,
+                    length=macro.length, M=macro.M, shape=macro.shape, counts=macro.counts, origin=macro.origin,
+                    boundary_facets=macro.boundary_facets,
                     boundary_tags=macro.boundary_tags)
     return m.build_topology()
 
@@ -241,8 +262,8 @@ def locate_in_kuhn(mesh: SimplexMesh, pts: np.ndarray) -> np.ndarray:
     centroids (strictly interior, so there are no ties).
     """
     d, h = mesh.dim, mesh.length / mesh.M
-    Ma = np.asarray([mesh.M * v for v in mesh.axis_shape], dtype=np.int64)
-    g = pts / h
+    Ma = np.asarray(mesh.axis_counts, dtype=np.int64)
+    g = (pts - mesh.lower[None, :]) / h
     ijk = np.clip(np.floor(g).astype(np.int64), 0, Ma[None, :] - 1)
     frac = g - ijk
     if d == 2:

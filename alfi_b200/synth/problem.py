@@ -171,10 +171,11 @@ def smoother_patches(cfg: Config, ld: LevelData) -> PatchSet:
     else:
         H, ents = star_points(plex)
     order = None
+    coords = np.array([plex.point_coords(p) for p in ents])
     if cfg.sort_order:
-        coords = np.array([plex.point_coords(p) for p in ents])
         order = iteration_order(coords, cfg.sort_order)
     ps = patch_dofs_from_points(plex, ld.V, H, bc_nodes=ld.bc_nodes, order=order)
+    ps.centres = coords
     greedy_colouring(ps, ld.V.ndofs)
     if cfg.bary:
         ps.blocks = macro_interior_blocks(plex, ld.V, ps)

@@ -1,0 +1,115 @@
+"""Rank-local generation (alfi_b200/synth/bricks.py): every rank builds only its brick + halo.  On small boxes the
+pieces are compared with the globally generated problem through the nodes' lattice keys: owned sets partition the
+nodes, exchange lists of neighbouring ranks match entry by entry, and SpMV / PCApply_PATCH / P_H executed on the
+rank-local data with the two exchange steps reproduce the global results."""
+import dataclasses
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from alfi_b200.synth.bricks import build_rank_local, node_keys
+from alfi_b200.synth.problem import CONFIGS, build_problem
+from oracle import distributed as od
+from oracle import hotpath as hp
+
+
+def update_ghosts(locs, xs):
+    for r, ll in enumerate(locs):
+        for peer, pos in ll.recv.items():
+            xs[r][pos] = xs[peer][locs[peer].send[r]]
+
+
+def reduce_ghosts(locs, ys):
+    packed = {(r, peer): ys[r][pos].copy() for r, ll in enumerate(locs) for peer, pos in ll.recv.items()}
+    for r, ll in enumerate(locs):
+        for peer in sorted(ll.send):
+            ys[r][ll.send[peer]] += packed[(peer, r)]
+        ys[r][ll.n_owned:] = 0.0
+
+
+@pytest.mark.parametrize("name,shape", [("ldc2d-sv-k2-tiny", (2, 1)), ("ldc2d-sv-k2-tiny", (2, 2)), ("ldc3d-sv-k3-tiny", (2, 1, 1)),
+                                        ("ldc2d-pkp0-tiny", (3, 1)), ("ldc3d-sv-k3-wtiny2", None), ("ldc3d-pkp0-tiny", (1, 2, 1))])
+def test_rank_local_generation_equals_the_global_problem(name, shape):
+    cfg = CONFIGS[name] if shape is None else dataclasses.replace(CONFIGS[name], shape=shape)
+    shape = cfg.shape
+    nranks = int(np.prod(shape))
+    glob = build_problem(cfg, gamma=10.0, nu=0.2)
+    rl = [build_rank_local(cfg, r, nu=0.2, gamma=10.0) for r in range(nranks)]
+    bs = glob.finest.V.bs
+    rng = np.random.default_rng(6)
+    # level 0 is the global coarse level
+    assert rl[0].level0.n_nodes == glob.levels[0].V.nnodes
+    assert np.allclose(rl[0].level0.vals, glob.levels[0].A.vals)
+    for l in range(1, len(glob.levels)):
+        ld = glob.levels[l]
+        lv = hp.level_from_host(ld)
+        _, gkey = node_keys(ld.V.node_coords, cfg.N * 2 ** l, cfg.length, shape)
+        order = np.argsort(gkey)
+        locs = [p.local[l] for p in rl]
+        g_of = []                                        # global dof of every local dof
+        for p, ll in zip(rl, locs):
+            pos = np.searchsorted(gkey[order], p.keys[l])
+            assert (gkey[order][pos] == p.keys[l]).all()
+            g_of.append((order[pos][:, None] * bs + np.arange(bs)[None, :]).ravel())
+        owned = np.concatenate([g[:ll.n_owned] for g, ll in zip(g_of, locs)])
+        assert np.array_equal(np.sort(owned), np.arange(ld.V.ndofs)), "owned sets must partition the dofs"
+        for r, ll in enumerate(locs):                    # exchange lists agree entry by entry
+            for peer, pos in ll.recv.items():
+                assert np.array_equal(g_of[r][pos], g_of[peer][locs[peer].send[r]])
+            assert sum(v.size for v in ll.recv.values()) == ll.n_local - ll.n_owned
+        assert sorted(np.concatenate([ll.patch_ids for ll in locs]).size for _ in [0]) == [ld.patches.npatch]
+        data = [od.LocalRankData(ll) for ll in locs]
+        x = rng.standard_normal(lv.n)
+        x[lv.bc_dofs] = 0
+
+        def gather(ys):
+            out = np.full(lv.n, np.nan)
+            for g, ll, y in zip(g_of, locs, ys):
+                out[g[:ll.n_owned]] = y[:ll.n_owned]
+            return out
+        xs = [x[g].copy() for g in g_of]
+        for ll, v in zip(locs, xs):
+            v[ll.n_owned:] = np.nan                      # ghosts arrive through the exchange only
+        update_ghosts(locs, xs)
+        assert all(np.isfinite(v).all() for v in xs)
+        # SpMV on the owned rows
+        ys = []
+        for ll, d_, v in zip(locs, data, xs):
+            y = np.zeros(ll.n_local)
+            y[:ll.n_owned] = (d_.A @ v)[:ll.n_owned]
+            ys.append(y)
+        assert np.linalg.norm(gather(ys) - lv.A @ x) <= 1e-12 * np.linalg.norm(lv.A @ x)
+        # PCApply_PATCH: this rank's patches, ghost -> owner sum, Dirichlet rows
+        ys = []
+        for ll, d_, v in zip(locs, data, xs):
+            y = np.zeros(ll.n_local)
+            for p in ll.patch_order:
+                I, X = d_.patches[p]
+                if I.size:
+                    y[I] += X @ v[I]
+            ys.append(y)
+        reduce_ghosts(locs, ys)
+        for ll, y, v in zip(locs, ys, xs):
+            bc = ll.bc_dofs[ll.bc_dofs < ll.n_owned]
+            y[bc] = v[bc]
+        want = hp.smoother_apply(x, lv.offsets, lv.dofs, lv.order, lv.factors, lv.bc_dofs)
+        assert np.linalg.norm(gather(ys) - want) <= 1e-11 * np.linalg.norm(want)
+        # P_H of the owned rows, columns in the coarser level's local set (or the replicated level 0)
+        P = ld.P.tocsr() if ld.P_dof_level else sp.kron(ld.P, sp.identity(bs), format="csr")
+        c = rng.standard_normal(P.shape[1])
+        if l == 1:
+            # global level-0 numbering of the bricks == numbering of the global generator (same mesh)
+            cs = [c] * nranks
+        else:
+            cs = [c[g] for g in g_of_prev]
+        got = [ll.P @ cv for ll, cv in zip(locs, cs)]
+        full = P @ c
+        for g, ll, v in zip(g_of, locs, got):
+            assert np.allclose(v, full[g[:ll.n_owned]], rtol=0, atol=1e-12)
+        # cell patches: every coarse cell owned once; coarse-boundary and Dirichlet lists are the global ones
+        assert sum(ll.cell_ids.size for ll in locs) == ld.cell_patches.npatch
+        for g, ll in zip(g_of, locs):
+            assert np.array_equal(np.sort(g[ll.cb_dofs]), np.intersect1d(ld.cb_dofs, g))
+            assert np.array_equal(np.sort(g[ll.bc_dofs]), np.intersect1d(ld.bc_dofs, g))
+        g_of_prev = g_of
