@@ -139,13 +139,17 @@ class SimplexMesh:
 
     @property
     def lower(self):
-        """Lower corner of the Kuhn box."""
+        """Lower corner of the Kuhn box (general meshes: of the bounding box)."""
+        if not self.M:
+            return self.coords.min(axis=0)
         h = self.length / self.M
         return h * np.asarray(self.origin if self.origin else (0,) * self.dim, dtype=np.float64)
 
     @property
     def extent(self):
         """Upper corner of the Kuhn box (lower corner: `lower`, the origin unless this is a sub-box)."""
+        if not self.M:
+            return self.coords.max(axis=0)
         return self.lower + (self.length / self.M) * np.asarray(self.axis_counts, dtype=np.float64)
 
     def boundary_vertex_mask(self, tol=1e-12):
