@@ -75,6 +75,10 @@ CONFIGS = {
     "ldc3d-sv-k3-w2": Config("ldc3d-sv-k3-w2", 3, 2, 3, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-", shape=(2, 1, 1)),
     "ldc3d-sv-k3-w4": Config("ldc3d-sv-k3-w4", 3, 2, 3, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-", shape=(2, 2, 1)),
     "ldc3d-sv-k3-w8": Config("ldc3d-sv-k3-w8", 3, 2, 3, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-", shape=(2, 2, 2)),
+    # cfg5 itself as a 2 x 2 x 2 grid of 8^3-cell bricks (strong scaling at 8 ranks with rank-local generation and a
+    # brick partition): base 2 cells per brick edge of length 1, so the domain is [0, 2]^3 and nu = 1 / 2500 = 2 / 5000
+    "ldc3d-sv-k3-s8": Config("ldc3d-sv-k3-s8", 3, 2, 2, "sv", 3, "macro", True, re=2500.0, sort_order="0+:1-", length=1.0,
+                             shape=(2, 2, 2)),
     # the same family at test size (one 4^3-cell brick per rank, three levels)
     "ldc3d-sv-k3-wtiny2": Config("ldc3d-sv-k3-wtiny2", 3, 1, 2, "sv", 3, "macro", True, re=100.0, sort_order="0+:1-", shape=(2, 1, 1)),
     # scaled-down members of the same families (tests, smoke, CPU-baseline sample)

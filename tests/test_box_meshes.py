@@ -61,3 +61,19 @@ def test_box_problem_patches_and_cycle(name, shape):
     f = np.random.default_rng(3).standard_normal(lv[L].n)
     f[lv[L].bc_dofs] = 0
     assert abs(f @ hp.prolong(lv[L], c) - hp.restrict(lv[L], f, lv[L - 1].bc_dofs) @ c) <= 1e-10 * np.linalg.norm(f) * np.linalg.norm(c)
+
+
+def test_brick_grid_of_a_cube_is_the_cube_problem():
+    """A 2 x 2 x 2 grid of unit bricks is the [0, 2]^3 cube (config ldc3d-sv-k3-s8 == cfg5): same mesh, numbering and
+    operator when the viscosity is the same."""
+    cube = dataclasses.replace(CONFIGS["ldc3d-sv-k3-tiny"], N=2, nref=1)
+    grid = dataclasses.replace(cube, N=1, length=1.0, shape=(2, 2, 2), re=cube.re / 2)
+    assert abs(cube.nu - grid.nu) < 1e-15
+    a, b = build_problem(cube), build_problem(grid)
+    for la, lb in zip(a.levels, b.levels):
+        assert np.array_equal(la.level.mesh.cells, lb.level.mesh.cells)
+        assert np.array_equal(la.A.colidx, lb.A.colidx) and np.allclose(la.A.vals, lb.A.vals, rtol=1e-13, atol=1e-13)
+        if la.patches is not None:
+            assert np.array_equal(la.patches.dofs, lb.patches.dofs) and np.array_equal(la.patches.order, lb.patches.order)
+    s8, c5 = CONFIGS["ldc3d-sv-k3-s8"], CONFIGS["ldc3d-sv-k3"]
+    assert abs(s8.nu - c5.nu) < 1e-18 and s8.N * 2 == c5.N and s8.nref == c5.nref and s8.length * 2 == c5.length
