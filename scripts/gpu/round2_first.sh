@@ -18,3 +18,5 @@ import json; d=json.load(open('gpurun_out/bench_r2_first.json')); print(d['ms_pe
 # after `git am scripts/r2_prep/*.patch` + build, 2 GPUs (distributed level vectors):
 #   gpurun --gpus 2 --timeout 900 -- 'for c in ldc3d-sv-k3-tiny ldc2d-pkp0-tiny ldc3d-pkp0-tiny; do timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 scripts/dist_check_halo.py $c; done; ALFIB_PEER=1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 scripts/dist_check_halo.py ldc3d-sv-k3-tiny; timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29515 scripts/dist_check_halo.py ldc3d-sv-k3 --time'
 # weak scaling (r2_prep/0007), 2 GPUs first:  gpurun --gpus 2 --timeout 1200 -- 'timeout 1000 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29516 bench.py --gpus 2 --steps 5 --warmup 3 --scaling weak --no-cpu-baseline > gpurun_out/bench_r2_weak2.json 2> gpurun_out/bench_r2_weak2.log; tail -3 gpurun_out/bench_r2_weak2.log'
+# rank-locally generated problem on 2 GPUs vs the serial oracle (r2_prep/0008), before the weak bench:
+#   gpurun --gpus 2 --timeout 600 -- 'timeout 250 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 scripts/dist_check_bricks.py; ALFIB_PEER=1 timeout 250 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 scripts/dist_check_bricks.py'
