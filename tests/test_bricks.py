@@ -113,3 +113,85 @@ def test_rank_local_generation_equals_the_global_problem(name, shape):
             assert np.array_equal(np.sort(g[ll.cb_dofs]), np.intersect1d(ld.cb_dofs, g))
             assert np.array_equal(np.sort(g[ll.bc_dofs]), np.intersect1d(ld.bc_dofs, g))
         g_of_prev = g_of
+
+
+def _brick_worker(rank, world, port, out):
+    """One process per rank (gloo): each builds ONLY its brick; ghost update / ghost->owner sum with point-to-point
+    messages driven by its own lists; rank 0 alone builds the global problem for the comparison."""
+    import os
+
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    cfg = dataclasses.replace(CONFIGS["ldc2d-sv-k2-tiny"], shape=(2, 1))
+    p = build_rank_local(cfg, rank, nu=0.2, gamma=10.0)
+    ll = p.local[1]
+    bs = ll.bs
+    key = p.keys[1]
+    x = (np.sin(0.37 * (key % 1000003))[:, None] + 0.1 * np.arange(bs)[None, :]).ravel()
+    x[ll.bc_dofs] = 0.0
+    truth = x.copy()
+    x[ll.n_owned:] = np.nan
+
+    def exchange(loc, mine, theirs, add):
+        reqs, bufs = [], {}
+        for peer in sorted(mine):
+            reqs.append(dist.isend(torch.from_numpy(loc[mine[peer]].copy()), dst=peer))
+        for peer in sorted(theirs):
+            bufs[peer] = torch.empty(theirs[peer].size, dtype=torch.float64)
+            reqs.append(dist.irecv(bufs[peer], src=peer))
+        for q in reqs:
+            q.wait()
+        for peer in sorted(bufs):
+            if add:
+                loc[theirs[peer]] += bufs[peer].numpy()
+            else:
+                loc[theirs[peer]] = bufs[peer].numpy()
+
+    exchange(x, ll.send, ll.recv, False)                        # owner -> ghost
+    ok_update = bool(np.array_equal(x, truth))                  # the key-defined field arrives bit for bit
+    d = od.LocalRankData(ll)
+    y = np.zeros(ll.n_local)
+    for q in ll.patch_order:
+        I, X = d.patches[q]
+        if I.size:
+            y[I] += X @ x[I]
+    exchange(y, ll.recv, ll.send, True)                         # ghost -> owner sum
+    y[ll.n_owned:] = 0.0
+    bc = ll.bc_dofs[ll.bc_dofs < ll.n_owned]
+    y[bc] = x[bc]
+    pieces = [None] * world
+    dist.all_gather_object(pieces, (key[:ll.n_owned // bs], y[:ll.n_owned]))
+    err = None
+    if rank == 0:
+        glob = build_problem(cfg, gamma=10.0, nu=0.2)
+        lv = hp.level_from_host(glob.levels[1])
+        _, gkey = node_keys(glob.levels[1].V.node_coords, cfg.N * 2, cfg.length, cfg.shape)
+        xg = (np.sin(0.37 * (gkey % 1000003))[:, None] + 0.1 * np.arange(bs)[None, :]).ravel()
+        xg[lv.bc_dofs] = 0.0
+        want = hp.smoother_apply(xg, lv.offsets, lv.dofs, lv.order, lv.factors, lv.bc_dofs)
+        order = np.argsort(gkey)
+        got = np.full(xg.size, np.nan)
+        for k, v in pieces:
+            pos = order[np.searchsorted(gkey[order], k)]
+            got[(pos[:, None] * bs + np.arange(bs)[None, :]).ravel()] = v
+        err = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    out[rank] = (ok_update, err, int(ll.n_local - ll.n_owned))
+    dist.destroy_process_group()
+
+
+def test_bricks_world2_gloo():
+    import os
+
+    import torch.multiprocessing as mp
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_brick_worker, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    assert all(res[r][0] and res[r][2] > 0 for r in range(world)), res
+    assert res[0][1] is not None and res[0][1] <= 1e-11, res
