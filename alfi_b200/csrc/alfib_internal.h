@@ -234,7 +234,7 @@ inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 void launch_bsr_spmv(alfib_ctx* c, const Level& L, const double* vals, const double* x, double* y,
                      const double* b /* nullptr: y = A x ; else y = b - A x */);
 void launch_csr_apply(alfib_ctx* c, int nrows, int bs, const int32_t* rowptr, const int32_t* colidx,
-                      const double* vals, const double* x, double* y);
+                      const double* vals, const double* x, double* y, int64_t nnz);
 void launch_transpose_blocks(alfib_ctx* c, double* vals, int64_t nnzb, int bs);
 // comm.cu
 void comm_unique_id(void* out128);

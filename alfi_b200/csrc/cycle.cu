@@ -53,7 +53,7 @@ void prolong_device(alfib_ctx* c, Level& L, int level, const double* coarse, dou
   L.t2.alloc(L.n);
   L.r.alloc(L.n);
   double* rhs = L.r.p;
-  launch_csr_apply(c, L.p_rows, L.p_bs, L.p_rowptr.p, L.p_colidx.p, L.p_vals.p, coarse, rhs);
+  launch_csr_apply(c, L.p_rows, L.p_bs, L.p_rowptr.p, L.p_colidx.p, L.p_vals.p, coarse, rhs, (int64_t)L.p_vals.n);
   if (L.has_d) {
     launch_bsr_spmv(c, L, L.dvals.p, rhs, L.t1.p, nullptr);          // b = gamma D rhs
     launch_set_rows(c, L.t1.p, nullptr, L.cb.p, L.ncb);              // coarse-boundary rows zeroed
@@ -80,7 +80,7 @@ void restrict_device(alfib_ctx* c, Level& L, Level& Lc, int level, const double*
     launch_sub(c, L.n, fine, L.t1.p, L.t2.p);                        // r2 = fine - b
     src = L.t2.p;
   }
-  launch_csr_apply(c, L.p_cols, L.p_bs, L.pt_rowptr.p, L.pt_colidx.p, L.pt_vals.p, src, coarse);
+  launch_csr_apply(c, L.p_cols, L.p_bs, L.pt_rowptr.p, L.pt_colidx.p, L.pt_vals.p, src, coarse, (int64_t)L.pt_vals.n);
   launch_set_rows(c, coarse, nullptr, Lc.bc.p, Lc.nbc);
 }
 

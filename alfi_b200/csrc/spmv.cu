@@ -79,6 +79,35 @@ __global__ void csr_apply_kernel(int nrows, const int32_t* __restrict__ rowptr, 
   for (int r = 0; r < BS; ++r) y[(int64_t)i * BS + r] = acc[r];
 }
 
+// Long rows (P_H^T on the coarser levels has hundreds of entries per row and few rows): one warp per row,
+// lanes stride over the entries, fixed-order shuffle reduction (deterministic).
+template <int BS>
+__global__ void csr_apply_warp_kernel(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                      const double* __restrict__ vals, const double* __restrict__ x,
+                                      double* __restrict__ y) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  double acc[BS];
+#pragma unroll
+  for (int r = 0; r < BS; ++r) acc[r] = 0.0;
+  const int k1 = __ldg(rowptr + row + 1);
+  for (int k = __ldg(rowptr + row) + lane; k < k1; k += 32) {
+    const double v = __ldg(vals + k);
+    const double* __restrict__ xc = x + (int64_t)__ldg(colidx + k) * BS;
+#pragma unroll
+    for (int r = 0; r < BS; ++r) acc[r] = fma(v, __ldg(xc + r), acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < BS; ++r)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < BS; ++r) y[(int64_t)row * BS + r] = acc[r];
+  }
+}
+
 template <int BS>
 __global__ void transpose_blocks_kernel(double* vals, int64_t nnzb) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,8 +155,24 @@ void launch_bsr_spmv(alfib_ctx* c, const Level& L, const double* vals, const dou
 }
 
 void launch_csr_apply(alfib_ctx* c, int nrows, int bs, const int32_t* rowptr, const int32_t* colidx,
-                      const double* vals, const double* x, double* y) {
+                      const double* vals, const double* x, double* y, int64_t nnz) {
   const int threads = 256;
+  if (nrows == 0) return;
+  // mean row length >= 16: a warp per row (restriction on the coarser levels); otherwise a thread per row
+  if (nnz >= (int64_t)16 * nrows) {
+    const int wblocks = cdiv((int64_t)nrows * 32, threads);
+    if (bs == 1)
+      csr_apply_warp_kernel<1><<<wblocks, threads, 0, c->stream>>>(nrows, rowptr, colidx, vals, x, y);
+    else if (bs == 2)
+      csr_apply_warp_kernel<2><<<wblocks, threads, 0, c->stream>>>(nrows, rowptr, colidx, vals, x, y);
+    else if (bs == 3)
+      csr_apply_warp_kernel<3><<<wblocks, threads, 0, c->stream>>>(nrows, rowptr, colidx, vals, x, y);
+    else
+      throw DeviceError{ALFIB_EINVAL, "block size must be 1, 2 or 3"};
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return;
+  }
   const int blocks = cdiv(nrows, threads);
   if (blocks == 0) return;
   if (bs == 1)
