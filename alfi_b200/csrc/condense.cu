@@ -48,7 +48,7 @@ __device__ __forceinline__ double fetch_src(const int32_t* __restrict__ ci, int 
   return e >= 0 ? __ldg(srcA + e) : __ldg(srcB + (~e));
 }
 
-template <int G, bool ATOMIC>
+template <int G, bool ATOMIC, bool ACCUM>
 __device__ __forceinline__ void tile_op_body(const double* __restrict__ mat, const int32_t* __restrict__ ci,
                                              const int32_t* __restrict__ ri, double* __restrict__ priv,
                                              const int nrows, const int n, const double* __restrict__ srcA,
@@ -96,8 +96,13 @@ __device__ __forceinline__ void tile_op_body(const double* __restrict__ mat, con
   if (grp == 0 && active) {
     const int r = 2 * l;
     if (priv) {
-      priv[r] = acc0;
-      if (r + 1 < nrows) priv[r + 1] = acc1;
+      if (ACCUM) {                                   // lists with column chunks of wide tiles: partial products
+        atomicAdd(priv + r, acc0);
+        if (r + 1 < nrows) atomicAdd(priv + r + 1, acc1);
+      } else {
+        priv[r] = acc0;
+        if (r + 1 < nrows) priv[r + 1] = acc1;
+      }
     }
     if (ri) {
       if (ATOMIC) {
@@ -118,7 +123,7 @@ __device__ __forceinline__ void tile_op_body(const double* __restrict__ mat, con
 // the gathered source has arrived, a partial last batch is just predicated loads, and there is no
 // drain between batches.  The source index list is read two 32-column chunks ahead and the source
 // values one chunk ahead (no dependent wait at a chunk switch).
-template <int G, bool ATOMIC>
+template <int G, bool ATOMIC, bool ACCUM>
 __device__ __forceinline__ void tile_op_body_v2(const double* __restrict__ mat, const int32_t* __restrict__ ci,
                                                 const int32_t* __restrict__ ri, double* __restrict__ priv,
                                                 const int nrows, const int n, const double* __restrict__ srcA,
@@ -169,8 +174,13 @@ __device__ __forceinline__ void tile_op_body_v2(const double* __restrict__ mat, 
   if (grp == 0 && active) {
     const int r = 2 * l;
     if (priv) {
-      priv[r] = acc0;
-      if (r + 1 < nrows) priv[r + 1] = acc1;
+      if (ACCUM) {                                   // lists with column chunks of wide tiles: partial products
+        atomicAdd(priv + r, acc0);
+        if (r + 1 < nrows) atomicAdd(priv + r + 1, acc1);
+      } else {
+        priv[r] = acc0;
+        if (r + 1 < nrows) priv[r + 1] = acc1;
+      }
     }
     if (ri) {
       if (ATOMIC) {
@@ -184,7 +194,7 @@ __device__ __forceinline__ void tile_op_body_v2(const double* __restrict__ mat, 
   }
 }
 
-template <bool ATOMIC>
+template <bool ATOMIC, bool ACCUM = false>
 __global__ void __launch_bounds__(128) tile_ops_kernel_v2(const TileOp* __restrict__ ops, int nops,
                                                           const int32_t* __restrict__ cidx,
                                                           const double* __restrict__ store,
@@ -204,14 +214,14 @@ __global__ void __launch_bounds__(128) tile_ops_kernel_v2(const TileOp* __restri
   const int nrows = op->nrows, ncols = op->ncols;
   const int half = (nrows + 1) >> 1;
   if (half <= 8)
-    tile_op_body_v2<4, ATOMIC>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+    tile_op_body_v2<4, ATOMIC, ACCUM>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
   else if (half <= 16)
-    tile_op_body_v2<2, ATOMIC>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+    tile_op_body_v2<2, ATOMIC, ACCUM>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
   else
-    tile_op_body_v2<1, ATOMIC>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+    tile_op_body_v2<1, ATOMIC, ACCUM>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
 }
 
-template <bool ATOMIC>
+template <bool ATOMIC, bool ACCUM = false>
 __global__ void __launch_bounds__(128) tile_ops_kernel(const TileOp* __restrict__ ops, int nops,
                                                        const int32_t* __restrict__ cidx,
                                                        const double* __restrict__ store,
@@ -231,11 +241,11 @@ __global__ void __launch_bounds__(128) tile_ops_kernel(const TileOp* __restrict_
   const int nrows = op->nrows, ncols = op->ncols;
   const int half = (nrows + 1) >> 1;
   if (half <= 8)
-    tile_op_body<4, ATOMIC>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+    tile_op_body<4, ATOMIC, ACCUM>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
   else if (half <= 16)
-    tile_op_body<2, ATOMIC>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+    tile_op_body<2, ATOMIC, ACCUM>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
   else
-    tile_op_body<1, ATOMIC>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+    tile_op_body<1, ATOMIC, ACCUM>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
 }
 
 // K2: separator right-hand sides, rs[e] = x[sepdofs[e]] - sum_j g1[cg1[j]], j in [cptr[e], cptr[e+1])
@@ -466,7 +476,7 @@ void condense_setup(alfib_ctx* c, Level& L, PatchSet& ps, const int32_t* block_o
   const char* env_shared = std::getenv("ALFIB_CONDENSE_SHARED");
   const bool allow_shared = !(env_shared && env_shared[0] == '0');
   try {
-    build_condensed_host(pv, block_of_dof, cd.h, allow_shared);
+    build_condensed_host(pv, block_of_dof, cd.h, allow_shared, /*split_wide=*/!c->deterministic);
   } catch (const std::runtime_error& e) {
     cd.h = CondensedHost();
     throw DeviceError{ALFIB_EINVAL, e.what()};
@@ -569,9 +579,20 @@ void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, P
     c->launches++;
   }
   // K3 (separator solve + scatter), K4 (block back-substitution + scatter)
+  if (h.any_accum) CUDA_TRY(cudaMemsetAsync(cd.us.p, 0, cd.us.n * sizeof(double), c->stream));
   const bool coloured = c->deterministic && !ps.repeated;
-  auto run = [&](const TileOp* ops, int nops, const double* srcA, const double* srcB, double* dstB, bool atomic) {
+  const bool s_atomic = ps.repeated || h.any_accum;      // column chunks of one tile add to the same rows
+  auto run = [&](const TileOp* ops, int nops, const double* srcA, const double* srcB, double* dstB, bool atomic,
+                 bool accum = false) {
     if (nops <= 0) return;
+    if (accum) {                     // X_SS lists with column chunks: every private write is an atomicAdd into zeroed us
+      if (v1)
+        tile_ops_kernel<true, true><<<cdiv(nops, wpb), threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB);
+      else
+        tile_ops_kernel_v2<true, true><<<cdiv(nops, wpb), threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB);
+      c->launches++;
+      return;
+    }
     if (v1) {
       if (atomic)
         tile_ops_kernel<true><<<cdiv(nops, wpb), threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB);
@@ -589,11 +610,11 @@ void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, P
     // shared blocks: K3 as below; K3b sums the separator solutions per distinct block; K4 is one launch
     // over the distinct blocks, which are pairwise disjoint (plain stores, deterministic in every mode)
     if (!coloured && ps.ncolour > 1) {
-      run(cd.opsS.p, nS, cd.rs.p, nullptr, cd.us.p, true);
+      run(cd.opsS.p, nS, cd.rs.p, nullptr, cd.us.p, true, h.any_accum);
     } else {
       for (int col = 0; col < ps.ncolour; ++col) {
         const int s = h.s_colour_start[col], e = h.s_colour_start[col + 1];
-        run(cd.opsS.p + s, e - s, cd.rs.p, nullptr, cd.us.p, ps.repeated);
+        run(cd.opsS.p + s, e - s, cd.rs.p, nullptr, cd.us.p, s_atomic, h.any_accum);
       }
     }
     if (h.g1_total) {
@@ -602,12 +623,12 @@ void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, P
     }
     run(cd.opsDW.p, nDW, x, cd.z.p, nullptr, false);
   } else if (!coloured && ps.ncolour > 1) {
-    run(cd.opsS.p, nS, cd.rs.p, nullptr, cd.us.p, true);
+    run(cd.opsS.p, nS, cd.rs.p, nullptr, cd.us.p, true, h.any_accum);
     run(cd.opsDW.p, nDW, x, cd.us.p, nullptr, true);
   } else {
     for (int col = 0; col < ps.ncolour; ++col) {
       const int s = h.s_colour_start[col], e = h.s_colour_start[col + 1];
-      run(cd.opsS.p + s, e - s, cd.rs.p, nullptr, cd.us.p, ps.repeated);
+      run(cd.opsS.p + s, e - s, cd.rs.p, nullptr, cd.us.p, s_atomic, h.any_accum);
     }
     for (int col = 0; col < ps.ncolour; ++col) {
       const int s = h.dw_colour_start[col], e = h.dw_colour_start[col + 1];

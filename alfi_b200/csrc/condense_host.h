@@ -24,7 +24,13 @@ struct TileOp {
   long long row;    // offset into cidx of the nrows global destination dofs, or -1
   long long priv;   // offset into the private destination buffer (plain store), or -1
   int nrows, ncols; // nrows <= ALFIB_TILE_ROWS
+  int flags;        // TILEOP_ACCUM: the private destination is accumulated (atomicAdd) instead of stored
+  int pad_;
 };
+enum { TILEOP_ACCUM = 1 };
+#ifndef ALFIB_SPLIT_COLS
+#define ALFIB_SPLIT_COLS 256   // X_SS tiles wider than 2x this are cut into column chunks (one op each)
+#endif
 
 // Per (patch, block) descriptor of the per-Newton-step block setup (D = A_kk^-1, V = A_Nk D, W = D A_kN)
 struct BlockDesc {
@@ -65,6 +71,7 @@ struct CondensedHost {
   std::vector<TileOp> opsV, opsS, opsDW;
   std::vector<int> s_colour_start, dw_colour_start;   // ncolour+1 ranges of opsS / opsDW
   int64_t index_bytes = 0;              // bytes of index data one apply reads (roofline accounting)
+  bool any_accum = false;               // some X_SS ops are column chunks: us is zeroed per apply and accumulated
 
   // ---- shared blocks -----------------------------------------------------------------------------------
   // A block with a given dof set occurs in several patches (a macro cell lies in the macro stars of all
@@ -236,8 +243,8 @@ inline void build_shared_blocks(const PatchView& pv, CondensedHost& cd) {
   for (int64_t k = 0; k < nd; ++k) {
     const BlockDesc& d = cd.sblocks[k];
     if (cd.svisits[k] == 0) continue;
-    if (d.m > 0) cd.opsV.push_back(TileOp{d.voff, sblk_list[k], -1, cd.uoff[k], d.m, d.b});
-    cd.opsDW.push_back(TileOp{d.dwoff, sblk_list[k], sblk_list[k], -1, d.b, d.b + d.m});
+    if (d.m > 0) cd.opsV.push_back(TileOp{d.voff, sblk_list[k], -1, cd.uoff[k], d.m, d.b, 0, 0});
+    cd.opsDW.push_back(TileOp{d.dwoff, sblk_list[k], sblk_list[k], -1, d.b, d.b + d.m, 0, 0});
   }
   cd.dw_colour_start.assign(pv.ncolour + 1, (int)cd.opsDW.size());
   if (pv.ncolour) cd.dw_colour_start[0] = 0;
@@ -251,7 +258,7 @@ inline void build_shared_blocks(const PatchView& pv, CondensedHost& cd) {
 // (any non-negative integer, local to the patch).  Blocks must be pairwise decoupled in the BSR
 // pattern; this is checked here, so a wrong hint is an error, never a wrong answer.
 inline void build_condensed_host(const PatchView& pv, const int32_t* block_of_dof, CondensedHost& cd,
-                                 bool allow_shared = true) {
+                                 bool allow_shared = true, bool split_wide = false) {
   cd = CondensedHost();
   const int npatch = pv.npatch, bs = pv.bs;
   cd.sepoff.assign(npatch + 1, 0);
@@ -429,7 +436,7 @@ inline void build_condensed_host(const PatchView& pv, const int32_t* block_of_do
   for (int64_t q = 0; q < cd.nblocks; ++q) {
     const BlockDesc& d = cd.blocks[q];
     if (d.m == 0) continue;
-    cd.opsV.push_back(TileOp{d.voff, blk_list[q], -1, cd.g1off[q], d.m, d.b});
+    cd.opsV.push_back(TileOp{d.voff, blk_list[q], -1, cd.g1off[q], d.m, d.b, 0, 0});
   }
   cd.s_colour_start.assign(pv.ncolour + 1, 0);
   cd.dw_colour_start.assign(pv.ncolour + 1, 0);
@@ -442,11 +449,23 @@ inline void build_condensed_host(const PatchView& pv, const int32_t* block_of_do
       const int ns = (int)(cd.sepoff[p + 1] - so);
       for (int row0 = 0; row0 < ns; row0 += ALFIB_TILE_ROWS) {
         const int rows = std::min(ns - row0, ALFIB_TILE_ROWS);
-        cd.opsS.push_back(TileOp{cd.ssoff[p] + (int64_t)row0 * ns, rs_list[p], sg_list[p] + row0, so + row0, rows, ns});
+        const int64_t tile = cd.ssoff[p] + (int64_t)row0 * ns;
+        if (split_wide && ns > 2 * ALFIB_SPLIT_COLS) {
+          // wide separator (a coarse level held as one patch, literal 3-D macro stars): column chunks, each op
+          // adds its partial product to us (atomicAdd) and to y
+          for (int c0 = 0; c0 < ns; c0 += ALFIB_SPLIT_COLS) {
+            const int nc = std::min(ns - c0, ALFIB_SPLIT_COLS);
+            cd.opsS.push_back(TileOp{tile + (int64_t)c0 * ch_roundup2(rows), rs_list[p] + c0, sg_list[p] + row0, so + row0,
+                                     rows, nc, TILEOP_ACCUM, 0});
+          }
+          cd.any_accum = true;
+        } else {
+          cd.opsS.push_back(TileOp{tile, rs_list[p], sg_list[p] + row0, so + row0, rows, ns, 0, 0});
+        }
       }
       for (int64_t q = cd.blk_start[p]; q < cd.blk_start[p + 1]; ++q) {
         const BlockDesc& d = cd.blocks[q];
-        cd.opsDW.push_back(TileOp{d.dwoff, blk_list[q], blk_list[q], -1, d.b, d.b + d.m});
+        cd.opsDW.push_back(TileOp{d.dwoff, blk_list[q], blk_list[q], -1, d.b, d.b + d.m, 0, 0});
       }
     }
   }

@@ -178,6 +178,28 @@ void coarse_gemv(alfib_ctx* c, const double* b, double* y, int accumulate) {
 
 }  // namespace
 
+namespace {
+
+// Condensed coarse inverse: the coarse level registered as ONE patch with macro-cell blocks on
+// (level 0, ALFIB_PATCHES_SMOOTHER) — X_SS = inv[S, S] of the dense inverse in the 64-row tile layout of
+// condense.cu; D, V, W of the blocks come from condense_blocks_kernel.  n = number of separator dofs.
+__global__ void extract_xss_kernel(const double* __restrict__ inv, int64_t ld, const int32_t* __restrict__ sepdofs,
+                                   int ns, double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)ns * ns) return;
+  const int r = (int)(e % ns), col = (int)(e / ns);                 // r fastest: consecutive rows of one column
+  const int t = r / ALFIB_TILE_ROWS, row0 = t * ALFIB_TILE_ROWS;
+  const int rows = min(ns - row0, ALFIB_TILE_ROWS), rt = (rows + 1) & ~1;
+  out[(int64_t)row0 * ns + (int64_t)col * rt + (r - row0)] = inv[(int64_t)sepdofs[r] + ld * (int64_t)sepdofs[col]];
+}
+
+bool coarse_is_condensed(const Level& L0) {
+  const PatchSet& ps = L0.ps[ALFIB_PATCHES_SMOOTHER];
+  return ps.npatch == 1 && ps.cond.on;
+}
+
+}  // namespace
+
 void coarse_factor_device(alfib_ctx* c) {
   Level* L0 = c->levels[0];
   ALFIB_REQUIRE(L0 && L0->has_values, "level 0 has no operator values");
@@ -213,6 +235,27 @@ void coarse_factor_device(alfib_ctx* c) {
   CUSOLVER_TRY(cusolverDnDgetrs(c->cusolver, CUBLAS_OP_N, n, n, c->coarse_lu.p, n, c->coarse_piv.p, c->coarse_inv.p,
                                 (int)ld, c->coarse_info.p));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (coarse_is_condensed(*L0)) {
+    PatchSet& ps = L0->ps[ALFIB_PATCHES_SMOOTHER];
+    const CondensedHost& h = ps.cond.h;
+    if (!ps.store) {
+      ps.store_buf.alloc((size_t)std::max<int64_t>(ps.store_elems, 2));
+      ps.store = ps.store_buf.p;
+      ps.store_owned = true;
+    }
+    const int ns = (int)h.nsep_total;
+    if (ns > 0) {
+      CUDA_TRY(cudaMemsetAsync(ps.store + h.ssoff[0], 0, sizeof(double) * (size_t)(h.ssoff[1] - h.ssoff[0]), c->stream));
+      extract_xss_kernel<<<cdiv((int64_t)ns * ns, 256), 256, 0, c->stream>>>(c->coarse_inv.p, ld, ps.cond.sepdofs.p, ns,
+                                                                             ps.store + h.ssoff[0]);
+      c->launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
+    launch_condense_blocks(c, *L0, ps, L0->vals.p);
+    ps.factored = true;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->coarse_inv.release();                      // 8 n^2 bytes: the condensed pieces replace it
+  }
   // the LU and its workspace are transient; small ones are kept for the next Newton step (cudaFree /
   // cudaMalloc per call cost more than the factorisation of a small coarse level)
   if ((size_t)n * n * sizeof(double) > ((size_t)256 << 20)) {
@@ -227,6 +270,20 @@ void coarse_solve_device(alfib_ctx* c, const double* b, double* x) {
   ALFIB_REQUIRE(x != b, "coarse solve: x and b must not alias");
   Level& L0 = *c->levels[0];
   ScopedEvent ev(c, ALFIB_EV_COARSE, 0);
+  if (coarse_is_condensed(L0)) {
+    // every rank applies the whole condensed inverse (0.4 GB at cfg5): no exchange
+    PatchSet& ps = L0.ps[ALFIB_PATCHES_SMOOTHER];
+    auto apply = [&](const double* src, double* dst) {
+      CUDA_TRY(cudaMemsetAsync(dst, 0, sizeof(double) * L0.n, c->stream));
+      launch_patch_apply(c, ps, src, plain_out(dst));
+      launch_set_rows(c, dst, src, L0.bc.p, L0.nbc);                    // identity rows of the Dirichlet dofs
+    };
+    apply(b, x);                                                        // x = Ainv b
+    launch_bsr_spmv(c, L0, L0.vals.p, x, c->coarse_r.p, b);             // r = b - A x
+    apply(c->coarse_r.p, c->coarse_dx.p);
+    launch_axpby(c, L0.n, 1.0, c->coarse_dx.p, 1.0, x);                 // x += Ainv r
+    return;
+  }
   coarse_gemv(c, b, x, 0);                                              // x = Ainv b
   launch_bsr_spmv(c, L0, L0.vals.p, x, c->coarse_r.p, b);               // r = b - A x
   coarse_gemv(c, c->coarse_r.p, x, 1);                                  // x += Ainv r

@@ -8,6 +8,7 @@ coarse-boundary dofs and the A0 / gamma*D values of the Schöberl transfer.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -38,6 +39,9 @@ class LevelInput:
     cb_dofs: np.ndarray | None = None
     a0_vals: np.ndarray | None = None
     d_vals: np.ndarray | None = None
+    # coarsest level only: its free dofs as ONE patch with macro-cell block labels -> condensed coarse inverse
+    coarse_dofs: np.ndarray | None = None
+    coarse_blocks: np.ndarray | None = None
 
 
 def level_input_from_synth(ld) -> LevelInput:
@@ -47,6 +51,13 @@ def level_input_from_synth(ld) -> LevelInput:
         ps = ld.patches
         li.patch_offsets, li.patch_dofs, li.patch_order, li.patch_colours = ps.offsets, ps.dofs, ps.order, ps.colours
         li.patch_blocks = ps.blocks
+    if ld.patches is None and getattr(ld.level, "bary", False):
+        from .patches import PatchSet, macro_interior_blocks
+        free = np.setdiff1d(np.arange(ld.V.ndofs), ld.bc_dofs).astype(np.int32)
+        one = PatchSet(offsets=np.array([0, free.size], np.int64), dofs=free, bs=ld.V.bs, order=np.zeros(1, np.int32))
+        blocks = macro_interior_blocks(ld.level.plex, ld.V, one)
+        if blocks is not None and (blocks >= 0).any():
+            li.coarse_dofs, li.coarse_blocks = free, blocks
     if ld.P is not None:
         li.P = ld.P
         li.P_dof_level = bool(getattr(ld, "P_dof_level", False))
@@ -89,6 +100,12 @@ class DeviceMultigrid:
             c.level_create(l, li.n_nodes, li.bs)
             c.set_bsr_pattern(l, li.rowptr, li.colidx)
             c.set_bc(l, li.bc_dofs)
+            if l == 0 and condense and li.coarse_blocks is not None and os.environ.get("ALFIB_COARSE_CONDENSED", "1") != "0":
+                # the coarse level as one patch with macro-cell blocks: coarse_factor keeps the condensed pieces of
+                # the dense inverse (X_SS of the separator + block tiles) instead of the inverse itself
+                c.set_patches(0, np.array([0, li.coarse_dofs.size], np.int64), li.coarse_dofs, np.zeros(1, np.int32),
+                              np.zeros(1, np.int32), PATCHES_SMOOTHER)
+                c.set_patch_blocks(0, li.coarse_blocks, PATCHES_SMOOTHER)
             if l > 0:
                 off, dofs, order, cols = li.patch_offsets, li.patch_dofs, li.patch_order, li.patch_colours
                 blocks = li.patch_blocks if condense else None

@@ -74,7 +74,12 @@ void run_op(const Shim& s, const TileOp& op, const double* srcA, const double* s
     for (int r = 0; r < op.nrows; ++r) acc[r] += T[(size_t)c * rt + r] * xc;
   }
   for (int r = 0; r < op.nrows; ++r) {
-    if (op.priv >= 0) dstB[op.priv + r] = acc[r];
+    if (op.priv >= 0) {
+      if (s.cd.any_accum && (&op >= s.cd.opsS.data() && &op < s.cd.opsS.data() + s.cd.opsS.size()))
+        dstB[op.priv + r] += acc[r];          // X_SS lists with column chunks: us is zeroed and accumulated
+      else
+        dstB[op.priv + r] = acc[r];
+    }
     if (op.row >= 0) y[s.cd.cidx[op.row + r]] += acc[r];
   }
 }
@@ -85,7 +90,7 @@ extern "C" {
 
 void* ch_create(int n_nodes, int bs, const int32_t* rowptr, const int32_t* colidx, int npatch, const int64_t* off,
                 const int32_t* dofs, int norder, const int32_t* order, const int32_t* colour, int ncolour,
-                const int32_t* blocks, int allow_shared, char* err, int errlen) {
+                const int32_t* blocks, int allow_shared, int split_wide, char* err, int errlen) {
   Shim* s = new Shim();
   s->npatch = npatch;
   s->ncolour = ncolour;
@@ -100,7 +105,7 @@ void* ch_create(int n_nodes, int bs, const int32_t* rowptr, const int32_t* colid
   PatchView pv{npatch, ncolour, bs, s->ndofs, s->off.data(), s->dofs.data(), &s->order, s->colour.data(),
                s->rowptr.data(), s->colidx.data()};
   try {
-    build_condensed_host(pv, blocks, s->cd, allow_shared != 0);
+    build_condensed_host(pv, blocks, s->cd, allow_shared != 0, split_wide != 0);
   } catch (const std::exception& e) {
     std::strncpy(err, e.what(), errlen - 1);
     err[errlen - 1] = 0;
@@ -117,7 +122,7 @@ void* ch_create(int n_nodes, int bs, const int32_t* rowptr, const int32_t* colid
 
 void ch_destroy(void* h) { delete static_cast<Shim*>(h); }
 
-// stats[0..9] = store_elems, index_bytes, nblocks, nsep_total, maxb, maxm, maxsep, #ops, shared, ndist
+// stats[0..10] = store_elems, index_bytes, nblocks, nsep_total, maxb, maxm, maxsep, #ops, shared, ndist, any_accum
 void ch_stats(void* h, int64_t* stats) {
   const CondensedHost& cd = static_cast<Shim*>(h)->cd;
   stats[0] = cd.store_elems;
@@ -130,6 +135,7 @@ void ch_stats(void* h, int64_t* stats) {
   stats[7] = (int64_t)(cd.opsV.size() + cd.opsS.size() + cd.opsDW.size());
   stats[8] = cd.shared ? 1 : 0;
   stats[9] = cd.ndist;
+  stats[10] = cd.any_accum ? 1 : 0;
 }
 
 // vals: nnzb x bs x bs row-major blocks.  Returns 0, or 1 + index of a singular patch / block.
@@ -228,6 +234,7 @@ void ch_apply(void* h, const double* x, double* y) {
     for (int j = cd.cptr[e]; j < cd.cptr[e + 1]; ++j) v -= s.g1[cd.cg1[j]];
     s.rs[e] = v;
   }
+  if (cd.any_accum) std::fill(s.us.begin(), s.us.end(), 0.0);
   for (int col = 0; col < s.ncolour; ++col)
     for (int i = cd.s_colour_start[col]; i < cd.s_colour_start[col + 1]; ++i)
       run_op(s, cd.opsS[i], s.rs.data(), nullptr, y, s.us.data());
@@ -264,7 +271,7 @@ int ch_check_disjoint(void* h) {
         }
     return true;
   };
-  if (!phase(cd.opsS, cd.s_colour_start)) return 1;
+  if (!cd.any_accum && !phase(cd.opsS, cd.s_colour_start)) return 1;   // column chunks share rows (atomics)
   if (!phase(cd.opsDW, cd.dw_colour_start)) return 2;
   std::vector<char> hit((size_t)std::max<int64_t>(cd.g1_total, 1), 0);
   for (const TileOp& op : cd.opsV)

@@ -207,7 +207,7 @@ def test_condensed_lists_on_the_unstructured_mesh(bfs):
     from tests.test_condense_host import _f64p, _i32p, _i64p
     lib.ch_create.restype = C.c_void_p
     lib.ch_create.argtypes = [C.c_int, C.c_int, _i32p, _i32p, C.c_int, _i64p, _i32p, C.c_int, _i32p, _i32p, C.c_int,
-                              _i32p, C.c_int, C.c_char_p, C.c_int]
+                              _i32p, C.c_int, C.c_int, C.c_char_p, C.c_int]
     lib.ch_destroy.argtypes = [C.c_void_p]
     lib.ch_stats.argtypes = [C.c_void_p, _i64p]
     lib.ch_factor.argtypes = [C.c_void_p, _f64p]

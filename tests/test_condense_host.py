@@ -31,7 +31,7 @@ def shim():
     lib = C.CDLL(so)
     lib.ch_create.restype = C.c_void_p
     lib.ch_create.argtypes = [C.c_int, C.c_int, _i32p, _i32p, C.c_int, _i64p, _i32p, C.c_int, _i32p, _i32p, C.c_int,
-                              _i32p, C.c_int, C.c_char_p, C.c_int]
+                              _i32p, C.c_int, C.c_int, C.c_char_p, C.c_int]
     lib.ch_destroy.argtypes = [C.c_void_p]
     lib.ch_stats.argtypes = [C.c_void_p, _i64p]
     lib.ch_factor.argtypes = [C.c_void_p, _f64p]
@@ -46,7 +46,7 @@ def _p(a, t):
 
 
 class Host:
-    def __init__(self, lib, ld, ps, blocks, shared=True):
+    def __init__(self, lib, ld, ps, blocks, shared=True, split_wide=False):
         self.lib = lib
         A = ld.A
         self.keep = [np.ascontiguousarray(a, dtype=t) for a, t in (
@@ -58,13 +58,13 @@ class Host:
         ncol = int(col.max()) + 1 if col.size else 0
         self.h = lib.ch_create(ld.V.nnodes, ld.V.bs, _p(rp, C.c_int32), _p(ci, C.c_int32), ps.npatch, _p(off, C.c_int64),
                                _p(dofs, C.c_int32), order.size, _p(order, C.c_int32), _p(col, C.c_int32), ncol,
-                               _p(blk, C.c_int32), int(shared), err, 512)
+                               _p(blk, C.c_int32), int(shared), int(split_wide), err, 512)
         self.err = err.value.decode()
 
     def stats(self):
-        s = np.zeros(10, np.int64)
+        s = np.zeros(11, np.int64)
         self.lib.ch_stats(self.h, _p(s, C.c_int64))
-        return dict(zip(["store_elems", "index_bytes", "nblocks", "nsep_total", "maxb", "maxm", "maxsep", "nops", "shared", "ndist"], s.tolist()))
+        return dict(zip(["store_elems", "index_bytes", "nblocks", "nsep_total", "maxb", "maxm", "maxsep", "nops", "shared", "ndist", "any_accum"], s.tolist()))
 
     def factor(self, vals):
         v = np.ascontiguousarray(vals, dtype=np.float64)
@@ -287,3 +287,60 @@ def test_edge_cases_on_clustered_operator(shim, bs, order, shared):
             X = host.inverse(p, I.size)
             assert np.abs(X @ case["A"][I][:, I].toarray() - np.eye(I.size)).max() < 1e-10
     host.close()
+
+
+@pytest.fixture(scope="module")
+def shim_split32():
+    """The shim compiled with ALFIB_SPLIT_COLS = 32, so that column chunks appear on test-sized separators."""
+    out = os.path.join(ROOT, "oracle", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libcondense_host_shim_split32.so")
+    src = os.path.join(ROOT, "tests", "condense_host_shim.cpp")
+    hdr = os.path.join(ROOT, "alfi_b200", "csrc", "condense_host.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DALFIB_SPLIT_COLS=32", "-I",
+                               os.path.dirname(hdr), src, "-o", so])
+    lib = C.CDLL(so)
+    lib.ch_create.restype = C.c_void_p
+    lib.ch_create.argtypes = [C.c_int, C.c_int, _i32p, _i32p, C.c_int, _i64p, _i32p, C.c_int, _i32p, _i32p, C.c_int,
+                              _i32p, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    lib.ch_destroy.argtypes = [C.c_void_p]
+    lib.ch_stats.argtypes = [C.c_void_p, _i64p]
+    lib.ch_factor.argtypes = [C.c_void_p, _f64p]
+    lib.ch_apply.argtypes = [C.c_void_p, _f64p, _f64p]
+    lib.ch_inverse.argtypes = [C.c_void_p, C.c_int, _f64p]
+    lib.ch_check_disjoint.argtypes = [C.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("name", ["ldc3d-sv-k3-tiny", "ldc2d-sv-k2-tiny", "ldc3d-sv-k3-small"])
+def test_coarse_level_as_one_condensed_patch(shim_split32, problems, name):
+    """The coarse level of an SV hierarchy is one patch with macro-cell blocks: its inverse in condensed form,
+    with the wide separator tiles cut into column chunks (accumulating ops), solves the coarse system."""
+    from alfi_b200.patches import PatchSet, macro_interior_blocks
+    prob = problems(name, gamma=10.0, nu=0.2)
+    ld = prob.levels[0]
+    n = ld.V.ndofs
+    free = np.setdiff1d(np.arange(n), ld.bc_dofs).astype(np.int32)
+    ps = PatchSet(offsets=np.array([0, free.size], np.int64), dofs=free, bs=ld.V.bs, order=np.zeros(1, np.int32))
+    ps.colours = np.zeros(1, np.int32)
+    blocks = macro_interior_blocks(ld.level.plex, ld.V, ps)
+    assert blocks is not None and (blocks >= 0).sum() > free.size // 3
+    host = Host(shim_split32, ld, ps, blocks, True, split_wide=True)
+    assert host.h, host.err
+    st = host.stats()
+    assert st["shared"] == 1 and st["store_elems"] < free.size ** 2
+    assert st["any_accum"] == int(st["maxsep"] > 64)                 # chunks of 32 columns once the separator exceeds 64
+    assert host.factor(ld.A.vals) == 0
+    b = np.random.default_rng(0).standard_normal(n)
+    b[ld.bc_dofs] = 0
+    y = host.apply(b)
+    A = ld.A.to_csr()
+    want = np.zeros(n)
+    want[free] = np.linalg.solve(A[free][:, free].toarray(), b[free])
+    assert rel(y, want) <= 1e-9
+    X = host.inverse(0, free.size)
+    assert np.abs(X @ A[free][:, free].toarray() - np.eye(free.size)).max() < 1e-8
+    host.close()
+    print("%s coarse level: %d free dofs, separator %d, chunks %d, condensed %.2f MB vs dense %.2f MB" % (
+        name, free.size, st["maxsep"], st["any_accum"], st["store_elems"] * 8e-6, free.size ** 2 * 8e-6))
