@@ -476,7 +476,11 @@ void condense_setup(alfib_ctx* c, Level& L, PatchSet& ps, const int32_t* block_o
   const char* env_shared = std::getenv("ALFIB_CONDENSE_SHARED");
   const bool allow_shared = !(env_shared && env_shared[0] == '0');
   try {
-    build_condensed_host(pv, block_of_dof, cd.h, allow_shared, /*split_wide=*/!c->deterministic);
+    // ALFIB_SPLIT_COLS=n: X_SS tiles wider than 2n columns are cut into n-column chunks (default 256: only coarse
+    // levels and literal 3-D macro stars; e.g. 64 also cuts the 195-column tiles of the open macro star in three)
+    const char* env_split = std::getenv("ALFIB_SPLIT_COLS");
+    const int split_cols = env_split ? std::atoi(env_split) : ALFIB_SPLIT_COLS;
+    build_condensed_host(pv, block_of_dof, cd.h, allow_shared, /*split_wide=*/!c->deterministic, split_cols);
   } catch (const std::runtime_error& e) {
     cd.h = CondensedHost();
     throw DeviceError{ALFIB_EINVAL, e.what()};

@@ -258,7 +258,8 @@ inline void build_shared_blocks(const PatchView& pv, CondensedHost& cd) {
 // (any non-negative integer, local to the patch).  Blocks must be pairwise decoupled in the BSR
 // pattern; this is checked here, so a wrong hint is an error, never a wrong answer.
 inline void build_condensed_host(const PatchView& pv, const int32_t* block_of_dof, CondensedHost& cd,
-                                 bool allow_shared = true, bool split_wide = false) {
+                                 bool allow_shared = true, bool split_wide = false,
+                                 int split_cols = ALFIB_SPLIT_COLS) {
   cd = CondensedHost();
   const int npatch = pv.npatch, bs = pv.bs;
   cd.sepoff.assign(npatch + 1, 0);
@@ -450,11 +451,11 @@ inline void build_condensed_host(const PatchView& pv, const int32_t* block_of_do
       for (int row0 = 0; row0 < ns; row0 += ALFIB_TILE_ROWS) {
         const int rows = std::min(ns - row0, ALFIB_TILE_ROWS);
         const int64_t tile = cd.ssoff[p] + (int64_t)row0 * ns;
-        if (split_wide && ns > 2 * ALFIB_SPLIT_COLS) {
+        if (split_wide && split_cols > 0 && ns > 2 * split_cols) {
           // wide separator (a coarse level held as one patch, literal 3-D macro stars): column chunks, each op
           // adds its partial product to us (atomicAdd) and to y
-          for (int c0 = 0; c0 < ns; c0 += ALFIB_SPLIT_COLS) {
-            const int nc = std::min(ns - c0, ALFIB_SPLIT_COLS);
+          for (int c0 = 0; c0 < ns; c0 += split_cols) {
+            const int nc = std::min(ns - c0, split_cols);
             cd.opsS.push_back(TileOp{tile + (int64_t)c0 * ch_roundup2(rows), rs_list[p] + c0, sg_list[p] + row0, so + row0,
                                      rows, nc, TILEOP_ACCUM, 0});
           }
