@@ -124,8 +124,46 @@ struct PatchSet {
   Condensed cond;                   // block/separator form of the inverses (alfib_level_set_patch_blocks)
 };
 
+// Exchange lists of one distributed-vector layout (alfib_level_set_halo): local vector = owned dofs
+// [0, n_owned) then ghosts [n_owned, n_local).  comm.cu: halo_update / halo_reduce.
+struct Halo {
+  bool on = false;
+  int n_owned = 0, n_local = 0;
+  std::vector<int> peers;                    // ascending rank order
+  std::vector<int64_t> send_off, recv_off;   // npeers + 1
+  DBuf<int32_t> send_idx, recv_idx;          // owned / ghost local dofs, grouped by peer
+  DBuf<double> sbuf, rbuf;                   // packed owned-side / ghost-side entries
+  // ghost -> owner sum as a gather: distinct owned interface dof d = red_dof[i] receives the packed entries
+  // red_src[red_ptr[i] .. red_ptr[i+1]) (positions in the send list, ascending = ascending peer rank)
+  int n_red = 0;
+  DBuf<int32_t> red_ptr, red_dof, red_src;
+  // NVLink peer-memory exchanges: where, in peer p's packed send / ghost buffer, the part for this rank starts
+  bool has_peer_off = false;
+  std::vector<int64_t> peer_send_off, peer_recv_off;
+  void release() {
+    send_idx.release(); recv_idx.release(); sbuf.release(); rbuf.release();
+    red_ptr.release(); red_dof.release(); red_src.release();
+    on = false;
+    has_peer_off = false;
+    n_red = 0;
+  }
+};
+
+// Peer lists of one exchange, passed to the pull kernels by value: segment p of this rank's list, [mine_off[p],
+// mine_off[p+1]), is found in rank peers[p]'s packed buffer from theirs_off[p] on.
+struct HaloPeers {
+  int npeers;
+  int peers[ALFIB_MAX_RANKS];
+  long long mine_off[ALFIB_MAX_RANKS + 1];
+  long long theirs_off[ALFIB_MAX_RANKS];
+};
+
 struct Level {
   int n_nodes = 0, bs = 0, n = 0;
+  int index = 0;                             // level number (event accounting)
+  int n_owned = 0;                           // == n unless the level has a halo
+  Halo halo, thalo;                          // own layout; layout in which this level's P_H reads level-1
+  DBuf<double> tc;                           // a level-1 vector in the thalo layout
   int64_t nnzb = 0;
   DBuf<int32_t> rowptr, colidx, bc, cb;
   std::vector<int32_t> h_rowptr, h_colidx;   // host copy of the pattern (block structure checks)
@@ -242,6 +280,11 @@ void comm_init(alfib_ctx* c, const void* id128, int rank, int nranks);
 void comm_destroy(alfib_ctx* c);
 void comm_allreduce_sum(alfib_ctx* c, double* y, size_t n);
 void comm_allgather_rows(alfib_ctx* c, double* y, const std::vector<int64_t>& dof_start);
+// distributed vectors: owner -> ghost copy / ghost -> owner sum (ghosts cleared) between neighbour ranks
+void halo_update(alfib_ctx* c, Halo& H, double* x, int level);
+void halo_reduce(alfib_ctx* c, Halo& H, double* y, int level);
+// v[0..nv) summed over the ranks, result on every rank (FGMRES dots); sqrt_mode: v[0] = sqrt(sum), inv = 1 / v[0]
+void comm_small_allreduce(alfib_ctx* c, double* v, int nv, int sqrt_mode, double* inv);
 void comm_peer_alloc(alfib_ctx* c);
 void comm_peer_handle(alfib_ctx* c, void* out64);
 void comm_peer_open(alfib_ctx* c, const void* handles);
@@ -256,6 +299,8 @@ void comm_peer_reduce(alfib_ctx* c, int64_t n, int hdr_slot, const long long* lo
 // patch_apply.cu
 void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, PeerOut y);
 // y = sum over ranks of this rank's patch contributions (zeroing, exchange included)
+// (a level with a halo: the ghosts of x are refreshed first — x is a local work vector there — and the ghost
+// contributions of y are summed into their owners; y is valid on the owned entries only)
 void patch_apply_sum(alfib_ctx* c, Level& L, int level, int which, const double* x, double* y);
 // condense.cu
 void condense_setup(alfib_ctx* c, Level& L, PatchSet& ps, const int32_t* block_of_dof);

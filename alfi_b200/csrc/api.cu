@@ -179,8 +179,10 @@ int alfib_destroy(alfib_ctx* c) {
     for (auto* b : {&L->rowptr, &L->colidx, &L->bc, &L->cb, &L->p_rowptr, &L->p_colidx, &L->pt_rowptr, &L->pt_colidx})
       b->release();
     for (auto* b : {&L->vals, &L->dvals, &L->a0vals, &L->p_vals, &L->pt_vals, &L->b, &L->x, &L->r, &L->w, &L->t1,
-                    &L->t2, &L->t3, &L->t4, &L->V, &L->Z})
+                    &L->t2, &L->t3, &L->t4, &L->V, &L->Z, &L->tc})
       b->release();
+    L->halo.release();
+    L->thalo.release();
     delete L;
     L = nullptr;
   }
@@ -271,6 +273,95 @@ int alfib_comm_init(alfib_ctx* c, const void* nccl_unique_id, int rank, int nran
   });
 }
 
+// ---- distributed level vectors ----------------------------------------------------------------
+int alfib_level_set_halo(alfib_ctx* c, int level, int which, int32_t n_owned, int32_t n_local, int32_t npeers,
+                         const int32_t* peers, const int64_t* send_off, const int32_t* send_idx,
+                         const int64_t* recv_off, const int32_t* recv_idx, const int64_t* peer_send_off,
+                         const int64_t* peer_recv_off) {
+  return guarded(c, [&] {
+    cycle_graph_invalidate(c);
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(which == 0 || which == 1, "which must be 0 (level vectors) or 1 (transfer halo)");
+    ALFIB_REQUIRE(n_owned >= 0 && n_local >= n_owned, "0 <= n_owned <= n_local required");
+    ALFIB_REQUIRE(npeers >= 0 && npeers < ALFIB_MAX_RANKS, "bad peer count");
+    ALFIB_REQUIRE(npeers == 0 || (peers && send_off && recv_off), "null exchange lists");
+    ALFIB_REQUIRE(npeers == 0 || c->comm, "alfib_comm_init first");
+    if (which == 0) {
+      ALFIB_REQUIRE(n_local == L.n && n_owned % L.bs == 0, "level halo: n_local must be the level's size, ownership node-wise");
+      ALFIB_REQUIRE(!L.has_transfer, "alfib_level_set_halo must precede alfib_transfer_set");
+    } else {
+      ALFIB_REQUIRE(level >= 1, "a transfer halo belongs to a level >= 1");
+      ALFIB_REQUIRE(!L.has_transfer, "alfib_level_set_halo must precede alfib_transfer_set");
+      ALFIB_REQUIRE(n_owned == get_level(c, level - 1).n_owned, "transfer halo: owned part must be the coarser level's");
+    }
+    Halo& H = which == 0 ? L.halo : L.thalo;
+    H.release();
+    H.n_owned = n_owned;
+    H.n_local = n_local;
+    H.peers.assign(peers, peers + npeers);
+    H.send_off.assign(1, 0);
+    H.recv_off.assign(1, 0);
+    for (int p = 0; p < npeers; ++p) {
+      ALFIB_REQUIRE(peers[p] >= 0 && peers[p] < c->nranks && peers[p] != c->rank, "bad peer rank");
+      ALFIB_REQUIRE(p == 0 || peers[p] > peers[p - 1], "peers must be ascending");
+      ALFIB_REQUIRE(send_off[p + 1] >= send_off[p] && recv_off[p + 1] >= recv_off[p] && send_off[0] == 0 && recv_off[0] == 0,
+                    "bad exchange offsets");
+      H.send_off.push_back(send_off[p + 1]);
+      H.recv_off.push_back(recv_off[p + 1]);
+    }
+    const int64_t ns = H.send_off.back(), nr = H.recv_off.back();
+    ALFIB_REQUIRE((ns == 0 || send_idx) && (nr == 0 || recv_idx), "null exchange indices");
+    for (int64_t k = 0; k < ns; ++k) ALFIB_REQUIRE(send_idx[k] >= 0 && send_idx[k] < n_owned, "send entry is not an owned dof");
+    {
+      std::vector<char> seen((size_t)(n_local - n_owned), 0);
+      for (int64_t k = 0; k < nr; ++k) {
+        ALFIB_REQUIRE(recv_idx[k] >= n_owned && recv_idx[k] < n_local, "receive entry is not a ghost dof");
+        ALFIB_REQUIRE(!seen[recv_idx[k] - n_owned], "a ghost dof is received twice");
+        seen[recv_idx[k] - n_owned] = 1;
+      }
+      ALFIB_REQUIRE(c->nranks == 1 || nr == (int64_t)(n_local - n_owned), "every ghost dof needs an owner to receive from");
+    }
+    for (int p = 0; p < npeers; ++p) {
+      std::vector<int32_t> part(send_idx + H.send_off[p], send_idx + H.send_off[p + 1]);
+      std::sort(part.begin(), part.end());
+      ALFIB_REQUIRE(std::adjacent_find(part.begin(), part.end()) == part.end(), "an owned dof is sent twice to one peer");
+    }
+    {
+      // ghost -> owner sum as a gather per distinct owned dof; positions ascending = peers in ascending rank order
+      std::vector<int32_t> pos((size_t)ns);
+      std::iota(pos.begin(), pos.end(), 0);
+      std::stable_sort(pos.begin(), pos.end(), [&](int32_t a, int32_t b) { return send_idx[a] < send_idx[b]; });
+      std::vector<int32_t> red_ptr(1, 0), red_dof, red_src((size_t)ns);
+      for (int64_t k = 0; k < ns; ++k) {
+        if (k == 0 || send_idx[pos[k]] != send_idx[pos[k - 1]]) {
+          if (k) red_ptr.push_back((int32_t)k);
+          red_dof.push_back(send_idx[pos[k]]);
+        }
+        red_src[k] = pos[k];
+      }
+      if (ns) red_ptr.push_back((int32_t)ns);
+      H.n_red = (int)red_dof.size();
+      H.red_ptr.upload(red_ptr.data(), red_ptr.size(), c->stream);
+      H.red_dof.upload(red_dof.data(), red_dof.size(), c->stream);
+      H.red_src.upload(red_src.data(), red_src.size(), c->stream);
+    }
+    if (peer_send_off && peer_recv_off) {
+      H.peer_send_off.assign(peer_send_off, peer_send_off + npeers);
+      H.peer_recv_off.assign(peer_recv_off, peer_recv_off + npeers);
+      for (int p = 0; p < npeers; ++p)
+        ALFIB_REQUIRE(H.peer_send_off[p] >= 0 && H.peer_recv_off[p] >= 0, "negative peer offset");
+      H.has_peer_off = true;
+    }
+    H.send_idx.upload(send_idx, ns, c->stream);
+    H.recv_idx.upload(recv_idx, nr, c->stream);
+    H.sbuf.alloc(std::max<int64_t>(ns, 1));
+    H.rbuf.alloc(std::max<int64_t>(nr, 1));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    H.on = true;
+    if (which == 0) L.n_owned = n_owned;
+  });
+}
+
 // ---- level operator ---------------------------------------------------------------------------
 int alfib_level_create(alfib_ctx* c, int level, int n_nodes, int bs) {
   return guarded(c, [&] {
@@ -282,6 +373,8 @@ int alfib_level_create(alfib_ctx* c, int level, int n_nodes, int bs) {
     L->n_nodes = n_nodes;
     L->bs = bs;
     L->n = n_nodes * bs;
+    L->n_owned = L->n;
+    L->index = level;
     set_row_partition(c, *L);
     c->levels[level] = L;
   });
@@ -566,7 +659,14 @@ int alfib_transfer_set(alfib_ctx* c, int level, int32_t n_fine_nodes, int32_t n_
     Level& L = get_level(c, level);
     ALFIB_REQUIRE(level >= 1, "transfers live on levels >= 1");
     Level& Lc = get_level(c, level - 1);
-    if (dof_level)
+    if (L.halo.on) {
+      // distributed vectors: P holds the owned fine rows; columns = the coarser level in the transfer-halo layout,
+      // or the whole (replicated) coarser level
+      ALFIB_REQUIRE(dof_level, "a level with a halo takes a dof-level P");
+      ALFIB_REQUIRE(L.thalo.on || !Lc.halo.on, "the coarser level is distributed: set the transfer halo (which = 1) first");
+      ALFIB_REQUIRE(n_fine_nodes == L.n_owned && n_coarse_nodes == (L.thalo.on ? L.thalo.n_local : Lc.n),
+                    "local P shape does not match the halo layouts");
+    } else if (dof_level)
       ALFIB_REQUIRE(n_fine_nodes == L.n && n_coarse_nodes == Lc.n, "dof-level P shape does not match the levels");
     else
       ALFIB_REQUIRE(n_fine_nodes == L.n_nodes && n_coarse_nodes == Lc.n_nodes, "P shape does not match the levels");
@@ -684,7 +784,10 @@ int alfib_cycle_setup(alfib_ctx* c, int nlevels, int smoothing) {
     ALFIB_REQUIRE(smoothing >= 1 && smoothing <= ALFIB_MAX_KRYLOV, "bad smoothing count");
     for (int l = 0; l < nlevels; ++l) {
       Level& L = get_level(c, l);
-      for (auto* v : {&L.b, &L.x, &L.w, &L.r, &L.t1, &L.t2}) v->alloc(L.n);
+      for (auto* v : {&L.b, &L.x, &L.w, &L.r, &L.t1, &L.t2}) {
+        v->alloc(L.n);
+        if (L.halo.on) CUDA_TRY(cudaMemsetAsync(v->p, 0, sizeof(double) * L.n, c->stream));   // ghost parts defined
+      }
       if (l > 0) ALFIB_REQUIRE(L.has_transfer, "level without transfer");
     }
     c->nlevels = nlevels;

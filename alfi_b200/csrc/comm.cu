@@ -25,6 +25,8 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -48,6 +50,8 @@ NcclApi& nccl() {
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
   g_nccl.Broadcast = (decltype(g_nccl.Broadcast))sym("ncclBroadcast");
+  g_nccl.Send = (decltype(g_nccl.Send))sym("ncclSend");
+  g_nccl.Recv = (decltype(g_nccl.Recv))sym("ncclRecv");
   g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
   g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
@@ -325,4 +329,276 @@ int comm_peer_error(alfib_ctx* c) {
   int e = 0;
   cudaMemcpy(&e, c->d_comm_err.p, sizeof(int), cudaMemcpyDeviceToHost);
   return e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Distributed level vectors (alfib_level_set_halo): the PetscSF bcast / reduce of the reference's
+// parallel PCPATCH and MatMult, between neighbouring ranks only.  Bytes moved per exchange and rank:
+// 8 x (ghost entries), e.g. <= 0.9 MB on cfg5's finest level at 8 ranks against the 11.7 MB
+// all-reduce of the replicated design.  Two transports, the same packed layout:
+//   * NCCL: pack -> one group of ncclSend/ncclRecv per neighbour -> unpack;
+//   * NVLink peer memory (alfib_comm_peer_open): pack into this rank's symmetric slot, then ONE kernel
+//     that runs the flag protocol of peer_reduce_kernel above (publish e, wait for every rank's flag,
+//     advance the exchange counter) and pulls the neighbours' packed entries straight into place — the
+//     transfer and the unpack (or the fixed-order sum) are the same loads.
+// Everything is enqueued on the ctx stream and replays inside the cycle's CUDA graph.
+namespace {
+
+// buf[i] = x[idx[i]]; idx == nullptr: buf[i] = x[i]
+__global__ void halo_pack_kernel(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ x, PeerOut out) {
+  double* __restrict__ buf = resolve(out);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    buf[i] = idx ? x[idx[i]] : x[i];
+}
+
+// x[idx[i]] = buf[i]; the ghost positions of one layout are distinct
+__global__ void halo_unpack_kernel(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ buf,
+                                   double* __restrict__ x) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[idx[i]] = buf[i];
+}
+
+// y[red_dof[i]] += sum_k buf[red_src[k]], k ascending = peers in ascending rank order (reproducible)
+__global__ void halo_sum_kernel(int n_red, const int32_t* __restrict__ red_ptr, const int32_t* __restrict__ red_dof,
+                                const int32_t* __restrict__ red_src, const double* __restrict__ buf,
+                                double* __restrict__ y) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_red; i += gridDim.x * blockDim.x) {
+    double v = y[red_dof[i]];
+    for (int k = red_ptr[i]; k < red_ptr[i + 1]; ++k) v += buf[red_src[k]];
+    y[red_dof[i]] = v;
+  }
+}
+
+inline int halo_grid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), 4 * 148)); }
+
+// one NCCL group: this rank sends `out` (grouped by peer with offsets out_off) and receives `in`
+void halo_sendrecv(alfib_ctx* c, const Halo& H, const double* out, const std::vector<int64_t>& out_off, double* in,
+                   const std::vector<int64_t>& in_off) {
+  nccl_check(nccl().GroupStart(), "ncclGroupStart");
+  for (size_t p = 0; p < H.peers.size(); ++p) {
+    const size_t ns = (size_t)(out_off[p + 1] - out_off[p]), nr = (size_t)(in_off[p + 1] - in_off[p]);
+    if (ns) nccl_check(nccl().Send(out + out_off[p], ns, ncclDouble, H.peers[p], (ncclComm_t)c->comm, c->stream), "ncclSend");
+    if (nr) nccl_check(nccl().Recv(in + in_off[p], nr, ncclDouble, H.peers[p], (ncclComm_t)c->comm, c->stream), "ncclRecv");
+  }
+  nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+}
+
+// ---- the flag protocol of peer_reduce_kernel as two device functions ---------------------------
+// begin: this rank's slot (e & 1) is complete (written by the preceding kernel on the stream); block 0
+// publishes flag = e, waits until every rank has published e and releases the other blocks.
+__device__ __forceinline__ void peer_exchange_begin(unsigned long long e, int nranks, int rank,
+                                                    double* const* __restrict__ peer_slot0, int* __restrict__ err,
+                                                    LocalGate* local) {
+  const size_t hdr_doubles = ALFIB_SYM_HEADER_BYTES / sizeof(double);
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      SymHeader* mine = reinterpret_cast<SymHeader*>(peer_slot0[rank] - hdr_doubles);
+      *reinterpret_cast<volatile unsigned long long*>(&mine->flag) = e;
+    }
+    if (threadIdx.x < nranks && threadIdx.x != rank) {
+      const SymHeader* h = reinterpret_cast<const SymHeader*>(peer_slot0[threadIdx.x] - hdr_doubles);
+      long long spins = 0;
+      while (*reinterpret_cast<const volatile unsigned long long*>(&h->flag) < e) {
+        if (++spins > SPIN_LIMIT) {
+          atomicExch(err, 1);
+          break;
+        }
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(&local->go) = e;
+  }
+  if (threadIdx.x == 0) {
+    long long spins = 0;
+    while (*reinterpret_cast<const volatile unsigned long long*>(&local->go) < e)
+      if (++spins > SPIN_LIMIT * 16) break;
+  }
+  __threadfence_system();
+  __syncthreads();
+}
+
+// end: the last block to finish advances the exchange counter (every block has read it by then)
+__device__ __forceinline__ void peer_exchange_end(unsigned long long e, unsigned long long* epoch_rw, unsigned int* done) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      *done = 0;
+      *epoch_rw = e + 1ull;
+    }
+  }
+}
+
+__device__ __forceinline__ int segment_of(const HaloPeers& hp, long long pos) {
+  int p = 0;
+  while (p + 1 < hp.npeers && pos >= hp.mine_off[p + 1]) ++p;
+  return p;
+}
+
+// owner -> ghost over peer memory: x[recv_idx[i]] = (packed send buffer of the owner)[...]
+__global__ void __launch_bounds__(256) peer_halo_update_kernel(long long nr, HaloPeers hp, int nranks, int rank,
+                                                               double* const* __restrict__ peer_slot0, size_t stride,
+                                                               const int32_t* __restrict__ recv_idx, double* __restrict__ x,
+                                                               int* __restrict__ err, unsigned long long* epoch_rw,
+                                                               unsigned int* __restrict__ done, LocalGate* local) {
+  const unsigned long long e = *epoch_rw;
+  peer_exchange_begin(e, nranks, rank, peer_slot0, err, local);
+  const size_t off = (size_t)(e & 1ull) * stride;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += (long long)gridDim.x * blockDim.x) {
+    const int p = segment_of(hp, i);
+    x[recv_idx[i]] = __ldcv(peer_slot0[hp.peers[p]] + off + hp.theirs_off[p] + (i - hp.mine_off[p]));
+  }
+  peer_exchange_end(e, epoch_rw, done);
+}
+
+// ghost -> owner over peer memory: y[d] += sum over the peers holding d as a ghost, ascending rank order
+__global__ void __launch_bounds__(256) peer_halo_sum_kernel(int n_red, HaloPeers hp, int nranks, int rank,
+                                                            double* const* __restrict__ peer_slot0, size_t stride,
+                                                            const int32_t* __restrict__ red_ptr,
+                                                            const int32_t* __restrict__ red_dof,
+                                                            const int32_t* __restrict__ red_src, double* __restrict__ y,
+                                                            int* __restrict__ err, unsigned long long* epoch_rw,
+                                                            unsigned int* __restrict__ done, LocalGate* local) {
+  const unsigned long long e = *epoch_rw;
+  peer_exchange_begin(e, nranks, rank, peer_slot0, err, local);
+  const size_t off = (size_t)(e & 1ull) * stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_red; i += gridDim.x * blockDim.x) {
+    double v = y[red_dof[i]];
+    for (int k = red_ptr[i]; k < red_ptr[i + 1]; ++k) {
+      const long long pos = red_src[k];
+      const int p = segment_of(hp, pos);
+      v += __ldcv(peer_slot0[hp.peers[p]] + off + hp.theirs_off[p] + (pos - hp.mine_off[p]));
+    }
+    y[red_dof[i]] = v;
+  }
+  peer_exchange_end(e, epoch_rw, done);
+}
+
+// v[j] = sum over ranks (rank order) of their packed v[j]; optional sqrt / reciprocal of v[0]
+__global__ void peer_small_sum_kernel(int nv, int nranks, int rank, double* const* __restrict__ peer_slot0, size_t stride,
+                                      double* __restrict__ v, int sqrt_mode, double* __restrict__ inv,
+                                      int* __restrict__ err, unsigned long long* epoch_rw, unsigned int* __restrict__ done,
+                                      LocalGate* local) {
+  const unsigned long long e = *epoch_rw;
+  peer_exchange_begin(e, nranks, rank, peer_slot0, err, local);
+  const size_t off = (size_t)(e & 1ull) * stride;
+  for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+    double s = 0.0;
+    for (int q = 0; q < nranks; ++q) s += __ldcv(peer_slot0[q] + off + j);
+    if (sqrt_mode) {
+      s = sqrt(s);
+      if (inv) inv[j] = s > 0.0 ? 1.0 / s : 0.0;
+    }
+    v[j] = s;
+  }
+  peer_exchange_end(e, epoch_rw, done);
+}
+
+__global__ void sqrt_inv_kernel(double* __restrict__ out, double* __restrict__ inv) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double v = sqrt(out[0]);
+  out[0] = v;
+  if (inv) inv[0] = v > 0.0 ? 1.0 / v : 0.0;
+}
+
+HaloPeers make_peers(const Halo& H, const std::vector<int64_t>& mine, const std::vector<int64_t>& theirs) {
+  HaloPeers hp;
+  memset(&hp, 0, sizeof(hp));
+  hp.npeers = (int)H.peers.size();
+  for (int p = 0; p < hp.npeers; ++p) {
+    hp.peers[p] = H.peers[p];
+    hp.mine_off[p] = mine[p];
+    hp.theirs_off[p] = theirs[p];
+  }
+  hp.mine_off[hp.npeers] = mine[hp.npeers];
+  return hp;
+}
+
+inline bool use_peers(const alfib_ctx* c, const Halo& H) { return c->nranks > 1 && c->peers_open && H.has_peer_off; }
+
+}  // namespace
+
+// owner -> ghost: every ghost entry of x takes its owner's value
+void halo_update(alfib_ctx* c, Halo& H, double* x, int level) {
+  if (!H.on || c->nranks <= 1) return;
+  ScopedEvent ev(c, ALFIB_EV_HALO, level);
+  const int64_t ns = H.send_off.back(), nr = H.recv_off.back();
+  if (use_peers(c, H)) {
+    // every rank takes part in every exchange (the flags count exchanges), also one without neighbours here
+    ALFIB_REQUIRE((size_t)ns <= c->sym_stride, "packed halo does not fit the symmetric buffer");
+    halo_pack_kernel<<<halo_grid(ns), 256, 0, c->stream>>>(ns, H.send_idx.p, x, comm_peer_out(c));
+    peer_halo_update_kernel<<<halo_grid(nr), 256, 0, c->stream>>>(
+        nr, make_peers(H, H.recv_off, H.peer_send_off), c->nranks, c->rank, c->d_peer_slot.p, c->sym_stride, H.recv_idx.p, x,
+        c->d_comm_err.p, c->d_epoch.p, reinterpret_cast<unsigned int*>(c->d_comm_err.p + 1),
+        reinterpret_cast<LocalGate*>(c->d_gate.p));
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return;
+  }
+  if (H.peers.empty()) return;
+  if (ns) {
+    halo_pack_kernel<<<halo_grid(ns), 256, 0, c->stream>>>(ns, H.send_idx.p, x, plain_out(H.sbuf.p));
+    c->launches++;
+  }
+  halo_sendrecv(c, H, H.sbuf.p, H.send_off, H.rbuf.p, H.recv_off);
+  if (nr) {
+    halo_unpack_kernel<<<halo_grid(nr), 256, 0, c->stream>>>(nr, H.recv_idx.p, H.rbuf.p, x);
+    c->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+}
+
+// ghost -> owner: the ghost entries of y are added to their owners' entries (peers in ascending rank order: a
+// fixed summation order) and cleared
+void halo_reduce(alfib_ctx* c, Halo& H, double* y, int level) {
+  if (!H.on) return;
+  ScopedEvent ev(c, ALFIB_EV_HALO, level);
+  if (c->nranks > 1) {
+    const int64_t ns = H.send_off.back(), nr = H.recv_off.back();
+    if (use_peers(c, H)) {
+      ALFIB_REQUIRE((size_t)nr <= c->sym_stride, "packed halo does not fit the symmetric buffer");
+      halo_pack_kernel<<<halo_grid(nr), 256, 0, c->stream>>>(nr, H.recv_idx.p, y, comm_peer_out(c));
+      peer_halo_sum_kernel<<<halo_grid(H.n_red), 256, 0, c->stream>>>(
+          H.n_red, make_peers(H, H.send_off, H.peer_recv_off), c->nranks, c->rank, c->d_peer_slot.p, c->sym_stride,
+          H.red_ptr.p, H.red_dof.p, H.red_src.p, y, c->d_comm_err.p, c->d_epoch.p,
+          reinterpret_cast<unsigned int*>(c->d_comm_err.p + 1), reinterpret_cast<LocalGate*>(c->d_gate.p));
+      c->launches += 2;
+    } else if (!H.peers.empty()) {
+      if (nr) {
+        halo_pack_kernel<<<halo_grid(nr), 256, 0, c->stream>>>(nr, H.recv_idx.p, y, plain_out(H.rbuf.p));
+        c->launches++;
+      }
+      halo_sendrecv(c, H, H.rbuf.p, H.recv_off, H.sbuf.p, H.send_off);
+      if (ns && H.n_red) {
+        halo_sum_kernel<<<halo_grid(H.n_red), 256, 0, c->stream>>>(H.n_red, H.red_ptr.p, H.red_dof.p, H.red_src.p,
+                                                                   H.sbuf.p, y);
+        c->launches++;
+      }
+    }
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (H.n_local > H.n_owned)
+    CUDA_TRY(cudaMemsetAsync(y + H.n_owned, 0, sizeof(double) * (size_t)(H.n_local - H.n_owned), c->stream));
+}
+
+void comm_small_allreduce(alfib_ctx* c, double* v, int nv, int sqrt_mode, double* inv) {
+  if (c->nranks > 1 && c->peers_open) {
+    ALFIB_REQUIRE((size_t)nv <= c->sym_stride, "too many values for the symmetric buffer");
+    halo_pack_kernel<<<1, 64, 0, c->stream>>>(nv, nullptr, v, comm_peer_out(c));
+    peer_small_sum_kernel<<<1, 64, 0, c->stream>>>(nv, c->nranks, c->rank, c->d_peer_slot.p, c->sym_stride, v, sqrt_mode, inv,
+                                                   c->d_comm_err.p, c->d_epoch.p,
+                                                   reinterpret_cast<unsigned int*>(c->d_comm_err.p + 1),
+                                                   reinterpret_cast<LocalGate*>(c->d_gate.p));
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return;
+  }
+  comm_allreduce_sum(c, v, (size_t)nv);
+  if (sqrt_mode) {
+    sqrt_inv_kernel<<<1, 32, 0, c->stream>>>(v, inv);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
 }

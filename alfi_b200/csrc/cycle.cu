@@ -53,7 +53,18 @@ void prolong_device(alfib_ctx* c, Level& L, int level, const double* coarse, dou
   L.t2.alloc(L.n);
   L.r.alloc(L.n);
   double* rhs = L.r.p;
-  launch_csr_apply(c, L.p_rows, L.p_bs, L.p_rowptr.p, L.p_colidx.p, L.p_vals.p, coarse, rhs, (int64_t)L.p_vals.n);
+  // Distributed vectors (alfib_level_set_halo; the sequence of oracle/distributed.py DistHierarchy.prolong): P_H
+  // holds this rank's owned fine rows; its columns are the coarser level's vector in the transfer-halo layout
+  // (owned part copied, ghosts fetched from their owners) or, with a replicated coarser level, that vector
+  // itself.  Every later step produces owned entries; the gathers refresh the ghosts they read.
+  const double* csrc = coarse;
+  if (L.thalo.on) {
+    L.tc.alloc(L.thalo.n_local);
+    CUDA_TRY(cudaMemcpyAsync(L.tc.p, coarse, sizeof(double) * L.thalo.n_owned, cudaMemcpyDeviceToDevice, c->stream));
+    halo_update(c, L.thalo, L.tc.p, level);
+    csrc = L.tc.p;
+  }
+  launch_csr_apply(c, L.p_rows, L.p_bs, L.p_rowptr.p, L.p_colidx.p, L.p_vals.p, csrc, rhs, (int64_t)L.p_vals.n);
   if (L.has_d) {
     launch_bsr_spmv(c, L, L.dvals.p, rhs, L.t1.p, nullptr);          // b = gamma D rhs
     launch_set_rows(c, L.t1.p, nullptr, L.cb.p, L.ncb);              // coarse-boundary rows zeroed
@@ -80,7 +91,18 @@ void restrict_device(alfib_ctx* c, Level& L, Level& Lc, int level, const double*
     launch_sub(c, L.n, fine, L.t1.p, L.t2.p);                        // r2 = fine - b
     src = L.t2.p;
   }
-  launch_csr_apply(c, L.p_cols, L.p_bs, L.pt_rowptr.p, L.pt_colidx.p, L.pt_vals.p, src, coarse, (int64_t)L.pt_vals.n);
+  if (L.thalo.on) {
+    // P_H^T of the owned fine rows lands on the transfer-halo layout of the coarser level; the ghost parts are
+    // summed into their owners (DistHierarchy.restrict)
+    L.tc.alloc(L.thalo.n_local);
+    launch_csr_apply(c, L.p_cols, L.p_bs, L.pt_rowptr.p, L.pt_colidx.p, L.pt_vals.p, src, L.tc.p, (int64_t)L.pt_vals.n);
+    halo_reduce(c, L.thalo, L.tc.p, level);
+    CUDA_TRY(cudaMemcpyAsync(coarse, L.tc.p, sizeof(double) * L.thalo.n_owned, cudaMemcpyDeviceToDevice, c->stream));
+  } else {
+    launch_csr_apply(c, L.p_cols, L.p_bs, L.pt_rowptr.p, L.pt_colidx.p, L.pt_vals.p, src, coarse, (int64_t)L.pt_vals.n);
+    // replicated coarser level under a distributed fine level: every rank holds the part of its owned fine rows
+    if (L.halo.on && c->nranks > 1) comm_allreduce_sum(c, coarse, (size_t)Lc.n);
+  }
   launch_set_rows(c, coarse, nullptr, Lc.bc.p, Lc.nbc);
 }
 

@@ -136,10 +136,20 @@ __global__ void hessenberg_solve_kernel(int m, double* __restrict__ H, const dou
 // scal layout: [0, MAXV*MAXV) H ; then beta, inv, y[MAXV], h[MAXV]
 void fgmres_device(alfib_ctx* c, Level& L, int level, int m, const double* b, double* x) {
   ALFIB_REQUIRE(m >= 1 && m <= ALFIB_MAX_KRYLOV, "smoothing iterations out of range");
+  // A level with a halo (alfib_level_set_halo) holds local vectors: n entries per basis vector, of which the
+  // first `no` are owned.  BLAS-1 runs over the owned entries, every dot / norm is completed by one small
+  // all-reduce (KSPFGMRES on an MPI Vec: VecMDot / VecNorm), the ghosts a gather reads are refreshed by the
+  // consumer (patch_apply_sum, launch_bsr_spmv).
   const int n = L.n;
+  const int no = L.halo.on ? L.n_owned : L.n;
+  const bool dist = L.halo.on && c->nranks > 1;
   if (L.krylov_m < m) {
     L.V.alloc((size_t)(m + 1) * n);
     L.Z.alloc((size_t)m * n);
+    if (L.halo.on) {                 // ghost parts are read by the exchanges' pack kernels before they are written
+      CUDA_TRY(cudaMemsetAsync(L.V.p, 0, sizeof(double) * (size_t)(m + 1) * n, c->stream));
+      CUDA_TRY(cudaMemsetAsync(L.Z.p, 0, sizeof(double) * (size_t)m * n, c->stream));
+    }
     L.krylov_m = m;
   }
   L.w.alloc(n);
@@ -155,6 +165,25 @@ void fgmres_device(alfib_ctx* c, Level& L, int level, int m, const double* b, do
   cudaStream_t s = c->stream;
   CUDA_TRY(cudaMemsetAsync(H, 0, sizeof(double) * MAXV * MAXV, s));
 
+  // out[j] = <V_j, w> over all ranks, j < nv
+  auto mdot = [&](int nv, const double* Vp, const double* wp, double* out) {
+    multi_dot_kernel<<<RGRID, RT, 0, s>>>(no, nv, Vp, n, wp, c->partial.p);
+    finalize_kernel<<<nv, 32, 0, s>>>(nv, c->partial.p, out, 0, nullptr);
+    c->launches += 2;
+    if (dist) comm_small_allreduce(c, out, nv, 0, nullptr);
+  };
+  // out = sqrt(sum of the |.|^2 partials over all ranks), invp = 1 / out
+  auto norm_of_partials = [&](double* out, double* invp) {
+    if (!dist) {
+      finalize_kernel<<<1, 32, 0, s>>>(1, c->partial.p, out, 1, invp);
+      c->launches += 1;
+    } else {
+      finalize_kernel<<<1, 32, 0, s>>>(1, c->partial.p, out, 0, nullptr);
+      c->launches += 1;
+      comm_small_allreduce(c, out, 1, 1, invp);
+    }
+  };
+
   // r0 = b - A x ; beta = |r0| ; v0 = r0 / beta
   {
     ScopedEvent ev(c, ALFIB_EV_MATMULT, level);
@@ -162,10 +191,11 @@ void fgmres_device(alfib_ctx* c, Level& L, int level, int m, const double* b, do
   }
   {
     ScopedEvent ev(c, ALFIB_EV_KSP_GMRES_ORTHOG, level);
-    multi_dot_kernel<<<RGRID, RT, 0, s>>>(n, 1, w, n, w, c->partial.p);
-    finalize_kernel<<<1, 32, 0, s>>>(1, c->partial.p, beta, 1, inv);
-    scale_kernel<<<RGRID, RT, 0, s>>>(n, inv, w, V);
-    c->launches += 3;
+    multi_dot_kernel<<<RGRID, RT, 0, s>>>(no, 1, w, n, w, c->partial.p);
+    c->launches += 1;
+    norm_of_partials(beta, inv);
+    scale_kernel<<<RGRID, RT, 0, s>>>(no, inv, w, V);
+    c->launches += 1;
   }
   for (int k = 0; k < m; ++k) {
     double* vk = V + (size_t)k * n;
@@ -177,16 +207,16 @@ void fgmres_device(alfib_ctx* c, Level& L, int level, int m, const double* b, do
     }
     ScopedEvent ev(c, ALFIB_EV_KSP_GMRES_ORTHOG, level);
     double* hcol = H + (size_t)k * MAXV;
-    multi_dot_kernel<<<RGRID, RT, 0, s>>>(n, k + 1, V, n, w, c->partial.p);    // h = V^T w  (CGS)
-    finalize_kernel<<<k + 1, 32, 0, s>>>(k + 1, c->partial.p, hcol, 0, nullptr);
-    maxpy_kernel<<<RGRID, RT, 0, s>>>(n, k + 1, hcol, -1.0, V, n, w, c->partial.p);   // w -= V h, |w|^2
-    finalize_kernel<<<1, 32, 0, s>>>(1, c->partial.p, hcol + k + 1, 1, inv);
-    scale_kernel<<<RGRID, RT, 0, s>>>(n, inv, w, V + (size_t)(k + 1) * n);
-    c->launches += 5;
+    mdot(k + 1, V, w, hcol);                                                          // h = V^T w  (CGS)
+    maxpy_kernel<<<RGRID, RT, 0, s>>>(no, k + 1, hcol, -1.0, V, n, w, c->partial.p);   // w -= V h, |w|^2
+    c->launches += 1;
+    norm_of_partials(hcol + k + 1, inv);
+    scale_kernel<<<RGRID, RT, 0, s>>>(no, inv, w, V + (size_t)(k + 1) * n);
+    c->launches += 1;
   }
   ScopedEvent ev(c, ALFIB_EV_KSP_GMRES_ORTHOG, level);
   hessenberg_solve_kernel<<<1, 32, 0, s>>>(m, H, beta, y);
-  maxpy_kernel<<<RGRID, RT, 0, s>>>(n, m, y, 1.0, Z, n, x, nullptr);          // x += Z y
+  maxpy_kernel<<<RGRID, RT, 0, s>>>(no, m, y, 1.0, Z, n, x, nullptr);          // x += Z y
   c->launches += 2;
   CUDA_TRY(cudaGetLastError());
 }

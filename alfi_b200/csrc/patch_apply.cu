@@ -120,6 +120,14 @@ void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, PeerO
 // reference's PetscSF in one pass.  Without peer memory: NCCL all-reduce of the whole vector.
 void patch_apply_sum(alfib_ctx* c, Level& L, int level, int which, const double* x, double* y) {
   const PatchSet& ps = L.ps[which];
+  if (L.halo.on) {
+    // distributed vectors: the PetscSF bcast of x, this rank's patches, the PetscSF reduce of y (Appendix A.3)
+    halo_update(c, L.halo, const_cast<double*>(x), level);
+    CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * L.n, c->stream));
+    launch_patch_apply(c, ps, x, plain_out(y));
+    halo_reduce(c, L.halo, y, level);
+    return;
+  }
   if (c->nranks > 1 && c->peers_open) {
     comm_peer_zero(c, ps.lo, ps.hi);
     launch_patch_apply(c, ps, x, comm_peer_out(c));

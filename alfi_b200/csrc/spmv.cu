@@ -129,9 +129,12 @@ void launch_bsr_spmv(alfib_ctx* c, const Level& L, const double* vals, const dou
                      const double* b) {
   const int threads = 256;
   // multi-GPU: this rank computes its own block rows, then the owned rows are broadcast
-  const bool sharded = c->nranks > 1 && !L.row_start.empty();
+  // distributed vectors (alfib_level_set_halo): refresh the ghosts of x, then the owned block rows only —
+  // x is a local work vector there, its ghost part is scratch
+  const bool sharded = c->nranks > 1 && !L.row_start.empty() && !L.halo.on;
+  if (L.halo.on) halo_update(c, const_cast<Level&>(L).halo, const_cast<double*>(x), L.index);
   const int row0 = sharded ? (int)L.row_start[c->rank] : 0;
-  const int row1 = sharded ? (int)L.row_start[c->rank + 1] : L.n_nodes;
+  const int row1 = sharded ? (int)L.row_start[c->rank + 1] : (L.halo.on ? L.n_owned / L.bs : L.n_nodes);
   const int blocks = cdiv((int64_t)(row1 - row0) * 16, threads);
   const bool peer = sharded && c->peers_open;
   const PeerOut out = peer ? comm_peer_out(c) : plain_out(y);

@@ -221,6 +221,7 @@ class LocalLevel:
     cb_dofs: np.ndarray | None = None
     a0_vals: np.ndarray | None = None
     d_vals: np.ndarray | None = None
+    vals_sel: np.ndarray | None = None      # positions of the local blocks in the global value arrays (per-Newton refresh)
 
     @property
     def n_owned(self):
@@ -277,7 +278,7 @@ def local_level(li, layout: Layout, rank: int, halo: Layout | None = None) -> Lo
         patch_blocks=None if li.patch_blocks is None else np.asarray(li.patch_blocks)[pidx],
         patch_ids=mine,
         send={p: v.copy() for p, v in r.send.items()},
-        recv={p: r.n_owned + v for p, v in r.recv.items()})
+        recv={p: r.n_owned + v for p, v in r.recv.items()}, vals_sel=sel)
     if li.P is not None:
         P = li.P.tocsr() if li.P_dof_level else sp.kron(li.P, sp.identity(bs), format="csr")
         Pr = P[r.owned]

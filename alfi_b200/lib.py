@@ -19,7 +19,7 @@ _lib = None
 
 # PETSc event names alfi reports (alfi/driver.py:80) in ALFIB_EV_* order
 EVENT_NAMES = ["PCPATCHApply", "MatMult", "SchoeberlProlong", "SchoeberlRestrict",
-               "KSPGMRESOrthog", "MGCoarseSolve", "PCSetUp_PATCH"]
+               "KSPGMRESOrthog", "MGCoarseSolve", "PCSetUp_PATCH", "SFBcastReduce"]
 
 PATCHES_SMOOTHER, PATCHES_TRANSFER = 0, 1
 OPT_DETERMINISTIC, OPT_SYNC_ALWAYS, OPT_ROBUST_RESTRICT = 1, 2, 3
@@ -43,6 +43,8 @@ SIGNATURES = {
     "alfib_comm_peer_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "alfib_comm_peer_open": (C.c_int, [C.c_void_p, C.c_void_p]),
     "alfib_level_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "alfib_level_set_halo": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_int32, _i32p, _i64p, _i32p,
+                                       _i64p, _i32p, _i64p, _i64p]),
     "alfib_level_set_bsr_pattern": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _i32p]),
     "alfib_level_set_bsr_values": (C.c_int, [C.c_void_p, C.c_int, _f64p, C.c_int]),
     "alfib_level_set_bc": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, _i32p]),
@@ -211,6 +213,42 @@ class Context:
     def level_create(self, level, n_nodes, bs):
         self._check(self.lib.alfib_level_create(self.h, level, n_nodes, bs))
         self._sizes[level] = n_nodes * bs
+
+    @staticmethod
+    def halo_peer_list(send: dict, recv: dict):
+        """(peers ascending, send offsets, recv offsets) — the packed layout alfib_level_set_halo uses."""
+        peers = sorted(set(send) | set(recv))
+        s_off = np.zeros(len(peers) + 1, np.int64)
+        r_off = np.zeros(len(peers) + 1, np.int64)
+        for k, q in enumerate(peers):
+            s_off[k + 1] = s_off[k] + np.asarray(send.get(q, ())).size
+            r_off[k + 1] = r_off[k] + np.asarray(recv.get(q, ())).size
+        return peers, s_off, r_off
+
+    def set_halo(self, level, n_owned, n_local, send: dict, recv: dict, which=0, peer_offsets=None):
+        """Distributed vectors on `level` (which = 0) or the transfer halo of `level` on level-1 (which = 1):
+        `send[peer]` = owned local dofs the peer holds as ghosts, `recv[peer]` = the matching ghost local dofs
+        (alfi_b200.halo.LocalLevel.send / .recv).  `peer_offsets` = {peer: (offset of this rank's segment in the
+        peer's send list, in its recv list)} enables the NVLink peer-memory transport.  See include/alfib.h."""
+        peers = sorted(set(send) | set(recv))
+        empty = np.empty(0, np.int32)
+        s_off = np.zeros(len(peers) + 1, np.int64)
+        r_off = np.zeros(len(peers) + 1, np.int64)
+        for k, q in enumerate(peers):
+            s_off[k + 1] = s_off[k] + np.asarray(send.get(q, empty)).size
+            r_off[k + 1] = r_off[k] + np.asarray(recv.get(q, empty)).size
+        s_idx = _i32(np.concatenate([np.asarray(send.get(q, empty)).ravel() for q in peers])) if peers else empty
+        r_idx = _i32(np.concatenate([np.asarray(recv.get(q, empty)).ravel() for q in peers])) if peers else empty
+        pa = _i32(peers)
+        pso = pro = None
+        if peer_offsets is not None:
+            pso = np.ascontiguousarray([peer_offsets[q][0] for q in peers], dtype=np.int64)
+            pro = np.ascontiguousarray([peer_offsets[q][1] for q in peers], dtype=np.int64)
+        self._check(self.lib.alfib_level_set_halo(self.h, level, which, int(n_owned), int(n_local), len(peers),
+                                                  _ptr(pa, C.c_int32), _ptr(s_off, C.c_int64), _ptr(s_idx, C.c_int32),
+                                                  _ptr(r_off, C.c_int64), _ptr(r_idx, C.c_int32),
+                                                  None if pso is None else _ptr(pso, C.c_int64),
+                                                  None if pro is None else _ptr(pro, C.c_int64)))
 
     def set_bsr_pattern(self, level, rowptr, colidx):
         rowptr, colidx = _i32(rowptr), _i32(colidx)

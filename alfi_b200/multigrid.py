@@ -15,7 +15,7 @@ import numpy as np
 
 from .lib import PATCHES_SMOOTHER, PATCHES_TRANSFER, Context
 
-__all__ = ["LevelInput", "DeviceMultigrid", "level_input_from_synth"]
+__all__ = ["LevelInput", "DeviceMultigrid", "DistributedMultigrid", "level_input_from_synth"]
 
 
 @dataclass
@@ -176,6 +176,156 @@ class DeviceMultigrid:
     def apply(self, b, x):
         """x = one fieldsplit_0 application (F-cycle) of b."""
         return self.ctx.cycle_apply(b, x)
+
+
+class DistributedMultigrid:
+    """The same cycle on `nranks` GPUs with DISTRIBUTED level vectors: every level >= 1
+    is handed to the library as this rank's `alfi_b200.halo.LocalLevel` — owned dofs first, then ghosts, operator
+    rows / patches / cell patches / P_H rows in local numbering — with the exchange lists of its halo
+    (`alfib_level_set_halo`); level 0 stays replicated (redundant solve after one small all-reduce).  Per Krylov
+    iteration the library then moves only ghost entries between neighbouring ranks (two owner->ghost updates, one
+    ghost->owner sum) and reduces the dots with one small all-reduce each, instead of the full-vector all-reduce /
+    all-gather of the replicated design (`DeviceMultigrid` with nranks > 1).
+
+    Every rank passes the same global `levels` here (a deployment would build the LocalLevels from its own mesh
+    partition).  Vectors given to `apply` are LOCAL (`scatter` / `local_dofs`); `gather` assembles the global
+    result with torch.distributed.  oracle/distributed.py is the CPU statement of the same algorithm."""
+
+    def __init__(self, levels: list[LevelInput], smoothing: int, rank: int, nranks: int, unique_id: bytes | None,
+                 device: int = 0, deterministic: bool = False, robust_restrict: bool = True, ctx=None,
+                 torch_storage: bool = False, condense: bool = True, peer_memory: bool = False):
+        """``peer_memory``: ghost exchanges and the dots' all-reduces over NVLink peer memory (one pull kernel per
+        exchange, csrc/comm.cu) instead of NCCL send/recv; collective (torch.distributed all-gather of the IPC
+        handles)."""
+        import scipy.sparse as sp
+
+        from .dist import condensed_cost, partition_patches
+        from .halo import build_layout, local_level, transfer_halo
+        self.ctx = c = ctx or Context(device, deterministic)
+        self.nlevels, self.smoothing = len(levels), smoothing
+        self.rank, self.nranks = rank, nranks
+        self._storage = []
+        c.set_option(3, robust_restrict)
+        c.comm_init(unique_id, rank, nranks)
+        # ---- layouts (identical on every rank: pure functions of the global data)
+        self.layouts, self.halos = [None], [None]
+        for l in range(1, self.nlevels):
+            li = levels[l]
+            blocks = li.patch_blocks if condense else None
+            cost = condensed_cost(li.patch_offsets, blocks) if blocks is not None else None
+            owner = partition_patches(li.patch_offsets, li.patch_dofs, nranks, cost)
+            extra = (li.cell_offsets, li.cell_dofs) if li.cell_offsets is not None else None
+            self.layouts.append(build_layout(li.patch_offsets, li.patch_dofs, li.patch_order, owner, li.rowptr, li.colidx,
+                                             li.bs, li.n_nodes * li.bs, extra_sets=extra, nranks=nranks))
+        for l in range(1, self.nlevels):
+            li = levels[l]
+            if l == 1:
+                self.halos.append(None)
+            else:
+                P = li.P.tocsr() if li.P_dof_level else sp.kron(li.P, sp.identity(li.bs), format="csr")
+                self.halos.append(transfer_halo(P, self.layouts[l], self.layouts[l - 1].owner))
+        self.local = [None] + [local_level(levels[l], self.layouts[l], rank, self.halos[l]) for l in range(1, self.nlevels)]
+        # ---- hand-over
+        li = levels[0]
+        c.level_create(0, li.n_nodes, li.bs)
+        c.set_bsr_pattern(0, li.rowptr, li.colidx)
+        c.set_bc(0, li.bc_dofs)
+        if condense and li.coarse_blocks is not None and os.environ.get("ALFIB_COARSE_CONDENSED", "1") != "0":
+            c.set_patches(0, np.array([0, li.coarse_dofs.size], np.int64), li.coarse_dofs, np.zeros(1, np.int32),
+                          np.zeros(1, np.int32), PATCHES_SMOOTHER)
+            c.set_patch_blocks(0, li.coarse_blocks, PATCHES_SMOOTHER)
+        for l in range(1, self.nlevels):
+            ll = self.local[l]
+            c.level_create(l, ll.n_local_nodes, ll.bs)
+            c.set_halo(l, ll.n_owned, ll.n_local, ll.send, ll.recv, 0,
+                       self._peer_offsets(self.layouts[l]) if peer_memory else None)
+            if self.halos[l] is not None:
+                hr = self.halos[l].ranks[rank]
+                c.set_halo(l, hr.n_owned, hr.n_local, hr.send, {q: hr.n_owned + v for q, v in hr.recv.items()}, 1,
+                           self._peer_offsets(self.halos[l]) if peer_memory else None)
+            c.set_bsr_pattern(l, ll.rowptr, ll.colidx)
+            c.set_bc(l, ll.bc_dofs)
+            c.set_patches(l, ll.patch_offsets, ll.patch_dofs, ll.patch_order, ll.patch_colours, PATCHES_SMOOTHER)
+            if condense and ll.patch_blocks is not None:
+                c.set_patch_blocks(l, ll.patch_blocks, PATCHES_SMOOTHER)
+            if torch_storage:
+                self._bind(l, PATCHES_SMOOTHER)
+            c.set_transfer(l, ll.P, ll.cb_dofs if ll.cb_dofs is not None else np.empty(0, np.int32), True)
+            if ll.cell_offsets is not None:
+                c.set_patches(l, ll.cell_offsets, ll.cell_dofs, None, np.zeros(ll.cell_offsets.size - 1, np.int32),
+                              PATCHES_TRANSFER)
+                if condense and ll.cell_blocks is not None:
+                    c.set_patch_blocks(l, ll.cell_blocks, PATCHES_TRANSFER)
+                if torch_storage:
+                    self._bind(l, PATCHES_TRANSFER)
+        if peer_memory and nranks > 1:
+            import torch.distributed as dist
+            handles = [None] * nranks
+            dist.all_gather_object(handles, c.comm_peer_handle())
+            c.comm_peer_open(b"".join(handles))
+        self.update_operators(levels)
+        self.update_transfers(levels)
+        c.cycle_setup(self.nlevels, smoothing)
+
+    _bind = DeviceMultigrid._bind
+
+    def _peer_offsets(self, layout):
+        """{peer: (start of this rank's segment in the peer's packed send list, in its packed ghost list)} — in a
+        deployment two integers per neighbour exchanged at setup; here read off the global layout."""
+        me = layout.ranks[self.rank]
+        out = {}
+        for q in sorted(set(me.send) | set(me.recv)):
+            rq = layout.ranks[q]
+            peers_q, s_off, r_off = Context.halo_peer_list(rq.send, rq.recv)
+            k = peers_q.index(self.rank)
+            out[q] = (int(s_off[k]), int(r_off[k]))
+        return out
+
+    def update_operators(self, levels):
+        """Once per Newton step: this rank's blocks of the new operator values, patch factors, coarse inverse."""
+        c = self.ctx
+        c.set_bsr_values(0, levels[0].vals)
+        for l in range(1, self.nlevels):
+            c.set_bsr_values(l, np.ascontiguousarray(np.asarray(levels[l].vals)[self.local[l].vals_sel]))
+            c.factor(l)
+        c.coarse_factor()
+
+    def update_transfers(self, levels):
+        for l in range(1, self.nlevels):
+            li, ll = levels[l], self.local[l]
+            if li.a0_vals is not None:
+                self.ctx.transfer_update(l, np.ascontiguousarray(np.asarray(li.a0_vals)[ll.vals_sel]),
+                                         np.ascontiguousarray(np.asarray(li.d_vals)[ll.vals_sel]))
+
+    # ---- vectors
+    @property
+    def local_dofs(self):
+        """Global dof of every local dof of the finest level (owned first)."""
+        return self.local[-1].local_dofs if self.nlevels > 1 else None
+
+    @property
+    def n_owned(self):
+        return self.local[-1].n_owned
+
+    def scatter(self, x_global):
+        """Global finest-level vector -> this rank's local vector (ghosts consistent)."""
+        return np.ascontiguousarray(np.asarray(x_global)[self.local_dofs])
+
+    def gather(self, x_local):
+        """This rank's local vector -> the global vector on every rank (sum of the owned parts over the ranks)."""
+        import torch
+        import torch.distributed as dist
+        ll = self.local[-1]
+        xl = x_local if isinstance(x_local, torch.Tensor) else torch.from_numpy(np.asarray(x_local))
+        out = torch.zeros(self.layouts[-1].ndofs, dtype=torch.float64, device=xl.device)
+        out[torch.from_numpy(ll.local_dofs[:ll.n_owned]).to(xl.device)] = xl[:ll.n_owned]
+        if self.nranks > 1:
+            dist.all_reduce(out)
+        return out
+
+    def apply(self, b_local, x_local):
+        """x = one fieldsplit_0 application of b, both LOCAL vectors of the finest level (owned part valid)."""
+        return self.ctx.cycle_apply(b_local, x_local)
 
 
 class DeviceBackend:

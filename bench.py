@@ -213,6 +213,9 @@ def ours(args):
     prob = build_problem(args.config, verbose=(rank == 0))
     cfg = prob.config
     log("rank %d: problem built in %.1fs" % (rank, time.time() - t0))
+    # N > 1: level vectors distributed (owned + ghosts per rank, neighbour exchanges) or replicated
+    distributed = world > 1 and args.vectors == "distributed"
+
     def make_mg(condense):
         """Device hierarchy + one per-Newton-step refresh; returns (mg, setup_s, newton_setup_s)."""
         t0 = time.time()
@@ -220,10 +223,16 @@ def ours(args):
         if world > 1:
             from alfi_b200.dist import bootstrap_unique_id
             uid = bootstrap_unique_id(rank)
-        mg = DeviceMultigrid([level_input_from_synth(l) for l in prob.levels], cfg.m, device=local,
-                             deterministic=bool(args.deterministic), torch_storage=True,
-                             rank=rank, nranks=world, unique_id=uid, peer_memory=bool(args.peer_memory),
-                             condense=bool(condense))
+        if distributed:
+            from alfi_b200.multigrid import DistributedMultigrid
+            mg = DistributedMultigrid([level_input_from_synth(l) for l in prob.levels], cfg.m, rank, world, uid,
+                                      device=local, deterministic=bool(args.deterministic), torch_storage=True,
+                                      condense=bool(condense), peer_memory=bool(args.peer_memory))
+        else:
+            mg = DeviceMultigrid([level_input_from_synth(l) for l in prob.levels], cfg.m, device=local,
+                                 deterministic=bool(args.deterministic), torch_storage=True,
+                                 rank=rank, nranks=world, unique_id=uid, peer_memory=bool(args.peer_memory),
+                                 condense=bool(condense))
         mg.ctx.synchronize()
         setup_s = time.time() - t0
         log("rank %d: device setup (upload + factor) %.1fs" % (rank, setup_s))
@@ -269,10 +278,13 @@ def ours(args):
 
     n = prob.finest.ndofs
     rng = np.random.default_rng(20261017)          # same right-hand side on every rank (replicated vectors)
-    bh = torch.empty(n, dtype=torch.float64).pin_memory()
-    xh = torch.empty(n, dtype=torch.float64).pin_memory()
     bnp = rng.standard_normal(n)
     bnp[prob.finest.bc_dofs] = 0.0
+    if distributed:
+        bnp = mg.scatter(bnp)                      # this rank's local vector: owned dofs, then ghosts
+    nvec = bnp.size
+    bh = torch.empty(nvec, dtype=torch.float64).pin_memory()
+    xh = torch.empty(nvec, dtype=torch.float64).pin_memory()
     bh.copy_(torch.from_numpy(bnp))
     bd = bh.cuda()
     xd = torch.empty_like(bd)
@@ -286,13 +298,17 @@ def ours(args):
         rr = torch.empty_like(xvec)
         mg.ctx.residual(len(prob.levels) - 1, bd, xvec, rr)
         mg.ctx.synchronize()
+        if distributed:                            # norms over the owned entries of all ranks
+            t = torch.stack([(rr[:mg.n_owned] ** 2).sum(), (bd[:mg.n_owned] ** 2).sum()])
+            dist.all_reduce(t)
+            return float(torch.sqrt(t[0] / t[1]))
         return float(torch.linalg.norm(rr) / torch.linalg.norm(bd))
 
     # ---- device-resident steps (value) ------------------------------------------------------
     for _ in range(args.warmup):
         mg.apply(bd, xd)
     mg.ctx.synchronize()
-    if world > 1 and args.condense:
+    if world > 1 and args.condense and not distributed:
         red0 = reduction(xd)
         if not all_ok(np.isfinite(red0) and red0 < 0.9):
             log("rank %d: sharded condensed cycle does not reduce the residual (%.3e); dense inverses instead" % (rank, red0))
@@ -444,10 +460,13 @@ def ours(args):
                    "l2_policy": "inputs larger than L2 (%.1f GB of patch inverses streamed per finest-level smoother "
                                 "application, 126 MB L2)" % (factor_bytes / 1e9),
                    "fallback": fallback, "deterministic": bool(args.deterministic), "parallelism": "1 GPU" if world == 1 else
+                   ("patches sharded over %d GPUs, level vectors distributed (owned + ghost dofs per rank): neighbour "
+                    "ncclSend/ncclRecv of ghost entries around every patch apply / SpMV, small ncclAllReduce per dot; "
+                    "level 0 replicated" % world) if distributed else
                    "patches + operator rows sharded over %d GPUs, level vectors replicated; ncclAllReduce after "
                    "every patch apply, grouped ncclBroadcast after every SpMV" % world},
         "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "DoF/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n},
+                "h2d_bytes_per_step": 8 * nvec, "d2h_bytes_per_step": 8 * nvec},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "breakdown_ms": breakdown, "setup_s": {"device_upload_factor": setup_s, "per_newton_step": newton_setup_s}, "continuation": continuation,
         "residual_reduction": red,
@@ -479,6 +498,8 @@ def main():
                     help="also run the Newton continuation on this 3-D config (e.g. ldc3d-sv-k3-half); minutes of host assembly")
     ap.add_argument("--continuation-3d-re", default="10,100,200,300,400,500", help="Reynolds numbers of --continuation-3d")
     ap.add_argument("--peer-memory", type=int, default=0, help="N > 1: NVLink peer-memory exchanges instead of NCCL")
+    ap.add_argument("--vectors", default="replicated", choices=["replicated", "distributed"],
+                    help="N > 1: replicated level vectors (measured in round 1) or distributed ones (DESIGN §6.1)")
     ap.add_argument("--condense", type=int, default=1,
                     help="1 (default): condensed block/separator patch inverses where the mesh has macro structure; 0: dense")
     args = ap.parse_args()

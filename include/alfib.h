@@ -91,6 +91,36 @@ int alfib_comm_init(alfib_ctx* ctx, const void* nccl_unique_id, int rank, int nr
 int alfib_comm_peer_handle(alfib_ctx* ctx, void* out64);
 int alfib_comm_peer_open(alfib_ctx* ctx, const void* handles);
 
+/* Distributed level vectors (the PetscSF pattern of the reference's parallel PCPATCH / MatMult on the
+ * vertex-overlap partition, solver.py:604-605, 661-662).  A level that is given a halo
+ * holds LOCAL vectors: this rank's owned dofs first (n_owned_dofs of them), then its ghosts, n_local
+ * dofs = the size alfib_level_create was called with; the operator pattern, patches, Dirichlet lists
+ * and cell patches of such a level are in local numbering, block rows complete for the owned nodes
+ * (alfi_b200.halo.local_level builds exactly this).  send_idx[send_off[p] .. send_off[p+1]) are the
+ * owned local dofs peer `peers[p]` holds as ghosts, recv_idx the matching ghost local dofs on this
+ * rank, both in the order the two ranks agree on.  The library then runs
+ *   owner->ghost update  before every gather of ghost entries (patch gather, SpMV, P_H),
+ *   ghost->owner sum     after every patch scatter-add (peers in ascending rank order: reproducible),
+ * between neighbouring ranks only (grouped ncclSend/ncclRecv of the packed entries), reduces the
+ * FGMRES dots over the owned entries with one small ncclAllReduce, and stops replicating vectors
+ * and sharding operator rows on that level.  which = 0: the level's own vectors.  which = 1: the
+ * "transfer halo" of level `level` — the layout in which P_H of level `level` reads the vectors of
+ * level-1 (same owned dofs as that level's halo, ghosts = the other coarse dofs in the columns of
+ * this rank's rows of P_H); without it level-1 must be replicated (no halo), its restricted
+ * right-hand side is then summed with one all-reduce.  Call after alfib_comm_init and
+ * alfib_level_create and before alfib_transfer_set; vectors passed to alfib_smooth / alfib_prolong /
+ * alfib_restrict / alfib_cycle_apply on such a level are local vectors whose owned part is valid
+ * on entry and on return.  peer_send_off[p] / peer_recv_off[p] (optional) = where, in peer p's
+ * own send_idx / recv_idx lists, the segment for THIS rank starts; with them and
+ * alfib_comm_peer_open the exchanges run over NVLink peer memory — pack into this rank's symmetric
+ * slot, then one kernel that pulls the neighbours' packed entries into place — instead of NCCL,
+ * and the small all-reduces of the dots take the same route.                                    */
+int alfib_level_set_halo(alfib_ctx* ctx, int level, int which, int32_t n_owned_dofs, int32_t n_local_dofs,
+                         int32_t npeers, const int32_t* peers, const int64_t* send_off,
+                         const int32_t* send_idx, const int64_t* recv_off, const int32_t* recv_idx,
+                         const int64_t* peer_send_off /* [npeers] or NULL */,
+                         const int64_t* peer_recv_off /* [npeers] or NULL */);
+
 /* ---- level operator: replaces the BAIJ Mat PETSc holds for fieldsplit_0 on each level
  *      (parameters["default_sub_matrix_type"] = "baij", solver.py:512)                        */
 int alfib_level_create(alfib_ctx* ctx, int level, int n_nodes, int bs);
@@ -188,7 +218,8 @@ int alfib_cycle_apply(alfib_ctx* ctx, const double* b, double* x);
 /* ---- instrumentation: names follow the PETSc events alfi reports (driver.py:80)              */
 enum {
   ALFIB_EV_PCPATCH_APPLY = 0, ALFIB_EV_MATMULT = 1, ALFIB_EV_PROLONG = 2, ALFIB_EV_RESTRICT = 3,
-  ALFIB_EV_KSP_GMRES_ORTHOG = 4, ALFIB_EV_COARSE = 5, ALFIB_EV_PCSETUP_PATCH = 6, ALFIB_EV_COUNT = 7
+  ALFIB_EV_KSP_GMRES_ORTHOG = 4, ALFIB_EV_COARSE = 5, ALFIB_EV_PCSETUP_PATCH = 6,
+  ALFIB_EV_HALO = 7 /* PetscSF bcast / reduce of ghost entries (distributed vectors) */, ALFIB_EV_COUNT = 8
 };
 /* enable/disable CUDA-event timing per kernel family and level.  Events are recorded on the ctx
  * stream without synchronising and resolved when read, so the timed region is not perturbed.  */
