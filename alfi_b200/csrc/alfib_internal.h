@@ -92,10 +92,20 @@ struct Condensed {
   DBuf<BlockDesc> blocks;               // what the block setup kernel runs over: instances, or distinct blocks (shared form)
   DBuf<TileOp> opsV, opsS, opsDW;
   DBuf<double> g1, rs, us, z;           // V outputs, per-patch separator rhs / solution, shared form: summed us per block
+  // Schur-complement setup (ALFIB_SCHUR_SETUP=1; condense_host.h build_schur_lists): X_SS = inverse of
+  // A_SS - sum_k A_Sk A_kk^-1 A_kS instead of the S x S cut of the inverse of the whole patch
+  bool schur = false;
+  SchurHost sh;
+  DBuf<int32_t> sepsorted, sepperm, nb_pos, sc_upos, sc_inst_ld, sforder;
+  DBuf<int64_t> blk_start, nb_off, sc_coff, sc_inst_c;
+  DBuf<double> cbuf;                    // C = A_Nk A_kk^-1 A_kN of every factor block (m x m)
   void release() {
     sepoff.release(); ssoff.release(); seplocal.release(); sepdofs.release(); cidx.release();
     bdofs.release(); bkeys.release(); bperm.release(); cptr.release(); cg1.release(); blocks.release();
     zptr.release(); zsrc.release(); z.release();
+    sepsorted.release(); sepperm.release(); nb_pos.release(); sc_upos.release(); sc_inst_ld.release(); sforder.release();
+    blk_start.release(); nb_off.release(); sc_coff.release(); sc_inst_c.release(); cbuf.release();
+    schur = false;
     opsV.release(); opsS.release(); opsDW.release(); g1.release(); rs.release(); us.release();
   }
 };
@@ -304,7 +314,7 @@ void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, PeerO
 void patch_apply_sum(alfib_ctx* c, Level& L, int level, int which, const double* x, double* y);
 // condense.cu
 void condense_setup(alfib_ctx* c, Level& L, PatchSet& ps, const int32_t* block_of_dof);
-void launch_condense_blocks(alfib_ctx* c, const Level& L, PatchSet& ps, const double* vals);
+void launch_condense_blocks(alfib_ctx* c, const Level& L, PatchSet& ps, const double* vals, bool schur = false);
 void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, PeerOut y);
 void condensed_extract_inverse(alfib_ctx* c, const PatchSet& ps, int patch, double* host_out);
 // patch_factor.cu

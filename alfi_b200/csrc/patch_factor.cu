@@ -70,6 +70,16 @@ struct FactorArgs {
   int* counter;
   int* info;                   // 0 or (1 + index of a singular patch)
   long long* timing;           // optional per-phase clock64 totals (ALFIB_FACTOR_TIMING=1), else null
+  // Schur-complement setup (condense.cu, condense_host.h build_schur_lists): the "patches" are the separators,
+  // and after the gather of A_SS every block instance q of patch p subtracts its C = A_Nk A_kk^-1 A_kN:
+  //   W[nb_pos[i], nb_pos[j]] -= C_q[upos[i], upos[j]],  i, j in [nb_off[q], nb_off[q+1]);   null: plain patches
+  const int64_t* sc_blk_start;
+  const int64_t* sc_nb_off;
+  const int32_t* sc_nb_pos;
+  const int32_t* sc_upos;
+  const int64_t* sc_inst_c;
+  const int32_t* sc_inst_ld;
+  const double* sc_cbuf;
 };
 
 enum { PH_GATHER, PH_PANEL_LOAD, PH_INNER_GJ, PH_INBLOCK, PH_FAR_SWAP, PH_FAR_NS, PH_FAR_RS, PH_FAR_MMA, PH_PACK, PH_COUNT };
@@ -182,6 +192,20 @@ __global__ void __launch_bounds__(FT, 1) patch_factor_kernel(FactorArgs a) {
       }
     }
     __syncthreads();
+    if (a.sc_blk_start) {
+      for (int64_t qi = a.sc_blk_start[p]; qi < a.sc_blk_start[p + 1]; ++qi) {
+        const int64_t o2 = a.sc_nb_off[qi];
+        const int mq = (int)(a.sc_nb_off[qi + 1] - o2);
+        const double* __restrict__ C = a.sc_cbuf + a.sc_inst_c[qi];
+        const int ldc = a.sc_inst_ld[qi];
+        for (int i = tid; i < mq * mq; i += FT) {
+          const int jj = i / mq, ii = i - jj * mq;
+          W[a.sc_nb_pos[o2 + ii] + (size_t)a.sc_nb_pos[o2 + jj] * ld] -=
+              C[a.sc_upos[o2 + ii] + (size_t)a.sc_upos[o2 + jj] * ldc];
+        }
+        __syncthreads();                 // the instances of a patch overlap on the separator
+      }
+    }
     pc.mark(PH_GATHER);
 
     // ---- two-level blocked Gauss-Jordan -----------------------------------------------------
@@ -545,7 +569,14 @@ void run_factor(alfib_ctx* c, FactorArgs a, size_t smem, int grid) {
 
 void launch_patch_factor(alfib_ctx* c, const Level& L, PatchSet& ps, const double* vals) {
   if (ps.npatch == 0 || ps.maxn == 0) { ps.factored = true; return; }
-  const int maxn = ps.maxn;
+  // Schur-complement setup of a condensed set: the block kernel first (it leaves C = A_Nk A_kk^-1 A_kN per block),
+  // then this kernel on the separators only
+  const bool schur = ps.cond.on && ps.cond.schur;
+  if (schur) {
+    launch_condense_blocks(c, L, ps, vals, true);
+    if (ps.cond.h.maxsep == 0) { ps.factored = true; return; }
+  }
+  const int maxn = schur ? ps.cond.h.maxsep : ps.maxn;
   const size_t budget = 220 * 1024;
   int NB = 16;
   while (NB > 4 && factor_smem_bytes(maxn, NB) > budget) NB >>= 1;
@@ -561,15 +592,22 @@ void launch_patch_factor(alfib_ctx* c, const Level& L, PatchSet& ps, const doubl
 
   FactorArgs a;
   a.npatch = ps.npatch;
-  a.forder = ps.forder.p;
-  a.poff = ps.off.p;
-  a.pdofs = ps.dofs.p;
-  a.sorted = ps.sorted.p;
-  a.sperm = ps.sperm.p;
+  a.forder = schur ? ps.cond.sforder.p : ps.forder.p;
+  a.poff = schur ? ps.cond.sepoff.p : ps.off.p;
+  a.pdofs = schur ? ps.cond.sepdofs.p : ps.dofs.p;
+  a.sorted = schur ? ps.cond.sepsorted.p : ps.sorted.p;
+  a.sperm = schur ? ps.cond.sepperm.p : ps.sperm.p;
   a.soff = ps.cond.on ? ps.cond.ssoff.p : ps.soff.p;
   a.store = ps.store;
-  a.sepoff = ps.cond.on ? ps.cond.sepoff.p : nullptr;
-  a.seplocal = ps.cond.on ? ps.cond.seplocal.p : nullptr;
+  a.sepoff = (ps.cond.on && !schur) ? ps.cond.sepoff.p : nullptr;
+  a.seplocal = (ps.cond.on && !schur) ? ps.cond.seplocal.p : nullptr;
+  a.sc_blk_start = schur ? ps.cond.blk_start.p : nullptr;
+  a.sc_nb_off = ps.cond.nb_off.p;
+  a.sc_nb_pos = ps.cond.nb_pos.p;
+  a.sc_upos = ps.cond.sc_upos.p;
+  a.sc_inst_c = ps.cond.sc_inst_c.p;
+  a.sc_inst_ld = ps.cond.sc_inst_ld.p;
+  a.sc_cbuf = ps.cond.cbuf.p;
   a.bs = L.bs;
   a.rowptr = L.rowptr.p;
   a.colidx = L.colidx.p;
@@ -609,7 +647,7 @@ void launch_patch_factor(alfib_ctx* c, const Level& L, PatchSet& ps, const doubl
   }
   if (info[0] != 0)
     throw DeviceError{ALFIB_ESINGULAR, "patch " + std::to_string(info[0] - 1) + " is singular"};
-  if (ps.cond.on) launch_condense_blocks(c, L, ps, vals);
+  if (ps.cond.on && !schur) launch_condense_blocks(c, L, ps, vals);
   ps.factored = true;
 }
 

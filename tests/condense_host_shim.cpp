@@ -224,6 +224,146 @@ int ch_factor(void* h, const double* vals) {
   return 0;
 }
 
+// The Schur-complement setup (ALFIB_SCHUR_SETUP; condense_host.h build_schur_lists) as the two kernels run it:
+//   block kernel  : per factor block the gather through the key tables, pivoted Gauss-Jordan of A_kk with A_kN
+//                   carried through the elimination (Ws = A_kk^-1 A_kN with solve accuracy), V = A_Nk D, [D | -Ws],
+//                   C = A_Nk Ws into the scratch buffer;
+//   factor kernel : per patch the gather of A_SS through the sorted separator tables, minus every instance's C
+//                   entries at nb_pos, pivoted Gauss-Jordan inverse, X_SS tiles.
+int ch_factor_schur(void* h, const double* vals) {
+  Shim& s = *static_cast<Shim*>(h);
+  const CondensedHost& cd = s.cd;
+  SchurHost sh;
+  build_schur_lists(cd, s.npatch, sh);
+  const int bs = s.bs, b2 = bs * bs;
+  std::vector<double> cbuf((size_t)std::max<int64_t>(sh.ctotal, 1), 0.0);
+  const std::vector<BlockDesc>& fblocks = cd.shared ? cd.sblocks : cd.blocks;
+  const std::vector<int32_t>& fdofs = cd.shared ? cd.sdofs : cd.bdofs;
+  const std::vector<int32_t>& fkeys = cd.shared ? cd.skeys : cd.bkeys;
+  const std::vector<int32_t>& fperm = cd.shared ? cd.sperm : cd.bperm;
+  for (int64_t q = 0; q < (int64_t)fblocks.size(); ++q) {
+    const BlockDesc& d = fblocks[q];
+    const int b = d.b, m = d.m, bm = b + m;
+    const int32_t* gd = fdofs.data() + d.dofs;
+    const int32_t* keys = fkeys.data() + d.keys;
+    const int32_t* perm = fperm.data() + d.keys;
+    std::vector<double> Akk((size_t)b * b, 0.0), AkN((size_t)b * std::max(m, 1), 0.0), ANk((size_t)std::max(m, 1) * b, 0.0);
+    for (int rp = 0; rp < bm; ++rp) {
+      const int node = gd[rp] / bs, comp = gd[rp] % bs;
+      for (int k = s.rowptr[node]; k < s.rowptr[node + 1]; ++k)
+        for (int c2 = 0; c2 < bs; ++c2) {
+          const int hit = bsearch_i32(keys, bm, s.colidx[k] * bs + c2);
+          if (hit < 0) continue;
+          const int cp = perm[hit];
+          const double v = vals[(size_t)k * b2 + comp * bs + c2];
+          if (rp < b) {
+            if (cp < b) Akk[rp + (size_t)cp * b] = v; else AkN[rp + (size_t)(cp - b) * b] = v;
+          } else if (cp < b) {
+            ANk[(rp - b) + (size_t)cp * m] = v;
+          }
+        }
+    }
+    // in-place pivoted Gauss-Jordan of Akk, the same row operations applied to AkN
+    {
+      std::vector<int> piv(b);
+      std::vector<double> prow(b), fcol(b), prowN(std::max(m, 1));
+      for (int j = 0; j < b; ++j) {
+        int bi = j;
+        double best = -1.0;
+        for (int r = j; r < b; ++r)
+          if (std::fabs(Akk[r + (size_t)j * b]) > best) { best = std::fabs(Akk[r + (size_t)j * b]); bi = r; }
+        if (!(best > 0.0)) return 1 + (int)q;
+        piv[j] = bi;
+        if (bi != j) {
+          for (int c = 0; c < b; ++c) std::swap(Akk[j + (size_t)c * b], Akk[bi + (size_t)c * b]);
+          for (int c = 0; c < m; ++c) std::swap(AkN[j + (size_t)c * b], AkN[bi + (size_t)c * b]);
+        }
+        const double dinv = 1.0 / Akk[j + (size_t)j * b];
+        for (int c = 0; c < b; ++c) prow[c] = (c == j) ? 0.0 : Akk[j + (size_t)c * b] * dinv;
+        for (int r = 0; r < b; ++r) fcol[r] = Akk[r + (size_t)j * b];
+        for (int c = 0; c < m; ++c) prowN[c] = AkN[j + (size_t)c * b] * dinv;
+        for (int c = 0; c < b; ++c)
+          for (int r = 0; r < b; ++r) {
+            double v;
+            if (r == j) v = (c == j) ? dinv : prow[c];
+            else if (c == j) v = -fcol[r] * dinv;
+            else v = Akk[r + (size_t)c * b] - fcol[r] * prow[c];
+            Akk[r + (size_t)c * b] = v;
+          }
+        for (int c = 0; c < m; ++c)
+          for (int r = 0; r < b; ++r)
+            AkN[r + (size_t)c * b] = (r == j) ? prowN[c] : AkN[r + (size_t)c * b] - fcol[r] * prowN[c];
+      }
+      for (int k = b - 1; k >= 0; --k)
+        if (piv[k] != k)
+          for (int r = 0; r < b; ++r) std::swap(Akk[r + (size_t)k * b], Akk[r + (size_t)piv[k] * b]);
+    }
+    const int mr = ch_roundup2(m), br = ch_roundup2(b);
+    double* Vt = s.store.data() + d.voff;
+    for (int c = 0; c < b; ++c)
+      for (int r = 0; r < mr; ++r) {
+        double v = 0.0;
+        if (r < m)
+          for (int k = 0; k < b; ++k) v += ANk[r + (size_t)k * m] * Akk[k + (size_t)c * b];
+        Vt[(size_t)c * mr + r] = v;
+      }
+    double* Dt = s.store.data() + d.dwoff;
+    for (int c = 0; c < b; ++c)
+      for (int r = 0; r < br; ++r) Dt[(size_t)c * br + r] = r < b ? Akk[r + (size_t)c * b] * d.dscale : 0.0;
+    double* Wt = Dt + (size_t)br * b;
+    for (int c = 0; c < m; ++c)
+      for (int r = 0; r < br; ++r) Wt[(size_t)c * br + r] = r < b ? -AkN[r + (size_t)c * b] : 0.0;
+    double* C = cbuf.data() + sh.coff[q];
+    for (int j = 0; j < m; ++j)
+      for (int i = 0; i < m; ++i) {
+        double v = 0.0;
+        for (int k = 0; k < b; ++k) v += ANk[i + (size_t)k * m] * AkN[k + (size_t)j * b];
+        C[i + (size_t)j * m] = v;
+      }
+  }
+  for (int p = 0; p < s.npatch; ++p) {
+    const int64_t so = cd.sepoff[p];
+    const int ns = (int)(cd.sepoff[p + 1] - so);
+    if (ns == 0) continue;
+    const int32_t* I = cd.sepdofs.data() + so;
+    const int32_t* sd = sh.sepsorted.data() + so;
+    const int32_t* sp = sh.sepperm.data() + so;
+    std::vector<double> W((size_t)ns * ns, 0.0);
+    for (int r = 0; r < ns; ++r) {
+      const int node = I[r] / bs, comp = I[r] % bs;
+      for (int k = s.rowptr[node]; k < s.rowptr[node + 1]; ++k)
+        for (int c2 = 0; c2 < bs; ++c2) {
+          const int hit = bsearch_i32(sd, ns, s.colidx[k] * bs + c2);
+          if (hit >= 0) W[r + (size_t)sp[hit] * ns] = vals[(size_t)k * b2 + comp * bs + c2];
+        }
+    }
+    for (int64_t q = cd.blk_start[p]; q < cd.blk_start[p + 1]; ++q) {
+      const int64_t o2 = cd.nb_off[q];
+      const int mq = (int)(cd.nb_off[q + 1] - o2);
+      const double* C = cbuf.data() + sh.inst_c[q];
+      const int ldc = sh.inst_ld[q];
+      for (int jj = 0; jj < mq; ++jj)
+        for (int ii = 0; ii < mq; ++ii)
+          W[cd.nb_pos[o2 + ii] + (size_t)cd.nb_pos[o2 + jj] * ns] -= C[sh.upos[o2 + ii] + (size_t)sh.upos[o2 + jj] * ldc];
+    }
+    if (!gj_inverse(W.data(), ns, ns)) return 1 + p;
+    double* out = s.store.data() + cd.ssoff[p];
+    for (int row0 = 0; row0 < ns; row0 += ALFIB_TILE_ROWS) {
+      const int rows = std::min(ns - row0, ALFIB_TILE_ROWS), rt = ch_roundup2(rows);
+      double* tile = out + (size_t)row0 * ns;
+      for (int c = 0; c < ns; ++c)
+        for (int r = 0; r < rt; ++r) tile[(size_t)c * rt + r] = r < rows ? W[(row0 + r) + (size_t)c * ns] : 0.0;
+    }
+  }
+  return 0;
+}
+
+// the whole store (X_SS tiles, V, [D | -W] tiles) — to compare the two setups
+void ch_store(void* h, double* out) {
+  Shim& s = *static_cast<Shim*>(h);
+  std::memcpy(out, s.store.data(), sizeof(double) * (size_t)s.cd.store_elems);
+}
+
 // y += sum_i R_i^T A_i^-1 R_i x through the op lists (y is NOT zeroed, like the device kernel)
 void ch_apply(void* h, const double* x, double* y) {
   Shim& s = *static_cast<Shim*>(h);
