@@ -123,11 +123,24 @@ __device__ __forceinline__ void tile_op_body(const double* __restrict__ mat, con
 // the gathered source has arrived, a partial last batch is just predicated loads, and there is no
 // drain between batches.  The source index list is read two 32-column chunks ahead and the source
 // values one chunk ahead (no dependent wait at a chunk switch).
-template <int G, bool ATOMIC, bool ACCUM>
+// ALFIB_FUSE_INDEX=1: the two index kernels are folded into the source fetch of the op that consumes their output
+// (same summation order, so the results are bitwise those of the separate kernels):
+//   MODE 1 (K3, X_SS ops): the entry e >= 0 of the separator right-hand side is formed on the fly,
+//                          x[idx[e]] - sum_j g[lst[j]], j in [ptr[e], ptr[e+1])          (= sep_rhs_kernel)
+//   MODE 2 (K4, shared form): the entry ~e of z is formed on the fly, sum_j g[lst[j]]     (= slot_sum_kernel)
+struct FusedSrc {
+  const int32_t* idx;
+  const int32_t* ptr;
+  const int32_t* lst;
+  const double* g;
+};
+
+template <int G, bool ATOMIC, bool ACCUM, int MODE = 0>
 __device__ __forceinline__ void tile_op_body_v2(const double* __restrict__ mat, const int32_t* __restrict__ ci,
                                                 const int32_t* __restrict__ ri, double* __restrict__ priv,
                                                 const int nrows, const int n, const double* __restrict__ srcA,
-                                                const double* __restrict__ srcB, double* __restrict__ y, int lane) {
+                                                const double* __restrict__ srcB, double* __restrict__ y, int lane,
+                                                const FusedSrc fs = FusedSrc{nullptr, nullptr, nullptr, nullptr}) {
   constexpr int LPG = 32 / G, UB = 8, CPB = UB * G;   // lanes per column group; ring slots; columns per round
   const int half = (nrows + 1) >> 1;
   const int grp = lane / LPG, l = lane - grp * LPG;
@@ -135,7 +148,23 @@ __device__ __forceinline__ void tile_op_body_v2(const double* __restrict__ mat, 
   const double2* __restrict__ T = reinterpret_cast<const double2*>(mat) + (active ? l : 0);
   auto column = [&](int c) { return (active && c < n) ? __ldcs(T + c * half) : make_double2(0.0, 0.0); };
   auto index_at = [&](int pos) { return pos < n ? __ldg(ci + pos) : 0; };
-  auto value_at = [&](int e, int pos) { return pos < n ? (e >= 0 ? __ldg(srcA + e) : __ldg(srcB + (~e))) : 0.0; };
+  auto value_at = [&](int e, int pos) {
+    if (pos >= n) return 0.0;
+    if (MODE == 1 && e >= 0) {
+      double v = __ldg(srcA + __ldg(fs.idx + e));
+      const int j1 = __ldg(fs.ptr + e + 1);
+      for (int j = __ldg(fs.ptr + e); j < j1; ++j) v -= fs.g[__ldg(fs.lst + j)];
+      return v;
+    }
+    if (MODE == 2 && e < 0) {
+      const int i = ~e;
+      double v = 0.0;
+      const int j1 = __ldg(fs.ptr + i + 1);
+      for (int j = __ldg(fs.ptr + i); j < j1; ++j) v += fs.g[__ldg(fs.lst + j)];
+      return v;
+    }
+    return e >= 0 ? __ldg(srcA + e) : __ldg(srcB + (~e));
+  };
   const int e0 = index_at(lane), e1 = index_at(32 + lane);
   double2 a[UB];
 #pragma unroll
@@ -194,13 +223,14 @@ __device__ __forceinline__ void tile_op_body_v2(const double* __restrict__ mat, 
   }
 }
 
-template <bool ATOMIC, bool ACCUM = false>
+template <bool ATOMIC, bool ACCUM = false, int MODE = 0>
 __global__ void __launch_bounds__(128) tile_ops_kernel_v2(const TileOp* __restrict__ ops, int nops,
                                                           const int32_t* __restrict__ cidx,
                                                           const double* __restrict__ store,
                                                           const double* __restrict__ srcA,
                                                           const double* __restrict__ srcB, PeerOut yout,
-                                                          double* __restrict__ dstB) {
+                                                          double* __restrict__ dstB,
+                                                          const FusedSrc fs = FusedSrc{nullptr, nullptr, nullptr, nullptr}) {
   double* __restrict__ y = resolve(yout);
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -214,11 +244,11 @@ __global__ void __launch_bounds__(128) tile_ops_kernel_v2(const TileOp* __restri
   const int nrows = op->nrows, ncols = op->ncols;
   const int half = (nrows + 1) >> 1;
   if (half <= 8)
-    tile_op_body_v2<4, ATOMIC, ACCUM>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+    tile_op_body_v2<4, ATOMIC, ACCUM, MODE>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane, fs);
   else if (half <= 16)
-    tile_op_body_v2<2, ATOMIC, ACCUM>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+    tile_op_body_v2<2, ATOMIC, ACCUM, MODE>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane, fs);
   else
-    tile_op_body_v2<1, ATOMIC, ACCUM>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane);
+    tile_op_body_v2<1, ATOMIC, ACCUM, MODE>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane, fs);
 }
 
 template <bool ATOMIC, bool ACCUM = false>
@@ -634,8 +664,13 @@ void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, P
                                                                            plain_out(nullptr), cd.g1.p);
     c->launches++;
   }
+  // ALFIB_FUSE_INDEX=1 (tile op v2 only): K2 and K3b are folded into the source fetch of K3 / K4
+  const char* env_fuse = std::getenv("ALFIB_FUSE_INDEX");
+  const bool fuse = !v1 && env_fuse && env_fuse[0] == '1';
+  const FusedSrc fs_rhs{cd.sepdofs.p, cd.cptr.p, cd.cg1.p, cd.g1.p};
+  const FusedSrc fs_z{nullptr, cd.zptr.p, cd.zsrc.p, cd.us.p};
   // K2: separator right-hand sides
-  if (h.nsep_total) {
+  if (h.nsep_total && !fuse) {
     sep_rhs_kernel<<<cdiv(h.nsep_total, 256), 256, 0, c->stream>>>(h.nsep_total, cd.sepdofs.p, cd.cptr.p, cd.cg1.p, x,
                                                                     cd.g1.p, cd.rs.p);
     c->launches++;
@@ -645,8 +680,25 @@ void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, P
   const bool coloured = c->deterministic && !ps.repeated;
   const bool s_atomic = ps.repeated || h.any_accum;      // column chunks of one tile add to the same rows
   auto run = [&](const TileOp* ops, int nops, const double* srcA, const double* srcB, double* dstB, bool atomic,
-                 bool accum = false) {
+                 bool accum = false, int mode = 0) {
     if (nops <= 0) return;
+    if (mode == 1) {                 // fused separator right-hand side: srcA is x
+      const int g = cdiv(nops, wpb);
+      if (accum)
+        tile_ops_kernel_v2<true, true, 1><<<g, threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB, fs_rhs);
+      else if (atomic)
+        tile_ops_kernel_v2<true, false, 1><<<g, threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB, fs_rhs);
+      else
+        tile_ops_kernel_v2<false, false, 1><<<g, threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB, fs_rhs);
+      c->launches++;
+      return;
+    }
+    if (mode == 2) {                 // fused slot sums (shared form, K4: plain stores)
+      tile_ops_kernel_v2<false, false, 2><<<cdiv(nops, wpb), threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y,
+                                                                                      dstB, fs_z);
+      c->launches++;
+      return;
+    }
     if (accum) {                     // X_SS lists with column chunks: every private write is an atomicAdd into zeroed us
       if (v1)
         tile_ops_kernel<true, true><<<cdiv(nops, wpb), threads, 0, c->stream>>>(ops, nops, cd.cidx.p, ps.store, srcA, srcB, y, dstB);
@@ -672,25 +724,25 @@ void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, P
     // shared blocks: K3 as below; K3b sums the separator solutions per distinct block; K4 is one launch
     // over the distinct blocks, which are pairwise disjoint (plain stores, deterministic in every mode)
     if (!coloured && ps.ncolour > 1) {
-      run(cd.opsS.p, nS, cd.rs.p, nullptr, cd.us.p, true, h.any_accum);
+      run(cd.opsS.p, nS, fuse ? x : cd.rs.p, nullptr, cd.us.p, true, h.any_accum, fuse ? 1 : 0);
     } else {
       for (int col = 0; col < ps.ncolour; ++col) {
         const int s = h.s_colour_start[col], e = h.s_colour_start[col + 1];
-        run(cd.opsS.p + s, e - s, cd.rs.p, nullptr, cd.us.p, s_atomic, h.any_accum);
+        run(cd.opsS.p + s, e - s, fuse ? x : cd.rs.p, nullptr, cd.us.p, s_atomic, h.any_accum, fuse ? 1 : 0);
       }
     }
-    if (h.g1_total) {
+    if (h.g1_total && !fuse) {
       slot_sum_kernel<<<cdiv(h.g1_total, 256), 256, 0, c->stream>>>(h.g1_total, cd.zptr.p, cd.zsrc.p, cd.us.p, cd.z.p);
       c->launches++;
     }
-    run(cd.opsDW.p, nDW, x, cd.z.p, nullptr, false);
+    run(cd.opsDW.p, nDW, x, cd.z.p, nullptr, false, false, fuse ? 2 : 0);
   } else if (!coloured && ps.ncolour > 1) {
-    run(cd.opsS.p, nS, cd.rs.p, nullptr, cd.us.p, true, h.any_accum);
+    run(cd.opsS.p, nS, fuse ? x : cd.rs.p, nullptr, cd.us.p, true, h.any_accum, fuse ? 1 : 0);
     run(cd.opsDW.p, nDW, x, cd.us.p, nullptr, true);
   } else {
     for (int col = 0; col < ps.ncolour; ++col) {
       const int s = h.s_colour_start[col], e = h.s_colour_start[col + 1];
-      run(cd.opsS.p + s, e - s, cd.rs.p, nullptr, cd.us.p, s_atomic, h.any_accum);
+      run(cd.opsS.p + s, e - s, fuse ? x : cd.rs.p, nullptr, cd.us.p, s_atomic, h.any_accum, fuse ? 1 : 0);
     }
     for (int col = 0; col < ps.ncolour; ++col) {
       const int s = h.dw_colour_start[col], e = h.dw_colour_start[col + 1];
