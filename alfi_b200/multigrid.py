@@ -225,8 +225,66 @@ class DistributedMultigrid:
                 P = li.P.tocsr() if li.P_dof_level else sp.kron(li.P, sp.identity(li.bs), format="csr")
                 self.halos.append(transfer_halo(P, self.layouts[l], self.layouts[l - 1].owner))
         self.local = [None] + [local_level(levels[l], self.layouts[l], rank, self.halos[l]) for l in range(1, self.nlevels)]
-        # ---- hand-over
-        li = levels[0]
+        thalo = [None] * self.nlevels
+        for l in range(2, self.nlevels):
+            hr = self.halos[l].ranks[rank]
+            thalo[l] = (hr.n_owned, hr.n_local, hr.send, {q: hr.n_owned + v for q, v in hr.recv.items()})
+        peer_off = {}
+        if peer_memory:
+            for l in range(1, self.nlevels):
+                peer_off[(l, 0)] = self._peer_offsets(self.layouts[l])
+                if self.halos[l] is not None:
+                    peer_off[(l, 1)] = self._peer_offsets(self.halos[l])
+        self._levels0 = levels[0]
+        self._handover(levels[0], thalo, peer_off, condense, torch_storage, peer_memory)
+        self.update_operators(levels)
+        self.update_transfers(levels)
+        c.cycle_setup(self.nlevels, smoothing)
+
+    @classmethod
+    def from_local(cls, problem, smoothing: int, unique_id: bytes | None, device: int = 0, deterministic: bool = False,
+                   robust_restrict: bool = True, ctx=None, torch_storage: bool = False, condense: bool = True,
+                   peer_memory: bool = False):
+        """From a rank-locally generated problem (`alfi_b200.synth.bricks.build_rank_local`): nothing global besides
+        the replicated level 0 exists on this rank.  The transfer halo of level l is the halo of level l-1 (P_H reads
+        that level in its own local set).  With ``peer_memory`` the neighbours' list offsets are all-gathered."""
+        self = cls.__new__(cls)
+        self.ctx = c = ctx or Context(device, deterministic)
+        self.nlevels, self.smoothing = len(problem.local), smoothing
+        self.rank, self.nranks = problem.rank, problem.nranks
+        self._storage = []
+        self.layouts = self.halos = None
+        self.local = problem.local
+        c.set_option(3, robust_restrict)
+        c.comm_init(unique_id, self.rank, self.nranks)
+        thalo = [None] * self.nlevels
+        for l in range(2, self.nlevels):
+            lc = self.local[l - 1]
+            thalo[l] = (lc.n_owned, lc.n_local, lc.send, lc.recv)
+        peer_off = {}
+        if peer_memory and self.nranks > 1:
+            import torch.distributed as dist
+            mine = {l: Context.halo_peer_list(self.local[l].send, self.local[l].recv) for l in range(1, self.nlevels)}
+            everyone = [None] * self.nranks
+            dist.all_gather_object(everyone, {l: (v[0], v[1].tolist(), v[2].tolist()) for l, v in mine.items()})
+            for l in range(1, self.nlevels):
+                off = {}
+                for q in mine[l][0]:
+                    peers_q, s_off, r_off = everyone[q][l]
+                    k = peers_q.index(self.rank)
+                    off[q] = (int(s_off[k]), int(r_off[k]))
+                peer_off[(l, 0)] = off
+                if l + 1 < self.nlevels:
+                    peer_off[(l + 1, 1)] = off
+        self._levels0 = problem.level0
+        self._handover(problem.level0, thalo, peer_off, condense, torch_storage, peer_memory)
+        self.update_operators(None)
+        self.update_transfers(None)
+        c.cycle_setup(self.nlevels, smoothing)
+        return self
+
+    def _handover(self, li, thalo, peer_off, condense, torch_storage, peer_memory):
+        c = self.ctx
         c.level_create(0, li.n_nodes, li.bs)
         c.set_bsr_pattern(0, li.rowptr, li.colidx)
         c.set_bc(0, li.bc_dofs)
@@ -237,12 +295,9 @@ class DistributedMultigrid:
         for l in range(1, self.nlevels):
             ll = self.local[l]
             c.level_create(l, ll.n_local_nodes, ll.bs)
-            c.set_halo(l, ll.n_owned, ll.n_local, ll.send, ll.recv, 0,
-                       self._peer_offsets(self.layouts[l]) if peer_memory else None)
-            if self.halos[l] is not None:
-                hr = self.halos[l].ranks[rank]
-                c.set_halo(l, hr.n_owned, hr.n_local, hr.send, {q: hr.n_owned + v for q, v in hr.recv.items()}, 1,
-                           self._peer_offsets(self.halos[l]) if peer_memory else None)
+            c.set_halo(l, ll.n_owned, ll.n_local, ll.send, ll.recv, 0, peer_off.get((l, 0)))
+            if thalo[l] is not None:
+                c.set_halo(l, thalo[l][0], thalo[l][1], thalo[l][2], thalo[l][3], 1, peer_off.get((l, 1)))
             c.set_bsr_pattern(l, ll.rowptr, ll.colidx)
             c.set_bc(l, ll.bc_dofs)
             c.set_patches(l, ll.patch_offsets, ll.patch_dofs, ll.patch_order, ll.patch_colours, PATCHES_SMOOTHER)
@@ -258,14 +313,11 @@ class DistributedMultigrid:
                     c.set_patch_blocks(l, ll.cell_blocks, PATCHES_TRANSFER)
                 if torch_storage:
                     self._bind(l, PATCHES_TRANSFER)
-        if peer_memory and nranks > 1:
+        if peer_memory and self.nranks > 1:
             import torch.distributed as dist
-            handles = [None] * nranks
+            handles = [None] * self.nranks
             dist.all_gather_object(handles, c.comm_peer_handle())
             c.comm_peer_open(b"".join(handles))
-        self.update_operators(levels)
-        self.update_transfers(levels)
-        c.cycle_setup(self.nlevels, smoothing)
 
     _bind = DeviceMultigrid._bind
 
@@ -282,20 +334,26 @@ class DistributedMultigrid:
         return out
 
     def update_operators(self, levels):
-        """Once per Newton step: this rank's blocks of the new operator values, patch factors, coarse inverse."""
+        """Once per Newton step: this rank's blocks of the new operator values, patch factors, coarse inverse.
+        `levels` = the global LevelInputs, or None to (re)use the values the LocalLevels carry (rank-local problems)."""
         c = self.ctx
-        c.set_bsr_values(0, levels[0].vals)
+        c.set_bsr_values(0, (levels[0] if levels is not None else self._levels0).vals)
         for l in range(1, self.nlevels):
-            c.set_bsr_values(l, np.ascontiguousarray(np.asarray(levels[l].vals)[self.local[l].vals_sel]))
+            ll = self.local[l]
+            vals = ll.vals if levels is None else np.asarray(levels[l].vals)[ll.vals_sel]
+            c.set_bsr_values(l, np.ascontiguousarray(vals))
             c.factor(l)
         c.coarse_factor()
 
     def update_transfers(self, levels):
         for l in range(1, self.nlevels):
-            li, ll = levels[l], self.local[l]
-            if li.a0_vals is not None:
-                self.ctx.transfer_update(l, np.ascontiguousarray(np.asarray(li.a0_vals)[ll.vals_sel]),
-                                         np.ascontiguousarray(np.asarray(li.d_vals)[ll.vals_sel]))
+            ll = self.local[l]
+            if levels is None:
+                if ll.a0_vals is not None:
+                    self.ctx.transfer_update(l, np.ascontiguousarray(ll.a0_vals), np.ascontiguousarray(ll.d_vals))
+            elif levels[l].a0_vals is not None:
+                self.ctx.transfer_update(l, np.ascontiguousarray(np.asarray(levels[l].a0_vals)[ll.vals_sel]),
+                                         np.ascontiguousarray(np.asarray(levels[l].d_vals)[ll.vals_sel]))
 
     # ---- vectors
     @property

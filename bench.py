@@ -28,7 +28,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DEFAULT_CONFIG = "ldc3d-sv-k3"
-CPU_SAMPLE_CONFIG = {"ldc3d-sv-k3": "ldc3d-sv-k3-half", "ldc3d-sv-k3-n5": "ldc3d-sv-k3-half", "ldc3d-sv-k3-n6": "ldc3d-sv-k3-half", "ldc2d-sv-k2": "ldc2d-sv-k2", "ldc2d-pkp0": "ldc2d-pkp0"}
+CPU_SAMPLE_CONFIG = {"ldc3d-sv-k3": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w1": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w2": "ldc3d-sv-k3-half",
+                     "ldc3d-sv-k3-w4": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w8": "ldc3d-sv-k3-half", "ldc3d-sv-k3-s8": "ldc3d-sv-k3-half", "ldc3d-sv-k3-n5": "ldc3d-sv-k3-half", "ldc3d-sv-k3-n6": "ldc3d-sv-k3-half", "ldc2d-sv-k2": "ldc2d-sv-k2", "ldc2d-pkp0": "ldc2d-pkp0"}
 METRIC = "V-cycle DoF/s (finest-level velocity dofs per second of one fieldsplit_0 PCMG-full application)"
 
 
@@ -210,11 +211,27 @@ def ours(args):
     build()
 
     t0 = time.time()
-    prob = build_problem(args.config, verbose=(rank == 0))
-    cfg = prob.config
+    # N > 1, --scaling weak: one cfg5-sized brick per rank (configs ldc3d-sv-k3-w{N}), generated rank-locally
+    # (alfi_b200/synth/bricks.py) — no rank ever builds a global level >= 1 — and run with distributed vectors
+    weak = world > 1 and args.scaling == "weak"
+    if weak:
+        from alfi_b200.synth.bricks import build_rank_local
+        from alfi_b200.synth.problem import CONFIGS as _CW
+        args.config = args.config if args.config != DEFAULT_CONFIG else "ldc3d-sv-k3-w%d" % world
+        cfg = _CW[args.config]
+        if int(np.prod(cfg.shape or (1,))) != world:
+            raise SystemExit("config %s is a %s rank grid, not %d ranks" % (args.config, cfg.shape, world))
+        rlp = build_rank_local(cfg, rank, verbose=(rank == 0))
+        prob = None
+        nlev = len(rlp.local)
+        fine_ll = rlp.local[-1]
+    else:
+        prob = build_problem(args.config, verbose=(rank == 0))
+        cfg = prob.config
+        nlev = len(prob.levels)
     log("rank %d: problem built in %.1fs" % (rank, time.time() - t0))
     # N > 1: level vectors distributed (owned + ghosts per rank, neighbour exchanges) or replicated
-    distributed = world > 1 and args.vectors == "distributed"
+    distributed = world > 1 and (args.vectors == "distributed" or weak)
 
     def make_mg(condense):
         """Device hierarchy + one per-Newton-step refresh; returns (mg, setup_s, newton_setup_s)."""
@@ -223,7 +240,12 @@ def ours(args):
         if world > 1:
             from alfi_b200.dist import bootstrap_unique_id
             uid = bootstrap_unique_id(rank)
-        if distributed:
+        if weak:
+            from alfi_b200.multigrid import DistributedMultigrid
+            mg = DistributedMultigrid.from_local(rlp, cfg.m, uid, device=local, deterministic=bool(args.deterministic),
+                                                 torch_storage=True, condense=bool(condense),
+                                                 peer_memory=bool(args.peer_memory))
+        elif distributed:
             from alfi_b200.multigrid import DistributedMultigrid
             mg = DistributedMultigrid([level_input_from_synth(l) for l in prob.levels], cfg.m, rank, world, uid,
                                       device=local, deterministic=bool(args.deterministic), torch_storage=True,
@@ -239,7 +261,7 @@ def ours(args):
         # what every Newton step pays again (alfi re-assembles J, PCSetUp_PATCH refactors the patches and the
         # coarse LU; solver.py:320-327, 369-378): values hand-over + all patch inverses + coarse inverse
         t0 = time.time()
-        mg.update_operators([level_input_from_synth(l) for l in prob.levels])
+        mg.update_operators(None if weak else [level_input_from_synth(l) for l in prob.levels])
         mg.ctx.synchronize()
         newton_setup_s = time.time() - t0
         log("rank %d: per-Newton-step setup (values + patch factors + coarse inverse) %.2fs" % (rank, newton_setup_s))
@@ -276,12 +298,20 @@ def ours(args):
         args.condense = 0
         mg, setup_s, newton_setup_s = make_mg(0)
 
-    n = prob.finest.ndofs
-    rng = np.random.default_rng(20261017)          # same right-hand side on every rank (replicated vectors)
-    bnp = rng.standard_normal(n)
-    bnp[prob.finest.bc_dofs] = 0.0
-    if distributed:
-        bnp = mg.scatter(bnp)                      # this rank's local vector: owned dofs, then ghosts
+    if weak:
+        rng = np.random.default_rng(20261017 + rank)
+        bnp = rng.standard_normal(fine_ll.n_local)     # this rank's local vector: owned dofs, then ghosts (refreshed by the library)
+        bnp[fine_ll.bc_dofs] = 0.0
+        tn = torch.tensor([float(fine_ll.n_owned), float(fine_ll.patch_ids.size)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tn)
+        n, npatch_total = int(tn[0].item()), int(tn[1].item())
+    else:
+        n = prob.finest.ndofs
+        rng = np.random.default_rng(20261017)          # same right-hand side on every rank (replicated vectors)
+        bnp = rng.standard_normal(n)
+        bnp[prob.finest.bc_dofs] = 0.0
+        if distributed:
+            bnp = mg.scatter(bnp)                      # this rank's local vector: owned dofs, then ghosts
     nvec = bnp.size
     bh = torch.empty(nvec, dtype=torch.float64).pin_memory()
     xh = torch.empty(nvec, dtype=torch.float64).pin_memory()
@@ -296,7 +326,7 @@ def ours(args):
 
     def reduction(xvec):
         rr = torch.empty_like(xvec)
-        mg.ctx.residual(len(prob.levels) - 1, bd, xvec, rr)
+        mg.ctx.residual(nlev - 1, bd, xvec, rr)
         mg.ctx.synchronize()
         if distributed:                            # norms over the owned entries of all ranks
             t = torch.stack([(rr[:mg.n_owned] ** 2).sum(), (bd[:mg.n_owned] ** 2).sum()])
@@ -338,12 +368,12 @@ def ours(args):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
     launches = (mg.ctx.launches - launches0) // args.steps
-    prof_fine = mg.ctx.profile_get(len(prob.levels) - 1)
+    prof_fine = mg.ctx.profile_get(nlev - 1)
     prof_all = mg.ctx.profile_get(-1)
     mg.ctx.profile(False)
-    patch_apply_bytes = mg.ctx.patch_apply_bytes(len(prob.levels) - 1)
-    mg_form = mg.ctx.patch_storage_form(len(prob.levels) - 1)
-    factor_bytes = mg.ctx.patch_storage_bytes(len(prob.levels) - 1)
+    patch_apply_bytes = mg.ctx.patch_apply_bytes(nlev - 1)
+    mg_form = mg.ctx.patch_storage_form(nlev - 1)
+    factor_bytes = mg.ctx.patch_storage_bytes(nlev - 1)
 
     # ---- end to end through the C-ABI with host buffers --------------------------------------
     bhn, xhn = bh.numpy(), xh.numpy()
@@ -372,10 +402,18 @@ def ours(args):
         peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, sustained copy)"
     except Exception:       # noqa: BLE001
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    fine = prob.finest
+    if weak:
+        sizes = np.diff(fine_ll.patch_offsets)
+        fine_npatch, fine_maxn, fine_dense = npatch_total, int(sizes.max()), float((sizes.astype(float) ** 2).sum() * 8)
+        has_blocks = fine_ll.patch_blocks is not None
+    else:
+        fine = prob.finest
+        fine_npatch, fine_maxn = int(fine.patches.npatch), int(fine.patches.sizes.max())
+        fine_dense = float((fine.patches.sizes.astype(float) ** 2).sum() * 8)
+        has_blocks = fine.patches.blocks is not None
     # algorithmic bytes of one finest-level PCApply_PATCH on this rank: stored factors
     # (dense: 8 n_i^2; condensed: X_SS + per-block V and [D | -W]) + index data + 16 N
-    condensed = bool(args.condense) and fine.patches.blocks is not None
+    condensed = bool(args.condense) and has_blocks
     bs_bytes = float(patch_apply_bytes)
     app_ms, app_calls = prof_fine["PCPATCHApply"]
     achieved = bs_bytes / (app_ms / max(app_calls, 1) * 1e-3) / 1e9 if app_calls else None
@@ -447,13 +485,15 @@ def ours(args):
     line = {
         "metric": METRIC, "value": total / (ms * 1e-3), "unit": "DoF/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak",
+        # ldc3d-sv-k3-s8 is cfg5 itself cut into bricks: rank-local generation, but the total problem is fixed
+        "scaling": "strong" if (world > 1 and (not weak or "-s%d" % world in args.config)) else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.config, "mesh": "Kuhn %d^%d x 2^%d, Alfeld split" % (cfg.N, cfg.dim, cfg.nref),
-                   "velocity_dofs": n, "levels": len(prob.levels), "smoothing": cfg.m, "re": cfg.re, "gamma": cfg.gamma,
-                   "patches_finest": int(fine.patches.npatch), "max_patch_dofs": int(fine.patches.sizes.max()),
+                   "velocity_dofs": n, "levels": nlev, "smoothing": cfg.m, "re": cfg.re, "gamma": cfg.gamma,
+                   "rank_grid": list(cfg.shape) if weak else None,
+                   "patches_finest": fine_npatch, "max_patch_dofs": fine_maxn,
                    "factor_bytes_finest": float(factor_bytes),
-                   "dense_factor_bytes_finest": float((fine.patches.sizes.astype(float) ** 2).sum() * 8),
+                   "dense_factor_bytes_finest": fine_dense,
                    "patch_inverses": ("condensed (block/separator form, blocks shared between patches, csrc/condense.cu)"
                                       if mg_form == 2 else "condensed (block/separator form, csrc/condense.cu)")
                    if condensed else "dense",
@@ -498,6 +538,8 @@ def main():
                     help="also run the Newton continuation on this 3-D config (e.g. ldc3d-sv-k3-half); minutes of host assembly")
     ap.add_argument("--continuation-3d-re", default="10,100,200,300,400,500", help="Reynolds numbers of --continuation-3d")
     ap.add_argument("--peer-memory", type=int, default=0, help="N > 1: NVLink peer-memory exchanges instead of NCCL")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: the same problem sharded (strong) or one cfg5-sized brick per rank, generated rank-locally (weak)")
     ap.add_argument("--vectors", default="replicated", choices=["replicated", "distributed"],
                     help="N > 1: replicated level vectors (measured in round 1) or distributed ones (DESIGN §6.1)")
     ap.add_argument("--condense", type=int, default=1,

@@ -444,3 +444,65 @@ def test_exchange_count_per_krylov_iteration(problems):
     m = prob.config.m
     model.fgmres(1, [g.scatter(b) for g in mgs], [np.zeros(g.local_dofs.size) for g in mgs], m)
     assert model.stats == {"update": 2 * m + 1, "reduce": m, "allreduce": 2 * m + 1}
+
+
+@pytest.mark.parametrize("name,shape", [("ldc2d-sv-k2-tiny", (2, 1)), ("ldc2d-sv-k2-tiny", (2, 2)), ("ldc3d-sv-k3-tiny", (2, 1, 1)),
+                                        ("ldc2d-pkp0-tiny", (3, 1)), ("ldc3d-pkp0-tiny", (1, 2, 1))])
+@pytest.mark.parametrize("peer", [False, True])
+def test_rank_locally_generated_problem_through_the_device_sequence(name, shape, peer):
+    """alfi_b200.synth.bricks.build_rank_local -> DistributedMultigrid.from_local -> the device step sequence on
+    every rank's own data == the serial oracle of the globally generated box problem (matched through the nodes'
+    lattice keys).  No rank ever sees a global level >= 1."""
+    import dataclasses
+
+    import torch.distributed as dist
+
+    from alfi_b200.synth.bricks import build_rank_local, node_keys
+    from alfi_b200.synth.problem import CONFIGS, build_problem
+    cfg = dataclasses.replace(CONFIGS[name], shape=shape)
+    nranks = int(np.prod(shape))
+    glob = build_problem(cfg, gamma=10.0, nu=0.2)
+    lv = [hp.level_from_host(l) for l in glob.levels]
+    b = np.random.default_rng(9).standard_normal(lv[-1].n)
+    b[lv[-1].bc_dofs] = 0
+    want = hp.fcycle(lv, b, cfg.m)
+    probs = [build_rank_local(cfg, r, nu=0.2, gamma=10.0) for r in range(nranks)]
+    gathered = []
+    orig = dist.all_gather_object
+
+    def fake_all_gather(out, obj):
+        gathered.append(obj)
+        # the lock-step construction below calls every rank in turn: hand each caller the full list once known
+        out[:] = [obj] * len(out) if isinstance(obj, bytes) or fake_all_gather.everyone is None else fake_all_gather.everyone
+    fake_all_gather.everyone = None
+    if peer:
+        from alfi_b200.lib import Context
+        fake_all_gather.everyone = [{l: (v[0], v[1].tolist(), v[2].tolist()) for l, v in
+                                     {l: Context.halo_peer_list(p.local[l].send, p.local[l].recv)
+                                      for l in range(1, len(p.local))}.items()} for p in probs]
+    dist.all_gather_object = fake_all_gather
+    try:
+        mgs = [DistributedMultigrid.from_local(p, cfg.m, None, ctx=(PeerRecordingContext() if peer else RecordingContext()),
+                                               peer_memory=peer) for p in probs]
+    finally:
+        dist.all_gather_object = orig
+    model = Lockstep([m.ctx for m in mgs])
+    L = len(lv) - 1
+    bs = glob.finest.V.bs
+    _, gkey = node_keys(glob.finest.V.node_coords, cfg.N * 2 ** L, cfg.length, shape)
+    order = np.argsort(gkey)
+    g_of, locs = [], []
+    for p in probs:
+        pos = np.searchsorted(gkey[order], p.keys[L])
+        g = (order[pos][:, None] * bs + np.arange(bs)[None, :]).ravel()
+        v = b[g].copy()
+        v[p.local[L].n_owned:] = NAN
+        g_of.append(g)
+        locs.append(v)
+    out = model.cycle(locs)
+    got = np.full(b.size, NAN)
+    for p, g, v in zip(probs, g_of, out):
+        no = p.local[L].n_owned
+        got[g[:no]] = v[:no]
+    assert np.isfinite(got).all()
+    assert np.linalg.norm(got - want) <= 1e-10 * np.linalg.norm(want)
