@@ -424,6 +424,16 @@ def test_coarse_level_as_one_condensed_patch(shim_split32, problems, name):
     assert rel(y, want) <= 1e-9
     X = host.inverse(0, free.size)
     assert np.abs(X @ A[free][:, free].toarray() - np.eye(free.size)).max() < 1e-8
+    # Schur-complement setup of the same coarse patch (coarse_factor_device with ALFIB_SCHUR_SETUP: only the separator
+    # system is factorised densely): the same stored pieces and the same solve
+    hs = Host(shim_split32, ld, ps, blocks, True, split_wide=True)
+    lib = shim_split32
+    lib.ch_factor_schur.argtypes = [C.c_void_p, _f64p]
+    lib.ch_store.argtypes = [C.c_void_p, _f64p]
+    assert hs.factor_schur(ld.A.vals) == 0
+    assert rel(hs.store(), host.store()) <= 1e-10
+    assert rel(hs.apply(b), want) <= 1e-9
+    hs.close()
     host.close()
     print("%s coarse level: %d free dofs, separator %d, chunks %d, condensed %.2f MB vs dense %.2f MB" % (
         name, free.size, st["maxsep"], st["any_accum"], st["store_elems"] * 8e-6, free.size ** 2 * 8e-6))
