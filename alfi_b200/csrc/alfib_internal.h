@@ -221,6 +221,7 @@ struct alfib_ctx {
   // patch factor workspace (one slot per resident CTA) + status word + work counter
   DBuf<double> fwork;
   DBuf<int> finfo;
+  DBuf<unsigned> tile_counter;          // work counter of the TMA tile-op kernel (resets itself)
   // reductions / Krylov scalars
   DBuf<double> partial, scal;
   // staging for host-pointer calls

@@ -251,6 +251,26 @@ __global__ void __launch_bounds__(128) tile_ops_kernel_v2(const TileOp* __restri
     tile_op_body_v2<1, ATOMIC, ACCUM, MODE>(mat, ci, ri, priv, nrows, ncols, srcA, srcB, y, lane, fs);
 }
 
+#include "tile_tma.cuh"
+
+template <bool ATOMIC, bool ACCUM, int MODE>
+void launch_tile_ops_tma(alfib_ctx* c, const TileOp* ops, int nops, const int32_t* cidx, const double* store,
+                         const double* srcA, const double* srcB, PeerOut y, double* dstB, const FusedSrc& fs) {
+  static bool configured = false;       // per instantiation
+  const size_t smem = tma::smem_bytes();
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(tile_ops_kernel_tma<ATOMIC, ACCUM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  if (!c->tile_counter.p) {
+    c->tile_counter.alloc(4);
+    CUDA_TRY(cudaMemsetAsync(c->tile_counter.p, 0, 4 * sizeof(unsigned), c->stream));
+  }
+  const int grid = std::min(c->num_sms, cdiv(nops, tma::WARPS));
+  tile_ops_kernel_tma<ATOMIC, ACCUM, MODE><<<grid, tma::WARPS * 32, smem, c->stream>>>(ops, nops, cidx, store, srcA, srcB, y, dstB,
+                                                                                       fs, c->tile_counter.p);
+}
+
 template <bool ATOMIC, bool ACCUM = false>
 __global__ void __launch_bounds__(128) tile_ops_kernel(const TileOp* __restrict__ ops, int nops,
                                                        const int32_t* __restrict__ cidx,
@@ -655,7 +675,15 @@ void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, P
   const char* env_v1 = std::getenv("ALFIB_TILE_V1");
   const bool v1 = env_v1 && env_v1[0] == '1';
   // K1: V ops, all patches, plain private stores
-  if (nV) {
+  const char* env_tma = std::getenv("ALFIB_TILE_TMA");
+  const bool tma_on = !v1 && env_tma && env_tma[0] == '1';
+  const char* env_tma_min = std::getenv("ALFIB_TILE_TMA_MIN_OPS");
+  const int tma_min_ops = env_tma_min ? std::atoi(env_tma_min) : 1;
+  if (nV && tma_on && nV >= tma_min_ops) {
+    launch_tile_ops_tma<false, false, 0>(c, cd.opsV.p, nV, cd.cidx.p, ps.store, x, nullptr, plain_out(nullptr), cd.g1.p,
+                                         FusedSrc{nullptr, nullptr, nullptr, nullptr});
+    c->launches++;
+  } else if (nV) {
     if (v1)
       tile_ops_kernel<false><<<cdiv(nV, wpb), threads, 0, c->stream>>>(cd.opsV.p, nV, cd.cidx.p, ps.store, x, nullptr,
                                                                         plain_out(nullptr), cd.g1.p);
@@ -682,6 +710,25 @@ void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, P
   auto run = [&](const TileOp* ops, int nops, const double* srcA, const double* srcB, double* dstB, bool atomic,
                  bool accum = false, int mode = 0) {
     if (nops <= 0) return;
+    if (tma_on && nops >= tma_min_ops) {   // v3: TMA bulk copies into per-warp shared-memory rings (tile_tma.cuh)
+      const FusedSrc none{nullptr, nullptr, nullptr, nullptr};
+      const int32_t* ci = cd.cidx.p;
+      if (mode == 1) {
+        if (accum) launch_tile_ops_tma<true, true, 1>(c, ops, nops, ci, ps.store, srcA, srcB, y, dstB, fs_rhs);
+        else if (atomic) launch_tile_ops_tma<true, false, 1>(c, ops, nops, ci, ps.store, srcA, srcB, y, dstB, fs_rhs);
+        else launch_tile_ops_tma<false, false, 1>(c, ops, nops, ci, ps.store, srcA, srcB, y, dstB, fs_rhs);
+      } else if (mode == 2) {
+        launch_tile_ops_tma<false, false, 2>(c, ops, nops, ci, ps.store, srcA, srcB, y, dstB, fs_z);
+      } else if (accum) {
+        launch_tile_ops_tma<true, true, 0>(c, ops, nops, ci, ps.store, srcA, srcB, y, dstB, none);
+      } else if (atomic) {
+        launch_tile_ops_tma<true, false, 0>(c, ops, nops, ci, ps.store, srcA, srcB, y, dstB, none);
+      } else {
+        launch_tile_ops_tma<false, false, 0>(c, ops, nops, ci, ps.store, srcA, srcB, y, dstB, none);
+      }
+      c->launches++;
+      return;
+    }
     if (mode == 1) {                 // fused separator right-hand side: srcA is x
       const int g = cdiv(nops, wpb);
       if (accum)

@@ -222,7 +222,12 @@ def assemble_transfer(cfg: Config, ld: LevelData, nu: float, gamma: float):
 
 def build_problem(cfg: Config | str, nu: float | None = None, with_transfer: bool = True,
                   verbose: bool = False, gamma: float | None = None) -> Problem:
+    """Generate the hand-over data of a configuration.  ALFIB_PROBLEM_CACHE=<dir> keeps a pickle per
+    (config, nu, gamma) there, so that several benchmark scripts of one GPU lease do not each spend the
+    ~40 s of host generation cfg5 takes (the cache is never read by tests of the generator itself)."""
     import dataclasses
+    import os
+    import pickle
     import time
     if isinstance(cfg, str):
         cfg = CONFIGS[cfg]
@@ -230,6 +235,20 @@ def build_problem(cfg: Config | str, nu: float | None = None, with_transfer: boo
         cfg = dataclasses.replace(cfg, gamma=gamma)
     nu = cfg.nu if nu is None else nu
     t0 = time.time()
+    cache_dir = os.environ.get("ALFIB_PROBLEM_CACHE")
+    cache = None
+    if cache_dir:
+        cache = os.path.join(cache_dir, "%s_nu%.6e_g%.6e_t%d.pkl" % (cfg.name, nu, cfg.gamma, int(with_transfer)))
+        if os.path.exists(cache):
+            try:
+                with open(cache, "rb") as f:
+                    prob = pickle.load(f)
+                if prob.config == cfg:
+                    if verbose:
+                        print("[synth] %s from cache in %.1fs" % (cfg.name, time.time() - t0), file=sys.stderr, flush=True)
+                    return prob
+            except Exception:       # noqa: BLE001 - a broken cache file is regenerated
+                pass
     if cfg.domain == "bfs":
         from .gmsh import read_msh, step_mesh
         base = read_msh(cfg.mesh_file) if cfg.mesh_file else step_mesh(cfg.N)
@@ -261,4 +280,14 @@ def build_problem(cfg: Config | str, nu: float | None = None, with_transfer: boo
             print("[synth] level %d: %d dofs, %d patches, %.1fs" % (
                 lev.index, V.ndofs, 0 if ld.patches is None else ld.patches.npatch, time.time() - t0),
                 file=sys.stderr, flush=True)
-    return Problem(cfg, levels, nu, cfg.gamma)
+    prob = Problem(cfg, levels, nu, cfg.gamma)
+    if cache:
+        try:
+            os.makedirs(cache_dir, exist_ok=True)
+            tmp = cache + ".%d.tmp" % os.getpid()
+            with open(tmp, "wb") as f:
+                pickle.dump(prob, f, protocol=pickle.HIGHEST_PROTOCOL)
+            os.replace(tmp, cache)
+        except Exception:           # noqa: BLE001 - caching is best effort
+            pass
+    return prob
