@@ -40,6 +40,23 @@ struct SymHeader {
 };
 #define ALFIB_SYM_HEADER_BYTES 4096
 
+// Mailbox ("push") transport of the distributed-vector exchanges (comm.cu): behind the two slots every rank's
+// symmetric buffer holds an arena of channels, one per (level, halo, direction) plus one for the small
+// all-reduces of the dots.  A channel is [2 slots x cap doubles | one flag per sender rank]; senders write the
+// receiver's slot with NVLink peer stores and then raise their flag there, the receiver polls LOCAL memory.
+// Where a rank keeps each channel is published in a table inside its header (read by the peers at
+// alfib_comm_peer_open), so the arenas need not be laid out identically on all ranks.
+#define ALFIB_MBOX_TABLE_OFF 2048
+#define ALFIB_MBOX_NV 64                                   // values per rank in a small all-reduce
+#define ALFIB_MBOX_CHANNELS (ALFIB_MAX_LEVELS * 4 + 1)
+#define ALFIB_MBOX_SMALL (ALFIB_MAX_LEVELS * 4)
+struct MboxEntry {
+  long long data_off;     // bytes from the start of the symmetric buffer to slot 0 of the channel (0 = none)
+  long long cap;          // doubles per slot
+  long long flags_off;    // bytes to the ALFIB_MAX_RANKS flags (unsigned long long) of the channel
+};
+static_assert(ALFIB_MBOX_TABLE_OFF + ALFIB_MBOX_CHANNELS * sizeof(MboxEntry) <= ALFIB_SYM_HEADER_BYTES, "channel table must fit the header");
+
 struct DeviceError {
   int code;
   std::string msg;
@@ -150,6 +167,7 @@ struct Halo {
   // NVLink peer-memory exchanges: where, in peer p's packed send / ghost buffer, the part for this rank starts
   bool has_peer_off = false;
   std::vector<int64_t> peer_send_off, peer_recv_off;
+  int ch_update = -1, ch_reduce = -1;        // mailbox channels of the two directions (comm_mbox_reserve)
   void release() {
     send_idx.release(); recv_idx.release(); sbuf.release(); rbuf.release();
     red_ptr.release(); red_dof.release(); red_src.release();
@@ -218,6 +236,14 @@ struct alfib_ctx {
   DBuf<unsigned long long> d_epoch;      // exchange counter (device)
   DBuf<int> d_comm_err;
   DBuf<long long> d_gate;                // block 0 -> other blocks gate of the reduction kernel
+  // mailbox transport (distributed vectors): this rank's channel table, the arena size reserved so far (relative
+  // to the arena start until the buffer is allocated), the peers' tables, per-channel exchange numbers and counters
+  MboxEntry mbox[ALFIB_MBOX_CHANNELS] = {};
+  size_t mbox_bytes = 0;
+  bool mbox_fixed = false;               // offsets made absolute (buffer allocated)
+  std::vector<MboxEntry> mbox_peer[ALFIB_MAX_RANKS];
+  DBuf<unsigned long long> mbox_seq;     // [channel]: number of completed exchanges
+  DBuf<unsigned int> mbox_cnt;           // [2 * channel]: blocks that have pushed / finished
   // patch factor workspace (one slot per resident CTA) + status word + work counter
   DBuf<double> fwork;
   DBuf<int> finfo;
@@ -296,6 +322,7 @@ void halo_update(alfib_ctx* c, Halo& H, double* x, int level);
 void halo_reduce(alfib_ctx* c, Halo& H, double* y, int level);
 // v[0..nv) summed over the ranks, result on every rank (FGMRES dots); sqrt_mode: v[0] = sqrt(sum), inv = 1 / v[0]
 void comm_small_allreduce(alfib_ctx* c, double* v, int nv, int sqrt_mode, double* inv);
+void comm_mbox_reserve(alfib_ctx* c, Halo& H, int level, int which);    // channels of a halo (before the peer buffer exists)
 void comm_peer_alloc(alfib_ctx* c);
 void comm_peer_handle(alfib_ctx* c, void* out64);
 void comm_peer_open(alfib_ctx* c, const void* handles);

@@ -98,6 +98,9 @@ struct OutVec {                      // output vector: compute into dev, copy ba
     if (host) {
       CUDA_TRY(cudaMemcpyAsync(user, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       CUDA_TRY(cudaStreamSynchronize(c->stream));
+      // a result handed to the host must not come out of an exchange that gave up waiting for a peer
+      if (c->nranks > 1 && c->peers_open && comm_peer_error(c))
+        throw DeviceError{ALFIB_ECUDA, "peer-memory exchange timed out waiting for another rank"};
     }
   }
 };
@@ -359,6 +362,7 @@ int alfib_level_set_halo(alfib_ctx* c, int level, int which, int32_t n_owned, in
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     H.on = true;
     if (which == 0) L.n_owned = n_owned;
+    comm_mbox_reserve(c, H, level, which);
   });
 }
 

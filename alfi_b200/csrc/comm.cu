@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstddef>
+#include <cstdlib>
 
 #include "alfib_internal.h"
 
@@ -190,7 +191,10 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(long long n, int nrank
   if (threadIdx.x == 0) {
     long long spins = 0;
     while (*reinterpret_cast<const volatile unsigned long long*>(&local->go) < e)
-      if (++spins > SPIN_LIMIT * 16) break;
+      if (++spins > SPIN_LIMIT * 16) {
+        atomicExch(err, 1);
+        break;
+      }
   }
   __syncthreads();
   if (threadIdx.x < nranks) {
@@ -219,19 +223,60 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(long long n, int nrank
 
 }  // namespace
 
+// Channels of one halo in the mailbox arena (called by alfib_level_set_halo; host bookkeeping only, so it is
+// harmless without peer memory): owner -> ghost needs room for this rank's ghosts, ghost -> owner for its send list.
+static void mbox_reserve_channel(alfib_ctx* c, int ch, long long cap) {
+  ALFIB_REQUIRE(ch >= 0 && ch < ALFIB_MBOX_CHANNELS, "mailbox channel out of range");
+  MboxEntry& e = c->mbox[ch];
+  if (e.data_off != 0 && e.cap >= cap) return;               // re-registration that still fits
+  ALFIB_REQUIRE(!c->mbox_fixed, "alfib_level_set_halo after alfib_comm_peer_handle: the exchange buffer is already laid out");
+  auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+  e.cap = std::max<long long>(cap, 2);
+  c->mbox_bytes = up(c->mbox_bytes);
+  e.data_off = (long long)c->mbox_bytes + 256;               // + 256: 0 means "no channel"; made absolute at allocation
+  c->mbox_bytes += up(2 * (size_t)e.cap * sizeof(double)) + 256;
+  e.flags_off = (long long)c->mbox_bytes;
+  c->mbox_bytes += up(ALFIB_MAX_RANKS * sizeof(unsigned long long));
+}
+
+void comm_mbox_reserve(alfib_ctx* c, Halo& H, int level, int which) {
+  H.ch_update = (level * 2 + which) * 2;
+  H.ch_reduce = H.ch_update + 1;
+  mbox_reserve_channel(c, H.ch_update, H.recv_off.back());
+  mbox_reserve_channel(c, H.ch_reduce, H.send_off.back());
+}
+
 // symmetric buffer sized for the largest level (and the coarse system); call after the levels exist
 void comm_peer_alloc(alfib_ctx* c) {
   size_t maxn = 0;
+  bool distributed = false;
   for (auto* L : c->levels)
-    if (L) maxn = std::max<size_t>(maxn, (size_t)L->n);
-  maxn = (maxn + 1) & ~size_t(1);
+    if (L) {
+      maxn = std::max<size_t>(maxn, (size_t)L->n);
+      distributed |= L->halo.on;
+    }
+  // distributed vectors: only the replicated level 0 goes through the slots, and the level sizes differ from rank
+  // to rank — the slot stride must not (the peers address each other's slot 1 with their own stride)
+  if (distributed && c->levels[0]) maxn = std::max<size_t>((size_t)c->levels[0]->n, 4096);
+  maxn = (maxn + 31) & ~size_t(31);
   ALFIB_REQUIRE(maxn > 0, "create the levels before enabling peer memory");
   if (c->sym && c->sym_stride == maxn) return;
   ALFIB_REQUIRE(!c->peers_open, "peer memory already mapped");
   if (c->sym) cudaFree(c->sym);
-  const size_t bytes = ALFIB_SYM_HEADER_BYTES + 2 * maxn * sizeof(double);
+  if (!c->mbox_fixed) {
+    mbox_reserve_channel(c, ALFIB_MBOX_SMALL, (long long)ALFIB_MAX_RANKS * ALFIB_MBOX_NV);
+    const size_t arena = ALFIB_SYM_HEADER_BYTES + 2 * maxn * sizeof(double);
+    for (auto& e : c->mbox)
+      if (e.data_off) {
+        e.data_off += (long long)arena - 256;
+        e.flags_off += (long long)arena;
+      }
+    c->mbox_fixed = true;
+  }
+  const size_t bytes = ALFIB_SYM_HEADER_BYTES + 2 * maxn * sizeof(double) + c->mbox_bytes + 512;
   CUDA_TRY(cudaMalloc(&c->sym, bytes));
   CUDA_TRY(cudaMemset(c->sym, 0, bytes));
+  CUDA_TRY(cudaMemcpy(c->sym + ALFIB_MBOX_TABLE_OFF, c->mbox, sizeof(c->mbox), cudaMemcpyHostToDevice));
   c->sym_stride = maxn;
   c->d_epoch.alloc(1);
   const unsigned long long one = 1;
@@ -240,6 +285,10 @@ void comm_peer_alloc(alfib_ctx* c) {
   CUDA_TRY(cudaMemset(c->d_gate.p, 0, sizeof(LocalGate)));
   c->d_comm_err.alloc(2);                                  // [0] time-out flag, [1] finished-block counter
   CUDA_TRY(cudaMemset(c->d_comm_err.p, 0, 2 * sizeof(int)));
+  c->mbox_seq.alloc(ALFIB_MBOX_CHANNELS);
+  CUDA_TRY(cudaMemset(c->mbox_seq.p, 0, ALFIB_MBOX_CHANNELS * sizeof(unsigned long long)));
+  c->mbox_cnt.alloc(2 * ALFIB_MBOX_CHANNELS);
+  CUDA_TRY(cudaMemset(c->mbox_cnt.p, 0, 2 * ALFIB_MBOX_CHANNELS * sizeof(unsigned int)));
 }
 
 void comm_peer_handle(alfib_ctx* c, void* out64) {
@@ -281,6 +330,13 @@ void comm_peer_open(alfib_ctx* c, const void* handles) {
   }
   c->d_peer_slot.alloc(c->nranks);
   CUDA_TRY(cudaMemcpy(c->d_peer_slot.p, slot0.data(), sizeof(double*) * c->nranks, cudaMemcpyHostToDevice));
+  // the peers' channel tables (written before they produced their handles, i.e. before the host-side all-gather)
+  for (int q = 0; q < c->nranks; ++q) {
+    c->mbox_peer[q].assign(ALFIB_MBOX_CHANNELS, MboxEntry{0, 0, 0});
+    const unsigned char* base = q == c->rank ? c->sym : static_cast<const unsigned char*>(c->peer_ptr[q]);
+    CUDA_TRY(cudaMemcpy(c->mbox_peer[q].data(), base + ALFIB_MBOX_TABLE_OFF, sizeof(MboxEntry) * ALFIB_MBOX_CHANNELS,
+                        cudaMemcpyDeviceToHost));
+  }
   comm_peer_publish_ranges(c);
   CUDA_TRY(cudaDeviceSynchronize());
   c->peers_open = true;
@@ -328,6 +384,7 @@ int comm_peer_error(alfib_ctx* c) {
   if (!c->d_comm_err.p) return 0;
   int e = 0;
   cudaMemcpy(&e, c->d_comm_err.p, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e) cudaMemset(c->d_comm_err.p, 0, sizeof(int));     // reported once; the next exchange starts clean
   return e;
 }
 
@@ -413,7 +470,10 @@ __device__ __forceinline__ void peer_exchange_begin(unsigned long long e, int nr
   if (threadIdx.x == 0) {
     long long spins = 0;
     while (*reinterpret_cast<const volatile unsigned long long*>(&local->go) < e)
-      if (++spins > SPIN_LIMIT * 16) break;
+      if (++spins > SPIN_LIMIT * 16) {
+        atomicExch(err, 1);
+        break;
+      }
   }
   __threadfence_system();
   __syncthreads();
@@ -518,6 +578,185 @@ HaloPeers make_peers(const Halo& H, const std::vector<int64_t>& mine, const std:
 
 inline bool use_peers(const alfib_ctx* c, const Halo& H) { return c->nranks > 1 && c->peers_open && H.has_peer_off; }
 
+// ---- mailbox ("push") transport ---------------------------------------------------------------------------------
+// One kernel per exchange.  Exchange number k of a channel (k = completed exchanges + 1, kept in device memory so
+// the sequence replays inside a CUDA graph) uses slot k & 1 of the RECEIVER's channel:
+//   push    every entry of this rank's outgoing list is written straight into its place in the neighbour's slot
+//           (NVLink peer stores, the pack and the transfer are the same instruction);
+//   signal  the last block to finish pushing raises flag[this rank] = k in every neighbour's channel
+//           (every thread fences system-wide before its block counts itself, the signalling thread fences again);
+//   wait    every block polls the flags of its neighbours in LOCAL memory until they reach k;
+//   unpack  the ghosts are copied out of the slot / the owned interface dofs gather-sum their contributions in
+//           ascending rank order (reproducible).
+// Two slots suffice: a neighbour's push k + 2 follows its wait k + 1, i.e. this rank's signal k + 1, which this
+// rank's stream issues only after its kernel k has finished reading slot k & 1.  The neighbour relation of a
+// channel is symmetric (every listed peer is signalled and waited for, also with an empty segment).  All blocks
+// of the kernel are resident (grid <= number of SMs), so blocks spinning in `wait` cannot starve blocks that
+// still have to push.  A time-out (20 s on %globaltimer) raises the error flag alfib_synchronize / alfib_cycle_apply report.
+struct MboxPeers {
+  int npeers;
+  int peers[ALFIB_MAX_RANKS];
+  long long mine_off[ALFIB_MAX_RANKS + 1];        // segments of this rank's outgoing list
+  double* data[ALFIB_MAX_RANKS];                  // slot 0 of the channel in the neighbour's memory
+  long long cap[ALFIB_MAX_RANKS];                 // its slot size
+  long long theirs_off[ALFIB_MAX_RANKS];          // where this rank's segment starts in the neighbour's incoming list
+  unsigned long long* flag[ALFIB_MAX_RANKS];      // flag[this rank] of the channel in the neighbour's memory
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ int mbox_segment(const MboxPeers& mp, long long pos) {
+  int p = 0;
+  while (p + 1 < mp.npeers && pos >= mp.mine_off[p + 1]) ++p;
+  return p;
+}
+
+// after the push loop: count this block; the last one signals the neighbours; then wait for theirs
+__device__ __forceinline__ void mbox_signal_and_wait(const MboxPeers& mp, unsigned long long k,
+                                                     const unsigned long long* my_flags, unsigned int* pushed,
+                                                     int* __restrict__ err) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(pushed, 1u) == gridDim.x - 1) {
+      *pushed = 0;
+      __threadfence_system();
+      for (int p = 0; p < mp.npeers; ++p) *reinterpret_cast<volatile unsigned long long*>(mp.flag[p]) = k;
+    }
+  }
+  if (threadIdx.x < mp.npeers) {
+    const volatile unsigned long long* f = my_flags + mp.peers[threadIdx.x];
+    const unsigned long long t0 = global_ns();
+    while (*f < k) {
+      if (global_ns() - t0 > 20000000000ull) {   // 20 s: the ranks enter the first exchange after rank-local setup phases
+        atomicExch(err, 1);
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+}
+
+__device__ __forceinline__ void mbox_finish(unsigned long long k, unsigned long long* seq, unsigned int* finished) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(finished, 1u) == gridDim.x - 1) {
+      *finished = 0;
+      *seq = k;
+    }
+  }
+}
+
+// owner -> ghost
+__global__ void __launch_bounds__(256) mbox_update_kernel(long long ns, long long nr, MboxPeers mp,
+                                                          const int32_t* __restrict__ send_idx,
+                                                          const int32_t* __restrict__ recv_idx, double* __restrict__ x,
+                                                          const double* my_data, long long my_cap,
+                                                          const unsigned long long* my_flags, unsigned long long* seq,
+                                                          unsigned int* cnt, int* __restrict__ err) {
+  const unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(seq) + 1ull;
+  const long long slot = (long long)(k & 1ull);
+  const long long stride = (long long)gridDim.x * blockDim.x, t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long i = t; i < ns; i += stride) {
+    const int p = mbox_segment(mp, i);
+    mp.data[p][slot * mp.cap[p] + mp.theirs_off[p] + (i - mp.mine_off[p])] = x[send_idx[i]];
+  }
+  mbox_signal_and_wait(mp, k, my_flags, cnt, err);
+  const double* in = my_data + slot * my_cap;
+  for (long long i = t; i < nr; i += stride) x[recv_idx[i]] = __ldcv(in + i);
+  mbox_finish(k, seq, cnt + 1);
+}
+
+// ghost -> owner: the ghost entries are pushed (and cleared), the owned interface dofs sum what arrives
+__global__ void __launch_bounds__(256) mbox_reduce_kernel(long long nr, int n_red, MboxPeers mp,
+                                                          const int32_t* __restrict__ recv_idx,
+                                                          const int32_t* __restrict__ red_ptr,
+                                                          const int32_t* __restrict__ red_dof,
+                                                          const int32_t* __restrict__ red_src, double* __restrict__ y,
+                                                          const double* my_data, long long my_cap,
+                                                          const unsigned long long* my_flags, unsigned long long* seq,
+                                                          unsigned int* cnt, int* __restrict__ err) {
+  const unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(seq) + 1ull;
+  const long long slot = (long long)(k & 1ull);
+  const long long stride = (long long)gridDim.x * blockDim.x, t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long i = t; i < nr; i += stride) {
+    const int p = mbox_segment(mp, i);
+    const int g = recv_idx[i];
+    mp.data[p][slot * mp.cap[p] + mp.theirs_off[p] + (i - mp.mine_off[p])] = y[g];
+    y[g] = 0.0;
+  }
+  mbox_signal_and_wait(mp, k, my_flags, cnt, err);
+  const double* in = my_data + slot * my_cap;
+  for (long long i = t; i < n_red; i += stride) {
+    double v = y[red_dof[i]];
+    for (int j = red_ptr[i]; j < red_ptr[i + 1]; ++j) v += __ldcv(in + red_src[j]);
+    y[red_dof[i]] = v;
+  }
+  mbox_finish(k, seq, cnt + 1);
+}
+
+// v[j] summed over all ranks in rank order (one block); optional sqrt / reciprocal of the result
+__global__ void __launch_bounds__(64) mbox_small_sum_kernel(int nv, int nranks, int rank, MboxPeers mp, double* __restrict__ v,
+                                                            int sqrt_mode, double* __restrict__ inv, const double* my_data,
+                                                            long long my_cap, const unsigned long long* my_flags,
+                                                            unsigned long long* seq, unsigned int* cnt, int* __restrict__ err) {
+  const unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(seq) + 1ull;
+  const long long slot = (long long)(k & 1ull);
+  for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+    const double mine = v[j];
+    for (int p = 0; p < mp.npeers; ++p) mp.data[p][slot * mp.cap[p] + (long long)rank * ALFIB_MBOX_NV + j] = mine;
+  }
+  mbox_signal_and_wait(mp, k, my_flags, cnt, err);
+  const double* in = my_data + slot * my_cap;
+  for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+    double s = 0.0;
+    for (int q = 0; q < nranks; ++q) s += (q == rank) ? v[j] : __ldcv(in + (long long)q * ALFIB_MBOX_NV + j);
+    if (sqrt_mode) {
+      s = sqrt(s);
+      if (inv) inv[j] = s > 0.0 ? 1.0 / s : 0.0;
+    }
+    v[j] = s;
+  }
+  mbox_finish(k, seq, cnt + 1);
+}
+
+// the neighbours of one channel as the kernels take them; `mine` = offsets of the outgoing list, `theirs` = where
+// each neighbour expects this rank's segment
+MboxPeers mbox_peers(alfib_ctx* c, int ch, const std::vector<int>& peers, const std::vector<int64_t>& mine,
+                     const std::vector<int64_t>& theirs) {
+  MboxPeers mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.npeers = (int)peers.size();
+  for (int p = 0; p < mp.npeers; ++p) {
+    const int q = peers[p];
+    const MboxEntry& e = c->mbox_peer[q][ch];
+    if (e.data_off == 0) throw DeviceError{ALFIB_EINVAL, "rank " + std::to_string(q) + " has no mailbox channel " + std::to_string(ch)};
+    unsigned char* base = static_cast<unsigned char*>(c->peer_ptr[q]);
+    mp.peers[p] = q;
+    mp.mine_off[p] = mine[p];
+    mp.theirs_off[p] = theirs[p];
+    mp.data[p] = reinterpret_cast<double*>(base + e.data_off);
+    mp.cap[p] = e.cap;
+    mp.flag[p] = reinterpret_cast<unsigned long long*>(base + e.flags_off) + c->rank;
+    if (theirs[p] + (mine[p + 1] - mine[p]) > e.cap)
+      throw DeviceError{ALFIB_EINVAL, "mailbox segment does not fit the neighbour's channel"};
+  }
+  mp.mine_off[mp.npeers] = mine[mp.npeers];
+  return mp;
+}
+
+inline int mbox_grid(alfib_ctx* c, int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 512), c->num_sms)); }
+inline bool use_mbox(const alfib_ctx* c, const Halo& H) {
+  return c->nranks > 1 && c->peers_open && H.has_peer_off && H.ch_update >= 0 && c->mbox_fixed &&
+         !std::getenv("ALFIB_MBOX_OFF");      // ALFIB_MBOX_OFF=1: the pull transport (pack + flag barrier + peer loads)
+}
+
 }  // namespace
 
 // owner -> ghost: every ghost entry of x takes its owner's value
@@ -525,6 +764,19 @@ void halo_update(alfib_ctx* c, Halo& H, double* x, int level) {
   if (!H.on || c->nranks <= 1) return;
   ScopedEvent ev(c, ALFIB_EV_HALO, level);
   const int64_t ns = H.send_off.back(), nr = H.recv_off.back();
+  if (use_mbox(c, H)) {
+    if (H.peers.empty()) return;
+    const int ch = H.ch_update;
+    const MboxEntry& me = c->mbox[ch];
+    mbox_update_kernel<<<mbox_grid(c, std::max(ns, nr)), 256, 0, c->stream>>>(
+        ns, nr, mbox_peers(c, ch, H.peers, H.send_off, H.peer_recv_off), H.send_idx.p, H.recv_idx.p, x,
+        reinterpret_cast<const double*>(c->sym + me.data_off), me.cap,
+        reinterpret_cast<const unsigned long long*>(c->sym + me.flags_off), c->mbox_seq.p + ch, c->mbox_cnt.p + 2 * ch,
+        c->d_comm_err.p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return;
+  }
   if (use_peers(c, H)) {
     // every rank takes part in every exchange (the flags count exchanges), also one without neighbours here
     ALFIB_REQUIRE((size_t)ns <= c->sym_stride, "packed halo does not fit the symmetric buffer");
@@ -557,7 +809,20 @@ void halo_reduce(alfib_ctx* c, Halo& H, double* y, int level) {
   ScopedEvent ev(c, ALFIB_EV_HALO, level);
   if (c->nranks > 1) {
     const int64_t ns = H.send_off.back(), nr = H.recv_off.back();
-    if (use_peers(c, H)) {
+    if (use_mbox(c, H)) {
+      if (!H.peers.empty()) {
+        const int ch = H.ch_reduce;
+        const MboxEntry& me = c->mbox[ch];
+        mbox_reduce_kernel<<<mbox_grid(c, std::max<int64_t>(nr, H.n_red)), 256, 0, c->stream>>>(
+            nr, H.n_red, mbox_peers(c, ch, H.peers, H.recv_off, H.peer_send_off), H.recv_idx.p, H.red_ptr.p, H.red_dof.p,
+            H.red_src.p, y, reinterpret_cast<const double*>(c->sym + me.data_off), me.cap,
+            reinterpret_cast<const unsigned long long*>(c->sym + me.flags_off), c->mbox_seq.p + ch, c->mbox_cnt.p + 2 * ch,
+            c->d_comm_err.p);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return;                                  // the kernel has cleared the ghosts it pushed (all of them)
+      }
+    } else if (use_peers(c, H)) {
       ALFIB_REQUIRE((size_t)nr <= c->sym_stride, "packed halo does not fit the symmetric buffer");
       halo_pack_kernel<<<halo_grid(nr), 256, 0, c->stream>>>(nr, H.recv_idx.p, y, comm_peer_out(c));
       peer_halo_sum_kernel<<<halo_grid(H.n_red), 256, 0, c->stream>>>(
@@ -584,6 +849,22 @@ void halo_reduce(alfib_ctx* c, Halo& H, double* y, int level) {
 }
 
 void comm_small_allreduce(alfib_ctx* c, double* v, int nv, int sqrt_mode, double* inv) {
+  if (c->nranks > 1 && c->peers_open && c->mbox_fixed && nv <= ALFIB_MBOX_NV && !std::getenv("ALFIB_MBOX_OFF")) {
+    const int ch = ALFIB_MBOX_SMALL;
+    const MboxEntry& me = c->mbox[ch];
+    std::vector<int> peers;
+    std::vector<int64_t> zeros;
+    for (int q = 0; q < c->nranks; ++q)
+      if (q != c->rank) peers.push_back(q);
+    zeros.assign(peers.size() + 1, 0);
+    mbox_small_sum_kernel<<<1, 64, 0, c->stream>>>(nv, c->nranks, c->rank, mbox_peers(c, ch, peers, zeros, zeros), v, sqrt_mode, inv,
+                                                   reinterpret_cast<const double*>(c->sym + me.data_off), me.cap,
+                                                   reinterpret_cast<const unsigned long long*>(c->sym + me.flags_off),
+                                                   c->mbox_seq.p + ch, c->mbox_cnt.p + 2 * ch, c->d_comm_err.p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return;
+  }
   if (c->nranks > 1 && c->peers_open) {
     ALFIB_REQUIRE((size_t)nv <= c->sym_stride, "too many values for the symmetric buffer");
     halo_pack_kernel<<<1, 64, 0, c->stream>>>(nv, nullptr, v, comm_peer_out(c));

@@ -604,9 +604,11 @@ void condense_setup(alfib_ctx* c, Level& L, PatchSet& ps, const int32_t* block_o
   CUDA_TRY(cudaMemsetAsync(cd.g1.p, 0, cd.g1.n * sizeof(double), c->stream));
   CUDA_TRY(cudaMemsetAsync(cd.us.p, 0, cd.us.n * sizeof(double), c->stream));
   if (cd.z.p) CUDA_TRY(cudaMemsetAsync(cd.z.p, 0, cd.z.n * sizeof(double), c->stream));
-  // ALFIB_SCHUR_SETUP=1: X_SS from the Schur complement (~200x fewer flops per Newton step on 3-D macro stars)
+  // X_SS from the Schur complement formed with solves (~200x fewer flops per Newton step on 3-D macro stars; measured
+  // on B200: 3.27 s -> 0.28 s per Newton step on cfg5).  Default; ALFIB_SCHUR_SETUP=0 cuts X_SS out of the pivoted
+  // inverse of the whole patch instead (round 1's setup).
   const char* env_schur = std::getenv("ALFIB_SCHUR_SETUP");
-  cd.schur = env_schur && env_schur[0] == '1';
+  cd.schur = !(env_schur && env_schur[0] == '0');
   if (cd.schur) {
     build_schur_lists(h, ps.npatch, cd.sh);
     const SchurHost& sh = cd.sh;

@@ -321,6 +321,18 @@ class DistributedMultigrid:
 
     _bind = DeviceMultigrid._bind
 
+    def _host_barrier(self):
+        """Ranks leave the rank-local setup phases (seconds of factorisation) at different times; the device-side
+        exchanges spin on their neighbours with a time-out, so the hosts meet before the next exchange is enqueued."""
+        if self.nranks > 1:
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    self.ctx.synchronize()
+                    dist.barrier()
+            except ImportError:
+                pass
+
     def _peer_offsets(self, layout):
         """{peer: (start of this rank's segment in the peer's packed send list, in its packed ghost list)} — in a
         deployment two integers per neighbour exchanged at setup; here read off the global layout."""
@@ -344,6 +356,7 @@ class DistributedMultigrid:
             c.set_bsr_values(l, np.ascontiguousarray(vals))
             c.factor(l)
         c.coarse_factor()
+        self._host_barrier()
 
     def update_transfers(self, levels):
         for l in range(1, self.nlevels):

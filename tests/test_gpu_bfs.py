@@ -1,18 +1,13 @@
 """GPU parity on BASELINE.json configs[2] (backward-facing step, Gmsh-style unstructured mesh).
 
-Written after round 1's GPU budget was spent: these tests have not been executed on a B200 yet, so they only
-run when ALFIB_GPU_PENDING=1 (first thing to do in the next round: run them, then drop the gate).  The CUDA
-library is mesh-agnostic, so they are expected to pass as they stand; the CPU side of this configuration is
-covered by tests/test_bfs.py, tests/test_golden.py and tests/test_oracle_properties.py.
+First run on a B200 in round 2 (9 passed, profiles/r2_gpu_tests.txt).  The CUDA library is mesh-agnostic; the
+CPU side of this configuration is covered by tests/test_bfs.py, tests/test_golden.py and
+tests/test_oracle_properties.py.
 """
-import os
-
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ALFIB_GPU_PENDING", "0") != "1",
-                                 reason="not yet run on a B200 (set ALFIB_GPU_PENDING=1)")]
+pytestmark = pytest.mark.gpu
 
 TOL = 1e-11
 EPS = np.finfo(np.float64).eps
