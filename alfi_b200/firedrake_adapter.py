@@ -12,7 +12,7 @@ import numpy as np
 
 from .pc import HostAdapter
 
-__all__ = ["FiredrakeAdapter", "attach", "transfer_backend"]
+__all__ = ["FiredrakeAdapter", "DMPlexView", "attach", "transfer_backend"]
 
 
 def baij_csr_to_blocks(indptr, indices, data, bs):
@@ -35,7 +35,8 @@ def baij_csr_to_blocks(indptr, indices, data, bs):
 
 
 class _Space:
-    """The view of a Firedrake FunctionSpace the patch builders need."""
+    """The view of a Firedrake FunctionSpace the patch builders need (``nnodes``, ``bs``, ``cell_nodes``) plus the
+    PetscSection that attaches its nodes to DMPlex points."""
 
     def __init__(self, V):
         self.V = V
@@ -43,16 +44,104 @@ class _Space:
         self.cell_nodes = np.asarray(V.cell_node_list, dtype=np.int64)
         self.nnodes = V.dof_dset.total_size
 
-    def node_points(self, plex):
-        """node -> DMPlex point, from the section of the scalar space (transfer.py:127-144)."""
-        section = self.V.dm.getDefaultSection()
-        pStart, pEnd = section.getChart()
-        out = np.full(self.nnodes, -1, dtype=np.int64)
-        for p in range(pStart, pEnd):
-            dof, off = section.getDof(p), section.getOffset(p)
-            if dof:
-                out[off // self.bs:(off + dof) // self.bs] = p
+    @property
+    def section(self):
+        return self.V.dm.getDefaultSection()
+
+
+class _Labels:
+    """``plex.labels`` of the synthetic DMPlex look-alike (name -> int array over the chart, -1 = unlabelled) read
+    lazily from a petsc4py DMPlex with ``getLabelValue`` (the call alfi itself uses: relaxation.py:34-50,
+    transfer.py:36-38,132)."""
+
+    def __init__(self, dm, npoints):
+        self.dm, self.npoints, self._cache = dm, npoints, {}
+
+    def get(self, name, default=None):
+        if name not in self._cache:
+            has = self.dm.hasLabel(name) if hasattr(self.dm, "hasLabel") else True
+            if not has:
+                self._cache[name] = None
+            else:
+                arr = np.fromiter((self.dm.getLabelValue(name, p) for p in range(self.npoints)), dtype=np.int64,
+                                  count=self.npoints)
+                self._cache[name] = arr if (arr != -1).any() else None
+        out = self._cache[name]
+        return default if out is None else out
+
+    def __getitem__(self, name):
+        out = self.get(name)
+        if out is None:
+            raise KeyError(name)
         return out
+
+    def __contains__(self, name):
+        return self.get(name) is not None
+
+
+class DMPlexView:
+    """What the vectorised builders (`star_points`, `macro_star_points`, `patch_dofs_from_points`,
+    `macro_interior_blocks`, `coarse_cell_points`, `fix_coarse_boundaries`) read from a mesh, built ONCE from a
+    petsc4py ``DMPlex`` through the calls alfi itself makes (``getChart``, ``getCone``, ``getDepthStratum`` /
+    ``getHeightStratum``, ``getLabelValue``, ``getTransitiveClosure``): the cone relation as CSR, its transitive
+    closure / star as sparse boolean matrices, the strata bounds and the labels.  Everything else
+    (``getTransitiveClosure`` for the per-entity callbacks of `alfi_b200.relaxation`, ...) is forwarded to the DM.
+    Tested against a petsc4py-shaped stand-in in tests/test_firedrake_adapter.py (petsc4py is absent here)."""
+
+    def __init__(self, dm):
+        import scipy.sparse as sp
+        self.dm = dm
+        pStart, pEnd = dm.getChart()
+        if pStart != 0:
+            raise ValueError("DMPlex chart must start at 0")
+        n = self.npoints = int(pEnd)
+        self.dim = int(dm.getDimension())
+        self.cStart, self.cEnd = (int(v) for v in dm.getHeightStratum(0))
+        self.vStart, self.vEnd = (int(v) for v in dm.getDepthStratum(0))
+        rows, cols = [], []
+        for p in range(n):
+            cone = np.asarray(dm.getCone(p), dtype=np.int64)
+            if cone.size:
+                rows.append(np.full(cone.size, p, dtype=np.int64))
+                cols.append(cone)
+        rows = np.concatenate(rows) if rows else np.empty(0, np.int64)
+        cols = np.concatenate(cols) if cols else np.empty(0, np.int64)
+        self.cone = sp.csr_matrix((np.ones(rows.size, dtype=np.int8), (rows, cols)), shape=(n, n))
+        self.cone.sort_indices()
+        eye = sp.identity(n, dtype=np.int32, format="csr")
+        D = self.cone.astype(np.int32)
+        C = eye + D
+        for _ in range(self.dim - 1):
+            C = eye + D @ C
+        C.data[:] = 1
+        C.sort_indices()
+        self.closure = C.tocsr()
+        self.star = C.T.tocsr()
+        self.star.sort_indices()
+        self.labels = _Labels(dm, n)
+
+    def __getattr__(self, name):                 # getDepthStratum, getTransitiveClosure, getLabelValue, getSupport, ...
+        return getattr(self.dm, name)
+
+    def node_points(self, V):
+        """node -> DMPlex point from the section of the space.  Firedrake's sections count NODES (alfi uses
+        ``section.getOffset(p) + d`` directly as node numbers, transfer.py:138-144)."""
+        section = V.section
+        out = np.full(V.nnodes, -1, dtype=np.int64)
+        for p in range(self.npoints):
+            dof = section.getDof(p)
+            if dof:
+                off = section.getOffset(p)
+                out[off:off + dof] = p
+        if (out < 0).any():
+            raise ValueError("the section does not attach every node to a mesh point")
+        return out
+
+    def point_coords(self, p):
+        """Mean of the vertex coordinates in the closure of p, read as alfi/relaxation.py:61-67 does."""
+        dm = self.dm
+        dim = dm.getCoordinateDM().getDimension()
+        return np.asarray(dm.getVecClosure(dm.getCoordinateSection(), dm.getCoordinatesLocal(), p)).reshape(-1, dim).mean(axis=0)
 
 
 class FiredrakeAdapter(HostAdapter):
@@ -73,6 +162,16 @@ class FiredrakeAdapter(HostAdapter):
     def function_space(self, pc):
         from firedrake import dmhooks
         return _Space(dmhooks.get_function_space(pc.getDM()))
+
+    def plex(self, pc):
+        """The DMPlex of the PC's level as a `DMPlexView` (cone / closure / star relations read once per mesh)."""
+        dm = pc.getDM()
+        view = dm.getAttr("alfi_b200_plex_view") if hasattr(dm, "getAttr") else None
+        if view is None:
+            view = DMPlexView(dm)
+            if hasattr(dm, "setAttr"):
+                dm.setAttr("alfi_b200_plex_view", view)
+        return view
 
     def bc_nodes(self, pc):
         from firedrake.dmhooks import get_appctx

@@ -39,6 +39,15 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def set_num_threads(n: int):
+    """Fix the OpenMP team size explicitly (launchers such as torchrun export OMP_NUM_THREADS=1)."""
+    os.environ["OMP_NUM_THREADS"] = str(int(n))
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
 def num_threads():
     try:
         omp = C.CDLL("libgomp.so.1")

@@ -4,6 +4,8 @@ First run on a B200 in round 2 (9 passed, profiles/r2_gpu_tests.txt).  The CUDA 
 CPU side of this configuration is covered by tests/test_bfs.py, tests/test_golden.py and
 tests/test_oracle_properties.py.
 """
+import os
+
 import numpy as np
 import pytest
 
