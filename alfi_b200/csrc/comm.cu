@@ -234,7 +234,7 @@ static void mbox_reserve_channel(alfib_ctx* c, int ch, long long cap) {
   e.cap = std::max<long long>(cap, 2);
   c->mbox_bytes = up(c->mbox_bytes);
   e.data_off = (long long)c->mbox_bytes + 256;               // + 256: 0 means "no channel"; made absolute at allocation
-  c->mbox_bytes += up(2 * (size_t)e.cap * sizeof(double)) + 256;
+  c->mbox_bytes += up(2 * (size_t)e.cap * 2 * sizeof(double)) + 256;     // 2 slots x cap entries x 16 bytes (LL words)
   e.flags_off = (long long)c->mbox_bytes;
   c->mbox_bytes += up(ALFIB_MAX_RANKS * sizeof(unsigned long long));
 }
@@ -579,28 +579,28 @@ HaloPeers make_peers(const Halo& H, const std::vector<int64_t>& mine, const std:
 inline bool use_peers(const alfib_ctx* c, const Halo& H) { return c->nranks > 1 && c->peers_open && H.has_peer_off; }
 
 // ---- mailbox ("push") transport ---------------------------------------------------------------------------------
-// One kernel per exchange.  Exchange number k of a channel (k = completed exchanges + 1, kept in device memory so
-// the sequence replays inside a CUDA graph) uses slot k & 1 of the RECEIVER's channel:
-//   push    every entry of this rank's outgoing list is written straight into its place in the neighbour's slot
-//           (NVLink peer stores, the pack and the transfer are the same instruction);
-//   signal  the last block to finish pushing raises flag[this rank] = k in every neighbour's channel
-//           (every thread fences system-wide before its block counts itself, the signalling thread fences again);
-//   wait    every block polls the flags of its neighbours in LOCAL memory until they reach k;
-//   unpack  the ghosts are copied out of the slot / the owned interface dofs gather-sum their contributions in
-//           ascending rank order (reproducible).
-// Two slots suffice: a neighbour's push k + 2 follows its wait k + 1, i.e. this rank's signal k + 1, which this
-// rank's stream issues only after its kernel k has finished reading slot k & 1.  The neighbour relation of a
-// channel is symmetric (every listed peer is signalled and waited for, also with an empty segment).  All blocks
-// of the kernel are resident (grid <= number of SMs), so blocks spinning in `wait` cannot starve blocks that
-// still have to push.  A time-out (20 s on %globaltimer) raises the error flag alfib_synchronize / alfib_cycle_apply report.
+// One kernel per exchange and no fences: every double travels as one 16-byte word {lo32, k, hi32, k} carrying the
+// exchange number k of its channel in both 8-byte halves (the LL protocol of NCCL's low-latency path, here with FP64
+// payload).  Exchange k (k = completed exchanges + 1, kept in device memory so the sequence replays inside a CUDA
+// graph) uses slot k & 1 of the RECEIVER's channel:
+//   push    every entry of this rank's outgoing list is written straight into its place in the neighbour's slot with
+//           one 128-bit NVLink peer store — pack, transfer and "ready" signal are the same instruction;
+//   pull    every incoming entry is polled in LOCAL memory until both halves carry k, then the ghosts are written /
+//           the owned interface dofs gather-sum their contributions in ascending rank order (reproducible).
+// A word of exchange k - 2 in the same slot carries k - 2 and cannot be mistaken for k.  Two slots suffice against
+// overwriting: a neighbour's push k + 2 follows its pull k + 1, i.e. this rank's push k + 1, which this rank's stream
+// issues only after its kernel k has finished reading slot k & 1 (the neighbour relation of a channel is symmetric:
+// every listed peer is written to and polled, also with an empty segment... an empty segment needs no word).  All
+// blocks of a kernel are resident (grid <= number of SMs), so blocks polling cannot starve blocks that still have
+// to push.  A time-out (20 s on %globaltimer) raises the error flag alfib_synchronize / alfib_cycle_apply report.
 struct MboxPeers {
   int npeers;
   int peers[ALFIB_MAX_RANKS];
   long long mine_off[ALFIB_MAX_RANKS + 1];        // segments of this rank's outgoing list
   double* data[ALFIB_MAX_RANKS];                  // slot 0 of the channel in the neighbour's memory
-  long long cap[ALFIB_MAX_RANKS];                 // its slot size
+  long long cap[ALFIB_MAX_RANKS];                 // its slot size (entries; an entry is 16 bytes)
   long long theirs_off[ALFIB_MAX_RANKS];          // where this rank's segment starts in the neighbour's incoming list
-  unsigned long long* flag[ALFIB_MAX_RANKS];      // flag[this rank] of the channel in the neighbour's memory
+  unsigned long long* flag[ALFIB_MAX_RANKS];      // (unused by the LL kernels)
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -615,31 +615,26 @@ __device__ __forceinline__ int mbox_segment(const MboxPeers& mp, long long pos) 
   return p;
 }
 
-// after the push loop: count this block; the last one signals the neighbours; then wait for theirs
-__device__ __forceinline__ void mbox_signal_and_wait(const MboxPeers& mp, unsigned long long k,
-                                                     const unsigned long long* my_flags, unsigned int* pushed,
-                                                     int* __restrict__ err) {
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (atomicAdd(pushed, 1u) == gridDim.x - 1) {
-      *pushed = 0;
-      __threadfence_system();
-      for (int p = 0; p < mp.npeers; ++p) *reinterpret_cast<volatile unsigned long long*>(mp.flag[p]) = k;
+__device__ __forceinline__ void ll_store(double* slot_entry /* 16-byte entry */, double v, unsigned int k) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot_entry), "r"((unsigned int)bits), "r"(k),
+               "r"((unsigned int)(bits >> 32)), "r"(k)
+               : "memory");
+}
+
+__device__ __forceinline__ double ll_load(const double* slot_entry, unsigned int k, int* __restrict__ err) {
+  unsigned int lo, f0, hi, f1;
+  unsigned long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(slot_entry) : "memory");
+    if (f0 == k && f1 == k) break;
+    if (t0 == 0) t0 = global_ns();
+    else if (global_ns() - t0 > 20000000000ull) {   // 20 s: the ranks enter the first exchange after rank-local setup phases
+      atomicExch(err, 1);
+      break;
     }
   }
-  if (threadIdx.x < mp.npeers) {
-    const volatile unsigned long long* f = my_flags + mp.peers[threadIdx.x];
-    const unsigned long long t0 = global_ns();
-    while (*f < k) {
-      if (global_ns() - t0 > 20000000000ull) {   // 20 s: the ranks enter the first exchange after rank-local setup phases
-        atomicExch(err, 1);
-        break;
-      }
-    }
-  }
-  __threadfence_system();
-  __syncthreads();
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 
 __device__ __forceinline__ void mbox_finish(unsigned long long k, unsigned long long* seq, unsigned int* finished) {
@@ -665,11 +660,10 @@ __global__ void __launch_bounds__(256) mbox_update_kernel(long long ns, long lon
   const long long stride = (long long)gridDim.x * blockDim.x, t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (long long i = t; i < ns; i += stride) {
     const int p = mbox_segment(mp, i);
-    mp.data[p][slot * mp.cap[p] + mp.theirs_off[p] + (i - mp.mine_off[p])] = x[send_idx[i]];
+    ll_store(mp.data[p] + 2 * (slot * mp.cap[p] + mp.theirs_off[p] + (i - mp.mine_off[p])), x[send_idx[i]], (unsigned int)k);
   }
-  mbox_signal_and_wait(mp, k, my_flags, cnt, err);
-  const double* in = my_data + slot * my_cap;
-  for (long long i = t; i < nr; i += stride) x[recv_idx[i]] = __ldcv(in + i);
+  const double* in = my_data + 2 * slot * my_cap;
+  for (long long i = t; i < nr; i += stride) x[recv_idx[i]] = ll_load(in + 2 * i, (unsigned int)k, err);
   mbox_finish(k, seq, cnt + 1);
 }
 
@@ -688,14 +682,13 @@ __global__ void __launch_bounds__(256) mbox_reduce_kernel(long long nr, int n_re
   for (long long i = t; i < nr; i += stride) {
     const int p = mbox_segment(mp, i);
     const int g = recv_idx[i];
-    mp.data[p][slot * mp.cap[p] + mp.theirs_off[p] + (i - mp.mine_off[p])] = y[g];
+    ll_store(mp.data[p] + 2 * (slot * mp.cap[p] + mp.theirs_off[p] + (i - mp.mine_off[p])), y[g], (unsigned int)k);
     y[g] = 0.0;
   }
-  mbox_signal_and_wait(mp, k, my_flags, cnt, err);
-  const double* in = my_data + slot * my_cap;
+  const double* in = my_data + 2 * slot * my_cap;
   for (long long i = t; i < n_red; i += stride) {
     double v = y[red_dof[i]];
-    for (int j = red_ptr[i]; j < red_ptr[i + 1]; ++j) v += __ldcv(in + red_src[j]);
+    for (int j = red_ptr[i]; j < red_ptr[i + 1]; ++j) v += ll_load(in + 2 * (long long)red_src[j], (unsigned int)k, err);
     y[red_dof[i]] = v;
   }
   mbox_finish(k, seq, cnt + 1);
@@ -710,13 +703,12 @@ __global__ void __launch_bounds__(64) mbox_small_sum_kernel(int nv, int nranks, 
   const long long slot = (long long)(k & 1ull);
   for (int j = threadIdx.x; j < nv; j += blockDim.x) {
     const double mine = v[j];
-    for (int p = 0; p < mp.npeers; ++p) mp.data[p][slot * mp.cap[p] + (long long)rank * ALFIB_MBOX_NV + j] = mine;
+    for (int p = 0; p < mp.npeers; ++p) ll_store(mp.data[p] + 2 * (slot * mp.cap[p] + (long long)rank * ALFIB_MBOX_NV + j), mine, (unsigned int)k);
   }
-  mbox_signal_and_wait(mp, k, my_flags, cnt, err);
-  const double* in = my_data + slot * my_cap;
+  const double* in = my_data + 2 * slot * my_cap;
   for (int j = threadIdx.x; j < nv; j += blockDim.x) {
     double s = 0.0;
-    for (int q = 0; q < nranks; ++q) s += (q == rank) ? v[j] : __ldcv(in + (long long)q * ALFIB_MBOX_NV + j);
+    for (int q = 0; q < nranks; ++q) s += (q == rank) ? v[j] : ll_load(in + 2 * ((long long)q * ALFIB_MBOX_NV + j), (unsigned int)k, err);
     if (sqrt_mode) {
       s = sqrt(s);
       if (inv) inv[j] = s > 0.0 ? 1.0 / s : 0.0;
@@ -760,8 +752,14 @@ inline bool use_mbox(const alfib_ctx* c, const Halo& H) {
 }  // namespace
 
 // owner -> ghost: every ghost entry of x takes its owner's value
+static bool debug_skip_exchange() {
+  static const bool skip = std::getenv("ALFIB_DEBUG_SKIP_EXCHANGE") != nullptr;   // timing experiments: WRONG results
+  return skip;
+}
+
 void halo_update(alfib_ctx* c, Halo& H, double* x, int level) {
   if (!H.on || c->nranks <= 1) return;
+  if (debug_skip_exchange()) return;
   ScopedEvent ev(c, ALFIB_EV_HALO, level);
   const int64_t ns = H.send_off.back(), nr = H.recv_off.back();
   if (use_mbox(c, H)) {
@@ -807,7 +805,7 @@ void halo_update(alfib_ctx* c, Halo& H, double* x, int level) {
 void halo_reduce(alfib_ctx* c, Halo& H, double* y, int level) {
   if (!H.on) return;
   ScopedEvent ev(c, ALFIB_EV_HALO, level);
-  if (c->nranks > 1) {
+  if (c->nranks > 1 && !debug_skip_exchange()) {
     const int64_t ns = H.send_off.back(), nr = H.recv_off.back();
     if (use_mbox(c, H)) {
       if (!H.peers.empty()) {
@@ -849,6 +847,13 @@ void halo_reduce(alfib_ctx* c, Halo& H, double* y, int level) {
 }
 
 void comm_small_allreduce(alfib_ctx* c, double* v, int nv, int sqrt_mode, double* inv) {
+  if (debug_skip_exchange()) {
+    if (sqrt_mode) {
+      sqrt_inv_kernel<<<1, 32, 0, c->stream>>>(v, inv);
+      c->launches++;
+    }
+    return;
+  }
   if (c->nranks > 1 && c->peers_open && c->mbox_fixed && nv <= ALFIB_MBOX_NV && !std::getenv("ALFIB_MBOX_OFF")) {
     const int ch = ALFIB_MBOX_SMALL;
     const MboxEntry& me = c->mbox[ch];

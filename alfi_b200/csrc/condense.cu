@@ -253,22 +253,42 @@ __global__ void __launch_bounds__(128) tile_ops_kernel_v2(const TileOp* __restri
 
 #include "tile_tma.cuh"
 
-template <bool ATOMIC, bool ACCUM, int MODE>
-void launch_tile_ops_tma(alfib_ctx* c, const TileOp* ops, int nops, const int32_t* cidx, const double* store,
-                         const double* srcA, const double* srcB, PeerOut y, double* dstB, const FusedSrc& fs) {
+template <bool ATOMIC, bool ACCUM, int MODE, int CFG, bool RED>
+void launch_tile_ops_tma_cfg(alfib_ctx* c, const TileOp* ops, int nops, const int32_t* cidx, const double* store,
+                             const double* srcA, const double* srcB, PeerOut y, double* dstB, const FusedSrc& fs) {
   static bool configured = false;       // per instantiation
-  const size_t smem = tma::smem_bytes();
+  constexpr int WARPS = tma::Cfg<CFG>::WARPS;
+  const size_t smem = tma::smem_bytes<CFG>();
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(tile_ops_kernel_tma<ATOMIC, ACCUM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(tile_ops_kernel_tma<ATOMIC, ACCUM, MODE, CFG, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
     configured = true;
   }
   if (!c->tile_counter.p) {
     c->tile_counter.alloc(4);
     CUDA_TRY(cudaMemsetAsync(c->tile_counter.p, 0, 4 * sizeof(unsigned), c->stream));
   }
-  const int grid = std::min(c->num_sms, cdiv(nops, tma::WARPS));
-  tile_ops_kernel_tma<ATOMIC, ACCUM, MODE><<<grid, tma::WARPS * 32, smem, c->stream>>>(ops, nops, cidx, store, srcA, srcB, y, dstB,
-                                                                                       fs, c->tile_counter.p);
+  const int grid = std::min(c->num_sms, cdiv(nops, WARPS));
+  tile_ops_kernel_tma<ATOMIC, ACCUM, MODE, CFG, RED><<<grid, WARPS * 32, smem, c->stream>>>(ops, nops, cidx, store, srcA, srcB, y,
+                                                                                            dstB, fs, c->tile_counter.p);
+}
+
+// ALFIB_TILE_TMA_CFG (measured on cfg5's finest level, ms per application, profiles/apply_variants_r2.txt; v2 = 0.567):
+//   0 = 8 warps x 8 KB stages, read-modify-write scatter (0.501)   1 = 16 warps x 4 KB (0.509)
+//   2 = 16 warps x 4 KB + RED scatter (0.506)                      3 = 8 warps x 8 KB + RED scatter (0.496, default)
+template <bool ATOMIC, bool ACCUM, int MODE>
+void launch_tile_ops_tma(alfib_ctx* c, const TileOp* ops, int nops, const int32_t* cidx, const double* store,
+                         const double* srcA, const double* srcB, PeerOut y, double* dstB, const FusedSrc& fs) {
+  const char* env_cfg = std::getenv("ALFIB_TILE_TMA_CFG");
+  const int cfg = env_cfg ? std::atoi(env_cfg) : 3;
+  if (cfg == 2)
+    launch_tile_ops_tma_cfg<ATOMIC, ACCUM, MODE, 1, true>(c, ops, nops, cidx, store, srcA, srcB, y, dstB, fs);
+  else if (cfg == 1)
+    launch_tile_ops_tma_cfg<ATOMIC, ACCUM, MODE, 1, false>(c, ops, nops, cidx, store, srcA, srcB, y, dstB, fs);
+  else if (cfg == 3)
+    launch_tile_ops_tma_cfg<ATOMIC, ACCUM, MODE, 0, true>(c, ops, nops, cidx, store, srcA, srcB, y, dstB, fs);
+  else
+    launch_tile_ops_tma_cfg<ATOMIC, ACCUM, MODE, 0, false>(c, ops, nops, cidx, store, srcA, srcB, y, dstB, fs);
 }
 
 template <bool ATOMIC, bool ACCUM = false>
@@ -678,7 +698,7 @@ void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, P
   const bool v1 = env_v1 && env_v1[0] == '1';
   // K1: V ops, all patches, plain private stores
   const char* env_tma = std::getenv("ALFIB_TILE_TMA");
-  const bool tma_on = !v1 && env_tma && env_tma[0] == '1';
+  const bool tma_on = !v1 && !(env_tma && env_tma[0] == '0');      // default; ALFIB_TILE_TMA=0: the LDG stream of v2
   const char* env_tma_min = std::getenv("ALFIB_TILE_TMA_MIN_OPS");
   const int tma_min_ops = env_tma_min ? std::atoi(env_tma_min) : 1;
   if (nV && tma_on && nV >= tma_min_ops) {

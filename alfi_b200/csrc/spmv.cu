@@ -8,6 +8,8 @@
 // than a warp-per-row kernel walking the row's flat value run with 128-bit loads, because the
 // 13 independent loads per lane hide the colidx -> x dependency; a 72-byte 3x3 block cannot be
 // 16-byte aligned for every block, so the values are read as 8-byte loads that coalesce in L1.
+#include <cstdlib>
+
 #include "alfib_internal.h"
 
 namespace {
@@ -135,7 +137,8 @@ void launch_bsr_spmv(alfib_ctx* c, const Level& L, const double* vals, const dou
   if (L.halo.on) halo_update(c, const_cast<Level&>(L).halo, const_cast<double*>(x), L.index);
   const int row0 = sharded ? (int)L.row_start[c->rank] : 0;
   const int row1 = sharded ? (int)L.row_start[c->rank + 1] : (L.halo.on ? L.n_owned / L.bs : L.n_nodes);
-  const int blocks = cdiv((int64_t)(row1 - row0) * 16, threads);
+  static const bool debug_skip_kernel = std::getenv("ALFIB_DEBUG_SKIP_SPMV") != nullptr;   // timing experiments only
+  const int blocks = debug_skip_kernel ? 0 : cdiv((int64_t)(row1 - row0) * 16, threads);
   const bool peer = sharded && c->peers_open;
   const PeerOut out = peer ? comm_peer_out(c) : plain_out(y);
   if (blocks > 0) {

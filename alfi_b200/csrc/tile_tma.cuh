@@ -9,10 +9,9 @@
 // with one issuing lane per warp.  A warp consumes its stages in order (LDS.128, lanes own row pairs exactly as in
 // v2, FP64 FMA) and refills a stage as soon as it has read it; the ring runs across op boundaries, so there is no
 // ramp-down between ops.  Ops are taken from an atomic counter (the first three per warp statically), the next op's
-// descriptor and the op after next's number are requested one op ahead, a stage's slice of the source index list
-// two stages before the stage is filled and its gathered source values when it is filled (two stages before they
-// are used) — nothing in the steady state waits on a dependent global load (first version: index one stage ahead;
-// ncu showed 38 % of the samples in long-scoreboard stalls on exactly that chain).
+// descriptor and the op after next's number are requested one op ahead, the gathered source values of a stage are
+// requested when the stage is filled (its index list one stage earlier) — nothing in the steady state waits on a
+// dependent global load.
 //
 // A stage holds a run of whole columns of one op: 32 columns if a column is <= 256 bytes (<= 32 rows), else 16
 // (<= 64 rows = 512 bytes), so a stage never straddles one of the 32-entry chunks the source values are held in.
@@ -20,15 +19,24 @@
 // v2 adds even/odd ring slots in two chains, v3 adds stage by stage; results agree to rounding, and are bitwise
 // reproducible run to run in deterministic mode (static order inside an op; ops write disjoint rows per launch).
 #pragma once
+// (A second version — ops in static byte-balanced ranges per warp, descriptors fetched 32 at a time, indices two
+// stages ahead, 4 FMA chains — measured 0.58-0.69 ms against 0.506 ms for this one on cfg5 and was dropped: the
+// larger code did not pay.  profiles/apply_variants_r2.txt)
 
 namespace tma {
 
-constexpr int WARPS = 8;
 constexpr int STAGES = 3;
-constexpr int STAGE_BYTES = 8192;
 constexpr int META_INTS = 12;   // per stage: id, c0, cnt, nrows, ncols, flags, row (2), priv (2), pad (2)
+// CFG 0: 8 warps x 3 stages x 8 KB (first version); CFG 1: 16 warps x 3 stages x 4 KB — the same bytes in flight per SM
+// behind twice as many independent instruction streams (ncu of CFG 0: the warps spend 64 % of their samples in
+// long-scoreboard / fixed-latency stalls of their own serial chain, not waiting for the copies)
+template <int CFG> struct Cfg;
+template <> struct Cfg<0> { static constexpr int WARPS = 8, STAGE_BYTES = 8192; };
+template <> struct Cfg<1> { static constexpr int WARPS = 16, STAGE_BYTES = 4096; };
+template <int CFG>
 constexpr size_t smem_bytes() {
-  return (size_t)WARPS * STAGES * STAGE_BYTES + (size_t)WARPS * STAGES * 8 + (size_t)WARPS * STAGES * META_INTS * 4;
+  return (size_t)Cfg<CFG>::WARPS * STAGES * Cfg<CFG>::STAGE_BYTES + (size_t)Cfg<CFG>::WARPS * STAGES * 8 +
+         (size_t)Cfg<CFG>::WARPS * STAGES * META_INTS * 4;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -78,26 +86,21 @@ __device__ __forceinline__ OpRegs load_op(const TileOp* __restrict__ ops, int id
   return o;
 }
 
-// columns cnt of a stage (in shared memory, column j at j * colbytes) times the source values held by the lanes;
-// even / odd trips go to separate accumulator pairs (two independent FMA chains per row)
-template <int G>
+// columns cnt of a stage (in shared memory, column j at j * colbytes) times the source values held by the lanes.
+// FULL = the number of columns of a full stage for this row count and stage size: known at compile time, so the
+// common case is straight-line code (measured: a run-time trip count costs 10 % of the whole application).
+template <int G, int FULL>
 __device__ __forceinline__ void consume_stage(const unsigned char* __restrict__ sp, int colbytes, int cnt, double xs,
-                                              bool active, int grp, double (&acc)[4]) {
-  if (cnt == 32 || (cnt == 16 && G == 1)) {
-    // full stages: fixed trip count (a multiple of 8)
-    const int trips = cnt / G;
-#pragma unroll 8
-    for (int jj = 0; jj < trips; jj += 2) {
-      const int j0 = jj * G + grp, j1 = j0 + G;
-      const double x0 = __shfl_sync(0xffffffffu, xs, j0);
-      const double x1 = __shfl_sync(0xffffffffu, xs, j1);
+                                              bool active, int grp, double& acc0, double& acc1) {
+  if (cnt == FULL) {
+#pragma unroll
+    for (int jj = 0; jj < FULL / G; ++jj) {
+      const int j = jj * G + grp;
+      const double xc = __shfl_sync(0xffffffffu, xs, j);
       if (active) {
-        const double2 a = *reinterpret_cast<const double2*>(sp + j0 * colbytes);
-        const double2 b = *reinterpret_cast<const double2*>(sp + j1 * colbytes);
-        acc[0] = fma(a.x, x0, acc[0]);
-        acc[1] = fma(a.y, x0, acc[1]);
-        acc[2] = fma(b.x, x1, acc[2]);
-        acc[3] = fma(b.y, x1, acc[3]);
+        const double2 a = *reinterpret_cast<const double2*>(sp + j * colbytes);
+        acc0 = fma(a.x, xc, acc0);
+        acc1 = fma(a.y, xc, acc1);
       }
     }
   } else {
@@ -106,8 +109,8 @@ __device__ __forceinline__ void consume_stage(const unsigned char* __restrict__ 
       const double xc = __shfl_sync(0xffffffffu, xs, j & 31);
       if (active && j < cnt) {
         const double2 a = *reinterpret_cast<const double2*>(sp + j * colbytes);
-        acc[0] = fma(a.x, xc, acc[0]);
-        acc[1] = fma(a.y, xc, acc[1]);
+        acc0 = fma(a.x, xc, acc0);
+        acc1 = fma(a.y, xc, acc1);
       }
     }
   }
@@ -115,13 +118,14 @@ __device__ __forceinline__ void consume_stage(const unsigned char* __restrict__ 
 
 }  // namespace tma
 
-template <bool ATOMIC, bool ACCUM, int MODE>
-__global__ void __launch_bounds__(tma::WARPS * 32, 1)
+template <bool ATOMIC, bool ACCUM, int MODE, int CFG, bool RED>
+__global__ void __launch_bounds__(tma::Cfg<CFG>::WARPS * 32, 1)
     tile_ops_kernel_tma(const TileOp* __restrict__ ops, int nops, const int32_t* __restrict__ cidx,
                         const double* __restrict__ store, const double* __restrict__ srcA,
                         const double* __restrict__ srcB, PeerOut yout, double* __restrict__ dstB, const FusedSrc fs,
                         unsigned* __restrict__ counter) {
   using namespace tma;
+  constexpr int WARPS = Cfg<CFG>::WARPS, STAGE_BYTES = Cfg<CFG>::STAGE_BYTES;
   extern __shared__ __align__(128) unsigned char smem[];
   double* __restrict__ y = resolve(yout);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,80 +161,66 @@ __global__ void __launch_bounds__(tma::WARPS * 32, 1)
     }
     return e >= 0 ? __ldg(srcA + e) : __ldg(srcB + (~e));
   };
-
-  // ---- the front: walks the warp's chunk sequence LOOK chunks ahead of the copies ----------------------------
-  // A chunk = a run of whole columns of one op that fills one stage.  The front takes ops (the first three per warp
-  // statically, then from the counter), keeps the next op's descriptor and the number of the op after next in
-  // flight, and requests every chunk's slice of the source index list when it generates the chunk; the copy, the
-  // gathered source values (which need the indices) and the stage's meta data follow LOOK produce steps later, so the
-  // chain op number -> descriptor -> index -> value never waits in the steady state.
-  struct Chunk {
-    const double* src;     // first column of the chunk in the store
-    long long row, priv;
-    int id, c0, cnt, nrows, ncols;   // id < 0: no more work
-    int e;                 // this lane's source index (valid for lane < cnt)
+  // columns per stage: the largest of 32 / 16 / 8 that fits (a column is roundup2(nrows) doubles, <= 512 bytes)
+  auto stage_cols = [](int nrows) {
+    const int colbytes = ((nrows + 1) >> 1) * 16;
+    return 32 * colbytes <= STAGE_BYTES ? 32 : (16 * colbytes <= STAGE_BYTES ? 16 : 8);
   };
-  int id0 = gw, id1 = gw + W, idp = gw + 2 * W;
+
+  // ---- producer state (uniform over the warp) -------------------------------------------------------------
+  int id0 = gw, id1 = gw + W;                  // current / next op; the one after next is in flight in lane 0
+  int idp = gw + 2 * W;
   OpRegs d0, d1;
   d0.mat = d0.col = d0.row = d0.priv = 0; d0.nrows = d0.ncols = d0.flags = 0;
   d1 = d0;
   if (id0 < nops) d0 = load_op(ops, id0);
   if (id1 < nops) d1 = load_op(ops, id1);
-  int f_c = 0;                                 // next column of the front's op
-  auto front = [&]() -> Chunk {
-    Chunk ch;
-    // op switch (exactly one counter increment per processed op: atomicInc wraps to 0 after the nops-th, so the
-    // counter resets itself for the next launch)
-    if (id0 < nops && f_c >= d0.ncols && !(f_c == 0 && d0.ncols == 0)) {
+  int p_c = 0;                                 // next column of the current op to be requested
+  // source index of this lane for the chunk to be produced next (requested one produce step earlier)
+  int e_cur = (id0 < nops && lane < min(stage_cols(d0.nrows), d0.ncols)) ? __ldg(cidx + d0.col + lane) : 0;
+  double xs[STAGES];
+
+  auto produce = [&](int s) {
+    // op switch: everything needed here was requested one op ago
+    // (exactly one counter increment per processed op: atomicInc wraps to 0 after the nops-th, so the counter
+    //  resets itself for the next launch)
+    if (id0 < nops && p_c >= d0.ncols && !(p_c == 0 && d0.ncols == 0)) {
       id0 = id1;
       d0 = d1;
       id1 = __shfl_sync(0xffffffffu, idp, 0);
       if (id1 < nops) d1 = load_op(ops, id1);
       if (lane == 0) idp = 3 * W + (int)atomicInc(counter, (unsigned)(nops - 1));
-      f_c = 0;
+      p_c = 0;
     }
-    if (id0 >= nops) {
-      ch.src = nullptr; ch.row = ch.priv = -1; ch.id = -1; ch.c0 = ch.cnt = ch.nrows = ch.ncols = 0; ch.e = 0;
-      return ch;
-    }
-    const int half = (d0.nrows + 1) >> 1;
-    const int cps = d0.nrows <= 32 ? 32 : 16;
-    ch.id = id0; ch.c0 = f_c; ch.cnt = min(cps, d0.ncols - f_c); ch.nrows = d0.nrows; ch.ncols = d0.ncols;
-    ch.row = d0.row; ch.priv = d0.priv;
-    ch.src = store + d0.mat + (long long)f_c * (half * 2);
-    ch.e = lane < ch.cnt ? __ldg(cidx + d0.col + f_c + lane) : 0;
-    f_c += ch.cnt;
-    if (d0.ncols == 0) f_c = 1;                 // an op without columns is one empty chunk
-    return ch;
-  };
-  constexpr int LOOK = 2;
-  Chunk q[LOOK];
-#pragma unroll
-  for (int i = 0; i < LOOK; ++i) q[i] = front();
-  double xs[STAGES];
-
-  auto produce = [&](int s) {
-    const Chunk ch = q[0];
-#pragma unroll
-    for (int i = 0; i + 1 < LOOK; ++i) q[i] = q[i + 1];
-    q[LOOK - 1] = front();
     int* m = meta + s * META_INTS;
-    if (ch.id < 0) {                            // no more work: sentinel
+    if (id0 >= nops) {                          // no more work: sentinel
       if (lane == 0) m[0] = -1;
       xs[s] = 0.0;
       return;
     }
-    const int colbytes = ((ch.nrows + 1) >> 1) * 16;
-    const uint32_t bytes = (uint32_t)(ch.cnt * colbytes);
+    const int colbytes = ((d0.nrows + 1) >> 1) * 16;
+    const int cps = stage_cols(d0.nrows);
+    const int c0 = p_c, cnt = min(cps, d0.ncols - c0);
+    const uint32_t bytes = (uint32_t)(cnt * colbytes);
     if (lane == 0) {
-      m[0] = ch.id; m[1] = ch.c0; m[2] = ch.cnt; m[3] = ch.nrows; m[4] = ch.ncols;
-      *reinterpret_cast<long long*>(m + 6) = ch.row;
-      *reinterpret_cast<long long*>(m + 8) = ch.priv;
+      m[0] = id0; m[1] = c0; m[2] = cnt; m[3] = d0.nrows; m[4] = d0.ncols; m[5] = d0.flags;
+      *reinterpret_cast<long long*>(m + 6) = d0.row;
+      *reinterpret_cast<long long*>(m + 8) = d0.priv;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the stage before the async write
       mbar_expect_tx(bar_u32 + s * 8, bytes);
-      if (bytes) bulk_g2s(ring_u32 + s * STAGE_BYTES, ch.src, bytes, bar_u32 + s * 8, pol);
+      if (bytes) bulk_g2s(ring_u32 + s * STAGE_BYTES, store + d0.mat + (long long)c0 * (colbytes >> 3), bytes, bar_u32 + s * 8, pol);
     }
-    xs[s] = value_at(ch.e, lane < ch.cnt);      // consumed STAGES - 1 stages later
+    // source values of this stage (index requested one step ago); index of the next stage
+    xs[s] = value_at(e_cur, lane < cnt);
+    p_c = c0 + cnt;
+    if (d0.ncols == 0) p_c = 1;                 // an op without columns is one empty stage
+    if (p_c < d0.ncols) {
+      e_cur = (lane < min(cps, d0.ncols - p_c)) ? __ldg(cidx + d0.col + p_c + lane) : 0;
+    } else if (id1 < nops) {
+      e_cur = (lane < min(stage_cols(d1.nrows), d1.ncols)) ? __ldg(cidx + d1.col + lane) : 0;
+    } else {
+      e_cur = 0;
+    }
   };
 
 #pragma unroll
@@ -238,7 +228,8 @@ __global__ void __launch_bounds__(tma::WARPS * 32, 1)
   __syncwarp();
 
   // ---- consumer ------------------------------------------------------------------------------------------------
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};        // rows (2l, 2l+1) x even / odd column trips: independent FMA chains
+  double acc0 = 0.0, acc1 = 0.0;
+  int ri0 = 0, ri1 = 0;
   uint32_t parity = 0;
   bool done = false;
   while (!done) {
@@ -255,14 +246,23 @@ __global__ void __launch_bounds__(tma::WARPS * 32, 1)
       const int LPG = 32 / G;
       const int grp = lane / LPG, l = lane - grp * LPG;
       const bool active = l < half;
-      if (c0 == 0) { acc[0] = acc[1] = acc[2] = acc[3] = 0.0; }
+      if (c0 == 0) {
+        acc0 = 0.0;
+        acc1 = 0.0;
+        if (RED && row >= 0 && grp == 0 && active) {      // destination dofs of this lane's two rows, requested early
+          ri0 = __ldg(cidx + row + 2 * l);
+          ri1 = (2 * l + 1 < nrows) ? __ldg(cidx + row + 2 * l + 1) : 0;
+        }
+      }
       mbar_wait(bar_u32 + s * 8, parity);
       const unsigned char* sp = ring + s * STAGE_BYTES + (active ? l : 0) * 16;
-      if (G == 4) consume_stage<4>(sp, colbytes, cnt, xs[s], active, grp, acc);
-      else if (G == 2) consume_stage<2>(sp, colbytes, cnt, xs[s], active, grp, acc);
-      else consume_stage<1>(sp, colbytes, cnt, xs[s], active, grp, acc);
+      // full stages: 32 columns of <= 16 rows; 32 (8 KB stages) / 16 (4 KB) columns of <= 32 rows; 16 / 8 of <= 64 rows
+      constexpr int FULL2 = STAGE_BYTES >= 8192 ? 32 : 16, FULL1 = STAGE_BYTES >= 8192 ? 16 : 8;
+      if (G == 4) consume_stage<4, 32>(sp, colbytes, cnt, xs[s], active, grp, acc0, acc1);
+      else if (G == 2) consume_stage<2, FULL2>(sp, colbytes, cnt, xs[s], active, grp, acc0, acc1);
+      else consume_stage<1, FULL1>(sp, colbytes, cnt, xs[s], active, grp, acc0, acc1);
       if (c0 + cnt >= ncols) {                  // last stage of the op: sum the column groups (fixed order), write
-        double r0 = acc[0] + acc[2], r1 = acc[1] + acc[3];
+        double r0 = acc0, r1 = acc1;
         for (int off = 16; off >= LPG; off >>= 1) {
           r0 += __shfl_xor_sync(0xffffffffu, r0, off);
           r1 += __shfl_xor_sync(0xffffffffu, r1, off);
@@ -279,7 +279,13 @@ __global__ void __launch_bounds__(tma::WARPS * 32, 1)
               if (r + 1 < nrows) priv[r + 1] = r1;
             }
           }
-          if (row >= 0) {
+          if (RED && row >= 0) {
+            // one reduction (RED.ADD.F64: no return value, no dependent load) per destination.  Launches without
+            // ATOMIC add to every destination at most once (patches of a colour share no dof, the tiles of a patch own
+            // disjoint rows, distinct shared blocks are disjoint), so the result is that of y[i] += r, bit for bit.
+            atomicAdd(y + ri0, r0);
+            if (r + 1 < nrows) atomicAdd(y + ri1, r1);
+          } else if (row >= 0) {
             const int32_t* __restrict__ ri = cidx + row;
             if (ATOMIC) {
               atomicAdd(y + ri[r], r0);

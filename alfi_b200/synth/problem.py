@@ -62,18 +62,34 @@ CONFIGS = {
     "ldc2d-pkp0": Config("ldc2d-pkp0", 2, 16, 3, "pkp0", 2, "star", False, re=10000.0),
     "ldc3d-sv-k3": Config("ldc3d-sv-k3", 3, 4, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
     "ldc3d-pkp0": Config("ldc3d-pkp0", 3, 16, 2, "pkp0", 1, "star", False, re=5000.0, element="p1fb"),
+    # configs[4] with the LITERAL 3-D MacroStar of the reference (relaxation.py:168-177 expands every non-macro point of
+    # closure(star(v)), so in 3-D the macro edges on the link of v pull in the neighbouring macro cells: 2 175-dof
+    # interior patches, 21-29 colours).  macro_expand="vertices" above is the open macro star (1 275 dofs)
+    # that SURVEY §8 / BASELINE.md size the benchmark by — an extension, labelled so in bench.py's `config`.
+    "ldc3d-sv-k3-literal": Config("ldc3d-sv-k3-literal", 3, 4, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-",
+                                  macro_expand="all"),
+    "ldc3d-sv-k3-half-literal": Config("ldc3d-sv-k3-half-literal", 3, 2, 2, "sv", 3, "macro", True, re=5000.0,
+                                       sort_order="0+:1-", macro_expand="all"),
+    "ldc3d-sv-k3-small-literal": Config("ldc3d-sv-k3-small-literal", 3, 2, 1, "sv", 3, "macro", True, re=5000.0,
+                                        sort_order="0+:1-", macro_expand="all"),
+    "ldc3d-sv-k3-tiny-literal": Config("ldc3d-sv-k3-tiny-literal", 3, 1, 1, "sv", 3, "macro", True, re=100.0,
+                                       sort_order="0+:1-", macro_expand="all"),
     # larger members of configs[4]'s family: baseN 6 is the reference's own choice for ldc3d (generate_submission:75;
     # 4 899 531 dofs, 15 625 patches: its dense coarse inverse (78.9 k dofs) does not fit — needs the condensed coarse
     # inverse of scripts/r2_prep), baseN 5 (2 840 943 dofs, 9 261 patches, coarse 46 038 dofs) runs as is.  The host
     # generator needs ~33 / ~57 GB of RAM and minutes for them (cfg5: 17 GB, 73 s).
     "ldc3d-sv-k3-n5": Config("ldc3d-sv-k3-n5", 3, 5, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
     "ldc3d-sv-k3-n6": Config("ldc3d-sv-k3-n6", 3, 6, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
-    # weak-scaling family of configs[4]: rank r of an sx x sy x sz rank grid gets one 16^3-cell brick (cfg5's
-    # finest mesh: 1.46 M dofs per rank); four levels from a base of 2 cells per brick edge, so that the coarsest
-    # level stays at cfg5's size (4^3 base cells, 23 871 dofs) on 8 ranks instead of growing with the rank count
-    "ldc3d-sv-k3-w1": Config("ldc3d-sv-k3-w1", 3, 2, 3, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
-    "ldc3d-sv-k3-w2": Config("ldc3d-sv-k3-w2", 3, 2, 3, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-", shape=(2, 1, 1)),
-    "ldc3d-sv-k3-w4": Config("ldc3d-sv-k3-w4", 3, 2, 3, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-", shape=(2, 2, 1)),
+    # weak-scaling family of configs[4]: rank r of an sx x sy x sz rank grid gets one 16^3-cell brick (cfg5's finest
+    # mesh: 1.46 M dofs per rank).  The coarsest mesh must keep >= 4 cells per direction: with 2 the F-cycle of this
+    # unstabilised Re = 5000 problem AMPLIFIES a random right-hand side (measured in round 2: 2e4 on the 4 x 2 x 2
+    # coarse mesh of a four-level 2 x 1 x 1 family, 8.5 on a 1-cube coarse mesh, against a reduction to 0.045 on cfg5).
+    # So 2 and 4 ranks keep cfg5's three levels over an 8 x 4 x 4 / 8 x 8 x 4 coarse mesh (46 k / 92 k coarse dofs, held
+    # as the condensed coarse inverse: 13 k / 26 k separator dofs), and 8 ranks use four levels over cfg5's own 4^3
+    # coarse mesh instead of an 8^3 one (185 k dofs, 47 k separator dofs: no replicated dense factorisation of that).
+    "ldc3d-sv-k3-w1": Config("ldc3d-sv-k3-w1", 3, 4, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),
+    "ldc3d-sv-k3-w2": Config("ldc3d-sv-k3-w2", 3, 4, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-", shape=(2, 1, 1)),
+    "ldc3d-sv-k3-w4": Config("ldc3d-sv-k3-w4", 3, 4, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-", shape=(2, 2, 1)),
     "ldc3d-sv-k3-w8": Config("ldc3d-sv-k3-w8", 3, 2, 3, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-", shape=(2, 2, 2)),
     # cfg5 itself as a 2 x 2 x 2 grid of 8^3-cell bricks (strong scaling at 8 ranks with rank-local generation and a
     # brick partition): base 2 cells per brick edge of length 1, so the domain is [0, 2]^3 and nu = 1 / 2500 = 2 / 5000

@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DEFAULT_CONFIG = "ldc3d-sv-k3"
-CPU_SAMPLE_CONFIG = {"ldc3d-sv-k3": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w1": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w2": "ldc3d-sv-k3-half",
+CPU_SAMPLE_CONFIG = {"ldc3d-sv-k3-literal": "ldc3d-sv-k3-half-literal", "ldc3d-sv-k3": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w1": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w2": "ldc3d-sv-k3-half",
                      "ldc3d-sv-k3-w4": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w8": "ldc3d-sv-k3-half", "ldc3d-sv-k3-s8": "ldc3d-sv-k3-half", "ldc3d-sv-k3-n5": "ldc3d-sv-k3-half", "ldc3d-sv-k3-n6": "ldc3d-sv-k3-half", "ldc2d-sv-k2": "ldc2d-sv-k2", "ldc2d-pkp0": "ldc2d-pkp0"}
 METRIC = "V-cycle DoF/s (finest-level velocity dofs per second of one fieldsplit_0 PCMG-full application)"
 
@@ -47,6 +47,44 @@ def smoother_bytes(ld):
 def spmv_bytes(ld):
     bs = ld.V.bs
     return float(ld.A.nnzb * (8 * bs * bs + 4) + 4 * (ld.V.nnodes + 1) + 16 * ld.ndofs)
+
+
+# --------------------------------------------------------------------------- the workload, described identically by both arms
+def workload_config(name):
+    """`config` of the JSON line: what is being solved, not how.  Both arms (`--impl ours` / `--impl reference`) print
+    exactly this dictionary.  Sizes of the 3-D Scott-Vogelius family follow from the mesh formulas of SURVEY App. B
+    (box of Mx x My x Mz Kuhn cubes, Alfeld split, P3: nodes = V + 2E + F + 15T); other configurations are generated."""
+    from alfi_b200.synth.problem import CONFIGS
+    cfg = CONFIGS[name]
+    shape = tuple(cfg.shape) if cfg.shape else (1,) * cfg.dim
+    if cfg.dim == 3 and cfg.discretisation == "sv" and cfg.k == 3 and cfg.bary and cfg.domain == "ldc":
+        mx, my, mz = (cfg.N * s * 2 ** cfg.nref for s in shape)
+        V = (mx + 1) * (my + 1) * (mz + 1)
+        sq = mx * my * (mz + 1) + my * mz * (mx + 1) + mx * mz * (my + 1)
+        E = mx * (my + 1) * (mz + 1) + my * (mx + 1) * (mz + 1) + mz * (mx + 1) * (my + 1) + sq + mx * my * mz
+        F = 2 * sq + 6 * mx * my * mz
+        T = 6 * mx * my * mz
+        ndofs, npatch, maxn = 3 * (V + 2 * E + F + 15 * T), V, (2175 if cfg.macro_expand == "all" else 1275)
+    else:
+        from alfi_b200.synth.problem import build_problem
+        fine = build_problem(name).finest
+        ndofs, npatch, maxn = int(fine.ndofs), int(fine.patches.npatch), int(fine.patches.sizes.max())
+    return {"workload": name,
+            "mesh": "Kuhn %s x 2^%d%s" % (" x ".join(str(cfg.N * s) for s in shape), cfg.nref, ", Alfeld split" if cfg.bary else ""),
+            "velocity_dofs": int(ndofs), "levels": cfg.nref + 1, "smoothing": cfg.m, "re": cfg.re, "gamma": cfg.gamma,
+            "rank_grid": list(cfg.shape) if cfg.shape else None, "patches_finest": int(npatch), "max_patch_dofs": int(maxn),
+            "patch_constructor": ("alfi.MacroStar, literal semantics of relaxation.py:168-177" if cfg.macro_expand == "all" else
+                                  "alfi.MacroStar restricted to the open macro star (-pc_patch_construction_MacroStar_expand vertices: "
+                                  "an extension; in 2-D identical to the reference, in 3-D the 1275-dof sets SURVEY §8 sizes the "
+                                  "benchmark by instead of the reference's 2175-dof ones)") if cfg.patch == "macro" else "star"}
+
+
+def default_workload(args, world):
+    """N = 1: BASELINE.json's configuration (cfg5).  N > 1 (unless --config / --scaling strong say otherwise): the
+    weak-scaling family, one cfg5-sized brick per rank."""
+    if world > 1 and args.scaling == "weak" and args.config == DEFAULT_CONFIG:
+        return "ldc3d-sv-k3-w%d" % world
+    return args.config
 
 
 # --------------------------------------------------------------------------- clocks
@@ -184,13 +222,15 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = CPU_SAMPLE_CONFIG.get(args.config, args.config)
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    workload = default_workload(args, args.gpus)
+    sample = CPU_SAMPLE_CONFIG.get(workload, workload)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)        # exactly the K / W of the command line
     base, dt = run_oracle(sample, steps, warmup)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "DoF/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong" if (args.scaling == "strong" or "-s%d" % args.gpus in workload) else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.config, "sample": sample}, "cpu_baseline": base,
+            "config": workload_config(workload), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "DoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -220,7 +260,7 @@ def ours(args):
     if weak:
         from alfi_b200.synth.bricks import build_rank_local
         from alfi_b200.synth.problem import CONFIGS as _CW
-        args.config = args.config if args.config != DEFAULT_CONFIG else "ldc3d-sv-k3-w%d" % world
+        args.config = default_workload(args, world)
         cfg = _CW[args.config]
         if int(np.prod(cfg.shape or (1,))) != world:
             raise SystemExit("config %s is a %s rank grid, not %d ranks" % (args.config, cfg.shape, world))
@@ -460,7 +500,8 @@ def ours(args):
                                                                 if condensed else ""))
         except Exception:   # noqa: BLE001
             traffic = None
-    tile = "tile_ops_kernel" if os.environ.get("ALFIB_TILE_V1", "0")[:1] == "1" else "tile_ops_kernel_v2"
+    tile = ("tile_ops_kernel" if os.environ.get("ALFIB_TILE_V1", "0")[:1] == "1" else
+            "tile_ops_kernel_v2" if os.environ.get("ALFIB_TILE_TMA", "1")[:1] == "0" else "tile_ops_kernel_tma")
     roofline = {"kernel": ("%s x3 + sep_rhs_kernel + slot_sum_kernel (finest-level PCApply_PATCH, condensed inverses with "
                            "shared blocks: memset, Vf ops, separator rhs, X_SS ops, z sums, [D|-Wf] ops, bc fix-up)" % tile)
                 if form == 2 else
@@ -517,30 +558,34 @@ def ours(args):
             except Exception as e:      # noqa: BLE001
                 continuation["three_d"] = {"error": repr(e)}
 
-    total = n            # N > 1: the same problem sharded over the ranks (strong scaling)
+    total = n            # all ranks together
+    wl_config = workload_config(args.config)
+    generated = {"velocity_dofs": int(n), "levels": int(nlev), "patches_finest": int(fine_npatch), "max_patch_dofs": int(fine_maxn)}
+    for k, v in generated.items():
+        if wl_config[k] != v:
+            raise SystemExit("bench: workload_config(%s)[%s] = %r but the generated problem has %r" % (args.config, k, wl_config[k], v))
     line = {
         "metric": METRIC, "value": total / (ms * 1e-3), "unit": "DoF/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         # ldc3d-sv-k3-s8 is cfg5 itself cut into bricks: rank-local generation, but the total problem is fixed
         "scaling": "strong" if (args.scaling == "strong" or "-s%d" % world in args.config) else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.config, "mesh": "Kuhn %d^%d x 2^%d, Alfeld split" % (cfg.N, cfg.dim, cfg.nref),
-                   "velocity_dofs": n, "levels": nlev, "smoothing": cfg.m, "re": cfg.re, "gamma": cfg.gamma,
-                   "rank_grid": list(cfg.shape) if weak else None,
-                   "patches_finest": fine_npatch, "max_patch_dofs": fine_maxn,
-                   "factor_bytes_finest": float(factor_bytes),
-                   "dense_factor_bytes_finest": fine_dense,
-                   "patch_inverses": ("condensed (block/separator form, blocks shared between patches, csrc/condense.cu)"
-                                      if mg_form == 2 else "condensed (block/separator form, csrc/condense.cu)")
-                   if condensed else "dense",
-                   "l2_policy": "inputs larger than L2 (%.1f GB of patch inverses streamed per finest-level smoother "
-                                "application, 126 MB L2)" % (factor_bytes / 1e9),
-                   "fallback": fallback, "deterministic": bool(args.deterministic), "parallelism": "1 GPU" if world == 1 else
-                   ("patches sharded over %d GPUs, level vectors distributed (owned + ghost dofs per rank): neighbour "
-                    "ncclSend/ncclRecv of ghost entries around every patch apply / SpMV, small ncclAllReduce per dot; "
-                    "level 0 replicated" % world) if distributed else
-                   "patches + operator rows sharded over %d GPUs, level vectors replicated; ncclAllReduce after "
-                   "every patch apply, grouped ncclBroadcast after every SpMV" % world},
+        "config": wl_config,
+        "implementation": {
+            "factor_bytes_finest": float(factor_bytes), "dense_factor_bytes_finest": fine_dense,
+            "patch_inverses": ("condensed (block/separator form, blocks shared between patches, csrc/condense.cu)"
+                               if mg_form == 2 else "condensed (block/separator form, csrc/condense.cu)")
+            if condensed else "dense",
+            "tile_ops": tile,
+            "l2_policy": "inputs larger than L2 (%.1f GB of patch inverses streamed per finest-level smoother "
+                         "application, 126 MB L2)" % (factor_bytes / 1e9),
+            "fallback": fallback, "deterministic": bool(args.deterministic), "parallelism": "1 GPU" if world == 1 else
+            ("one mesh brick per GPU (%d), level vectors distributed (owned + ghost dofs per rank): ghost exchanges with the "
+             "neighbouring ranks around every patch apply / SpMV and the dots' small all-reduces %s; level 0 replicated"
+             % (world, "as single kernels over NVLink peer memory (128-bit flag-in-data stores, csrc/comm.cu)"
+                if args.peer_memory else "over NCCL send/recv + all-reduce")) if distributed else
+            "patches + operator rows sharded over %d GPUs, level vectors replicated; ncclAllReduce after "
+            "every patch apply, grouped ncclBroadcast after every SpMV" % world},
         "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "DoF/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 8 * nvec, "d2h_bytes_per_step": 8 * nvec},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
@@ -576,10 +621,10 @@ def main():
     ap.add_argument("--continuation-3d", default="", metavar="CONFIG",
                     help="also run the Newton continuation on this 3-D config (e.g. ldc3d-sv-k3-half); minutes of host assembly")
     ap.add_argument("--continuation-3d-re", default="10,100,200,300,400,500", help="Reynolds numbers of --continuation-3d")
-    ap.add_argument("--peer-memory", type=int, default=0, help="N > 1: NVLink peer-memory exchanges instead of NCCL")
-    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+    ap.add_argument("--peer-memory", type=int, default=1, help="N > 1: NVLink peer-memory exchanges (default) instead of NCCL")
+    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
                     help="N > 1: the same problem sharded (strong) or one cfg5-sized brick per rank, generated rank-locally (weak)")
-    ap.add_argument("--vectors", default="replicated", choices=["replicated", "distributed"],
+    ap.add_argument("--vectors", default="distributed", choices=["replicated", "distributed"],
                     help="N > 1: replicated level vectors (measured in round 1) or distributed ones (DESIGN §6.1)")
     ap.add_argument("--condense", type=int, default=1,
                     help="1 (default): condensed block/separator patch inverses where the mesh has macro structure; 0: dense")

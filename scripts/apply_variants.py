@@ -26,12 +26,15 @@ mg = DeviceMultigrid([level_input_from_synth(l) for l in prob.levels], prob.conf
 mg.ctx.synchronize()
 stream = torch.cuda.ExternalStream(mg.ctx.stream)
 nbytes = mg.ctx.patch_apply_bytes(L)
-variants = [("v2", {}), ("v2+fuse", {"ALFIB_FUSE_INDEX": "1"}), ("tma", {"ALFIB_TILE_TMA": "1"}),
-            ("tma+fuse", {"ALFIB_TILE_TMA": "1", "ALFIB_FUSE_INDEX": "1"}), ("v2 again", {})]
+variants = [("v2", {"ALFIB_TILE_TMA": "0"}),
+            ("tma 8w x 8KB", {"ALFIB_TILE_TMA": "1", "ALFIB_TILE_TMA_CFG": "0"}),
+            ("tma 16w x 4KB", {"ALFIB_TILE_TMA": "1", "ALFIB_TILE_TMA_CFG": "1"}),
+            ("tma 16w x 4KB + RED", {"ALFIB_TILE_TMA": "1", "ALFIB_TILE_TMA_CFG": "2"}),
+            ("tma 8w x 8KB + RED", {"ALFIB_TILE_TMA": "1", "ALFIB_TILE_TMA_CFG": "3"})]
 ref = None
 rows = []
 for label, env in variants:
-    for k in ("ALFIB_FUSE_INDEX", "ALFIB_TILE_TMA"):
+    for k in ("ALFIB_FUSE_INDEX", "ALFIB_TILE_TMA", "ALFIB_TILE_TMA_CFG"):
         os.environ.pop(k, None)
     os.environ.update(env)
     for lvl in range(1, L + 1):        # every level once (smaller op lists, boundary-only patches)

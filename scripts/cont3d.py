@@ -1,0 +1,62 @@
+"""Newton continuation of the 3-D Scott-Vogelius k = 3 lid-driven cavity to Re 5000 (north-star condition 3) around a
+`fieldsplit_0` backend — the reference's own ladder, Re = 1, 10, 100, 200, ..., 5000 (examples/iters.py:33-37).
+
+    python scripts/cont3d.py oracle CONFIG OUT.npz      CPU oracle (numpy/C port): writes the fixture (minutes to hours)
+    python scripts/cont3d.py device CONFIG FIXTURE.npz  CUDA library; compares iteration counts (+-1 per Newton step) and
+                                                        the final velocity / pressure (<= 1e-8) with the fixture
+
+The host stand-in of the outer solver (alfi_b200/synth/outer.py) assembles in numpy; the time split is printed."""
+import json
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from alfi_b200.synth.outer import ContinuationSolver  # noqa: E402
+from alfi_b200.synth.problem import CONFIGS  # noqa: E402
+
+mode, name, path = sys.argv[1], sys.argv[2], sys.argv[3]
+res = [1, 10, 100] + list(range(200, 5001, 100))
+if len(sys.argv) > 4:
+    res = [float(r) for r in sys.argv[4].split(",")]
+cfg = CONFIGS[name]
+if mode == "oracle":
+    from oracle.backend import OracleBackend
+    # patch sub-solver of the reference's Scott-Vogelius path: preonly + LU solves (solver.py:326-327, 655-659), not an
+    # explicit inverse — the device applies explicit (condensed) inverses, so equal iteration counts are the evidence
+    # that this difference does not matter
+    backend = OracleBackend(cfg.m, mode="lu")
+else:
+    from alfi_b200.multigrid import DeviceBackend
+    backend = DeviceBackend(cfg.m, deterministic=False)
+s = ContinuationSolver(cfg, backend)
+t0 = time.time()
+rows = []
+for re in res:
+    t1 = time.time()
+    info = s.solve(re)
+    rows.append((re, info["nonlinear_iter"], info["linear_iter"], float(info["residual"])))
+    print("Re %6g  Newton %d  Krylov %3d  residual %.2e  %.1fs" % (re, info["nonlinear_iter"], info["linear_iter"],
+                                                                 info["residual"], time.time() - t1), flush=True)
+total = time.time() - t0
+rows = np.array(rows)
+if mode == "oracle":
+    np.savez_compressed(path, config=name, re=rows[:, 0], nonlinear_iter=rows[:, 1].astype(int), linear_iter=rows[:, 2].astype(int),
+                        residual=rows[:, 3], u=s.u, p=s.p, time_s=total)
+    print("fixture written:", path, "%.0fs" % total)
+else:
+    ref = np.load(path)
+    assert str(ref["config"]) == name and np.array_equal(ref["re"], rows[:, 0])
+    nl_ok = np.array_equal(ref["nonlinear_iter"], rows[:, 1].astype(int))
+    dk = np.abs(ref["linear_iter"] - rows[:, 2].astype(int))
+    k_ok = bool((dk <= ref["nonlinear_iter"]).all())
+    du = float(np.linalg.norm(s.u - ref["u"]) / np.linalg.norm(ref["u"]))
+    dp = float(np.linalg.norm(s.p - ref["p"]) / np.linalg.norm(ref["p"]))
+    out = {"config": name, "velocity_dofs": int(s.nu_dofs), "re_max": float(rows[-1, 0]), "steps": int(len(res)),
+           "newton_iterations": int(rows[:, 1].sum()), "krylov_iterations": int(rows[:, 2].sum()),
+           "newton_counts_equal": bool(nl_ok), "krylov_counts_within_1_per_newton_step": k_ok,
+           "max_krylov_count_difference": int(dk.max()), "velocity_rel_diff": du, "pressure_rel_diff": dp,
+           "time_s_device": total, "time_s_cpu_oracle": float(ref["time_s"]),
+           "pass": bool(nl_ok and k_ok and du <= 1e-8 and dp <= 1e-8)}
+    print(json.dumps(out), flush=True)
