@@ -26,7 +26,7 @@ from .relaxation import _make_is
 
 __all__ = ["CoarseCellPatches", "CoarseCellMacroPatches", "coarse_cell_points",
            "fix_coarse_boundaries", "fix_coarse_boundaries_loop", "AutoSchoeberlTransfer",
-           "SVSchoeberlTransfer", "PkP0SchoeberlTransfer", "NullTransfer"]
+           "SVSchoeberlTransfer", "PkP0SchoeberlTransfer", "NullTransfer", "device_transfer_backend"]
 
 
 def _hierarchy_of(pc):
@@ -207,3 +207,34 @@ class NullTransfer:
     inject = transfer
     prolong = transfer
     restrict = transfer
+
+
+def device_transfer_backend(levels, values_for=None, device=0, deterministic=False, condense=True):
+    """``backend=`` / ``values_for=`` of the transfer classes for a hierarchy handed over as
+    :class:`alfi_b200.multigrid.LevelInput` (coarsest first): a device context whose levels hold what
+    ``restrict_or_prolong`` needs and nothing else — the operator pattern, the Dirichlet dofs, ``P_H`` with the
+    coarse-boundary dofs (`alfib_transfer_set`), the cell patches (with their macro-cell blocks) and, through
+    `alfib_transfer_update`, the ``A0`` / ``gamma D`` values.  ``values_for(level, nu, gamma)`` must return the
+    re-assembled ``(A0 values, D values)``; None keeps the values the levels carry (no parameter change possible).
+    This is what `alfi_b200.firedrake_adapter.transfer_backend` returns for a live solver and what the tests build from
+    the synthetic hierarchy: the reference's ``SVSchoeberlTransfer((nu, gamma), tdim, hierarchy)`` line then only
+    gains ``**device_transfer_backend(...)``."""
+    from .lib import PATCHES_TRANSFER, Context
+    ctx = Context(device, deterministic)
+    for l, li in enumerate(levels):
+        ctx.level_create(l, li.n_nodes, li.bs)
+        ctx.set_bsr_pattern(l, li.rowptr, li.colidx)
+        ctx.set_bc(l, li.bc_dofs)
+        if l > 0:
+            cb = li.cb_dofs if li.cb_dofs is not None else np.empty(0, np.int32)
+            ctx.set_transfer(l, li.P, cb, li.P_dof_level)
+            if li.cell_offsets is not None:
+                ctx.set_patches(l, li.cell_offsets, li.cell_dofs, None, np.zeros(li.cell_offsets.size - 1, np.int32),
+                                PATCHES_TRANSFER)
+                if condense and li.cell_blocks is not None:
+                    ctx.set_patch_blocks(l, li.cell_blocks, PATCHES_TRANSFER)
+    carried = {l: (li.a0_vals, li.d_vals) for l, li in enumerate(levels) if l > 0 and li.a0_vals is not None}
+
+    def default_values(level, nu, gamma):
+        return carried[level]
+    return {"backend": ctx, "values_for": values_for or default_values}
