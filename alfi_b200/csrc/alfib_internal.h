@@ -150,6 +150,13 @@ struct PatchSet {
   bool store_owned = false;
   DBuf<double> store_buf;
   Condensed cond;                   // block/separator form of the inverses (alfib_level_set_patch_blocks)
+  // multiplicative composition (alfib_level_set_sweep_stages): per stage the (patch, tile) work items and the block
+  // rows whose residual the stage reads
+  int nstage = 0;
+  bool symmetric_sweep = false;
+  std::vector<int> stage_work_start, stage_row_start;   // nstage + 1
+  DBuf<int2> stage_work;
+  DBuf<int32_t> stage_rows;
 };
 
 // Exchange lists of one distributed-vector layout (alfib_level_set_halo): local vector = owned dofs
@@ -337,6 +344,11 @@ void comm_peer_zero(alfib_ctx* c, long long lo, long long hi);
 void comm_peer_reduce(alfib_ctx* c, int64_t n, int hdr_slot, const long long* lo, const long long* hi, double* y);
 // patch_apply.cu
 void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, PeerOut y);
+// multiplicative sweep(s) over the stages of alfib_level_set_sweep_stages: y = 0; per stage r = x - A y on the rows
+// the stage reads, y[I_i] += A_i^-1 r[I_i]
+void patch_apply_multiplicative(alfib_ctx* c, Level& L, int which, const double* x, double* y);
+void launch_bsr_residual_rows(alfib_ctx* c, const Level& L, const double* vals, const int32_t* rows, int nrows,
+                              const double* x, const double* y, double* r);
 // y = sum over ranks of this rank's patch contributions (zeroing, exchange included)
 // (a level with a halo: the ghosts of x are refreshed first — x is a local work vector there — and the ghost
 // contributions of y are summed into their owners; y is valid on the owned entries only)

@@ -49,6 +49,8 @@ void release_patchset(PatchSet& ps) {
   ps.work.release();
   ps.store_buf.release();
   ps.cond.release();
+  ps.stage_work.release();
+  ps.stage_rows.release();
 }
 
 // equal split of the block rows across ranks (contiguous ranges)
@@ -565,6 +567,79 @@ int alfib_level_set_patch_blocks(alfib_ctx* c, int level, int which, const int32
       return;
     }
     condense_setup(c, L, ps, block_of_dof);
+  });
+}
+
+int alfib_level_set_sweep_stages(alfib_ctx* c, int level, int which, int32_t nvisit, const int32_t* stage_of_visit,
+                                 int32_t nstage, int symmetric) {
+  return guarded(c, [&] {
+    cycle_graph_invalidate(c);
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(which == 0 || which == 1, "which must be 0 or 1");
+    PatchSet& ps = L.ps[which];
+    ps.nstage = 0;
+    ps.symmetric_sweep = false;
+    ps.stage_work.release();
+    ps.stage_rows.release();
+    if (nstage == 0) return;                                   // additive composition
+    ALFIB_REQUIRE(!ps.cond.on, "multiplicative composition needs dense patch inverses (no patch blocks)");
+    ALFIB_REQUIRE(c->nranks == 1 && !L.halo.on, "multiplicative composition is single-GPU");
+    ALFIB_REQUIRE(nvisit == (int32_t)ps.h_order.size() && stage_of_visit, "one stage per entry of the iteration set");
+    ALFIB_REQUIRE(!L.h_rowptr.empty(), "set the BSR pattern before the sweep stages");
+    const int bs = L.bs;
+    // check: within a stage no two visits are coupled (node adjacency of the pattern, which includes shared nodes),
+    // and a coupled pair of visits keeps its iteration order across stages
+    std::vector<int> last_stage_of_node(L.n_nodes, -1), last_visit_of_node(L.n_nodes, -1);   // writer of each node so far
+    std::vector<std::vector<int>> visits_of_stage(nstage);
+    for (int k = 0; k < nvisit; ++k) {
+      ALFIB_REQUIRE(stage_of_visit[k] >= 0 && stage_of_visit[k] < nstage, "stage out of range");
+      visits_of_stage[stage_of_visit[k]].push_back(k);
+    }
+    for (int k = 0; k < nvisit; ++k) {                         // iteration order
+      const int p = ps.h_order[k], s = stage_of_visit[k];
+      const int64_t o = ps.h_off[p], e = ps.h_off[p + 1];
+      for (int64_t i = o; i < e; i += bs) {                    // node-wise patches: bs consecutive dofs per node
+        const int node = ps.h_dofs[i] / bs;
+        for (int q = L.h_rowptr[node]; q < L.h_rowptr[node + 1]; ++q) {
+          const int nb = L.h_colidx[q];                        // this visit reads y at nb
+          if (last_visit_of_node[nb] >= 0 && last_visit_of_node[nb] != k)
+            ALFIB_REQUIRE(last_stage_of_node[nb] < s, "sweep stages: coupled visits must lie in increasing stages");
+        }
+      }
+      for (int64_t i = o; i < e; ++i) {
+        const int node = ps.h_dofs[i] / bs;
+        last_stage_of_node[node] = s;
+        last_visit_of_node[node] = k;
+      }
+    }
+    std::vector<int2> work;
+    std::vector<int32_t> rows;
+    ps.stage_work_start.assign(nstage + 1, 0);
+    ps.stage_row_start.assign(nstage + 1, 0);
+    std::vector<int> mark(L.n_nodes, -1);
+    for (int s = 0; s < nstage; ++s) {
+      ps.stage_work_start[s] = (int)work.size();
+      ps.stage_row_start[s] = (int)rows.size();
+      for (int k : visits_of_stage[s]) {
+        const int p = ps.h_order[k];
+        const int n = (int)(ps.h_off[p + 1] - ps.h_off[p]);
+        for (int t = 0; t * ALFIB_TILE_ROWS < n; ++t) work.push_back(make_int2(p, t));
+        for (int64_t i = ps.h_off[p]; i < ps.h_off[p + 1]; ++i) {
+          const int node = ps.h_dofs[i] / bs;
+          if (mark[node] != s) {
+            mark[node] = s;
+            rows.push_back(node);
+          }
+        }
+      }
+    }
+    ps.stage_work_start[nstage] = (int)work.size();
+    ps.stage_row_start[nstage] = (int)rows.size();
+    ps.stage_work.upload(work.data(), work.size(), c->stream);
+    ps.stage_rows.upload(rows.data(), rows.size(), c->stream);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    ps.nstage = nstage;
+    ps.symmetric_sweep = symmetric != 0;
   });
 }
 

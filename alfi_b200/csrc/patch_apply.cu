@@ -113,6 +113,35 @@ void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, PeerO
   CUDA_TRY(cudaGetLastError());
 }
 
+// Multiplicative composition: the sequential sweep of PCApply_PATCH as a schedule of stages (include/alfib.h,
+// alfib_level_set_sweep_stages).  Per stage: the residual x - A y on the block rows the stage's patches read (a
+// component-wise sum: lanes over the row's blocks, fixed shuffle tree), then the dense-inverse apply of the stage's
+// (patch, tile) items with plain stores — patches of a stage share no dof.  Backward sweep = stages in reverse.
+void patch_apply_multiplicative(alfib_ctx* c, Level& L, int which, const double* x, double* y) {
+  PatchSet& ps = L.ps[which];
+  ALFIB_REQUIRE(ps.nstage > 0, "no sweep stages on this patch set");
+  ALFIB_REQUIRE(!ps.cond.on, "multiplicative composition needs dense patch inverses");
+  ALFIB_REQUIRE(c->nranks == 1 && !L.halo.on, "multiplicative composition is single-GPU");
+  L.t3.alloc(L.n);
+  double* r = L.t3.p;
+  CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * L.n, c->stream));
+  const int threads = 128, wpb = threads / 32;
+  auto stage = [&](int s) {
+    const int r0 = ps.stage_row_start[s], r1 = ps.stage_row_start[s + 1];
+    launch_bsr_residual_rows(c, L, L.vals.p, ps.stage_rows.p + r0, r1 - r0, x, y, r);
+    const int w0 = ps.stage_work_start[s], w1 = ps.stage_work_start[s + 1];
+    if (w1 > w0) {
+      patch_apply_kernel<false><<<cdiv(w1 - w0, wpb), threads, 0, c->stream>>>(ps.stage_work.p + w0, w1 - w0, ps.off.p, ps.dofs.p,
+                                                                               ps.soff.p, ps.store, r, plain_out(y));
+      c->launches++;
+    }
+  };
+  for (int s = 0; s < ps.nstage; ++s) stage(s);
+  if (ps.symmetric_sweep)
+    for (int s = ps.nstage - 1; s >= 0; --s) stage(s);
+  CUDA_TRY(cudaGetLastError());
+}
+
 // Sum of the patch contributions over all ranks.  Serial: zero + apply.  Multi-GPU with peer
 // memory: every rank applies its patches into its symmetric slot (only the slab the patches
 // touch is zeroed) and then *pulls* the overlapping ranges of the other ranks' slots over NVLink
@@ -120,6 +149,10 @@ void launch_patch_apply(alfib_ctx* c, const PatchSet& ps, const double* x, PeerO
 // reference's PetscSF in one pass.  Without peer memory: NCCL all-reduce of the whole vector.
 void patch_apply_sum(alfib_ctx* c, Level& L, int level, int which, const double* x, double* y) {
   const PatchSet& ps = L.ps[which];
+  if (ps.nstage > 0) {
+    patch_apply_multiplicative(c, L, which, x, y);
+    return;
+  }
   if (L.halo.on) {
     // distributed vectors: the PetscSF bcast of x, this rank's patches, the PetscSF reduce of y (Appendix A.3)
     halo_update(c, L.halo, const_cast<double*>(x), level);

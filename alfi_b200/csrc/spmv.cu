@@ -160,6 +160,48 @@ void launch_bsr_spmv(alfib_ctx* c, const Level& L, const double* vals, const dou
   }
 }
 
+namespace {
+// r[row] = x[row] - (A y)[row] for the block rows of a list; one warp per block row, lanes over its blocks
+template <int BS>
+__global__ void __launch_bounds__(256) bsr_residual_rows_kernel(int nrows, const int32_t* __restrict__ rows,
+                                                                const int32_t* __restrict__ rowptr,
+                                                                const int32_t* __restrict__ colidx,
+                                                                const double* __restrict__ vals, const double* __restrict__ x,
+                                                                const double* __restrict__ y, double* __restrict__ r) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= nrows) return;
+  const int row = rows[w];
+  double acc[BS];
+#pragma unroll
+  for (int i = 0; i < BS; ++i) acc[i] = 0.0;
+  for (int k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) {
+    const double* __restrict__ B = vals + (int64_t)k * BS * BS;
+    const double* __restrict__ yc = y + (int64_t)colidx[k] * BS;
+#pragma unroll
+    for (int i = 0; i < BS; ++i)
+#pragma unroll
+      for (int j = 0; j < BS; ++j) acc[i] = fma(B[i * BS + j], yc[j], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < BS; ++i)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  if (lane < BS) r[(int64_t)row * BS + lane] = x[(int64_t)row * BS + lane] - acc[lane];
+}
+}  // namespace
+
+void launch_bsr_residual_rows(alfib_ctx* c, const Level& L, const double* vals, const int32_t* rows, int nrows,
+                              const double* x, const double* y, double* r) {
+  if (nrows <= 0) return;
+  const int blocks = cdiv((int64_t)nrows * 32, 256);
+  if (L.bs == 2)
+    bsr_residual_rows_kernel<2><<<blocks, 256, 0, c->stream>>>(nrows, rows, L.rowptr.p, L.colidx.p, vals, x, y, r);
+  else
+    bsr_residual_rows_kernel<3><<<blocks, 256, 0, c->stream>>>(nrows, rows, L.rowptr.p, L.colidx.p, vals, x, y, r);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+}
+
 void launch_csr_apply(alfib_ctx* c, int nrows, int bs, const int32_t* rowptr, const int32_t* colidx,
                       const double* vals, const double* x, double* y, int64_t nnz) {
   const int threads = 256;

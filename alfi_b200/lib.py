@@ -53,6 +53,7 @@ SIGNATURES = {
     "alfib_level_set_patches": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int32, _i64p, _i32p, C.c_int32,
                                           _i32p, _i32p]),
     "alfib_level_set_patch_blocks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i32p]),
+    "alfib_level_set_sweep_stages": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int32, _i32p, C.c_int32, C.c_int]),
     "alfib_patch_apply_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int]),
     "alfib_patch_storage_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int]),
     "alfib_patch_storage_form": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -296,6 +297,16 @@ class Context:
             return
         b = _i32(blocks)
         self._check(self.lib.alfib_level_set_patch_blocks(self.h, level, which, _ptr(b, C.c_int32)))
+
+    def set_sweep_stages(self, level, stage_of_visit, symmetric=False, which=PATCHES_SMOOTHER):
+        """Multiplicative composition of the patch set (`alfi_b200.patches.sweep_stages`); None: additive."""
+        if stage_of_visit is None:
+            self._check(self.lib.alfib_level_set_sweep_stages(self.h, level, which, 0, None, 0, 0))
+            return
+        st = _i32(stage_of_visit)
+        nstage = int(st.max()) + 1 if st.size else 0
+        self._check(self.lib.alfib_level_set_sweep_stages(self.h, level, which, st.size, _ptr(st, C.c_int32), nstage,
+                                                          int(bool(symmetric))))
 
     def patch_apply_bytes(self, level, which=PATCHES_SMOOTHER):
         """Algorithmic bytes of one application of the patch set (factors + indices + 16 N)."""

@@ -31,6 +31,8 @@ class LevelInput:
     patch_order: np.ndarray | None = None
     patch_colours: np.ndarray | None = None
     patch_blocks: np.ndarray | None = None   # condensed form: block label per patch dof, -1 = separator
+    patch_stages: np.ndarray | None = None   # multiplicative composition: stage per entry of the iteration set
+    symmetrise_sweep: bool = False           # ... with the backward sweep after the forward one
     P: object | None = None               # scipy CSR: scalar per node, or on dofs if P_dof_level
     P_dof_level: bool = False
     cell_offsets: np.ndarray | None = None
@@ -51,6 +53,8 @@ def level_input_from_synth(ld) -> LevelInput:
         ps = ld.patches
         li.patch_offsets, li.patch_dofs, li.patch_order, li.patch_colours = ps.offsets, ps.dofs, ps.order, ps.colours
         li.patch_blocks = ps.blocks
+        li.patch_stages = getattr(ps, "stages", None)
+        li.symmetrise_sweep = bool(getattr(ps, "symmetrise", False))
     if ld.patches is None and getattr(ld.level, "bary", False):
         from .patches import PatchSet, macro_interior_blocks
         free = np.setdiff1d(np.arange(ld.V.ndofs), ld.bc_dofs).astype(np.int32)
@@ -108,7 +112,9 @@ class DeviceMultigrid:
                 c.set_patch_blocks(0, li.coarse_blocks, PATCHES_SMOOTHER)
             if l > 0:
                 off, dofs, order, cols = li.patch_offsets, li.patch_dofs, li.patch_order, li.patch_colours
-                blocks = li.patch_blocks if condense else None
+                blocks = li.patch_blocks if (condense and li.patch_stages is None) else None   # sweeps: dense inverses
+                if li.patch_stages is not None and nranks > 1:
+                    raise NotImplementedError("multiplicative patch composition is single-GPU")
                 if nranks > 1:
                     # balance what is streamed per application: condensed bytes where blocks are given
                     cost = condensed_cost(off, blocks) if blocks is not None else None
@@ -120,6 +126,8 @@ class DeviceMultigrid:
                 c.set_patches(l, off, dofs, order, cols, PATCHES_SMOOTHER)
                 if blocks is not None:
                     c.set_patch_blocks(l, blocks, PATCHES_SMOOTHER)
+                if li.patch_stages is not None:
+                    c.set_sweep_stages(l, li.patch_stages, li.symmetrise_sweep, PATCHES_SMOOTHER)
                 if torch_storage:
                     self._bind(l, PATCHES_SMOOTHER)
                 cb = li.cb_dofs if li.cb_dofs is not None else np.empty(0, np.int32)

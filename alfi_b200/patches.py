@@ -37,6 +37,8 @@ class PatchSet:
     colours: np.ndarray | None = None     # int32 (npatch,), greedy colouring in iteration order
     blocks: np.ndarray | None = None      # int32 per dof entry: -1 separator, else block label (condensed form)
     centres: np.ndarray | None = None     # (npatch, dim) coordinates of the patches' entities (partitioning only)
+    stages: np.ndarray | None = None      # multiplicative composition: stage per entry of `order` (sweep_stages)
+    symmetrise: bool = False              # ... followed by the backward sweep (patch_pc_patch_symmetrise_sweep)
 
     @property
     def npatch(self):
@@ -133,6 +135,33 @@ def greedy_colouring(ps: PatchSet, ndofs: int) -> np.ndarray:
         used[d] |= one << np.uint64(c)
     ps.colours = colours
     return colours
+
+
+def sweep_stages(ps: PatchSet, rowptr, colidx) -> np.ndarray:
+    """Schedule of the SEQUENTIAL (multiplicative) patch sweep of PCApply_PATCH (`pc_patch_local_type multiplicative`,
+    alfi/solver.py:306-308,322): stage of every entry of the iteration set, such that two visits whose patches are
+    coupled through the operator (block pattern ``rowptr`` / ``colidx``; patches sharing a node are coupled through the
+    diagonal block) lie in different stages, the earlier visit in the lower one:
+    ``stage[k] = 1 + max(stage[k'] : k' < k, visit k' coupled with visit k)``.  Visits of one stage commute exactly,
+    so executing stage after stage reproduces the sequential sweep — forwards, and with the stages reversed the
+    backward sweep of `symmetrise_sweep` (handed over with ``alfib_level_set_sweep_stages``)."""
+    import scipy.sparse as sp
+    npatch, bs = ps.npatch, ps.bs
+    nn = len(rowptr) - 1
+    nodes = ps.dofs[::bs] // bs                                   # patches are node-wise: bs consecutive dofs per node
+    counts = np.diff(ps.offsets) // bs
+    Pn = sp.csr_matrix((np.ones(nodes.size, dtype=np.int32), nodes, np.concatenate(([0], np.cumsum(counts)))), shape=(npatch, nn))
+    An = sp.csr_matrix((np.ones(len(colidx), dtype=np.int32), colidx, rowptr), shape=(nn, nn))
+    C = ((Pn @ An) @ Pn.T).tocsr()                                # C[i, j] != 0: patch i reads what patch j writes
+    C = (C + C.T).tocsr()
+    stage_of_patch_last = np.full(npatch, -1, dtype=np.int64)     # stage of the latest visit of each patch so far
+    stages = np.zeros(ps.order.size, dtype=np.int32)
+    for k, p in enumerate(ps.order):
+        nb = C.indices[C.indptr[p]:C.indptr[p + 1]]
+        s = int(stage_of_patch_last[nb].max()) + 1 if nb.size else 0
+        stages[k] = s
+        stage_of_patch_last[p] = s
+    return stages
 
 
 def macro_interior_blocks(plex, V, ps: PatchSet, label: str = "MacroVertices") -> np.ndarray | None:

@@ -26,7 +26,7 @@ import numpy as np
 
 from .lib import PATCHES_SMOOTHER, Context
 from .multigrid import DeviceMultigrid, LevelInput
-from .patches import greedy_colouring, patch_dofs_from_points, points_to_csr
+from .patches import greedy_colouring, patch_dofs_from_points, points_to_csr, sweep_stages
 from .relaxation import _Options, star_points
 
 __all__ = ["fieldsplit0_config", "PatchPC", "VelocityMGPC", "HostAdapter"]
@@ -92,16 +92,17 @@ class PatchPC:
         g = lambda key, default=None: opts.getString(self._prefix + key, default=default)   # noqa: E731
         if _truthy(g("pc_patch_partition_of_unity", "false")):
             raise NotImplementedError("partition_of_unity weighting is off in alfi (solver.py:321)")
-        if g("pc_patch_local_type", "additive") != "additive":
-            raise NotImplementedError("only additive patch composition is on the GPU path (SURVEY §8f rank 4)")
+        self.local_type = g("pc_patch_local_type", "additive")
+        if self.local_type not in ("additive", "multiplicative"):
+            raise NotImplementedError("patch composition %r" % self.local_type)
+        self.symmetrise = _truthy(g("pc_patch_symmetrise_sweep", "false"))
         if g("sub_pc_type", "lu") != "lu" or g("sub_ksp_type", "preonly") != "preonly":
             raise NotImplementedError("patch sub-solver must be preonly + lu (solver.py:326-327)")
         # accepted and implied by the implementation: save_operators, precompute_element_tensors,
         # sub_mat_type, dense_inverse (always an explicit inverse), factor_mat_solver_type, statistics
         self.options_seen = {k: g(k) for k in ("pc_patch_save_operators", "pc_patch_precompute_element_tensors",
                                                 "pc_patch_sub_mat_type", "pc_patch_dense_inverse",
-                                                "sub_pc_factor_mat_solver_type", "pc_patch_statistics",
-                                                "pc_patch_symmetrise_sweep")}
+                                                "sub_pc_factor_mat_solver_type", "pc_patch_statistics")}
         plex, V = ad.plex(pc), ad.function_space(pc)
         ctype = g("pc_patch_construct_type", "star")
         if ctype == "star":
@@ -134,6 +135,10 @@ class PatchPC:
         c.set_bc(0, (self.bc_nodes[:, None] * bs + np.arange(bs)[None, :]).ravel())
         ps = self.patches
         c.set_patches(0, ps.offsets, ps.dofs, ps.order, ps.colours, PATCHES_SMOOTHER)
+        if self.local_type == "multiplicative":
+            # the sequential sweep as a schedule of stages of mutually uncoupled patches (solver.py:322-335)
+            self.stages = sweep_stages(ps, rowptr, colidx)
+            c.set_sweep_stages(0, self.stages, self.symmetrise, PATCHES_SMOOTHER)
         c.set_bsr_values(0, vals, colmajor)
         c.factor(0)
 
@@ -181,7 +186,7 @@ def fieldsplit0_config(fs0: dict) -> dict:
     need(lv, "pc_type", "python")
     need(lv, "pc_python_type", "firedrake.PatchPC", "alfi_b200.PatchPC")
     need(lv, "patch_pc_patch_partition_of_unity", False, None)
-    need(lv, "patch_pc_patch_local_type", "additive")
+    need(lv, "patch_pc_patch_local_type", "additive", "multiplicative")
     need(lv, "patch_sub_ksp_type", "preonly")
     need(lv, "patch_sub_pc_type", "lu")
     ctype = lv.get("patch_pc_patch_construct_type", "star")
@@ -198,6 +203,7 @@ def fieldsplit0_config(fs0: dict) -> dict:
     if coarse and coarse.get("telescope_pc_type", coarse.get("pc_type")) != "lu":
         raise NotImplementedError("fieldsplit_0: the coarse solve must be a direct LU (solver.py:369-378)")
     return {"smoothing": int(lv["ksp_max_it"]), "construct": construct, "sort_order": sort_order,
+            "local_type": lv["patch_pc_patch_local_type"], "symmetrise_sweep": bool(lv.get("patch_pc_patch_symmetrise_sweep", False)),
             "sub_mat_type": lv.get("patch_pc_patch_sub_mat_type"), "dense_inverse": bool(lv.get("patch_pc_patch_dense_inverse", False)),
             "patch_lu": lv.get("patch_sub_pc_factor_mat_solver_type")}
 

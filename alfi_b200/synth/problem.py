@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from ..patches import PatchSet, greedy_colouring, macro_interior_blocks, patch_dofs_from_points
+from ..patches import PatchSet, greedy_colouring, macro_interior_blocks, patch_dofs_from_points, sweep_stages
 from ..relaxation import macro_star_points, star_points, iteration_order
 from ..transfer import cell_patch_set
 from .fem import BSR, BlockPattern, VectorSpace, apply_dirichlet, assemble_parts, assemble_velocity_block
@@ -44,6 +44,8 @@ class Config:
     mesh_file: str | None = None  # bfs: a Gmsh 2.2 file (examples/bfs2d/coarse*.msh); None = synth.gmsh.step_mesh(N)
     dirichlet_tags: tuple = (1, 2)  # bfs: Inflow + NoSlip (examples/bfs2d/bfs2d.py:25-27); Outflow stays natural
     shape: tuple = ()            # ldc: box [0, length * shape[a]] with N * shape[a] base cells per axis (() = cube)
+    composition: str = "additive"   # "multiplicative": --patch-composition multiplicative (solver.py:306-308): sequential
+                                    # sweep in the relaxation direction + the backward sweep (symmetrise_sweep)
 
     @property
     def m(self):
@@ -199,6 +201,9 @@ def smoother_patches(cfg: Config, ld: LevelData) -> PatchSet:
     greedy_colouring(ps, ld.V.ndofs)
     if cfg.bary:
         ps.blocks = macro_interior_blocks(plex, ld.V, ps)
+    if cfg.composition == "multiplicative":
+        ps.stages = sweep_stages(ps, ld.pattern.rowptr, ld.pattern.colidx)
+        ps.symmetrise = True                     # solver.py:324: symmetrise_sweep = multiplicative
     return ps
 
 

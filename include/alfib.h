@@ -161,6 +161,17 @@ int alfib_level_set_patches(alfib_ctx* ctx, int level, int which, int32_t npatch
  * ALFIB_CONDENSE_SHARED=0 keeps one copy per (patch, block).
  * NULL returns the set to dense inverses.                                                      */
 int alfib_level_set_patch_blocks(alfib_ctx* ctx, int level, int which, const int32_t* block_of_dof);
+/* Multiplicative composition (`patch_pc_patch_local_type multiplicative`, with `symmetrise_sweep` the backward
+ * sweep after the forward one; alfi/solver.py:306-308,322,324,331-335 — PCApply_PATCH then runs the patches of the
+ * iteration set one after the other, y += R_i^T A_i^-1 R_i (x - A y)).  The sequential sweep is executed as a
+ * schedule of STAGES: stage_of_visit[k] (0 <= . < nstage) for the k-th entry of the iteration set, such that two
+ * visits whose patches are coupled through the operator (A[I_i, I_j] != 0, in particular patches sharing a dof) lie
+ * in different stages, the earlier visit in the lower one (alfi_b200.patches.sweep_stages; checked here against the
+ * BSR pattern's node adjacency).  Patches of one stage commute exactly, so the result is that of the sequential
+ * sweep, bit for bit, whatever the stage is executed with.  Dense inverses only (no patch blocks); nstage = 0
+ * returns the set to additive composition.                                                                  */
+int alfib_level_set_sweep_stages(alfib_ctx* ctx, int level, int which, int32_t nvisit, const int32_t* stage_of_visit,
+                                 int32_t nstage, int symmetric);
 /* algorithmic bytes of one application of that patch set: stored factors + index data + 16 N   */
 int64_t alfib_patch_apply_bytes(alfib_ctx* ctx, int level, int which);
 /* bytes of device storage the inverse factors of that patch set need                          */

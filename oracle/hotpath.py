@@ -74,6 +74,24 @@ def smoother_apply(x, offsets, dofs, order, factors, bc_dofs):
     return y
 
 
+def smoother_apply_multiplicative(A, x, offsets, dofs, order, factors, bc_dofs, symmetric=False):
+    """PCApply_PATCH with `pc_patch_local_type multiplicative` (solver.py:322): the patches of the iteration set one
+    after the other, each solving for the CURRENT residual on its dofs, y += R_j^T A_j^-1 R_j (x - A y)
+    (PETSc: the residual update with the patch operator including its artificial-boundary columns — every row of a
+    patch dof only couples to dofs of the patch's cells, so this is the global residual on those rows);
+    `symmetrise_sweep` (solver.py:324) adds the same sweep backwards.  Then y[bc] = x[bc]."""
+    y = np.zeros_like(x)
+    A = A.tocsr()
+    sweeps = [list(order)] + ([list(order)[::-1]] if symmetric else [])
+    for sw in sweeps:
+        for j in sw:
+            I = dofs[offsets[j]:offsets[j + 1]]
+            if I.size:
+                y[I] += _solve(factors[j], x[I] - A[I] @ y)
+    y[bc_dofs] = x[bc_dofs]
+    return y
+
+
 def backward_error(mats, offsets, dofs, x, u_by_patch):
     """max_i ||A_i u_i - r_i|| / (||A_i|| ||u_i|| + ||r_i||): the conditioning-free check (H3)."""
     worst = 0.0

@@ -85,13 +85,22 @@ def test_patchpc_builtin_star_and_rejections(problems, monkeypatch):
     p = alfi_b200.PatchPC()
     p.initialize(pc)
     assert np.array_equal(p.patches.dofs, prob.levels[2].patches.dofs)
-    for key, val in (("patch_pc_patch_partition_of_unity", True), ("patch_pc_patch_local_type", "multiplicative"),
+    for key, val in (("patch_pc_patch_partition_of_unity", True), ("patch_pc_patch_local_type", "symmetric_multiplicative"),
                      ("patch_sub_pc_type", "ilu")):
         bad = dict(opts)
         bad[key] = val
         _, pc2 = make_pc(problems, "ldc2d-pkp0-tiny", 2, bad)
         with pytest.raises(NotImplementedError):
             alfi_b200.PatchPC().initialize(pc2)
+    # multiplicative composition: the sweep stages are handed over between the patches and the values
+    mult = dict(opts)
+    mult.update({"patch_pc_patch_local_type": "multiplicative", "patch_pc_patch_symmetrise_sweep": True})
+    _, pc3 = make_pc(problems, "ldc2d-pkp0-tiny", 2, mult)
+    pm = alfi_b200.PatchPC()
+    pm.initialize(pc3)
+    names = [c[0] for c in pm.ctx.calls]
+    assert names == ["level_create", "set_bsr_pattern", "set_bc", "set_patches", "set_sweep_stages", "set_bsr_values", "factor"]
+    assert pm.symmetrise and pm.stages.size == pm.patches.order.size
 
 
 def test_transfer_rebuild_logic():

@@ -140,9 +140,18 @@ def test_fieldsplit0_dictionary_is_accepted_unchanged(name, m, construct, sort):
 
 
 @pytest.mark.parametrize("name", ["ldc3d-sv-k3-multiplicative", "ldc2d-pkp0-star-multiplicative"])
-def test_unsupported_dictionaries_are_refused(name):
-    with pytest.raises(NotImplementedError, match="local_type"):
-        fieldsplit0_config(PARAMS[name]["outer"]["fieldsplit_0"])
+def test_multiplicative_dictionaries_are_read(name):
+    """`--patch-composition multiplicative` (solver.py:306-308): symmetrised sequential sweeps in the relaxation direction."""
+    got = fieldsplit0_config(PARAMS[name]["outer"]["fieldsplit_0"])
+    assert got["local_type"] == "multiplicative" and got["symmetrise_sweep"] and got["sort_order"] == "0+:1-"
+
+
+def test_unsupported_dictionaries_are_refused():
+    import copy
+    fs0 = copy.deepcopy(PARAMS["ldc3d-sv-k3"]["outer"]["fieldsplit_0"])
+    fs0["mg_levels"]["patch_pc_patch_partition_of_unity"] = True
+    with pytest.raises(NotImplementedError, match="partition_of_unity"):
+        fieldsplit0_config(fs0)
 
 
 class _Recorder:
