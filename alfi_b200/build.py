@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libalfib.so")
-SOURCES = ["api.cu", "spmv.cu", "patch_apply.cu", "patch_factor.cu", "condense.cu", "vector.cu", "krylov.cu", "cycle.cu", "comm.cu"]
+SOURCES = ["api.cu", "spmv.cu", "patch_apply.cu", "patch_factor.cu", "condense.cu", "vector.cu", "krylov.cu", "cycle.cu", "comm.cu", "outer.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]

@@ -219,6 +219,19 @@ struct Level {
   int krylov_m = 0;
 };
 
+// Pressure-side operators of the outer Schur-complement fieldsplit on the finest level (outer.cu; alfib_schur_set)
+struct Schur {
+  bool on = false;
+  int nu = 0, np = 0;                      // velocity dofs of the finest level, pressure dofs
+  int remove_mean = 0;                     // constant-pressure nullspace removed after the Schur solve
+  int64_t b_nnz = 0, mi_nnz = 0;
+  DBuf<int32_t> b_rowptr, b_colidx, bt_rowptr, bt_colidx, mi_rowptr, mi_colidx;
+  DBuf<double> b_vals, bt_vals, mi_vals;   // B (np x nu), its explicit transpose, M_p^-1 (np x np), scalar CSR
+  DBuf<double> y1, tu, tp, tp2;            // work vectors of one preconditioner application
+  DBuf<double> V, Z, w, r, xs, hd;         // outer FGMRES: bases, work vectors, device scalars
+  int restart = 0;
+};
+
 struct EventRec;
 struct alfib_ctx {
   int device = 0;
@@ -267,6 +280,7 @@ struct alfib_ctx {
   DBuf<int> coarse_piv, coarse_info;
   int coarse_n = 0;
   bool coarse_factored = false;
+  Schur schur;                          // outer fieldsplit pieces (alfib_schur_set)
   // profiling
   int profile = 0;
   double ev_ms[ALFIB_MAX_LEVELS][ALFIB_EV_COUNT] = {{0}};
@@ -330,6 +344,7 @@ void halo_update(alfib_ctx* c, Halo& H, double* x, int level);
 void halo_reduce(alfib_ctx* c, Halo& H, double* y, int level);
 // v[0..nv) summed over the ranks, result on every rank (FGMRES dots); sqrt_mode: v[0] = sqrt(sum), inv = 1 / v[0]
 void comm_small_allreduce(alfib_ctx* c, double* v, int nv, int sqrt_mode, double* inv);
+bool comm_small_allreduce_partials(alfib_ctx* c, const double* partial, int nparts, double* v, int nv, int sqrt_mode, double* inv);
 void comm_mbox_reserve(alfib_ctx* c, Halo& H, int level, int which);    // channels of a halo (before the peer buffer exists)
 void comm_peer_alloc(alfib_ctx* c);
 void comm_peer_handle(alfib_ctx* c, void* out64);
@@ -368,6 +383,16 @@ void launch_sub(alfib_ctx* c, int n, const double* a, const double* b, double* o
 void launch_bsr_to_dense(alfib_ctx* c, const Level& L, double* dense /* col-major n x n */);
 // krylov.cu
 void fgmres_device(alfib_ctx* c, Level& L, int level, int m, const double* b, double* x);
+void krylov_reserve(alfib_ctx* c);
+void launch_multi_dot(alfib_ctx* c, int n, int nv, const double* V, int64_t ldv, const double* w, double* out);
+void launch_maxpy_norm(alfib_ctx* c, int n, int nv, const double* coef, double sign, const double* V, int64_t ldv,
+                       double* w, double* nrm, double* inv);
+void launch_scale_by(alfib_ctx* c, int n, const double* scale, const double* in, double* out);
+// outer.cu
+void schur_apply_device(alfib_ctx* c, double nu, double gamma, const double* r, double* y);
+void jacobian_apply_device(alfib_ctx* c, const double* z, double* out);
+void outer_solve_device(alfib_ctx* c, double nu, double gamma, const double* b, double* x, double rtol, double atol,
+                        int maxit, int restart, int* iterations, double* history, int nhistory);
 // cycle.cu
 void smoother_apply_device(alfib_ctx* c, Level& L, int level, const double* x, double* y);
 void prolong_device(alfib_ctx* c, Level& Lf, int level, const double* coarse, double* fine);

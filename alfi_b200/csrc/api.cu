@@ -194,6 +194,12 @@ int alfib_destroy(alfib_ctx* c) {
   for (auto* b : {&c->fwork, &c->partial, &c->scal, &c->stage_in, &c->stage_in2, &c->stage_out, &c->coarse_lu,
                   &c->coarse_work, &c->coarse_inv, &c->coarse_partial, &c->coarse_r, &c->coarse_dx})
     b->release();
+  {
+    Schur& S = c->schur;
+    for (auto* b : {&S.b_rowptr, &S.b_colidx, &S.bt_rowptr, &S.bt_colidx, &S.mi_rowptr, &S.mi_colidx}) b->release();
+    for (auto* b : {&S.b_vals, &S.bt_vals, &S.mi_vals, &S.y1, &S.tu, &S.tp, &S.tp2, &S.V, &S.Z, &S.w, &S.r, &S.xs, &S.hd})
+      b->release();
+  }
   c->d_peer_slot.release();
   c->d_epoch.release();
   c->d_comm_err.release();
@@ -406,7 +412,9 @@ int alfib_level_set_bsr_values(alfib_ctx* c, int level, const double* vals, int 
   return guarded(c, [&] {
     Level& L = get_level(c, level);
     ALFIB_REQUIRE(vals, "null values");
+    const double* before = L.vals.p;
     upload_values(c, L, L.vals, vals, block_col_major);
+    if (L.vals.p != before) cycle_graph_invalidate(c);        // the captured cycle holds the old pointer
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     L.has_values = true;
     L.ps[ALFIB_PATCHES_SMOOTHER].factored = false;
@@ -489,6 +497,18 @@ int alfib_level_set_patches(alfib_ctx* c, int level, int which, int32_t npatch, 
     if (colours) {
       ps.h_colour.assign(colours, colours + npatch);
       for (int32_t col : ps.h_colour) ALFIB_REQUIRE(col >= 0 && col < 64, "colour out of range");
+      // two patches of one colour must not share a dof: the deterministic scatter is a plain read-modify-write per colour
+      std::vector<uint64_t> used(L.n, 0);
+      std::vector<char> done(npatch, 0);
+      for (int32_t p : ps.h_order) {
+        if (done[p]) continue;
+        done[p] = 1;
+        const uint64_t bit = uint64_t(1) << ps.h_colour[p];
+        for (int64_t k = offsets[p]; k < offsets[p + 1]; ++k) {
+          ALFIB_REQUIRE(!(used[dofs[k]] & bit), "two patches of the same colour share a dof");
+          used[dofs[k]] |= bit;
+        }
+      }
     } else {
       greedy_colour(ps, L.n);
     }
@@ -787,13 +807,18 @@ int alfib_transfer_update(alfib_ctx* c, int level, const double* A0_vals, const 
     Level& L = get_level(c, level);
     ALFIB_REQUIRE(L.has_transfer, "alfib_transfer_set first");
     ALFIB_REQUIRE(A0_vals || D_vals, "nothing to update");
+    // the captured cycle follows the transfer sequence has_d selects and holds the value pointers
+    const double *d_before = L.dvals.p, *a0_before = L.a0vals.p;
+    const bool had_d = L.has_d;
     if (D_vals) {
       upload_values(c, L, L.dvals, D_vals, block_col_major);
       L.has_d = true;
     }
+    if (L.has_d != had_d || L.dvals.p != d_before) cycle_graph_invalidate(c);
     if (A0_vals) {
       PatchSet& ps = L.ps[ALFIB_PATCHES_TRANSFER];
       upload_values(c, L, L.a0vals, A0_vals, block_col_major);
+      if (L.a0vals.p != a0_before) cycle_graph_invalidate(c);
       if (ps.npatch > 0) {
         ensure_storage(ps);
         ScopedEvent ev(c, ALFIB_EV_PCSETUP_PATCH, level);
@@ -881,6 +906,95 @@ int alfib_cycle_apply(alfib_ctx* c, const double* b, double* x) {
     const double* db = in_vec(c, b, L.n, c->stage_in);
     OutVec out(c, x, L.n);
     cycle_apply_device(c, db, out.dev);
+    out.finish();
+  });
+}
+
+// ---- outer Schur-complement fieldsplit (outer.cu) -------------------------------------------------
+int alfib_schur_set(alfib_ctx* c, int32_t n_p, const int32_t* B_rowptr, const int32_t* B_colidx, const double* B_vals,
+                    const int32_t* Mi_rowptr, const int32_t* Mi_colidx, const double* Mi_vals, int remove_constant) {
+  return guarded(c, [&] {
+    ALFIB_REQUIRE(c->nlevels >= 1, "alfib_cycle_setup first");
+    Level& L = get_level(c, c->nlevels - 1);
+    ALFIB_REQUIRE(!L.halo.on && c->nranks == 1, "the outer pieces run on one GPU (finest level not distributed)");
+    ALFIB_REQUIRE(n_p >= 1 && B_rowptr && B_colidx && B_vals && B_rowptr[0] == 0, "bad divergence matrix");
+    ALFIB_REQUIRE(Mi_rowptr && Mi_colidx && Mi_vals && Mi_rowptr[0] == 0, "bad pressure mass inverse");
+    const int nu = L.n;
+    const int64_t nnz = B_rowptr[n_p], mnnz = Mi_rowptr[n_p];
+    for (int i = 0; i < n_p; ++i)
+      ALFIB_REQUIRE(B_rowptr[i + 1] >= B_rowptr[i] && Mi_rowptr[i + 1] >= Mi_rowptr[i], "row pointers must not decrease");
+    for (int64_t k = 0; k < nnz; ++k) ALFIB_REQUIRE(B_colidx[k] >= 0 && B_colidx[k] < nu, "B column out of range");
+    for (int64_t k = 0; k < mnnz; ++k) ALFIB_REQUIRE(Mi_colidx[k] >= 0 && Mi_colidx[k] < n_p, "M_p^-1 column out of range");
+    Schur& S = c->schur;
+    S.on = false;
+    S.nu = nu;
+    S.np = n_p;
+    S.remove_mean = remove_constant != 0;
+    S.b_nnz = nnz;
+    S.mi_nnz = mnnz;
+    S.b_rowptr.upload(B_rowptr, n_p + 1, c->stream);
+    S.b_colidx.upload(B_colidx, nnz, c->stream);
+    S.b_vals.upload(B_vals, nnz, c->stream);
+    S.mi_rowptr.upload(Mi_rowptr, n_p + 1, c->stream);
+    S.mi_colidx.upload(Mi_colidx, mnnz, c->stream);
+    S.mi_vals.upload(Mi_vals, mnnz, c->stream);
+    // explicit transpose, rows in ascending pressure-dof order => fixed summation order
+    std::vector<int32_t> trow(nu + 1, 0), tcol(nnz);
+    std::vector<double> tval(nnz);
+    for (int64_t k = 0; k < nnz; ++k) trow[B_colidx[k] + 1]++;
+    for (int i = 0; i < nu; ++i) trow[i + 1] += trow[i];
+    std::vector<int32_t> cursor(trow.begin(), trow.end() - 1);
+    for (int i = 0; i < n_p; ++i)
+      for (int k = B_rowptr[i]; k < B_rowptr[i + 1]; ++k) {
+        const int dst = cursor[B_colidx[k]]++;
+        tcol[dst] = i;
+        tval[dst] = B_vals[k];
+      }
+    S.bt_rowptr.upload(trow.data(), nu + 1, c->stream);
+    S.bt_colidx.upload(tcol.data(), nnz, c->stream);
+    S.bt_vals.upload(tval.data(), nnz, c->stream);
+    S.y1.alloc(nu);
+    S.tu.alloc(nu);
+    S.tp.alloc(n_p);
+    S.tp2.alloc(n_p);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    S.on = true;
+  });
+}
+
+int alfib_schur_apply(alfib_ctx* c, double nu, double gamma, const double* r, double* y) {
+  return guarded(c, [&] {
+    ALFIB_REQUIRE(c->schur.on, "alfib_schur_set first");
+    const size_t n = (size_t)c->schur.nu + c->schur.np;
+    const double* dr = in_vec(c, r, n, c->stage_in2);
+    OutVec out(c, y, n);
+    schur_apply_device(c, nu, gamma, dr, out.dev);
+    out.finish();
+  });
+}
+
+int alfib_jacobian_apply(alfib_ctx* c, const double* z, double* Jz) {
+  return guarded(c, [&] {
+    ALFIB_REQUIRE(c->schur.on, "alfib_schur_set first");
+    const size_t n = (size_t)c->schur.nu + c->schur.np;
+    const double* dz = in_vec(c, z, n, c->stage_in2);
+    OutVec out(c, Jz, n);
+    jacobian_apply_device(c, dz, out.dev);
+    out.finish();
+  });
+}
+
+int alfib_outer_solve(alfib_ctx* c, double nu, double gamma, const double* rhs, double* x, double rtol, double atol,
+                      int32_t maxit, int32_t restart, int32_t* iterations, double* history, int32_t nhistory) {
+  return guarded(c, [&] {
+    ALFIB_REQUIRE(c->schur.on, "alfib_schur_set first");
+    ALFIB_REQUIRE(nhistory >= 0 && (nhistory == 0 || history), "bad history buffer");
+    const size_t n = (size_t)c->schur.nu + c->schur.np;
+    const double* db = in_vec(c, rhs, n, c->stage_in2);
+    OutVec out(c, x, n);
+    int its = 0;
+    outer_solve_device(c, nu, gamma, db, out.dev, rtol, atol, maxit, restart, &its, history, nhistory);
+    if (iterations) *iterations = its;
     out.finish();
   });
 }

@@ -718,6 +718,38 @@ __global__ void __launch_bounds__(64) mbox_small_sum_kernel(int nv, int nranks, 
   mbox_finish(k, seq, cnt + 1);
 }
 
+// The same with the second pass of a two-pass dot folded in: v[j] is first formed as the fixed-order sum of the
+// nparts partial sums partial[j * nparts + b] (exactly finalize_kernel of krylov.cu: lanes stride over b, shuffle
+// tree), one warp per j — one launch less per dot / norm of the distributed FGMRES.
+__global__ void __launch_bounds__(256) mbox_small_sum_partials_kernel(int nv, int nparts, const double* __restrict__ partial,
+                                                                      int nranks, int rank, MboxPeers mp, double* __restrict__ v,
+                                                                      int sqrt_mode, double* __restrict__ inv, const double* my_data,
+                                                                      long long my_cap, unsigned long long* seq, unsigned int* cnt,
+                                                                      int* __restrict__ err) {
+  const unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(seq) + 1ull;
+  const long long slot = (long long)(k & 1ull);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const double* in = my_data + 2 * slot * my_cap;
+  for (int j = warp; j < nv; j += nwarp) {
+    double mine = 0.0;
+    for (int b = lane; b < nparts; b += 32) mine += partial[(long long)j * nparts + b];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if (lane == 0) {
+      for (int p = 0; p < mp.npeers; ++p)
+        ll_store(mp.data[p] + 2 * (slot * mp.cap[p] + (long long)rank * ALFIB_MBOX_NV + j), mine, (unsigned int)k);
+      double s = 0.0;
+      for (int q = 0; q < nranks; ++q) s += (q == rank) ? mine : ll_load(in + 2 * ((long long)q * ALFIB_MBOX_NV + j), (unsigned int)k, err);
+      if (sqrt_mode) {
+        s = sqrt(s);
+        if (inv) inv[j] = s > 0.0 ? 1.0 / s : 0.0;
+      }
+      v[j] = s;
+    }
+  }
+  mbox_finish(k, seq, cnt + 1);
+}
+
 // the neighbours of one channel as the kernels take them; `mine` = offsets of the outgoing list, `theirs` = where
 // each neighbour expects this rank's segment
 MboxPeers mbox_peers(alfib_ctx* c, int ch, const std::vector<int>& peers, const std::vector<int64_t>& mine,
@@ -844,6 +876,28 @@ void halo_reduce(alfib_ctx* c, Halo& H, double* y, int level) {
   }
   if (H.n_local > H.n_owned)
     CUDA_TRY(cudaMemsetAsync(y + H.n_owned, 0, sizeof(double) * (size_t)(H.n_local - H.n_owned), c->stream));
+}
+
+// out[j] = (sqrt of) the sum over all ranks of the fixed-order sum of partial[j * nparts .. + nparts); returns false if
+// the mailbox transport is not available (the caller then finalises and all-reduces separately)
+bool comm_small_allreduce_partials(alfib_ctx* c, const double* partial, int nparts, double* v, int nv, int sqrt_mode, double* inv) {
+  if (!(c->nranks > 1 && c->peers_open && c->mbox_fixed && nv <= ALFIB_MBOX_NV) || std::getenv("ALFIB_MBOX_OFF") ||
+      debug_skip_exchange())
+    return false;
+  const int ch = ALFIB_MBOX_SMALL;
+  const MboxEntry& me = c->mbox[ch];
+  std::vector<int> peers;
+  for (int q = 0; q < c->nranks; ++q)
+    if (q != c->rank) peers.push_back(q);
+  std::vector<int64_t> zeros(peers.size() + 1, 0);
+  const int threads = 32 * std::min(nv, 8);
+  mbox_small_sum_partials_kernel<<<1, threads, 0, c->stream>>>(nv, nparts, partial, c->nranks, c->rank,
+                                                               mbox_peers(c, ch, peers, zeros, zeros), v, sqrt_mode, inv,
+                                                               reinterpret_cast<const double*>(c->sym + me.data_off), me.cap,
+                                                               c->mbox_seq.p + ch, c->mbox_cnt.p + 2 * ch, c->d_comm_err.p);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return true;
 }
 
 void comm_small_allreduce(alfib_ctx* c, double* v, int nv, int sqrt_mode, double* inv) {

@@ -715,8 +715,10 @@ void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, P
     c->launches++;
   }
   // ALFIB_FUSE_INDEX=1 (tile op v2 only): K2 and K3b are folded into the source fetch of K3 / K4
+  // Default: fused on SMALL sets (launch-bound: two launches fewer per application), separate kernels on large ones
+  // (measured on cfg5's finest level: fused 0.583 ms against 0.566 ms; the fused source fetch stalls the matrix stream).
   const char* env_fuse = std::getenv("ALFIB_FUSE_INDEX");
-  const bool fuse = !v1 && env_fuse && env_fuse[0] == '1';
+  const bool fuse = !v1 && (env_fuse ? env_fuse[0] == '1' : h.nsep_total < (1 << 18));
   const FusedSrc fs_rhs{cd.sepdofs.p, cd.cptr.p, cd.cg1.p, cd.g1.p};
   const FusedSrc fs_z{nullptr, cd.zptr.p, cd.zsrc.p, cd.us.p};
   // K2: separator right-hand sides

@@ -471,6 +471,10 @@ void cycle_apply_device(alfib_ctx* c, const double* b, double* x) {
   if (!want_graph) {
     cycle_body(c);
   } else if (c->graph_exec) {
+    // the eager path checks these inside its steps; a replay must not run on stale inverses either
+    for (int l = 1; l < nl; ++l)
+      ALFIB_REQUIRE(c->levels[l]->ps[ALFIB_PATCHES_SMOOTHER].factored, "alfib_level_factor has not been called since the values changed");
+    ALFIB_REQUIRE(c->coarse_factored, "alfib_coarse_factor has not been called since the values changed");
     CUDA_TRY(cudaGraphLaunch((cudaGraphExec_t)c->graph_exec, c->stream));
     c->launches += c->graph_launches;
   } else if (c->cycles_run == 0) {

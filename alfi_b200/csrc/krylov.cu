@@ -133,6 +133,43 @@ __global__ void hessenberg_solve_kernel(int m, double* __restrict__ H, const dou
 
 }  // namespace
 
+// ---- the same BLAS-1 pieces for the outer solver (outer.cu): fixed-order two-pass reductions over n entries --------
+void krylov_reserve(alfib_ctx* c) {
+  c->partial.alloc((size_t)MAXV * RGRID);
+  c->scal.alloc(MAXV * MAXV + 2 + 2 * MAXV);
+}
+
+// out[j] = <V_j, w>, j < nv <= ALFIB_MAX_KRYLOV + 1 (device pointers)
+void launch_multi_dot(alfib_ctx* c, int n, int nv, const double* V, int64_t ldv, const double* w, double* out) {
+  ALFIB_REQUIRE(nv >= 1 && nv <= MAXV, "too many simultaneous dots");
+  krylov_reserve(c);
+  multi_dot_kernel<<<RGRID, RT, 0, c->stream>>>(n, nv, V, ldv, w, c->partial.p);
+  finalize_kernel<<<nv, 32, 0, c->stream>>>(nv, c->partial.p, out, 0, nullptr);
+  c->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+}
+
+// w += sign * sum_j coef[j] V_j ; if nrm: nrm[0] = |w| afterwards, inv[0] = 1 / |w| (0 if w = 0)
+void launch_maxpy_norm(alfib_ctx* c, int n, int nv, const double* coef, double sign, const double* V, int64_t ldv,
+                       double* w, double* nrm, double* inv) {
+  ALFIB_REQUIRE(nv >= 0 && nv <= MAXV, "too many vectors in one update");
+  krylov_reserve(c);
+  maxpy_kernel<<<RGRID, RT, 0, c->stream>>>(n, nv, coef, sign, V, ldv, w, nrm ? c->partial.p : nullptr);
+  c->launches += 1;
+  if (nrm) {
+    finalize_kernel<<<1, 32, 0, c->stream>>>(1, c->partial.p, nrm, 1, inv);
+    c->launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+}
+
+// out = scale[0] * in
+void launch_scale_by(alfib_ctx* c, int n, const double* scale, const double* in, double* out) {
+  scale_kernel<<<RGRID, RT, 0, c->stream>>>(n, scale, in, out);
+  c->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+}
+
 // scal layout: [0, MAXV*MAXV) H ; then beta, inv, y[MAXV], h[MAXV]
 void fgmres_device(alfib_ctx* c, Level& L, int level, int m, const double* b, double* x) {
   ALFIB_REQUIRE(m >= 1 && m <= ALFIB_MAX_KRYLOV, "smoothing iterations out of range");
@@ -168,8 +205,10 @@ void fgmres_device(alfib_ctx* c, Level& L, int level, int m, const double* b, do
   // out[j] = <V_j, w> over all ranks, j < nv
   auto mdot = [&](int nv, const double* Vp, const double* wp, double* out) {
     multi_dot_kernel<<<RGRID, RT, 0, s>>>(no, nv, Vp, n, wp, c->partial.p);
+    c->launches += 1;
+    if (dist && comm_small_allreduce_partials(c, c->partial.p, RGRID, out, nv, 0, nullptr)) return;   // second pass + exchange: one kernel
     finalize_kernel<<<nv, 32, 0, s>>>(nv, c->partial.p, out, 0, nullptr);
-    c->launches += 2;
+    c->launches += 1;
     if (dist) comm_small_allreduce(c, out, nv, 0, nullptr);
   };
   // out = sqrt(sum of the |.|^2 partials over all ranks), invp = 1 / out
@@ -178,6 +217,7 @@ void fgmres_device(alfib_ctx* c, Level& L, int level, int m, const double* b, do
       finalize_kernel<<<1, 32, 0, s>>>(1, c->partial.p, out, 1, invp);
       c->launches += 1;
     } else {
+      if (comm_small_allreduce_partials(c, c->partial.p, RGRID, out, 1, 1, invp)) return;
       finalize_kernel<<<1, 32, 0, s>>>(1, c->partial.p, out, 0, nullptr);
       c->launches += 1;
       comm_small_allreduce(c, out, 1, 1, invp);

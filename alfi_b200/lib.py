@@ -72,6 +72,11 @@ SIGNATURES = {
     "alfib_coarse_solve": (C.c_int, [C.c_void_p, _f64p, _f64p]),
     "alfib_cycle_setup": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "alfib_cycle_apply": (C.c_int, [C.c_void_p, _f64p, _f64p]),
+    "alfib_schur_set": (C.c_int, [C.c_void_p, C.c_int32, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p, C.c_int]),
+    "alfib_schur_apply": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _f64p, _f64p]),
+    "alfib_jacobian_apply": (C.c_int, [C.c_void_p, _f64p, _f64p]),
+    "alfib_outer_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _f64p, _f64p, C.c_double, C.c_double, C.c_int32,
+                                    C.c_int32, _i32p, C.POINTER(C.c_double), C.c_int32]),
     "alfib_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "alfib_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), _i64p]),
     "alfib_profile_reset": (C.c_int, [C.c_void_p]),
@@ -396,6 +401,43 @@ class Context:
         vb, vx = _Vec(b, n), _Vec(x, n, True)
         self._check(self.lib.alfib_cycle_apply(self.h, vb.ptr, vx.ptr))
         return x
+
+    # -- outer Schur-complement fieldsplit (alfi/solver.py:15-38, 405-421, 463-474)
+    def schur_set(self, B, Minv, remove_constant=True):
+        """B: scipy sparse (pressure dofs x finest-level velocity dofs), Dirichlet columns removed; Minv: the
+        (block-diagonal) inverse pressure mass matrix."""
+        B = B.tocsr()
+        B.sort_indices()
+        Minv = Minv.tocsr()
+        Minv.sort_indices()
+        n_p = B.shape[0]
+        if B.shape[1] != self._sizes[self._nlevels - 1] or Minv.shape != (n_p, n_p):
+            raise AlfibError("B / M_p^-1 shapes do not match the finest level")
+        brp, bci, bv = _i32(B.indptr), _i32(B.indices), np.ascontiguousarray(B.data, dtype=np.float64)
+        mrp, mci, mv = _i32(Minv.indptr), _i32(Minv.indices), np.ascontiguousarray(Minv.data, dtype=np.float64)
+        self._check(self.lib.alfib_schur_set(self.h, n_p, _ptr(brp, C.c_int32), _ptr(bci, C.c_int32), bv.ctypes.data,
+                                             _ptr(mrp, C.c_int32), _ptr(mci, C.c_int32), mv.ctypes.data,
+                                             int(bool(remove_constant))))
+        self._n_outer = B.shape[1] + n_p
+
+    def schur_apply(self, nu, gamma, r, y):
+        vr, vy = _Vec(r, self._n_outer), _Vec(y, self._n_outer, True)
+        self._check(self.lib.alfib_schur_apply(self.h, float(nu), float(gamma), vr.ptr, vy.ptr))
+        return y
+
+    def jacobian_apply(self, z, out):
+        vz, vo = _Vec(z, self._n_outer), _Vec(out, self._n_outer, True)
+        self._check(self.lib.alfib_jacobian_apply(self.h, vz.ptr, vo.ptr))
+        return out
+
+    def outer_solve(self, nu, gamma, rhs, x, rtol, atol, maxit=500, restart=30):
+        """Returns (x, iterations, residual history)."""
+        vb, vx = _Vec(rhs, self._n_outer), _Vec(x, self._n_outer, True)
+        its = C.c_int32(0)
+        hist = (C.c_double * (maxit + 1))()
+        self._check(self.lib.alfib_outer_solve(self.h, float(nu), float(gamma), vb.ptr, vx.ptr, float(rtol), float(atol),
+                                               int(maxit), int(restart), C.byref(its), hist, maxit + 1))
+        return x, int(its.value), [hist[i] for i in range(its.value + 1)]
 
     # -- instrumentation
     def profile(self, enable=True):

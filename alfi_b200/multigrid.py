@@ -428,3 +428,27 @@ class DeviceBackend:
         out = np.empty_like(self._out)
         self.mg.apply(np.ascontiguousarray(b), out)
         return out
+
+    # -- the outer pieces on the device (include/alfib.h "outer Schur-complement fieldsplit")
+    def setup_outer(self, B, Minv, bc_dofs, remove_constant=True):
+        """B = (div u, q) block of the Jacobian (pressure x velocity dofs), Minv = inverse pressure mass matrix,
+        bc_dofs = Dirichlet velocity dofs: their columns of B are removed, as Firedrake's bcs do for the
+        off-diagonal blocks of the assembled Jacobian."""
+        import scipy.sparse as sp
+        keep = np.ones(B.shape[1])
+        keep[np.asarray(bc_dofs, dtype=np.int64)] = 0.0
+        Bz = (B.tocsr() @ sp.diags(keep)).tocsr()
+        Bz.eliminate_zeros()
+        self.mg.ctx.schur_set(Bz, Minv, remove_constant)
+        self._n_outer = B.shape[0] + B.shape[1]
+
+    def schur_apply(self, nu, gamma, r):
+        """One application of the Schur-complement fieldsplit preconditioner to r = [r_u; r_p]."""
+        return self.mg.ctx.schur_apply(nu, gamma, np.ascontiguousarray(r), np.empty(self._n_outer))
+
+    def jacobian_apply(self, z):
+        return self.mg.ctx.jacobian_apply(np.ascontiguousarray(z), np.empty(self._n_outer))
+
+    def outer_solve(self, nu, gamma, rhs, rtol, atol, maxit=500, restart=30):
+        """The whole outer FGMRES solve of one Newton step; returns (x, iterations, residual history)."""
+        return self.mg.ctx.outer_solve(nu, gamma, np.ascontiguousarray(rhs), np.empty(self._n_outer), rtol, atol, maxit, restart)

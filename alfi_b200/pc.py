@@ -29,7 +29,7 @@ from .multigrid import DeviceMultigrid, LevelInput
 from .patches import greedy_colouring, patch_dofs_from_points, points_to_csr, sweep_stages
 from .relaxation import _Options, star_points
 
-__all__ = ["fieldsplit0_config", "PatchPC", "VelocityMGPC", "HostAdapter"]
+__all__ = ["fieldsplit0_config", "PatchPC", "VelocityMGPC", "ALFieldsplitPC", "HostAdapter"]
 
 
 class HostAdapter:
@@ -263,3 +263,35 @@ class VelocityMGPC:
 
     def applyTranspose(self, pc, x, y):
         raise NotImplementedError("Sorry!")
+
+
+class ALFieldsplitPC(VelocityMGPC):
+    """The whole ``outer_fieldsplit`` preconditioner of alfi/solver.py:405-421 as one python PC: PCFIELDSPLIT schur
+    with ``full`` factorisation, ``fieldsplit_0`` = the multigrid cycle above, ``fieldsplit_1`` =
+    ``alfi.solver.DGMassInv`` (solver.py:15-38, i.e. -(nu + gamma) M_p^-1) — one H2D/D2H pair per OUTER Krylov
+    iteration instead of one per velocity-block application (two per iteration).  Selected by replacing the
+    ``"pc_type": "fieldsplit"`` block by ``"pc_type": "python", "pc_python_type": "alfi_b200.ALFieldsplitPC"``;
+    the outer KSP (fgmres) stays PETSc's.
+
+    Besides what `VelocityMGPC` needs, the adapter provides ``pressure_operators(pc) -> (B, Minv, bc_dofs)`` (scipy
+    sparse: the assembled (div u, q) block and the inverse pressure mass matrix — `DGMassInv.initialize` assembles the
+    same, solver.py:21-31 — and the Dirichlet velocity dofs) and ``parameters(pc) -> (nu, gamma)``.  Vectors are the
+    monolithic [velocity; pressure] layout of the nest matrix."""
+
+    def initialize(self, pc):
+        super().initialize(pc)
+        ad = _adapter(pc)
+        B, Minv, bc_dofs = ad.pressure_operators(pc)
+        import scipy.sparse as sp
+        keep = np.ones(B.shape[1])
+        keep[np.asarray(bc_dofs, dtype=np.int64)] = 0.0
+        Bz = (B.tocsr() @ sp.diags(keep)).tocsr()
+        Bz.eliminate_zeros()
+        self.mg.ctx.schur_set(Bz, Minv, getattr(ad, "remove_constant_pressure", True))
+        self.n_total = self.n + B.shape[0]
+
+    def apply(self, pc, x, y):
+        nu, gamma = self._params[:2]
+        out = np.empty(self.n_total)
+        self.mg.ctx.schur_apply(nu, gamma, np.ascontiguousarray(x.array_r), out)
+        y.array_w[:] = out

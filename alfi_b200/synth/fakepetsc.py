@@ -74,3 +74,10 @@ class SynthAdapter(HostAdapter):
 
     def parameters(self, pc):
         return (self.problem.nu, self.problem.gamma)
+
+    def pressure_operators(self, pc):
+        """(B, M_p^-1, Dirichlet velocity dofs) of the finest level — what alfi_b200.ALFieldsplitPC adds to the levels."""
+        from .fem import assemble_divergence
+        cfg, fine = self.problem.config, self.problem.finest
+        B, Minv = assemble_divergence(fine.V, cfg.k - 1 if cfg.discretisation == "sv" else 0)
+        return B, Minv, fine.bc_dofs

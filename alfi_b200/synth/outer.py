@@ -113,6 +113,10 @@ class ContinuationSolver:
     config: object
     backend: object
     verbose: bool = False
+    # "host": numpy outer FGMRES + Schur pieces around backend.apply (what PETSc does in a deployment);
+    # "schur": the Schur-complement preconditioner application on the device (backend.schur_apply), host FGMRES;
+    # "device": the whole linear solve of a Newton step on the device (backend.outer_solve)
+    outer: str = "host"
     prob: Problem = field(init=False)
 
     def __post_init__(self):
@@ -201,6 +205,8 @@ class ContinuationSolver:
             levels = [level_input_from_synth(l) for l in self.prob.levels]
             if not self._setup_done:
                 self.backend.setup(levels)
+                if self.outer != "host":
+                    self.backend.setup_outer(self.B, self.Minv, nbc)
                 self._setup_done = True
                 self._transfer_key = (nu, gamma)
             else:
@@ -234,7 +240,12 @@ class ContinuationSolver:
                 return np.concatenate([yu, yp])
 
             rhs = -np.concatenate([Fu, Fp])
-            dz, its, _ = fgmres_outer(Jop, Pop, rhs, tol["ksp_rtol"], tol["ksp_atol"])
+            if self.outer == "device":
+                dz, its, _ = self.backend.outer_solve(nu, gamma, rhs, tol["ksp_rtol"], tol["ksp_atol"], KSP_MAX_IT, 30)
+            elif self.outer == "schur":
+                dz, its, _ = fgmres_outer(Jop, lambda r: self.backend.schur_apply(nu, gamma, r), rhs, tol["ksp_rtol"], tol["ksp_atol"])
+            else:
+                dz, its, _ = fgmres_outer(Jop, Pop, rhs, tol["ksp_rtol"], tol["ksp_atol"])
             lin_its += its
             self.u += dz[:nu_d].reshape(self.u.shape)
             self.p += dz[nu_d:]

@@ -226,6 +226,26 @@ int alfib_cycle_setup(alfib_ctx* ctx, int nlevels, int smoothing);
 /* one application of fieldsplit_0: x = Fcycle(b) on the finest level                           */
 int alfib_cycle_apply(alfib_ctx* ctx, const double* b, double* x);
 
+/* ---- outer Schur-complement fieldsplit: the pieces that bracket fieldsplit_0 in alfi's outer
+ *      solver, so that one outer Krylov iteration costs one PCIe round trip instead of two velocity-block applications
+ *      with their own.  Replaces PCFIELDSPLIT schur / full (solver.py:405-421) with fieldsplit_1 = alfi.solver.DGMassInv
+ *      (solver.py:15-38): y1 = A^-1 r_u ; y_p = -(nu + gamma) M_p^-1 (r_p - B y1), constants removed if remove_constant
+ *      (the pressure nullspace, problem.py:33-38) ; y_u = A^-1 (r_u - B^T y_p), A^-1 = alfib_cycle_apply.
+ *      B (n_p x n_u: the assembled (div u, q) block of the Jacobian, Dirichlet columns removed as Firedrake's bcs do)
+ *      and M_p^-1 (n_p x n_p, block diagonal for the discontinuous pressure spaces) are scalar CSR matrices on the
+ *      dofs of the FINEST level; vectors are [velocity dofs ; pressure dofs].  One GPU; after alfib_cycle_setup.   */
+int alfib_schur_set(alfib_ctx* ctx, int32_t n_p, const int32_t* B_rowptr, const int32_t* B_colidx, const double* B_vals,
+                    const int32_t* Minv_rowptr, const int32_t* Minv_colidx, const double* Minv_vals,
+                    int remove_constant);
+int alfib_schur_apply(alfib_ctx* ctx, double nu, double gamma, const double* r, double* y);
+/* MatMult of the saddle-point Jacobian [A B^T; B 0] (A = the finest level's BSR values)                          */
+int alfib_jacobian_apply(alfib_ctx* ctx, const double* z, double* Jz);
+/* The outer KSP of a Newton step (solver.py:463-474: fgmres, right preconditioning, classical Gram-Schmidt,
+ * restart <= 32, zero initial guess; converged when the recurrence residual <= max(rtol |rhs|, atol)).
+ * iterations: Krylov iterations taken; history[0 .. min(nhistory, iterations + 1)): residual norms (may be NULL). */
+int alfib_outer_solve(alfib_ctx* ctx, double nu, double gamma, const double* rhs, double* x, double rtol, double atol,
+                      int32_t maxit, int32_t restart, int32_t* iterations, double* history, int32_t nhistory);
+
 /* ---- instrumentation: names follow the PETSc events alfi reports (driver.py:80)              */
 enum {
   ALFIB_EV_PCPATCH_APPLY = 0, ALFIB_EV_MATMULT = 1, ALFIB_EV_PROLONG = 2, ALFIB_EV_RESTRICT = 3,

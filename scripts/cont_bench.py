@@ -1,7 +1,9 @@
 """Where the Newton continuation (BASELINE configs[0]) spends its time with the CUDA library as fieldsplit_0:
 wall-clock per backend method, for the condensed-form variants (environment switches of csrc/condense.cu).
 
-    python scripts/cont_bench.py
+    python scripts/cont_bench.py [N [host|schur|device]]     N runs of the default variant; the last argument moves the
+                                                            Schur-complement application / the whole linear solve of a
+                                                            Newton step onto the device (csrc/outer.cu)
 """
 import json
 import os
@@ -52,6 +54,15 @@ class Timed:
     def apply(self, b):
         return self._wrap("apply", b)
 
+    def setup_outer(self, *a):
+        return self._wrap("setup_outer", *a)
+
+    def schur_apply(self, *a):
+        return self._wrap("schur_apply", *a)
+
+    def outer_solve(self, *a):
+        return self._wrap("outer_solve", *a)
+
 
 cfg = CONFIGS[CONT_CONFIG]
 OLD = {"ALFIB_CONDENSE_SHARED": "0", "ALFIB_TILE_V1": "1"}
@@ -59,15 +70,16 @@ VARIANTS = (("warm-up", {}), ("default", {}), ("per-instance blocks, tile v1", O
             ("per-instance blocks, tile v1", OLD), ("dense", {"dense": "1"}), ("default", {}))
 if len(sys.argv) > 1:                       # python scripts/cont_bench.py N: N runs of the default variant
     VARIANTS = (("warm-up", {}),) + (("default", {}),) * int(sys.argv[1])
+OUTER = sys.argv[2] if len(sys.argv) > 2 else "host"
 for label, env in VARIANTS:
     for k in ("ALFIB_CONDENSE_SHARED", "ALFIB_TILE_V1"):
         os.environ.pop(k, None)
     os.environ.update({k: v for k, v in env.items() if k.startswith("ALFIB")})
     backend = Timed(DeviceBackend(cfg.m, device=0, condense=("dense" not in env)))
-    solver = ContinuationSolver(cfg, backend)
+    solver = ContinuationSolver(cfg, backend, outer=OUTER)
     t0 = time.perf_counter()
     infos = [solver.solve(re) for re in CONT_RES]
     dt = time.perf_counter() - t0
-    print(json.dumps({"variant": label, "time_s": dt, "backend_s": backend.t, "calls": backend.n,
+    print(json.dumps({"variant": label, "outer": OUTER, "time_s": dt, "backend_s": backend.t, "calls": backend.n,
                       "linear_iter": [i["linear_iter"] for i in infos]}), flush=True)
     backend.inner.mg.ctx.close()

@@ -3,6 +3,7 @@ pieces are compared with the globally generated problem through the nodes' latti
 nodes, exchange lists of neighbouring ranks match entry by entry, and SpMV / PCApply_PATCH / P_H executed on the
 rank-local data with the two exchange steps reproduce the global results."""
 import dataclasses
+import os
 
 import numpy as np
 import pytest
@@ -28,8 +29,14 @@ def reduce_ghosts(locs, ys):
         ys[r][ll.n_owned:] = 0.0
 
 
+# the three-level 3-D case takes minutes of host generation: ALFIB_SLOW_TESTS=1 runs it (the CPU suite has to stay short;
+# three levels are covered in 2-D, 3-D bricks by the two-level case and on the GPU by scripts/dist_check_bricks.py)
+SLOW = pytest.mark.skipif(not os.environ.get("ALFIB_SLOW_TESTS"), reason="minutes of host generation; set ALFIB_SLOW_TESTS=1")
+
+
 @pytest.mark.parametrize("name,shape", [("ldc2d-sv-k2-tiny", (2, 1)), ("ldc2d-sv-k2-tiny", (2, 2)), ("ldc3d-sv-k3-tiny", (2, 1, 1)),
-                                        ("ldc2d-pkp0-tiny", (3, 1)), ("ldc3d-sv-k3-wtiny2", None), ("ldc3d-pkp0-tiny", (1, 2, 1))])
+                                        ("ldc2d-pkp0-tiny", (3, 1)), pytest.param("ldc3d-sv-k3-wtiny2", None, marks=SLOW),
+                                        ("ldc3d-pkp0-tiny", (1, 2, 1))])
 def test_rank_local_generation_equals_the_global_problem(name, shape):
     cfg = CONFIGS[name] if shape is None else dataclasses.replace(CONFIGS[name], shape=shape)
     shape = cfg.shape
