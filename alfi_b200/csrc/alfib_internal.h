@@ -157,6 +157,12 @@ struct PatchSet {
   std::vector<int> stage_work_start, stage_row_start;   // nstage + 1
   DBuf<int2> stage_work;
   DBuf<int32_t> stage_rows;
+  // patch operators that are not sub-matrices (alfib_level_set_patch_corrections): A_i = A[I_i, I_i] + C_i
+  bool has_corr = false, corr_fresh = false;      // fresh: values received since the operator values changed
+  DBuf<int64_t> corr_off;
+  DBuf<int32_t> corr_rows, corr_cols;
+  DBuf<double> corr_vals;
+  int64_t corr_nnz = 0;
 };
 
 // Exchange lists of one distributed-vector layout (alfib_level_set_halo): local vector = owned dofs
@@ -278,6 +284,7 @@ struct alfib_ctx {
   DBuf<double> coarse_lu, coarse_work, coarse_inv, coarse_partial, coarse_r, coarse_dx;
   int64_t coarse_ld = 0;
   DBuf<int> coarse_piv, coarse_info;
+  DBuf<int32_t> coarse_seppos;
   int coarse_n = 0;
   bool coarse_factored = false;
   Schur schur;                          // outer fieldsplit pieces (alfib_schur_set)

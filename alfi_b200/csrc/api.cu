@@ -51,6 +51,10 @@ void release_patchset(PatchSet& ps) {
   ps.cond.release();
   ps.stage_work.release();
   ps.stage_rows.release();
+  ps.corr_off.release();
+  ps.corr_rows.release();
+  ps.corr_cols.release();
+  ps.corr_vals.release();
 }
 
 // equal split of the block rows across ranks (contiguous ranges)
@@ -206,6 +210,7 @@ int alfib_destroy(alfib_ctx* c) {
   c->d_gate.release();
   c->finfo.release();
   c->coarse_piv.release();
+  c->coarse_seppos.release();
   c->coarse_info.release();
   cycle_graph_invalidate(c);
   comm_peer_close(c);
@@ -418,6 +423,7 @@ int alfib_level_set_bsr_values(alfib_ctx* c, int level, const double* vals, int 
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     L.has_values = true;
     L.ps[ALFIB_PATCHES_SMOOTHER].factored = false;
+    L.ps[ALFIB_PATCHES_SMOOTHER].corr_fresh = false;
     if (level == 0) c->coarse_factored = false;
   });
 }
@@ -660,6 +666,61 @@ int alfib_level_set_sweep_stages(alfib_ctx* c, int level, int which, int32_t nvi
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     ps.nstage = nstage;
     ps.symmetric_sweep = symmetric != 0;
+  });
+}
+
+int alfib_level_set_patch_corrections(alfib_ctx* c, int level, int which, const int64_t* corr_off, const int32_t* rows,
+                                      const int32_t* cols) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(which == 0 || which == 1, "which must be 0 or 1");
+    PatchSet& ps = L.ps[which];
+    ps.factored = false;
+    ps.has_corr = ps.corr_fresh = false;
+    if (!corr_off) {
+      ps.corr_off.release(); ps.corr_rows.release(); ps.corr_cols.release(); ps.corr_vals.release();
+      ps.corr_nnz = 0;
+      return;
+    }
+    ALFIB_REQUIRE(ps.npatch > 0, "alfib_level_set_patches first");
+    ALFIB_REQUIRE(!ps.cond.on, "patch corrections need dense patch inverses (no patch blocks)");
+    ALFIB_REQUIRE(corr_off[0] == 0, "bad correction offsets");
+    const int64_t nnz = corr_off[ps.npatch];
+    ALFIB_REQUIRE(nnz == 0 || (rows && cols), "null correction pattern");
+    for (int p = 0; p < ps.npatch; ++p) {
+      ALFIB_REQUIRE(corr_off[p + 1] >= corr_off[p], "correction offsets must be non-decreasing");
+      const int n = (int)(ps.h_off[p + 1] - ps.h_off[p]);
+      for (int64_t e = corr_off[p]; e < corr_off[p + 1]; ++e) {
+        ALFIB_REQUIRE(rows[e] >= 0 && rows[e] < n && cols[e] >= 0 && cols[e] < n, "correction entry outside its patch");
+        // distinct entries: the kernel adds them without atomics
+        ALFIB_REQUIRE(e == corr_off[p] || rows[e] > rows[e - 1] || (rows[e] == rows[e - 1] && cols[e] > cols[e - 1]),
+                      "correction entries must be sorted by (row, col) and distinct");
+      }
+    }
+    ps.corr_off.upload(corr_off, ps.npatch + 1, c->stream);
+    ps.corr_rows.upload(rows, nnz, c->stream);
+    ps.corr_cols.upload(cols, nnz, c->stream);
+    ps.corr_vals.alloc(nnz);
+    ps.corr_nnz = nnz;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    ps.has_corr = true;
+  });
+}
+
+int alfib_level_set_patch_correction_values(alfib_ctx* c, int level, int which, const double* vals) {
+  return guarded(c, [&] {
+    Level& L = get_level(c, level);
+    ALFIB_REQUIRE(which == 0 || which == 1, "which must be 0 or 1");
+    PatchSet& ps = L.ps[which];
+    ALFIB_REQUIRE(ps.has_corr, "alfib_level_set_patch_corrections first");
+    ALFIB_REQUIRE(vals || ps.corr_nnz == 0, "null correction values");
+    if (ps.corr_nnz) {
+      const cudaMemcpyKind kind = is_device_ptr(vals) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+      CUDA_TRY(cudaMemcpyAsync(ps.corr_vals.p, vals, sizeof(double) * (size_t)ps.corr_nnz, kind, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    ps.factored = false;
+    ps.corr_fresh = true;
   });
 }
 

@@ -301,7 +301,7 @@ void coarse_factor_device(alfib_ctx* c) {
     c->coarse_inv.alloc((size_t)lds * ns);                           // identity, then X_SS (column-major)
     c->coarse_piv.alloc(ns);
     c->coarse_info.alloc(1);
-    DBuf<int32_t> seppos;
+    DBuf<int32_t>& seppos = c->coarse_seppos;               // kept: a cudaMalloc / cudaFree pair per Newton step otherwise
     seppos.alloc(n);
     CUDA_TRY(cudaMemsetAsync(seppos.p, 0xff, sizeof(int32_t) * n, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->coarse_lu.p, 0, sizeof(double) * lds * ns, c->stream));
@@ -320,7 +320,6 @@ void coarse_factor_device(alfib_ctx* c) {
     int info = 0;
     CUDA_TRY(cudaMemcpyAsync(&info, c->coarse_info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    seppos.release();
     if (info != 0) throw DeviceError{ALFIB_ESINGULAR, "coarse Schur complement LU failed, info = " + std::to_string(info)};
     CUDA_TRY(cudaMemsetAsync(c->coarse_inv.p, 0, sizeof(double) * lds * ns, c->stream));
     set_identity_kernel<<<cdiv(ns, 256), 256, 0, c->stream>>>(c->coarse_inv.p, ns, lds);
@@ -333,8 +332,10 @@ void coarse_factor_device(alfib_ctx* c) {
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     ps.factored = true;
-    c->coarse_inv.release();
+    // transient buffers: small ones are kept for the next Newton step (cudaFree / cudaMalloc per call cost more than
+    // the factorisation of a small coarse level)
     if ((size_t)lds * ns * sizeof(double) > ((size_t)256 << 20)) {
+      c->coarse_inv.release();
       c->coarse_work.release();
       c->coarse_lu.release();
     }
@@ -383,7 +384,8 @@ void coarse_factor_device(alfib_ctx* c) {
     launch_condense_blocks(c, *L0, ps, L0->vals.p);
     ps.factored = true;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    c->coarse_inv.release();                      // 8 n^2 bytes: the condensed pieces replace it
+    if ((size_t)ld * n * sizeof(double) > ((size_t)256 << 20))
+      c->coarse_inv.release();                    // 8 n^2 bytes: the condensed pieces replace it
   }
   // the LU and its workspace are transient; small ones are kept for the next Newton step (cudaFree /
   // cudaMalloc per call cost more than the factorisation of a small coarse level)

@@ -80,6 +80,12 @@ struct FactorArgs {
   const int64_t* sc_inst_c;
   const int32_t* sc_inst_ld;
   const double* sc_cbuf;
+  // patch operators that are not sub-matrices (alfib_level_set_patch_corrections): after the gather
+  //   W[rows[e], cols[e]] += vals[e],  e in [corr_off[p], corr_off[p+1]), entries distinct;   null: none
+  const int64_t* corr_off;
+  const int32_t* corr_rows;
+  const int32_t* corr_cols;
+  const double* corr_vals;
 };
 
 enum { PH_GATHER, PH_PANEL_LOAD, PH_INNER_GJ, PH_INBLOCK, PH_FAR_SWAP, PH_FAR_NS, PH_FAR_RS, PH_FAR_MMA, PH_PACK, PH_COUNT };
@@ -205,6 +211,11 @@ __global__ void __launch_bounds__(FT, 1) patch_factor_kernel(FactorArgs a) {
         }
         __syncthreads();                 // the instances of a patch overlap on the separator
       }
+    }
+    if (a.corr_off) {
+      for (int64_t e = a.corr_off[p] + tid; e < a.corr_off[p + 1]; e += FT)
+        W[a.corr_rows[e] + (size_t)a.corr_cols[e] * ld] += a.corr_vals[e];
+      __syncthreads();
     }
     pc.mark(PH_GATHER);
 
@@ -608,6 +619,17 @@ void launch_patch_factor(alfib_ctx* c, const Level& L, PatchSet& ps, const doubl
   a.sc_inst_c = ps.cond.sc_inst_c.p;
   a.sc_inst_ld = ps.cond.sc_inst_ld.p;
   a.sc_cbuf = ps.cond.cbuf.p;
+  a.corr_off = nullptr;
+  a.corr_rows = a.corr_cols = nullptr;
+  a.corr_vals = nullptr;
+  if (ps.has_corr) {
+    ALFIB_REQUIRE(!ps.cond.on, "patch corrections need dense patch inverses (no patch blocks)");
+    ALFIB_REQUIRE(ps.corr_fresh, "alfib_level_set_patch_correction_values has not been called since the values changed");
+    a.corr_off = ps.corr_off.p;
+    a.corr_rows = ps.corr_rows.p;
+    a.corr_cols = ps.corr_cols.p;
+    a.corr_vals = ps.corr_vals.p;
+  }
   a.bs = L.bs;
   a.rowptr = L.rowptr.p;
   a.colidx = L.colidx.p;

@@ -54,6 +54,8 @@ SIGNATURES = {
                                           _i32p, _i32p]),
     "alfib_level_set_patch_blocks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i32p]),
     "alfib_level_set_sweep_stages": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int32, _i32p, C.c_int32, C.c_int]),
+    "alfib_level_set_patch_corrections": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i64p, _i32p, _i32p]),
+    "alfib_level_set_patch_correction_values": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f64p]),
     "alfib_patch_apply_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int]),
     "alfib_patch_storage_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int]),
     "alfib_patch_storage_form": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -312,6 +314,21 @@ class Context:
         nstage = int(st.max()) + 1 if st.size else 0
         self._check(self.lib.alfib_level_set_sweep_stages(self.h, level, which, st.size, _ptr(st, C.c_int32), nstage,
                                                           int(bool(symmetric))))
+
+    def set_patch_corrections(self, level, corr_off, rows, cols, which=PATCHES_SMOOTHER):
+        """A_i = A[I_i, I_i] + C_i: COO pattern of the C_i in patch-local indices (Burman stabilisation; include/alfib.h).
+        None removes them."""
+        if corr_off is None:
+            self._check(self.lib.alfib_level_set_patch_corrections(self.h, level, which, None, None, None))
+            return
+        off = np.ascontiguousarray(corr_off, dtype=np.int64)
+        r, cidx = _i32(rows), _i32(cols)
+        self._check(self.lib.alfib_level_set_patch_corrections(self.h, level, which, _ptr(off, C.c_int64),
+                                                               _ptr(r, C.c_int32), _ptr(cidx, C.c_int32)))
+
+    def set_patch_correction_values(self, level, vals, which=PATCHES_SMOOTHER):
+        v = _Vec(np.ascontiguousarray(vals, dtype=np.float64) if isinstance(vals, np.ndarray) else vals)
+        self._check(self.lib.alfib_level_set_patch_correction_values(self.h, level, which, v.ptr))
 
     def patch_apply_bytes(self, level, which=PATCHES_SMOOTHER):
         """Algorithmic bytes of one application of the patch set (factors + indices + 16 N)."""

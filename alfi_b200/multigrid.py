@@ -33,6 +33,12 @@ class LevelInput:
     patch_blocks: np.ndarray | None = None   # condensed form: block label per patch dof, -1 = separator
     patch_stages: np.ndarray | None = None   # multiplicative composition: stage per entry of the iteration set
     symmetrise_sweep: bool = False           # ... with the backward sweep after the forward one
+    # patch operators that are not sub-matrices (Burman's interior-facet term): A_i = A[I_i, I_i] + C_i,
+    # C_i as COO entries in patch-local indices (pattern once, values with every operator hand-over)
+    patch_corr_off: np.ndarray | None = None
+    patch_corr_rows: np.ndarray | None = None
+    patch_corr_cols: np.ndarray | None = None
+    patch_corr_vals: np.ndarray | None = None
     P: object | None = None               # scipy CSR: scalar per node, or on dofs if P_dof_level
     P_dof_level: bool = False
     cell_offsets: np.ndarray | None = None
@@ -55,7 +61,10 @@ def level_input_from_synth(ld) -> LevelInput:
         li.patch_blocks = ps.blocks
         li.patch_stages = getattr(ps, "stages", None)
         li.symmetrise_sweep = bool(getattr(ps, "symmetrise", False))
-    if ld.patches is None and getattr(ld.level, "bary", False):
+        if getattr(ps, "corrections", None) is not None:
+            pc = ps.corrections
+            li.patch_corr_off, li.patch_corr_rows, li.patch_corr_cols, li.patch_corr_vals = pc.off, pc.rows, pc.cols, ps.corr_vals
+    if ld.patches is None and getattr(ld.level, "bary", False) and not hasattr(ld.pattern, "facet_cells"):
         from .patches import PatchSet, macro_interior_blocks
         free = np.setdiff1d(np.arange(ld.V.ndofs), ld.bc_dofs).astype(np.int32)
         one = PatchSet(offsets=np.array([0, free.size], np.int64), dofs=free, bs=ld.V.bs, order=np.zeros(1, np.int32))
@@ -126,6 +135,10 @@ class DeviceMultigrid:
                 c.set_patches(l, off, dofs, order, cols, PATCHES_SMOOTHER)
                 if blocks is not None:
                     c.set_patch_blocks(l, blocks, PATCHES_SMOOTHER)
+                if li.patch_corr_off is not None:
+                    if nranks > 1:
+                        raise NotImplementedError("patch corrections (Burman stabilisation) are single-GPU")
+                    c.set_patch_corrections(l, li.patch_corr_off, li.patch_corr_rows, li.patch_corr_cols, PATCHES_SMOOTHER)
                 if li.patch_stages is not None:
                     c.set_sweep_stages(l, li.patch_stages, li.symmetrise_sweep, PATCHES_SMOOTHER)
                 if torch_storage:
@@ -172,6 +185,8 @@ class DeviceMultigrid:
         for l, li in enumerate(levels):
             c.set_bsr_values(l, li.vals)
             if l > 0:
+                if li.patch_corr_off is not None:
+                    c.set_patch_correction_values(l, li.patch_corr_vals, PATCHES_SMOOTHER)
                 c.factor(l)
         c.coarse_factor()
 

@@ -39,6 +39,9 @@ class PatchSet:
     centres: np.ndarray | None = None     # (npatch, dim) coordinates of the patches' entities (partitioning only)
     stages: np.ndarray | None = None      # multiplicative composition: stage per entry of `order` (sweep_stages)
     symmetrise: bool = False              # ... followed by the backward sweep (patch_pc_patch_symmetrise_sweep)
+    cells: object | None = None           # scipy CSR (npatch x ncells): the patch cells PCPATCH integrates over
+    corrections: "PatchCorrections | None" = None   # A_i = A[I_i, I_i] + C_i (forms with interior-facet integrals)
+    corr_vals: np.ndarray | None = None   # ... the entries of C for the current operator values (per Newton step)
 
     @property
     def npatch(self):
@@ -64,6 +67,14 @@ def points_to_csr(point_lists, npoints):
     return H
 
 
+def patch_cells(plex, H):
+    """CSR (npatch x ncells): the cells in the star of any point of a patch's point set — the cells PCPATCH
+    integrates over."""
+    Hc = (H.tocsr().astype(np.int32) @ plex.star.astype(np.int32)).tocsr()[:, plex.cStart:plex.cEnd].tocsr()
+    Hc.sort_indices()
+    return Hc
+
+
 def patch_dofs_from_points(plex, V, H, bc_nodes=None, order=None) -> PatchSet:
     """Patch dof lists for point sets H (CSR npatch x npoints) on space V (see module doc)."""
     npatch = H.shape[0]
@@ -71,8 +82,7 @@ def patch_dofs_from_points(plex, V, H, bc_nodes=None, order=None) -> PatchSet:
     nn = np.int64(V.nnodes)
     H = H.tocsr().astype(np.int32)
     # patch cells: cells in the star of any point of ht
-    Hc = (H @ plex.star.astype(np.int32)).tocsr()[:, plex.cStart:plex.cEnd].tocsr()
-    Hc.sort_indices()
+    Hc = patch_cells(plex, H)
     # owned nodes: nodes attached to points of ht
     npt = plex.node_points(V)
     NP = sp.csr_matrix((np.ones(V.nnodes, dtype=np.int32), (npt, np.arange(V.nnodes))),
@@ -104,7 +114,92 @@ def patch_dofs_from_points(plex, V, H, bc_nodes=None, order=None) -> PatchSet:
     dofs = (node[:, None] * bs + np.arange(bs)[None, :]).ravel().astype(np.int32)
     if order is None:
         order = np.arange(npatch, dtype=np.int32)
-    return PatchSet(offsets, dofs, np.asarray(order, dtype=np.int32), bs)
+    return PatchSet(offsets, dofs, np.asarray(order, dtype=np.int32), bs, cells=Hc)
+
+
+@dataclass
+class PatchCorrections:
+    """What separates PCPATCH's patch operator from the sub-matrix of the assembled operator when the form has
+    interior-facet integrals (Burman's stabilisation, alfi/stabilisation.py:156-162): PCPATCH integrates
+    over the patch cells and over the facets whose BOTH cells are patch cells, while A[I_i, I_i] also holds the
+    inside-inside part of the facets on the patch boundary.  A_i = A[I_i, I_i] + C_i with C_i in COO form, patch-local
+    indices, sorted by (patch, row, col); `values(S)` turns the macro-element tensors of the interior facets
+    (`synth.fem.burman_facet_tensors`) into the entries: minus the sum of the boundary facets' inside-inside blocks."""
+    off: np.ndarray            # int64 (npatch + 1)
+    rows: np.ndarray           # int32 patch-local row of every entry
+    cols: np.ndarray
+    src_f: np.ndarray          # entry slot[e] -= S[src_f[e], src_i[e], src_j[e]]
+    src_i: np.ndarray
+    src_j: np.ndarray
+    slot: np.ndarray
+
+    def values(self, S, scale=1.0):
+        return -scale * np.bincount(self.slot, weights=S[self.src_f, self.src_i, self.src_j], minlength=self.rows.size)
+
+
+def facet_corrections(V, ps: PatchSet, facet_cells) -> PatchCorrections:
+    """Patch-boundary facets of every patch of `ps` (interior facets of the mesh with exactly one of their two cells
+    among the patch cells `ps.cells`) and the entries their inside-inside blocks touch.  `facet_cells` (nF, 2): the
+    cells of the interior facets, in the numbering of the facet tensors."""
+    Hc = ps.cells.tocsr()
+    npatch, nc = Hc.shape
+    bs, nl = ps.bs, V.cell_nodes.shape[1]
+    nn = np.int64(V.nnodes)
+    nF = facet_cells.shape[0]
+    # (cell, side) -> interior facets
+    cs = np.concatenate([facet_cells[:, 0], facet_cells[:, 1]])
+    fs = np.concatenate([np.arange(nF), np.arange(nF)])
+    ss = np.concatenate([np.zeros(nF, np.int64), np.ones(nF, np.int64)])
+    o = np.argsort(cs, kind="stable")
+    cs, fs, ss = cs[o], fs[o], ss[o]
+    cptr = np.searchsorted(cs, np.arange(nc + 1))
+    # every (patch, patch cell, interior facet of the cell)
+    p_of = np.repeat(np.arange(npatch, dtype=np.int64), np.diff(Hc.indptr))
+    cells = Hc.indices.astype(np.int64)
+    cnt = cptr[cells + 1] - cptr[cells]
+    pp = np.repeat(p_of, cnt)
+    idx = np.repeat(cptr[cells] - np.concatenate(([0], np.cumsum(cnt)[:-1])), cnt) + np.arange(cnt.sum())
+    ff, sd = fs[idx], ss[idx]
+    other = facet_cells[ff, 1 - sd]
+    pairs = p_of * nc + cells                                     # sorted: CSR rows ascending, indices sorted
+    pos = np.searchsorted(pairs, pp * nc + other)
+    pos[pos == pairs.size] = 0
+    boundary = pairs[pos] != pp * nc + other
+    pp, ff, sd = pp[boundary], ff[boundary], sd[boundary]
+    # patch-local position of the inside cell's nodes
+    pnode = ps.dofs[::bs].astype(np.int64) // bs                  # patch nodes in patch-local order
+    ppatch = np.repeat(np.arange(npatch, dtype=np.int64), np.diff(ps.offsets) // bs)
+    plocal = np.arange(pnode.size) - np.repeat(ps.offsets[:-1] // bs, np.diff(ps.offsets) // bs)
+    pk = ppatch * nn + pnode
+    ok = np.argsort(pk)
+    pk_s, pl_s = pk[ok], plocal[ok]
+    inside = facet_cells[ff, sd]
+    nodes = V.cell_nodes[inside]                                  # (nb, nl)
+    key = pp[:, None] * nn + nodes
+    q = np.searchsorted(pk_s, key)
+    q[q == pk_s.size] = 0
+    loc = np.where(pk_s[q] == key, pl_s[q], -1)                   # (nb, nl): -1 = not a dof of the patch
+    I, J = np.meshgrid(np.arange(nl), np.arange(nl), indexing="ij")
+    li, lj = loc[:, I.ravel()], loc[:, J.ravel()]                 # (nb, nl*nl)
+    keep = (li >= 0) & (lj >= 0)
+    b_idx, e_idx = np.nonzero(keep)
+    li, lj = li[keep], lj[keep]
+    si = sd[b_idx] * nl + I.ravel()[e_idx]
+    sj = sd[b_idx] * nl + J.ravel()[e_idx]
+    ent_p, ent_f = pp[b_idx], ff[b_idx]
+    # one entry per velocity component (the form is the same scalar matrix for each)
+    comp = np.arange(bs)
+    rows = (li[:, None] * bs + comp[None, :]).ravel()
+    cols = (lj[:, None] * bs + comp[None, :]).ravel()
+    ent_p, ent_f, si, sj = (np.repeat(a, bs) for a in (ent_p, ent_f, si, sj))
+    nmax = np.int64(max(int(np.diff(ps.offsets).max()) if npatch else 1, 1))
+    k = (ent_p * nmax + rows) * nmax + cols
+    uk, slot = np.unique(k, return_inverse=True)
+    up = uk // (nmax * nmax)
+    off = np.zeros(npatch + 1, dtype=np.int64)
+    np.cumsum(np.bincount(up, minlength=npatch), out=off[1:])
+    return PatchCorrections(off, ((uk // nmax) % nmax).astype(np.int32), (uk % nmax).astype(np.int32),
+                            ent_f, si, sj, slot)
 
 
 def greedy_colouring(ps: PatchSet, ndofs: int) -> np.ndarray:

@@ -41,6 +41,10 @@ class HostAdapter:
     `plex(pc)`          -> DMPlex-like object (petsc4py DMPlex or SynthPlex)
     `bc_nodes(pc)`      -> node indices of the global Dirichlet conditions
     `options(pc)`       -> PETSc.Options-like object for the PC's prefix
+    `patch_corrections(pc, patches)` (optional) -> None, or (off, rows, cols, vals): what separates PCPATCH's patch
+                           operators from sub-matrices of ``P`` when the form has interior-facet integrals (Burman
+                           stabilisation; include/alfib.h alfib_level_set_patch_corrections).  Called at every set-up;
+                           the pattern must not change.
     """
 
     def operator(self, pc):
@@ -140,13 +144,25 @@ class PatchPC:
             self.stages = sweep_stages(ps, rowptr, colidx)
             c.set_sweep_stages(0, self.stages, self.symmetrise, PATCHES_SMOOTHER)
         c.set_bsr_values(0, vals, colmajor)
+        self._corrections(pc, first=True)
         c.factor(0)
+
+    def _corrections(self, pc, first=False):
+        ad = _adapter(pc)
+        corr = ad.patch_corrections(pc, self.patches) if hasattr(ad, "patch_corrections") else None
+        if corr is None:
+            return
+        off, rows, cols, vals = corr
+        if first:
+            self.ctx.set_patch_corrections(0, off, rows, cols, PATCHES_SMOOTHER)
+        self.ctx.set_patch_correction_values(0, vals, PATCHES_SMOOTHER)
 
     def update(self, pc):
         """Called on every PCSetUp after the first, i.e. once per Newton step: new operator values
         → re-gather and re-invert every patch (PCSetUp_PATCH)."""
         rowptr, colidx, vals, colmajor = _adapter(pc).operator(pc)
         self.ctx.set_bsr_values(0, vals, colmajor)
+        self._corrections(pc)
         self.ctx.factor(0)
 
     def apply(self, pc, x, y):

@@ -75,6 +75,12 @@ class SynthAdapter(HostAdapter):
     def parameters(self, pc):
         return (self.problem.nu, self.problem.gamma)
 
+    def patch_corrections(self, pc, patches):
+        ps = self._ld().patches
+        if ps is None or ps.corrections is None:
+            return None
+        return ps.corrections.off, ps.corrections.rows, ps.corrections.cols, ps.corr_vals
+
     def pressure_operators(self, pc):
         """(B, M_p^-1, Dirichlet velocity dofs) of the finest level — what alfi_b200.ALFieldsplitPC adds to the levels."""
         from .fem import assemble_divergence

@@ -26,7 +26,7 @@ from scipy.special import roots_jacobi
 from .mesh import LOCAL_EDGES, LOCAL_FACES, SimplexMesh
 
 __all__ = ["LagrangeElement", "P1FBElement", "make_element", "VectorSpace", "assemble_velocity_block", "BSR",
-           "reference_tensors"]
+           "reference_tensors", "FacetBlockPattern", "facet_adjacency", "burman_facet_tensors"]
 
 
 # --------------------------------------------------------------------------- reference element
@@ -379,6 +379,106 @@ class BlockPattern:
         """elem: (nc, nl, nl) scalar contributions → (nnzb,) summed per block slot."""
         v = elem.reshape(-1)[self.perm]
         return np.add.reduceat(v, self.start)
+
+
+class FacetBlockPattern(BlockPattern):
+    """Sparsity of a form with interior-facet (dS) integrals — Burman's jump stabilisation, alfi/stabilisation.py:
+    156-162 — on top of the cell integrals: a node couples to the nodes of its cells AND of their facet neighbours.
+    `scatter` takes cell tensors, `scatter_facets` the (2 nl) x (2 nl) macro-element tensors of the interior facets."""
+
+    def __init__(self, V: VectorSpace):
+        cn = V.cell_nodes
+        nn = np.int64(V.nnodes)
+        nl = cn.shape[1]
+        self.facets, self.facet_cells, self.facet_local = facet_adjacency(V.mesh)
+        fn = np.concatenate([cn[self.facet_cells[:, 0]], cn[self.facet_cells[:, 1]]], axis=1)     # (nF, 2 nl)
+        self.facet_nodes = fn
+        ckeys = (cn[:, :, None] * nn + cn[:, None, :]).reshape(-1)
+        fkeys = (fn[:, :, None] * nn + fn[:, None, :]).reshape(-1)
+        uk = np.unique(np.concatenate([ckeys, fkeys]))
+        self.cell_slot = np.searchsorted(uk, ckeys)
+        self.facet_slot = np.searchsorted(uk, fkeys)
+        rows = (uk // nn).astype(np.int64)
+        self.colidx = (uk % nn).astype(np.int32)
+        self.rowptr = np.zeros(V.nnodes + 1, dtype=np.int32)
+        np.add.at(self.rowptr, rows + 1, 1)
+        self.rowptr = np.cumsum(self.rowptr).astype(np.int32)
+        self.rows = rows
+        self.nl = nl
+        self.nnzb = uk.size
+
+    def scatter(self, elem: np.ndarray) -> np.ndarray:
+        return np.bincount(self.cell_slot, weights=elem.reshape(-1), minlength=self.nnzb)
+
+    def scatter_facets(self, elem: np.ndarray) -> np.ndarray:
+        return np.bincount(self.facet_slot, weights=elem.reshape(-1), minlength=self.nnzb)
+
+
+def facet_adjacency(mesh: SimplexMesh):
+    """Interior facets: (facet ids (nF,), their two cells (nF, 2), the local facet index in each (nF, 2))."""
+    cf = mesh.cell_facets
+    nlf = cf.shape[1]
+    f = cf.ravel()
+    order = np.argsort(f, kind="stable")
+    fs = f[order]
+    first = np.flatnonzero(fs[1:] == fs[:-1])
+    c, j = order // nlf, order % nlf
+    return fs[first], np.stack([c[first], c[first + 1]], axis=1), np.stack([j[first], j[first + 1]], axis=1)
+
+
+def _facet_quadrature(dim: int, degree: int):
+    """Barycentric points (q, dim) on a facet of a dim-simplex and weights that sum to one."""
+    if dim == 2:
+        n = degree // 2 + 1
+        x, w = roots_jacobi(n, 0, 0)
+        x, w = (x + 1) / 2, w / 2
+        return np.stack([1 - x, x], axis=1), w
+    pts, w = simplex_quadrature(2, degree)
+    return np.concatenate([1 - pts.sum(axis=1, keepdims=True), pts], axis=1), w / w.sum()
+
+
+def burman_facet_tensors(V: VectorSpace, wind, weight: float):
+    """Macro-element tensors of Burman's stabilisation (alfi/stabilisation.py:139-162),
+
+        0.5 * weight * avg(h)^2 * beta * dot(jump(grad(u), n), jump(grad(v), n)) * dS,
+        h = FacetArea (2-D) / FacetArea^0.5 (3-D),   beta = avg(facet_avg(sqrt(inner(wind, wind) + 1e-10))),
+
+    for every interior facet: S[f, a*nl + i, b*nl + j] couples node i of side a with node j of side b; the form is the
+    same scalar matrix for every velocity component (jump(grad(u), n) = the jump of the normal derivative, component
+    by component).  Returns (facet ids, cells (nF, 2), S (nF, 2 nl, 2 nl))."""
+    mesh, d, el = V.mesh, V.mesh.dim, V.element
+    nl = el.nnodes
+    fid, fc, fj = facet_adjacency(mesh)
+    lam, wq = _facet_quadrature(d, 2 * el.degree)
+    LF = LOCAL_EDGES[2] if d == 2 else LOCAL_FACES[3]
+    opp = np.array([next(v for v in range(d + 1) if v not in lf) for lf in LF])
+    PHI = np.empty((d + 1, lam.shape[0], nl))
+    DPHI = np.empty((d + 1, lam.shape[0], nl, d))
+    for j, lf in enumerate(LF):                       # facet vertices and cell vertices are both in ascending global order
+        lamK = np.zeros((lam.shape[0], d + 1))
+        lamK[:, list(lf)] = lam
+        PHI[j], DPHI[j] = el.tabulate(lamK[:, 1:]), el.tabulate_grad(lamK[:, 1:])
+    G, _ = cell_geometry(mesh)
+    gradlam = np.concatenate([-G.sum(axis=1, keepdims=True), G], axis=1)         # grad of the barycentric coordinates
+    dn = []
+    for a in range(2):
+        c, j = fc[:, a], fj[:, a]
+        g = gradlam[c, opp[j]]
+        n = -g / np.linalg.norm(g, axis=1, keepdims=True)                        # outward normal of side a
+        Gn = np.einsum("fab,fb->fa", G[c], n)
+        dn.append(np.einsum("fqia,fa->fqi", DPHI[j], Gn))                        # grad(phi_i) . n_a at the facet points
+    X = mesh.coords[mesh.facets[fid]]
+    if d == 2:
+        area = np.linalg.norm(X[:, 1] - X[:, 0], axis=1)
+        h = area
+    else:
+        area = 0.5 * np.linalg.norm(np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), axis=1)
+        h = np.sqrt(area)
+    wf = np.einsum("fqi,fib->fqb", PHI[fj[:, 0]], wind[V.cell_nodes[fc[:, 0]]])
+    beta = np.sqrt(np.einsum("fqb,fqb->fq", wf, wf) + 1e-10) @ wq
+    DN = np.concatenate(dn, axis=2)
+    S = np.einsum("f,q,fqi,fqj->fij", 0.5 * weight * h ** 2 * beta * area, wq, DN, DN, optimize=True)
+    return fid, fc, S
 
 
 def cell_geometry(mesh: SimplexMesh):

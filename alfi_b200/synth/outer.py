@@ -168,6 +168,8 @@ class ContinuationSolver:
                 vals = nu * lin["visc"] + gamma * lin["div"]
                 if advect != 0.0:
                     vals = vals + advect * ld.adv1
+                    if cfg.stabilisation == "burman":           # F += advect * stabilisation_form (solver.py:233-234)
+                        vals = vals + advect * ld.stab
                 self.M1 = _bsr(ld, vals).to_csr()
         self.Afine = self.prob.finest.A.to_csr()
 

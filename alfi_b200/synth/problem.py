@@ -14,10 +14,12 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from ..patches import PatchSet, greedy_colouring, macro_interior_blocks, patch_dofs_from_points, sweep_stages
+from ..patches import (PatchSet, facet_corrections, greedy_colouring, macro_interior_blocks, patch_dofs_from_points,
+                       sweep_stages)
 from ..relaxation import macro_star_points, star_points, iteration_order
 from ..transfer import cell_patch_set
-from .fem import BSR, BlockPattern, VectorSpace, apply_dirichlet, assemble_parts, assemble_velocity_block
+from .fem import (BSR, BlockPattern, FacetBlockPattern, VectorSpace, apply_dirichlet, assemble_parts, assemble_velocity_block,
+                  burman_facet_tensors)
 from .hierarchy import Level, build_hierarchy, build_hierarchy_from, prolongation_matrix
 
 __all__ = ["Config", "CONFIGS", "LevelData", "Problem", "build_problem", "lid_wind"]
@@ -46,6 +48,9 @@ class Config:
     shape: tuple = ()            # ldc: box [0, length * shape[a]] with N * shape[a] base cells per axis (() = cube)
     composition: str = "additive"   # "multiplicative": --patch-composition multiplicative (solver.py:306-308): sequential
                                     # sweep in the relaxation direction + the backward sweep (symmetrise_sweep)
+    stabilisation: str = "none"     # "burman": --stabilisation-type burman (solver.py:226-228, stabilisation.py:139-162):
+                                    # interior-facet jump term; the patch operators are then NOT sub-matrices
+    stab_weight: float = 5e-3       # --stabilisation-weight of the reference's jobs (examples/Makefile:12-16)
 
     @property
     def m(self):
@@ -101,6 +106,16 @@ CONFIGS = {
     "ldc3d-sv-k3-wtiny2": Config("ldc3d-sv-k3-wtiny2", 3, 1, 2, "sv", 3, "macro", True, re=100.0, sort_order="0+:1-", shape=(2, 1, 1)),
     # scaled-down members of the same families (tests, smoke, CPU-baseline sample)
     "ldc2d-sv-k2-tiny": Config("ldc2d-sv-k2-tiny", 2, 2, 1, "sv", 2, "macro", True, re=100.0, sort_order="0+:1-"),
+    # --stabilisation-type burman --stabilisation-weight 5e-3: what the reference's own Scott-Vogelius jobs run with
+    # (examples/Makefile:12-16, 24-25; generate_submission:77).  Patch operators are not sub-matrices, the
+    # macro-cell interiors couple across macro faces: dense patch inverses + patch corrections.
+    "ldc2d-sv-k2-burman": Config("ldc2d-sv-k2-burman", 2, 10, 1, "sv", 2, "macro", True, re=1000.0, sort_order="0+:1-",
+                                 stabilisation="burman"),
+    "ldc2d-sv-k2-tiny-burman": Config("ldc2d-sv-k2-tiny-burman", 2, 2, 1, "sv", 2, "macro", True, re=100.0, sort_order="0+:1-",
+                                      stabilisation="burman"),
+    "ldc3d-sv-k3-tiny-burman": Config("ldc3d-sv-k3-tiny-burman", 3, 1, 1, "sv", 3, "macro", True, re=100.0, sort_order="0+:1-",
+                                      stabilisation="burman"),
+    "ldc2d-pkp0-tiny-burman": Config("ldc2d-pkp0-tiny-burman", 2, 2, 2, "pkp0", 2, "star", False, re=100.0, stabilisation="burman"),
     "ldc2d-pkp0-tiny": Config("ldc2d-pkp0-tiny", 2, 2, 2, "pkp0", 2, "star", False, re=100.0),
     "ldc3d-sv-k3-tiny": Config("ldc3d-sv-k3-tiny", 3, 1, 1, "sv", 3, "macro", True, re=100.0, sort_order="0+:1-"),
     "ldc3d-pkp0-tiny": Config("ldc3d-pkp0-tiny", 3, 1, 2, "pkp0", 1, "star", False, re=100.0, element="p1fb"),
@@ -199,8 +214,10 @@ def smoother_patches(cfg: Config, ld: LevelData) -> PatchSet:
     ps = patch_dofs_from_points(plex, ld.V, H, bc_nodes=ld.bc_nodes, order=order)
     ps.centres = coords
     greedy_colouring(ps, ld.V.ndofs)
-    if cfg.bary:
+    if cfg.bary and cfg.stabilisation != "burman":     # the jump terms couple the macro-cell interiors across macro faces
         ps.blocks = macro_interior_blocks(plex, ld.V, ps)
+    if cfg.stabilisation == "burman":
+        ps.corrections = facet_corrections(ld.V, ps, ld.pattern.facet_cells)
     if cfg.composition == "multiplicative":
         ps.stages = sweep_stages(ps, ld.pattern.rowptr, ld.pattern.colidx)
         ps.symmetrise = True                     # solver.py:324: symmetrise_sweep = multiplicative
@@ -229,6 +246,19 @@ def assemble_level(cfg: Config, ld: LevelData, nu: float, gamma: float, advect: 
         adv = assemble_parts(ld.V, ld.pattern, wind, cfg.discretisation, want=("adv1", "adv2"))
         ld.adv1 = adv["adv1"]
         vals += advect * (adv["adv1"] + adv["adv2"])
+        if cfg.stabilisation == "burman":
+            # F += advect * stabilisation_form (solver.py:233-234); the wind inside beta is a frozen copy of the state
+            # (stabilisation.py:19-44), so the term is linear in u and enters residual and Jacobian alike
+            _, _, S = burman_facet_tensors(ld.V, wind, cfg.stab_weight)
+            sv = ld.pattern.scatter_facets(S)
+            ld.stab = np.zeros_like(vals)
+            for r in range(ld.V.bs):
+                ld.stab[:, r, r] = sv
+            vals += advect * ld.stab
+            if ld.patches is not None and ld.patches.corrections is not None:
+                ld.patches.corr_vals = ld.patches.corrections.values(S, advect)
+    elif cfg.stabilisation == "burman" and ld.patches is not None and ld.patches.corrections is not None:
+        ld.patches.corr_vals = np.zeros(ld.patches.corrections.rows.size)
     ld.A = apply_dirichlet(_bsr(ld, vals), ld.bc_nodes, ld.pattern.rows)
     return ld.A
 
@@ -280,10 +310,14 @@ def build_problem(cfg: Config | str, nu: float | None = None, with_transfer: boo
     for lev in hier:
         V = VectorSpace(lev.mesh, cfg.k, cfg.element)
         bc = V.tagged_boundary_nodes(cfg.dirichlet_tags) if cfg.domain == "bfs" else V.boundary_nodes()
-        ld = LevelData(lev.index, lev, V, BlockPattern(V), bc.astype(np.int32))
+        burman = cfg.stabilisation == "burman"
+        ld = LevelData(lev.index, lev, V, FacetBlockPattern(V) if burman else BlockPattern(V), bc.astype(np.int32))
+        if lev.index > 0 and burman:
+            ld.patches = smoother_patches(cfg, ld)       # before the assembly: it fills the patch corrections
         assemble_level(cfg, ld, nu, cfg.gamma)
         if lev.index > 0:
-            ld.patches = smoother_patches(cfg, ld)
+            if not burman:
+                ld.patches = smoother_patches(cfg, ld)
             if cfg.element == "p1fb":
                 # PkP0SchoeberlTransfer.standard_transfer -> BubbleTransfer (alfi/transfer.py:334-356)
                 from ..bubble import bubble_transfer_matrix
@@ -293,7 +327,7 @@ def build_problem(cfg: Config | str, nu: float | None = None, with_transfer: boo
                 ld.P = prolongation_matrix(levels[-1].V, V, hier[lev.index - 1].c2f)
             if with_transfer:
                 ld.cell_patches, ld.cb_nodes = cell_patch_set(hier, lev.index, V, cfg.bary)
-                if cfg.bary:
+                if cfg.bary and not burman:
                     ld.cell_patches.blocks = macro_interior_blocks(lev.plex, V, ld.cell_patches)
                 assemble_transfer(cfg, ld, nu, cfg.gamma)
         levels.append(ld)

@@ -172,6 +172,18 @@ int alfib_level_set_patch_blocks(alfib_ctx* ctx, int level, int which, const int
  * returns the set to additive composition.                                                                  */
 int alfib_level_set_sweep_stages(alfib_ctx* ctx, int level, int which, int32_t nvisit, const int32_t* stage_of_visit,
                                  int32_t nstage, int symmetric);
+/* Patch operators that are NOT sub-matrices of the level operator.  With Burman's interior-facet
+ * stabilisation (alfi/stabilisation.py:139-162, --stabilisation-type burman: what the reference's Scott-Vogelius jobs
+ * run with, examples/Makefile:12-16) PCPATCH integrates a patch over its cells and over the facets whose BOTH cells are
+ * patch cells, while A[I_i, I_i] also holds the inside-inside part of the facet integrals on the patch boundary.  The
+ * host hands the difference over: A_i = A[I_i, I_i] + C_i, C_i in COO form with patch-local indices (rows / cols index
+ * the patch's dof list), entries of patch i = [corr_off[i], corr_off[i+1]), sorted by (row, col) and distinct.  The
+ * pattern is set once (after alfib_level_set_patches); the values follow every alfib_level_set_bsr_values, before
+ * alfib_level_factor (which refuses to run on stale ones).  Dense inverses only: the jump terms couple the macro-cell
+ * interiors across macro faces, so there is no block structure to condense.  corr_off = NULL removes them.        */
+int alfib_level_set_patch_corrections(alfib_ctx* ctx, int level, int which, const int64_t* corr_off,
+                                      const int32_t* rows, const int32_t* cols);
+int alfib_level_set_patch_correction_values(alfib_ctx* ctx, int level, int which, const double* vals);
 /* algorithmic bytes of one application of that patch set: stored factors + index data + 16 N   */
 int64_t alfib_patch_apply_bytes(alfib_ctx* ctx, int level, int which);
 /* bytes of device storage the inverse factors of that patch set need                          */

@@ -20,7 +20,10 @@ class OracleBackend:
         lv = hp.OracleLevel(A=A, bc_dofs=np.asarray(li.bc_dofs), bs=li.bs)
         if li.patch_offsets is not None:
             lv.offsets, lv.dofs, lv.order = li.patch_offsets, li.patch_dofs, li.patch_order
-            lv.factors = hp.factor_patches(hp.patch_matrices(A, lv.offsets, lv.dofs), self.mode)
+            corr = None
+            if getattr(li, "patch_corr_off", None) is not None:
+                corr = (li.patch_corr_off, li.patch_corr_rows, li.patch_corr_cols, li.patch_corr_vals)
+            lv.factors = hp.factor_patches(hp.patch_matrices(A, lv.offsets, lv.dofs, corr), self.mode)
         if li.P is not None:
             if old is not None:
                 lv.P = old.P

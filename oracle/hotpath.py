@@ -29,18 +29,27 @@ __all__ = ["OracleLevel", "patch_matrices", "factor_patches", "smoother_apply", 
 
 
 # --------------------------------------------------------------------------- S1: patch setup
-def patch_matrices(A_csr, offsets, dofs):
-    """A_i = A[I_i, I_i] for every patch.
+def patch_matrices(A_csr, offsets, dofs, corr=None):
+    """A_i = A[I_i, I_i] (+ C_i) for every patch.
 
     PCPATCH with ``save_operators`` + ``precompute_element_tensors`` (alfi/solver.py:320,325)
     sums the element tensors of the patch cells restricted to the kept dofs (Appendix A.2).
     Without interior-facet integrals (stabilisation none/supg/gls) every cell containing two
     kept dofs is a patch cell, so this equals the sub-matrix of the assembled operator.
+    With Burman's interior-facet term (stabilisation.py:156-162) PCPATCH integrates only over the
+    facets whose both cells are patch cells, and the difference to the sub-matrix is handed over as
+    ``corr = (off, rows, cols, vals)``: COO entries in patch-local indices (SURVEY H4;
+    tests/test_burman.py checks them against a patch-by-patch assembly).
     """
     out = []
     for i in range(len(offsets) - 1):
         I = dofs[offsets[i]:offsets[i + 1]]
-        out.append(A_csr[I][:, I].toarray() if I.size else np.zeros((0, 0)))
+        M = A_csr[I][:, I].toarray() if I.size else np.zeros((0, 0))
+        if corr is not None:
+            off, rows, cols, vals = corr
+            e = slice(off[i], off[i + 1])
+            np.add.at(M, (rows[e], cols[e]), vals[e])
+        out.append(M)
     return out
 
 
@@ -154,7 +163,10 @@ def level_from_host(ld, mode="inverse", with_transfer=True, transfer_mode="lu"):
     if ld.patches is not None:
         ps = ld.patches
         lv.offsets, lv.dofs, lv.order = ps.offsets, ps.dofs, ps.order
-        lv.factors = factor_patches(patch_matrices(A, ps.offsets, ps.dofs), mode)
+        corr = None
+        if getattr(ps, "corrections", None) is not None:
+            corr = (ps.corrections.off, ps.corrections.rows, ps.corrections.cols, ps.corr_vals)
+        lv.factors = factor_patches(patch_matrices(A, ps.offsets, ps.dofs, corr), mode)
     if ld.P is not None:
         lv.P = ld.P.tocsr() if getattr(ld, "P_dof_level", False) else sp.kron(ld.P, sp.identity(bs), format="csr")
         if with_transfer and ld.cell_patches is not None:
