@@ -288,6 +288,7 @@ struct alfib_ctx {
   int coarse_n = 0;
   bool coarse_factored = false;
   Schur schur;                          // outer fieldsplit pieces (alfib_schur_set)
+  std::vector<void*> host_registered;   // caller buffers page-locked through alfib_host_register
   // profiling
   int profile = 0;
   double ev_ms[ALFIB_MAX_LEVELS][ALFIB_EV_COUNT] = {{0}};

@@ -212,6 +212,8 @@ int alfib_destroy(alfib_ctx* c) {
   c->coarse_piv.release();
   c->coarse_seppos.release();
   c->coarse_info.release();
+  for (void* p : c->host_registered) cudaHostUnregister(p);
+  c->host_registered.clear();
   cycle_graph_invalidate(c);
   comm_peer_close(c);
   comm_destroy(c);
@@ -253,6 +255,30 @@ int alfib_synchronize(alfib_ctx* c) {
 int64_t alfib_launch_count(const alfib_ctx* c) { return c ? c->launches : -1; }
 
 void* alfib_stream(alfib_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int alfib_host_register(alfib_ctx* c, void* ptr, int64_t bytes) {
+  return guarded(c, [&] {
+    ALFIB_REQUIRE(ptr && bytes > 0, "bad host buffer");
+    if (std::find(c->host_registered.begin(), c->host_registered.end(), ptr) != c->host_registered.end()) return;
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {       // e.g. a torch pinned tensor: nothing to do, nothing to undo
+      cudaGetLastError();
+      return;
+    }
+    CUDA_TRY(e);
+    c->host_registered.push_back(ptr);
+  });
+}
+
+int alfib_host_unregister(alfib_ctx* c, void* ptr) {
+  return guarded(c, [&] {
+    auto it = std::find(c->host_registered.begin(), c->host_registered.end(), ptr);
+    if (it == c->host_registered.end()) return;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->host_registered.erase(it);
+    CUDA_TRY(cudaHostUnregister(ptr));
+  });
+}
 
 int alfib_comm_unique_id(void* out128) {
   if (!out128) return ALFIB_EINVAL;

@@ -38,6 +38,8 @@ SIGNATURES = {
     "alfib_synchronize": (C.c_int, [C.c_void_p]),
     "alfib_launch_count": (C.c_int64, [C.c_void_p]),
     "alfib_stream": (C.c_void_p, [C.c_void_p]),
+    "alfib_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "alfib_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "alfib_comm_unique_id": (C.c_int, [C.c_void_p]),
     "alfib_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "alfib_comm_peer_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -189,6 +191,17 @@ class Context:
     @property
     def stream(self):
         return int(self.lib.alfib_stream(self.h) or 0)
+
+    def host_register(self, arr):
+        """Page-lock a numpy array that will be handed over repeatedly (operator values, vectors); the array is kept
+        alive by the context until `host_unregister` / `close`."""
+        if not (isinstance(arr, np.ndarray) and arr.flags.c_contiguous):
+            raise AlfibError("host_register takes a C-contiguous numpy array")
+        self._check(self.lib.alfib_host_register(self.h, arr.ctypes.data, arr.nbytes))
+        self._keep.append(arr)
+
+    def host_unregister(self, arr):
+        self._check(self.lib.alfib_host_unregister(self.h, arr.ctypes.data))
 
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -179,10 +179,16 @@ class DeviceMultigrid:
         self._storage.append(buf)
         self.ctx.bind_patch_storage(level, buf, which)
 
-    def update_operators(self, levels):
-        """Once per Newton step: new BSR values on every level, patch factors, coarse LU."""
+    def update_operators(self, levels, pin_values=False):
+        """Once per Newton step: new BSR values on every level, patch factors, coarse LU.  pin_values: page-lock the
+        value arrays on first sight (they must then be the SAME arrays, refilled, on later calls — as PETSc's are)."""
         c = self.ctx
         for l, li in enumerate(levels):
+            if pin_values and isinstance(li.vals, np.ndarray) and li.vals.flags.c_contiguous and li.vals.nbytes >= (1 << 20):
+                seen = self.__dict__.setdefault("_pinned", set())
+                if li.vals.ctypes.data not in seen:
+                    c.host_register(li.vals)
+                    seen.add(li.vals.ctypes.data)
             c.set_bsr_values(l, li.vals)
             if l > 0:
                 if li.patch_corr_off is not None:

@@ -181,7 +181,9 @@ class ContinuationSolver:
         return Fu, Fp
 
     # -- one Reynolds number ----------------------------------------------------------------------
-    def solve(self, re):
+    def solve(self, re, min_newton=0):
+        """One Reynolds number.  min_newton: take at least that many Newton steps even if the residual already meets
+        the tolerances (used to polish a converged state: scripts/cont3d.py)."""
         cfg = self.config
         tdim = self.d
         tol = tolerances(tdim)
@@ -202,7 +204,7 @@ class ContinuationSolver:
             fnorm0 = fnorm if fnorm0 is None else fnorm0
             if self.verbose:
                 print("  Re %g  SNES %d  |F| = %.6e" % (re, newton, fnorm), flush=True)
-            if fnorm <= max(tol["snes_atol"], tol["snes_rtol"] * fnorm0) or newton == SNES_MAX_IT:
+            if (newton >= min_newton and fnorm <= max(tol["snes_atol"], tol["snes_rtol"] * fnorm0)) or newton == SNES_MAX_IT:
                 break
             levels = [level_input_from_synth(l) for l in self.prob.levels]
             if not self._setup_done:

@@ -328,6 +328,24 @@ def ours(args):
             log("rank %d: per-Newton-step setup #%d %.3fs (values hand-over %.3fs, patch inverses + coarse inverse %.3fs)"
                 % (rank, rep, newton_setup_s, handover[0], newton_setup_s - handover[0]))
         make_mg.handover_s = handover[0]
+        # the same with the value arrays page-locked once (alfib_host_register: what a shim does with PETSc's value
+        # arrays, whose addresses do not change between Newton steps): first pass registers, second is the steady state
+        make_mg.pinned = None
+        if lv_in is not None and hasattr(mg, "update_operators") and not distributed:
+            try:
+                for rep in range(2):
+                    handover[0] = 0.0
+                    mg.ctx.set_bsr_values = timed_set
+                    t0 = time.time()
+                    mg.update_operators(lv_in, pin_values=True)
+                    mg.ctx.synchronize()
+                    dt = time.time() - t0
+                    mg.ctx.set_bsr_values = orig_set
+                    log("rank %d: per-Newton-step setup, page-locked values #%d %.3fs (hand-over %.3fs)" % (rank, rep, dt, handover[0]))
+                make_mg.pinned = {"per_newton_step": dt, "values_handover": handover[0], "device_work": dt - handover[0]}
+            except Exception as e:      # noqa: BLE001
+                mg.ctx.set_bsr_values = orig_set
+                make_mg.pinned = {"error": repr(e)}
         return mg, setup_s, newton_setup_s
 
     def all_ok(flag):
@@ -545,17 +563,21 @@ def ours(args):
                 continuation["pressure_rel_diff_vs_cpu"] = float(np.linalg.norm(sdev.p - sref.p) / np.linalg.norm(sref.p))
         except Exception as e:      # noqa: BLE001
             continuation = {"error": repr(e)}
-        if args.continuation_3d and isinstance(continuation, dict) and "error" not in continuation:
-            # opt-in: the same continuation on a 3-D Scott-Vogelius k=3 mesh (the family BASELINE's metric names).  The
-            # host stand-in assembles in numpy (~4 s per Newton step at 185 k dofs, ~30 s at cfg5's size), which is not the
-            # library's job, so the line splits the time into library and host parts.
+        if not args.no_continuation_3d and isinstance(continuation, dict) and "error" not in continuation:
+            # North-star condition 3 on the family BASELINE's metric names: the 3-D Scott-Vogelius k = 3 continuation on the
+            # reference's ladder Re = 1, 10, 100, 200, ... against the committed fixture of the CPU oracle with LU patch
+            # solves (tests/golden/continuation_3d_small.npz, written by scripts/cont3d.py oracle in hours of CPU time):
+            # Newton counts equal, Krylov counts within +-1 per Newton step, final u / p within 1e-8.  The host stand-in
+            # assembles in numpy, which is not the library's job; `outer` says where the linear solves ran.
             try:
-                from alfi_b200.multigrid import DeviceBackend
-                from alfi_b200.synth.problem import CONFIGS as _C3
-                name3 = args.continuation_3d
-                res3 = [int(r) for r in args.continuation_3d_re.split(",")]
-                c3, _ = run_continuation(DeviceBackend(_C3[name3].m, device=local), "CUDA library (alfib_cycle_apply)", name3, res3)
-                continuation["three_d"] = c3
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("cont3d", os.path.join(ROOT, "scripts", "cont3d.py"))
+                cont3d = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(cont3d)
+                fixture = os.path.join(ROOT, "tests", "golden", "continuation_3d_small.npz")
+                quiet = lambda *a: print("[bench] 3-D continuation:", *a, file=sys.stderr, flush=True)   # noqa: E731
+                continuation["three_d"] = cont3d.compare_with_fixture(args.continuation_3d, fixture, args.continuation_3d_outer,
+                                                                      device=local, log=quiet)
             except Exception as e:      # noqa: BLE001
                 continuation["three_d"] = {"error": repr(e)}
 
@@ -593,6 +615,7 @@ def ours(args):
         "breakdown_ms": breakdown, "profile_pass_ms_per_step": prof_ms, "setup_s": {"device_upload_factor": setup_s, "per_newton_step": newton_setup_s,
                     "per_newton_step_values_handover": getattr(make_mg, "handover_s", None),
                     "per_newton_step_device_work": newton_setup_s - getattr(make_mg, "handover_s", 0.0),
+                    "page_locked_values": getattr(make_mg, "pinned", None),
                     "note": "steady state (second refresh); Schur-complement setup of the condensed inverses"}, "continuation": continuation,
         "residual_reduction": red,
     }
@@ -619,9 +642,11 @@ def main():
     ap.add_argument("--deterministic", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-continuation", action="store_true")
-    ap.add_argument("--continuation-3d", default="", metavar="CONFIG",
-                    help="also run the Newton continuation on this 3-D config (e.g. ldc3d-sv-k3-half); minutes of host assembly")
-    ap.add_argument("--continuation-3d-re", default="10,100,200,300,400,500", help="Reynolds numbers of --continuation-3d")
+    ap.add_argument("--no-continuation-3d", action="store_true")
+    ap.add_argument("--continuation-3d", default="ldc3d-sv-k3-small", metavar="CONFIG",
+                    help="3-D configuration of the committed continuation fixture (tests/golden/continuation_3d_small.npz)")
+    ap.add_argument("--continuation-3d-outer", default="device", choices=["host", "schur", "device"],
+                    help="where the outer linear solves of the 3-D continuation run (csrc/outer.cu for schur / device)")
     ap.add_argument("--peer-memory", type=int, default=1, help="N > 1: NVLink peer-memory exchanges (default) instead of NCCL")
     ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
                     help="N > 1: the same problem sharded (strong) or one cfg5-sized brick per rank, generated rank-locally (weak)")

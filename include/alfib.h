@@ -70,6 +70,14 @@ int64_t alfib_launch_count(const alfib_ctx* ctx);
 /* CUDA stream handle (cudaStream_t) the ctx enqueues on, for event timing by the caller */
 void* alfib_stream(alfib_ctx* ctx);
 
+/* Optional: page-lock a HOST buffer the caller hands over repeatedly (the value array of the level operator, which
+ * PETSc keeps at a fixed address from one Newton step to the next; right-hand-side / solution vectors), so that the
+ * copies of alfib_level_set_bsr_values / alfib_cycle_apply run at PCIe speed instead of through the driver's staging
+ * of pageable memory (1.8 GB of values per Newton step on the headline configuration).  The buffer must stay allocated
+ * until alfib_host_unregister or alfib_destroy; registering twice, or a buffer that is already page-locked, is a no-op. */
+int alfib_host_register(alfib_ctx* ctx, void* ptr, int64_t bytes);
+int alfib_host_unregister(alfib_ctx* ctx, void* ptr);
+
 /* Multi-GPU: one rank per GPU on one NVSwitch box.  Each rank passes only ITS patches to
  * alfib_level_set_patches (the owned vertices of the DMPlex vertex-overlap partition the
  * reference uses, solver.py:604-605, 661-662, relaxation.py:120-121); level vectors are
