@@ -714,11 +714,12 @@ void launch_condensed_apply(alfib_ctx* c, const PatchSet& ps, const double* x, P
                                                                            plain_out(nullptr), cd.g1.p);
     c->launches++;
   }
-  // ALFIB_FUSE_INDEX=1 (tile op v2 only): K2 and K3b are folded into the source fetch of K3 / K4
-  // Default: fused on SMALL sets (launch-bound: two launches fewer per application), separate kernels on large ones
-  // (measured on cfg5's finest level: fused 0.583 ms against 0.566 ms; the fused source fetch stalls the matrix stream).
+  // ALFIB_FUSE_INDEX=1 (tile op v2 only): K2 and K3b are folded into the source fetch of K3 / K4.  Off by default:
+  // measured on B200 (profiles/bench_r2_*): cfg5's finest level 0.583 ms fused against 0.566 ms, and with the fused form
+  // on the SMALL sets only (level 1, coarse patch) a cycle is 1.9 ms slower (PCPATCHApply 16.1 against 14.2 ms, coarse
+  // solve 0.63 against 0.54 ms) — under graph replay the two launches cost less than the stalled matrix stream.
   const char* env_fuse = std::getenv("ALFIB_FUSE_INDEX");
-  const bool fuse = !v1 && (env_fuse ? env_fuse[0] == '1' : h.nsep_total < (1 << 18));
+  const bool fuse = !v1 && env_fuse && env_fuse[0] == '1';
   const FusedSrc fs_rhs{cd.sepdofs.p, cd.cptr.p, cd.cg1.p, cd.g1.p};
   const FusedSrc fs_z{nullptr, cd.zptr.p, cd.zsrc.p, cd.us.p};
   // K2: separator right-hand sides
