@@ -161,8 +161,9 @@ class ContinuationSolver:
         cfg = self.config
         winds = self._winds()
         nl = len(self.prob.levels)
+        stab = getattr(self, "_stab_winds", None)
         for l, ld in enumerate(self.prob.levels):
-            assemble_level(cfg, ld, nu, gamma, advect, wind=winds[l])
+            assemble_level(cfg, ld, nu, gamma, advect, wind=winds[l], stab_wind=None if stab is None else stab[l])
             if l == nl - 1:
                 lin = _linear_parts(cfg, ld)
                 vals = nu * lin["visc"] + gamma * lin["div"]
@@ -181,12 +182,18 @@ class ContinuationSolver:
         return Fu, Fp
 
     # -- one Reynolds number ----------------------------------------------------------------------
-    def solve(self, re, min_newton=0):
+    def solve(self, re, min_newton=0, ksp_tol=None):
         """One Reynolds number.  min_newton: take at least that many Newton steps even if the residual already meets
-        the tolerances (used to polish a converged state: scripts/cont3d.py)."""
+        the tolerances; ksp_tol = (rtol, atol) overrides the linear tolerances (both used to polish a converged state:
+        scripts/cont3d.py — the reference's ksp_atol would stop the linear solve of such a step at iteration 0)."""
         cfg = self.config
         tdim = self.d
         tol = tolerances(tdim)
+        if ksp_tol is not None:
+            tol["ksp_rtol"], tol["ksp_atol"] = ksp_tol
+        # the wind inside the stabilisation is the state BEFORE this Reynolds number's Newton solve (solver.py:270-271:
+        # stabilisation.update(z) precedes solver.solve(); Stabilisation.update injects it to the coarse levels)
+        self._stab_winds = {l: w.copy() for l, w in self._winds().items()} if cfg.stabilisation == "burman" else None
         nu = cfg.length * 1.0 / re if re > 0 else cfg.length
         advect = 1.0 if re > 0 else 0.0
         gamma = cfg.gamma

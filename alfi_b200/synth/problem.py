@@ -115,6 +115,13 @@ CONFIGS = {
                                       stabilisation="burman"),
     "ldc3d-sv-k3-tiny-burman": Config("ldc3d-sv-k3-tiny-burman", 3, 1, 1, "sv", 3, "macro", True, re=100.0, sort_order="0+:1-",
                                       stabilisation="burman"),
+    "ldc3d-sv-k3-small-burman": Config("ldc3d-sv-k3-small-burman", 3, 2, 1, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-",
+                                       stabilisation="burman"),
+    # configs[4] as the reference's own job runs it (examples/generate_submission:69-87: burman, weight 5e-3)
+    "ldc3d-sv-k3-burman": Config("ldc3d-sv-k3-burman", 3, 4, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-",
+                                 stabilisation="burman"),
+    "ldc3d-sv-k3-half-burman": Config("ldc3d-sv-k3-half-burman", 3, 2, 2, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-",
+                                      stabilisation="burman"),
     "ldc2d-pkp0-tiny-burman": Config("ldc2d-pkp0-tiny-burman", 2, 2, 2, "pkp0", 2, "star", False, re=100.0, stabilisation="burman"),
     "ldc2d-pkp0-tiny": Config("ldc2d-pkp0-tiny", 2, 2, 2, "pkp0", 2, "star", False, re=100.0),
     "ldc3d-sv-k3-tiny": Config("ldc3d-sv-k3-tiny", 3, 1, 1, "sv", 3, "macro", True, re=100.0, sort_order="0+:1-"),
@@ -234,9 +241,11 @@ def _bsr(ld: LevelData, vals):
     return BSR(ld.V.nnodes, ld.V.bs, ld.pattern.rowptr, ld.pattern.colidx, vals)
 
 
-def assemble_level(cfg: Config, ld: LevelData, nu: float, gamma: float, advect: float = 1.0, wind=None):
+def assemble_level(cfg: Config, ld: LevelData, nu: float, gamma: float, advect: float = 1.0, wind=None, stab_wind=None):
     """(Re)assemble the level operator — the once-per-Newton-step hand-over.  The viscous and
-    div-div parts are linear in (nu, gamma) and cached; only the advection parts are re-assembled."""
+    div-div parts are linear in (nu, gamma) and cached; only the advection parts are re-assembled.
+    stab_wind: the wind inside Burman's beta if it differs from the linearisation point (the reference updates it
+    once per Reynolds number, before the Newton solve: solver.py:270-271)."""
     lin = _linear_parts(cfg, ld)
     vals = nu * lin["visc"] + gamma * lin["div"]
     if advect != 0.0:
@@ -249,7 +258,7 @@ def assemble_level(cfg: Config, ld: LevelData, nu: float, gamma: float, advect: 
         if cfg.stabilisation == "burman":
             # F += advect * stabilisation_form (solver.py:233-234); the wind inside beta is a frozen copy of the state
             # (stabilisation.py:19-44), so the term is linear in u and enters residual and Jacobian alike
-            _, _, S = burman_facet_tensors(ld.V, wind, cfg.stab_weight)
+            _, _, S = burman_facet_tensors(ld.V, wind if stab_wind is None else stab_wind, cfg.stab_weight)
             sv = ld.pattern.scatter_facets(S)
             ld.stab = np.zeros_like(vals)
             for r in range(ld.V.bs):

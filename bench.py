@@ -30,7 +30,8 @@ sys.path.insert(0, ROOT)
 DEFAULT_CONFIG = "ldc3d-sv-k3"
 CPU_SAMPLE_CONFIG = {"ldc3d-sv-k3-literal": "ldc3d-sv-k3-half-literal", "ldc3d-sv-k3": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w1": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w2": "ldc3d-sv-k3-half",
                      "ldc3d-sv-k3-w4": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w8": "ldc3d-sv-k3-half", "ldc3d-sv-k3-s8": "ldc3d-sv-k3-half", "ldc3d-sv-k3-n5": "ldc3d-sv-k3-half", "ldc3d-sv-k3-n6": "ldc3d-sv-k3-half", "ldc2d-sv-k2": "ldc2d-sv-k2", "ldc2d-pkp0": "ldc2d-pkp0",
-                     "ldc3d-pkp0": "ldc3d-pkp0-small", "ldc3d-pkp0-mid": "ldc3d-pkp0-small", "bfs2d-sv-k2": "bfs2d-sv-k2-small"}
+                     "ldc3d-pkp0": "ldc3d-pkp0-small", "ldc3d-pkp0-mid": "ldc3d-pkp0-small", "bfs2d-sv-k2": "bfs2d-sv-k2-small",
+                     "ldc3d-sv-k3-burman": "ldc3d-sv-k3-half-burman", "ldc3d-sv-k3-half-burman": "ldc3d-sv-k3-half-burman"}
 METRIC = "V-cycle DoF/s (finest-level velocity dofs per second of one fieldsplit_0 PCMG-full application)"
 
 
@@ -74,6 +75,8 @@ def workload_config(name):
             "mesh": "Kuhn %s x 2^%d%s" % (" x ".join(str(cfg.N * s) for s in shape), cfg.nref, ", Alfeld split" if cfg.bary else ""),
             "velocity_dofs": int(ndofs), "levels": cfg.nref + 1, "smoothing": cfg.m, "re": cfg.re, "gamma": cfg.gamma,
             "rank_grid": list(cfg.shape) if cfg.shape else None, "patches_finest": int(npatch), "max_patch_dofs": int(maxn),
+            "stabilisation": ("burman, weight %g (interior-facet jump term: patch operators are not sub-matrices, dense inverses + "
+                              "patch corrections)" % cfg.stab_weight) if cfg.stabilisation == "burman" else "none",
             "patch_constructor": ("alfi.MacroStar, literal semantics of relaxation.py:168-177" if cfg.macro_expand == "all" else
                                   "alfi.MacroStar restricted to the open macro star (-pc_patch_construction_MacroStar_expand vertices: "
                                   "an extension; in 2-D identical to the reference, in 3-D the 1275-dof sets SURVEY §8 sizes the "

@@ -28,6 +28,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 LADDER = [1, 10, 100] + list(range(200, 5001, 100))
+POLISH_KSP_TOL = (1e-6, 0.0)       # linear tolerances of the polishing Newton step (relative to a residual of ~1e-8)
 
 
 def oracle_backend(cfg):
@@ -74,7 +75,7 @@ def polish_fixture(name, path, log=print):
     old = dict(np.load(path))
     s = ContinuationSolver(cfg, oracle_backend(cfg))
     s.u[:], s.p[:] = old["u"], old["p"]
-    info = s.solve(float(old["re"][-1]), min_newton=1)
+    info = s.solve(float(old["re"][-1]), min_newton=1, ksp_tol=POLISH_KSP_TOL)
     log("polish at Re %g: Newton %d, Krylov %d, residual %.2e" % (old["re"][-1], info["nonlinear_iter"], info["linear_iter"], info["residual"]))
     old.update(u_polished=s.u, p_polished=s.p, polish_re=float(old["re"][-1]), polish_residual=float(info["residual"]))
     np.savez_compressed(path, **old)
@@ -115,7 +116,7 @@ def compare_with_fixture(name, path, outer="host", device=0, log=print, max_step
         out["pressure_rel_diff"] = float(np.linalg.norm(s.p - ref["p"]) / np.linalg.norm(ref["p"]))
         out["final_residual"] = float(rows[-1, 3])
         if "u_polished" in ref.files and float(ref["polish_re"]) == res[-1]:
-            s.solve(res[-1], min_newton=1)          # one more Newton step on this side as well
+            s.solve(res[-1], min_newton=1, ksp_tol=POLISH_KSP_TOL)          # one more Newton step on this side as well
             out["velocity_rel_diff_polished"] = float(np.linalg.norm(s.u - ref["u_polished"]) / np.linalg.norm(ref["u_polished"]))
             out["pressure_rel_diff_polished"] = float(np.linalg.norm(s.p - ref["p_polished"]) / np.linalg.norm(ref["p_polished"]))
         du = out.get("velocity_rel_diff_polished", out["velocity_rel_diff"])
