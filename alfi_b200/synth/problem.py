@@ -126,6 +126,11 @@ CONFIGS = {
     "ldc2d-pkp0-tiny": Config("ldc2d-pkp0-tiny", 2, 2, 2, "pkp0", 2, "star", False, re=100.0),
     "ldc3d-sv-k3-tiny": Config("ldc3d-sv-k3-tiny", 3, 1, 1, "sv", 3, "macro", True, re=100.0, sort_order="0+:1-"),
     "ldc3d-pkp0-tiny": Config("ldc3d-pkp0-tiny", 3, 1, 2, "pkp0", 1, "star", False, re=100.0, element="p1fb"),
+    # configs[3] at BASELINE size (M = 64: 10.33 M dofs, 274 625 star patches) over FIVE levels: the reference's baseN 16 /
+    # nref 2 hierarchy has a 167 k-dof coarse level without macro structure, which needs a sparse direct solver; the same
+    # finest mesh over baseN 4 / nref 4 has a 2 967-dof one ("prefer smaller baseN + more levels, state it")
+    "ldc3d-pkp0-l5": Config("ldc3d-pkp0-l5", 3, 4, 4, "pkp0", 1, "star", False, re=5000.0, element="p1fb"),
+    "ldc3d-pkp0-l5-tiny": Config("ldc3d-pkp0-l5-tiny", 3, 1, 4, "pkp0", 1, "star", False, re=100.0, element="p1fb"),
     "ldc3d-pkp0-mid": Config("ldc3d-pkp0-mid", 3, 8, 2, "pkp0", 1, "star", False, re=5000.0, element="p1fb"),
     "ldc3d-pkp0-small": Config("ldc3d-pkp0-small", 3, 4, 2, "pkp0", 1, "star", False, re=1000.0, element="p1fb"),
     "ldc3d-sv-k3-small": Config("ldc3d-sv-k3-small", 3, 2, 1, "sv", 3, "macro", True, re=5000.0, sort_order="0+:1-"),

@@ -225,3 +225,23 @@ def test_caller_colours_are_validated():
     ctx.set_patches(0, off, dofs, None, np.array([0, 1], np.int32))
     assert ctx.colours(0, 2).tolist() == [0, 1]
     ctx.close()
+
+
+def test_five_level_cycle_equals_oracle(problems):
+    """configs[3] at BASELINE size runs over five levels (ldc3d-pkp0-l5: baseN 4, nref 4); the same hierarchy depth on a
+    16^3 mesh here: F-cycle (PCMG full: 1 + 2 + 3 + 4 + 5 level visits) against the oracle."""
+    from alfi_b200.multigrid import DeviceMultigrid, level_input_from_synth
+    from oracle import hotpath as hp
+    prob = problems("ldc3d-pkp0-l5-tiny", gamma=10.0, nu=0.2)
+    assert len(prob.levels) == 5 and prob.finest.ndofs == 3 * (17 ** 3 + 12 * 16 ** 3 + 6 * 16 ** 2)
+    mg = DeviceMultigrid([level_input_from_synth(l) for l in prob.levels], prob.config.m, deterministic=True)
+    olv = [hp.level_from_host(l) for l in prob.levels]
+    b = np.random.default_rng(12).standard_normal(prob.finest.ndofs)
+    b[prob.finest.bc_dofs] = 0
+    x = mg.apply(b, np.empty_like(b))
+    want = hp.fcycle(olv, b, prob.config.m)
+    assert rel(x, want) <= 1e-11
+    for _ in range(2):
+        x = mg.apply(b, np.empty_like(b))                   # captured, replayed
+    assert rel(x, want) <= 1e-11
+    mg.ctx.close()
