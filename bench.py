@@ -580,10 +580,19 @@ def ours(args):
                 spec = importlib.util.spec_from_file_location("cont3d", os.path.join(ROOT, "scripts", "cont3d.py"))
                 cont3d = importlib.util.module_from_spec(spec)
                 spec.loader.exec_module(cont3d)
-                fixture = os.path.join(ROOT, "tests", "golden", "continuation_3d_small.npz")
                 quiet = lambda *a: print("[bench] 3-D continuation:", *a, file=sys.stderr, flush=True)   # noqa: E731
-                continuation["three_d"] = cont3d.compare_with_fixture(args.continuation_3d, fixture, args.continuation_3d_outer,
-                                                                      device=local, log=quiet)
+                # three_d: no stabilisation (the benchmark's operator); three_d_burman: --stabilisation-type burman,
+                # weight 5e-3, what the reference's own ldc3d Scott-Vogelius job runs with (generate_submission:69-87)
+                for key, name3, fname in (("three_d", args.continuation_3d, "continuation_3d_small.npz"),
+                                          ("three_d_burman", args.continuation_3d + "-burman", "continuation_3d_small_burman.npz")):
+                    fixture = os.path.join(ROOT, "tests", "golden", fname)
+                    if not os.path.exists(fixture):
+                        continue
+                    try:
+                        continuation[key] = cont3d.compare_with_fixture(name3, fixture, args.continuation_3d_outer,
+                                                                        device=local, log=quiet)
+                    except Exception as e:      # noqa: BLE001
+                        continuation[key] = {"error": repr(e)}
             except Exception as e:      # noqa: BLE001
                 continuation["three_d"] = {"error": repr(e)}
 

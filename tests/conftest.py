@@ -8,6 +8,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# Small dense factorisations dominate the oracle; with one BLAS thread per core and anything else running on the machine
+# the threads spin on each other (measured: 200 s instead of 4 s for one oracle level).  A few threads are enough.
+try:
+    from threadpoolctl import threadpool_limits
+    _blas_limit = threadpool_limits(limits=int(os.environ.get("ALFIB_TEST_BLAS_THREADS", "4")))
+except Exception:       # noqa: BLE001 - threadpoolctl is optional
+    _blas_limit = None
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
