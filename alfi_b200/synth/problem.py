@@ -130,6 +130,7 @@ CONFIGS = {
     # nref 2 hierarchy has a 167 k-dof coarse level without macro structure, which needs a sparse direct solver; the same
     # finest mesh over baseN 4 / nref 4 has a 2 967-dof one ("prefer smaller baseN + more levels, state it")
     "ldc3d-pkp0-l5": Config("ldc3d-pkp0-l5", 3, 4, 4, "pkp0", 1, "star", False, re=5000.0, element="p1fb"),
+    "ldc3d-pkp0-l5-re100": Config("ldc3d-pkp0-l5-re100", 3, 4, 4, "pkp0", 1, "star", False, re=100.0, element="p1fb"),
     "ldc3d-pkp0-l5-tiny": Config("ldc3d-pkp0-l5-tiny", 3, 1, 4, "pkp0", 1, "star", False, re=100.0, element="p1fb"),
     "ldc3d-pkp0-mid": Config("ldc3d-pkp0-mid", 3, 8, 2, "pkp0", 1, "star", False, re=5000.0, element="p1fb"),
     "ldc3d-pkp0-small": Config("ldc3d-pkp0-small", 3, 4, 2, "pkp0", 1, "star", False, re=1000.0, element="p1fb"),

@@ -31,7 +31,7 @@ DEFAULT_CONFIG = "ldc3d-sv-k3"
 CPU_SAMPLE_CONFIG = {"ldc3d-sv-k3-literal": "ldc3d-sv-k3-half-literal", "ldc3d-sv-k3": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w1": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w2": "ldc3d-sv-k3-half",
                      "ldc3d-sv-k3-w4": "ldc3d-sv-k3-half", "ldc3d-sv-k3-w8": "ldc3d-sv-k3-half", "ldc3d-sv-k3-s8": "ldc3d-sv-k3-half", "ldc3d-sv-k3-n5": "ldc3d-sv-k3-half", "ldc3d-sv-k3-n6": "ldc3d-sv-k3-half", "ldc2d-sv-k2": "ldc2d-sv-k2", "ldc2d-pkp0": "ldc2d-pkp0",
                      "ldc3d-pkp0": "ldc3d-pkp0-small", "ldc3d-pkp0-mid": "ldc3d-pkp0-small", "bfs2d-sv-k2": "bfs2d-sv-k2-small",
-                     "ldc3d-pkp0-l5": "ldc3d-pkp0-small", "ldc3d-sv-k3-burman": "ldc3d-sv-k3-half-burman", "ldc3d-sv-k3-half-burman": "ldc3d-sv-k3-half-burman"}
+                     "ldc3d-pkp0-l5": "ldc3d-pkp0-small", "ldc3d-pkp0-l5-re100": "ldc3d-pkp0-small", "ldc3d-sv-k3-burman": "ldc3d-sv-k3-half-burman", "ldc3d-sv-k3-half-burman": "ldc3d-sv-k3-half-burman"}
 METRIC = "V-cycle DoF/s (finest-level velocity dofs per second of one fieldsplit_0 PCMG-full application)"
 
 
