@@ -325,7 +325,16 @@ __global__ void sep_rhs_kernel(int64_t nsep, const int32_t* __restrict__ sepdofs
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nsep) return;
   double v = __ldg(x + sepdofs[e]);
-  for (int j = cptr[e]; j < cptr[e + 1]; ++j) v -= g1[cg1[j]];
+  // four index -> value pairs in flight per thread (the plain loop is a chain of dependent loads: long_scoreboard was
+  // its only stall); subtracted in list order, and v - 0.0 == v, so the bits are those of the plain loop
+  const int j1 = cptr[e + 1];
+  for (int j = cptr[e]; j < j1; j += 4) {
+    double g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) g[u] = (j + u < j1) ? g1[cg1[j + u]] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v -= g[u];
+  }
   rs[e] = v;
 }
 
@@ -336,7 +345,14 @@ __global__ void slot_sum_kernel(int64_t nslots, const int32_t* __restrict__ zptr
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nslots) return;
   double v = 0.0;
-  for (int j = zptr[e]; j < zptr[e + 1]; ++j) v += us[zsrc[j]];
+  const int j1 = zptr[e + 1];
+  for (int j = zptr[e]; j < j1; j += 4) {          // as in sep_rhs_kernel: independent loads, list order
+    double g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) g[u] = (j + u < j1) ? us[zsrc[j + u]] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v += g[u];
+  }
   z[e] = v;
 }
 
