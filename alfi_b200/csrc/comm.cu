@@ -731,8 +731,16 @@ __global__ void __launch_bounds__(256) mbox_small_sum_partials_kernel(int nv, in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const double* in = my_data + 2 * slot * my_cap;
   for (int j = warp; j < nv; j += nwarp) {
+    // eight loads in flight per lane (the plain loop is a chain of 19 dependent-latency loads for 592 partials); added in
+    // the order of that loop, and x + 0.0 == x here, so the bits are finalize_kernel's
     double mine = 0.0;
-    for (int b = lane; b < nparts; b += 32) mine += partial[(long long)j * nparts + b];
+    for (int b0 = lane; b0 < nparts; b0 += 32 * 8) {
+      double a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = (b0 + 32 * u < nparts) ? partial[(long long)j * nparts + b0 + 32 * u] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) mine += a[u];
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
     if (lane == 0) {
