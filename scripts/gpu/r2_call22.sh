@@ -22,9 +22,9 @@ except Exception as e:
 PY
 timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/r2_pytest_gpu_final2.log 2>&1; el pytest $?; tail -3 gpurun_out/r2_pytest_gpu_final2.log
 for f in 1 0; do
-  ALFIB_FUSE_DOTS=$f timeout 300 python scripts/kernel_bench.py ldc3d-sv-k3 20 > gpurun_out/r2_kernel_bench_fuse$f.txt 2>&1; el kb-fuse$f $?
+  ALFIB_FUSE_DOTS=$f timeout 300 python scripts/kernel_bench.py ldc3d-sv-k3 10 > gpurun_out/r2_kernel_bench_fuse$f.txt 2>&1; el kb-fuse$f $?
   grep -E "^(smooth|cycle|apply|spmv)" gpurun_out/r2_kernel_bench_fuse$f.txt
 done
-timeout 420 compute-sanitizer --tool memcheck --print-limit 5 python scripts/sanitize.py > gpurun_out/r2_sanitizer_memcheck.txt 2>&1; el memcheck $?
+timeout 300 compute-sanitizer --tool memcheck --print-limit 5 python scripts/sanitize.py > gpurun_out/r2_sanitizer_memcheck.txt 2>&1; el memcheck $?
 grep -E " ok |ERROR SUMMARY|Error|error:" gpurun_out/r2_sanitizer_memcheck.txt | head -14
 el done 0
