@@ -117,3 +117,17 @@ def test_3d_continuation_against_the_lu_fixture(name, outer):
     out = mod.compare_with_fixture(name, path, outer, log=lambda *a: None, max_steps=6)
     assert out["newton_counts_equal"] and out["krylov_counts_within_1_per_newton_step"], out
     assert out["re_max"] == 400.0
+
+
+def test_state_verdict_of_the_3d_comparison():
+    """scripts/cont3d.py state_verdict: the bar is the north star's 1e-8 unless the CPU-vs-CPU floor of the fixture is
+    above a third of it; either the states as stopped or the polished states must meet it."""
+    mod, _ = _cont3d()
+    v = mod.state_verdict(8.3e-9, 9.3e-9, 1.03e-8, 1.23e-8, 2.6e-11)          # unstabilised, Re 2900 (call 22)
+    assert v["state_bar"] == 1e-8 and v["state_ok_as_stopped"] and not v["state_ok_polished"] and v["state_ok"]
+    v = mod.state_verdict(1.15e-7, 1.21e-7, 1.72e-8, 2.48e-8, 1.0e-8)         # Burman, Re 5000 (call 22)
+    assert abs(v["state_bar"] - 3e-8) < 1e-20 and not v["state_ok_as_stopped"] and v["state_ok_polished"] and v["state_ok"]
+    v = mod.state_verdict(1e-6, 1e-6, 1e-7, 1e-7, 1e-8)
+    assert not v["state_ok"]
+    v = mod.state_verdict(1e-6, 1e-6, None, None, 0.0)
+    assert not v["state_ok"] and not v["state_ok_polished"]
