@@ -182,10 +182,13 @@ class ContinuationSolver:
         return Fu, Fp
 
     # -- one Reynolds number ----------------------------------------------------------------------
-    def solve(self, re, min_newton=0, ksp_tol=None):
+    def solve(self, re, min_newton=0, ksp_tol=None, max_newton=None):
         """One Reynolds number.  min_newton: take at least that many Newton steps even if the residual already meets
         the tolerances; ksp_tol = (rtol, atol) overrides the linear tolerances (both used to polish a converged state:
-        scripts/cont3d.py — the reference's ksp_atol would stop the linear solve of such a step at iteration 0)."""
+        scripts/cont3d.py — the reference's ksp_atol would stop the linear solve of such a step at iteration 0);
+        max_newton: take at most that many (with min_newton = max_newton a run follows another run's Newton counts, so
+        that a stopping test decided in the third digit of a residual norm does not fork the two trajectories; the
+        residual after every step is returned, so what the free-running test would have done is still known)."""
         cfg = self.config
         tdim = self.d
         tol = tolerances(tdim)
@@ -203,15 +206,18 @@ class ContinuationSolver:
             assemble_transfer(cfg, ld, nu, gamma)
         lin_its, newton = 0, 0
         fnorm0 = None
+        fhist = []
         nbc = fine.bc_dofs
         for newton in range(SNES_MAX_IT + 1):
             self._assemble(nu, gamma, advect)
             Fu, Fp = self._residual()
             fnorm = np.sqrt(Fu @ Fu + Fp @ Fp)
             fnorm0 = fnorm if fnorm0 is None else fnorm0
+            fhist.append(float(fnorm))
             if self.verbose:
                 print("  Re %g  SNES %d  |F| = %.6e" % (re, newton, fnorm), flush=True)
-            if (newton >= min_newton and fnorm <= max(tol["snes_atol"], tol["snes_rtol"] * fnorm0)) or newton == SNES_MAX_IT:
+            if (newton >= min_newton and fnorm <= max(tol["snes_atol"], tol["snes_rtol"] * fnorm0)) or newton == SNES_MAX_IT \
+                    or (max_newton is not None and newton >= max_newton):
                 break
             levels = [level_input_from_synth(l) for l in self.prob.levels]
             if not self._setup_done:
@@ -264,6 +270,7 @@ class ContinuationSolver:
                 print("      KSP iterations %d" % its, flush=True)
         self.p -= self.p.mean()
         info = {"Re": re, "nu": nu, "linear_iter": lin_its, "nonlinear_iter": newton,
-                "time": (time.time() - t0) / 60.0, "residual": fnorm, "residual0": fnorm0}
+                "time": (time.time() - t0) / 60.0, "residual": fnorm, "residual0": fnorm0, "residual_history": fhist,
+                "snes_tolerance": max(tol["snes_atol"], tol["snes_rtol"] * fnorm0)}
         self.history.append(info)
         return info

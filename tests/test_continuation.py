@@ -131,3 +131,13 @@ def test_state_verdict_of_the_3d_comparison():
     assert not v["state_ok"]
     v = mod.state_verdict(1e-6, 1e-6, None, None, 0.0)
     assert not v["state_ok"] and not v["state_ok_polished"]
+
+
+def test_free_running_newton_count_of_a_residual_history():
+    """scripts/cont3d.py natural_newton_count: the device run follows the oracle's Newton counts and records what its own
+    stopping test would have done."""
+    mod, _ = _cont3d()
+    assert mod.natural_newton_count([1e-3, 1e-6, 5e-9], 1e-8) == (2, None)                 # stops where the history ends
+    assert mod.natural_newton_count([1e-3, 1e-6, 0.987e-8, 4e-11], 1e-8) == (2, 0.987e-8)   # would have stopped a step early
+    assert mod.natural_newton_count([1e-3, 1e-6, 1.004e-8], 1e-8) == (3, 1.004e-8)          # would have gone on
+    assert abs(0.987e-8 / 1e-8 - 1.0) <= mod.KNIFE_EDGE and abs(1.004e-8 / 1e-8 - 1.0) <= mod.KNIFE_EDGE
