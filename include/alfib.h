@@ -78,7 +78,8 @@ void* alfib_stream(alfib_ctx* ctx);
 int alfib_host_register(alfib_ctx* ctx, void* ptr, int64_t bytes);
 int alfib_host_unregister(alfib_ctx* ctx, void* ptr);
 
-/* Multi-GPU: one rank per GPU on one NVSwitch box.  Each rank passes only ITS patches to
+/* Multi-GPU: one rank per GPU on one NVSwitch box.  (This paragraph is the replicated-vector mode of round 1, still
+ * selectable; the default for N > 1 is the distributed mode of alfib_level_set_halo below.)  Each rank passes only ITS patches to
  * alfib_level_set_patches (the owned vertices of the DMPlex vertex-overlap partition the
  * reference uses, solver.py:604-605, 661-662, relaxation.py:120-121); level vectors are
  * replicated, block rows of the operators are split evenly.  The library then inserts the two
