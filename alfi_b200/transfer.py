@@ -129,6 +129,25 @@ def cell_patch_set(levels, level, V, macro) -> tuple[PatchSet, np.ndarray]:
     return patch_dofs_from_points(plex, V, H, bc_nodes=cb), cb
 
 
+def _values(x):
+    """Read-only flat float64 view of a numpy array or of a Firedrake Function's owned values."""
+    if hasattr(x, "dat"):
+        return np.ascontiguousarray(x.dat.data_ro, dtype=np.float64).reshape(-1)
+    return x
+
+
+def _buffer(x):
+    """The array a device call writes into: the array itself, or a flat buffer for a Firedrake Function."""
+    if hasattr(x, "dat"):
+        return np.empty(int(np.prod(x.dat.data_ro.shape)), dtype=np.float64)
+    return x
+
+
+def _store(x, buf):
+    if hasattr(x, "dat"):
+        x.dat.data[...] = buf.reshape(x.dat.data_ro.shape)
+
+
 class AutoSchoeberlTransfer:
     """``prolong(coarse, fine)`` / ``restrict(fine, coarse)`` on device (transfer.py:91-290).
 
@@ -168,16 +187,22 @@ class AutoSchoeberlTransfer:
             self.prev_parameters[level] = [float(p) for p in self.parameters]
 
     def prolong(self, coarse, fine, level=None):
-        """fine <- (I - A0^-1 gamma D) P_H coarse   (transfer.py:246-259)."""
-        level = self._level_of(fine) if level is None else level
+        """fine <- (I - A0^-1 gamma D) P_H coarse   (transfer.py:246-259).  ``coarse`` / ``fine`` are numpy arrays or
+        Firedrake Functions (what the TransferManager passes, solver.py:593-596): those are read / written through
+        ``.dat.data_ro`` / ``.dat.data`` like the reference does (transfer.py:256)."""
+        c, f = _values(coarse), _buffer(fine)
+        level = self._level_of(f) if level is None else level
         self._ensure(level)
-        self.backend.prolong(level, coarse, fine)
+        self.backend.prolong(level, c, f)
+        _store(fine, f)
 
     def restrict(self, fine, coarse, level=None):
         """coarse <- P_H^T (I - gamma D A0^-1) fine   (transfer.py:261-275)."""
-        level = self._level_of(fine) if level is None else level
+        f, c = _values(fine), _buffer(coarse)
+        level = self._level_of(f) if level is None else level
         self._ensure(level)
-        self.backend.restrict(level, fine, coarse)
+        self.backend.restrict(level, f, c)
+        _store(coarse, c)
 
     def _level_of(self, fine):
         n = fine.size
