@@ -211,9 +211,11 @@ class FiredrakeAccess:
     def bc_nodes(self, l):
         """Homogeneous Dirichlet nodes of the velocity: the solver's bcs re-applied on the level's space, as Firedrake's
         coarsening of the problem does (`firedrake.mg.ufl_utils.coarsen` of a DirichletBC keeps ``sub_domain``)."""
+        import ufl
         from firedrake import DirichletBC
         V = self.function_space(l)
-        nodes = [np.asarray(DirichletBC(V, 0 * bc.function_arg if hasattr(bc, "function_arg") else 0, bc.sub_domain).nodes)
+        zero = ufl.zero(V.ufl_element().value_shape())                 # only .nodes is read (as transfer.py:155)
+        nodes = [np.asarray(DirichletBC(V, zero, bc.sub_domain).nodes)
                  for bc in self.solver.bcs if bc.function_space().index == 0]
         return np.unique(np.concatenate(nodes)) if nodes else np.empty(0, np.int32)
 
@@ -227,9 +229,8 @@ class FiredrakeAccess:
     def operator_blocks(self, l):
         """The velocity block of the Jacobian rediscretised on level l: the (0, 0) split of the coarsened
         SNES context, i.e. what PCMG's level KSPs get from Firedrake's dmhooks (``get_appctx(dm).J``)."""
-        from firedrake.dmhooks import get_appctx
         from firedrake.mg.ufl_utils import coarsen
-        ctx = get_appctx(self.solver.Z.dm)
+        ctx = self.solver.solver._ctx                                  # _SNESContext of the NonlinearVariationalSolver
         for _ in range(self.nlevels() - 1 - l):
             ctx = coarsen(ctx, coarsen)
         ctx0, = ctx.split([(0,)])
@@ -273,13 +274,15 @@ class FiredrakeAccess:
         """(B, M_p^-1): the assembled (div u, q) block and the inverse of the DG pressure mass matrix that
         DGMassInv.initialize assembles (solver.py:21-31)."""
         import scipy.sparse as sp
-        from firedrake import TestFunction, TrialFunction, assemble, div, dx, inner
-        V, Q = self.solver.Z.sub(0), self.solver.Z.sub(1)
+        from firedrake import FunctionSpace, Tensor, TestFunction, TrialFunction, assemble, div, dx, inner
+        fine = self.solver.mh[-1]
+        V = self.function_space(self.nlevels() - 1)
+        Q = FunctionSpace(fine, self.solver.Z.sub(1).ufl_element())
         u, q = TrialFunction(V), TestFunction(Q)
-        ip, ix, dv = assemble(-div(u) * q * dx, mat_type="aij").petscmat.getValuesCSR()
+        ip, ix, dv = assemble(-div(u) * q * dx, mat_type="aij").petscmat.getValuesCSR()     # the (1, 0) block of the residual's Jacobian
         B = sp.csr_matrix((dv, ix, ip), shape=(Q.dim(), V.dim()))
         p = TrialFunction(Q)
-        ip, ix, dv = assemble(inner(p, q) * dx, inverse=True, mat_type="aij").petscmat.getValuesCSR()
+        ip, ix, dv = assemble(Tensor(inner(p, q) * dx).inv).petscmat.getValuesCSR()          # solver.py:24
         return B, sp.csr_matrix((dv, ix, ip), shape=(Q.dim(), Q.dim()))
 
 
